@@ -1,0 +1,997 @@
+/*
+ * ddc_oracle.c -- CPU ORACLE for the domain-decomposition hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the shipped product (the CUDA library,
+ * the C++ host API, the `decomp` CLI) links, imports or calls this file.  It is
+ * used by tests/, by __graft_entry__.smoke() and by bench.py's cpu_baseline /
+ * `--impl reference` leg, and only as the checker / the reported CPU baseline.
+ *
+ * It is a plain-C restatement of the reference algorithm, function by function
+ * (citations are file:line into the reference checkout, nextsimhub/domain_decomp):
+ *
+ *   orc_find_factors / orc_naive_block    Grid.cpp:18-35, 150-166
+ *   ocean test (mask > 0), dot ids        Grid.cpp:176-188
+ *   dot coordinates (id % NX, id / NX)    ZoltanPartitioner.cpp:61-64
+ *   orc_rcb_dots  (Zoltan RCB, literal)   ZoltanPartitioner.cpp:125-139,161-163
+ *   orc_rcb_hist  (same, on histograms)   -- cross-checked against orc_rcb_dots
+ *   box conversion ceil / clamp           ZoltanPartitioner.cpp:172-195
+ *   `changes` fallback to naive blocks    ZoltanPartitioner.cpp:172-187
+ *   owner labelling                       ZoltanPartitioner.cpp:201-219
+ *   domain_overlap                        DomainUtils.cpp:15-35
+ *   is_neighbour / halo_start             Partitioner.cpp:20-80
+ *   discover_neighbours (O(P^2))          Partitioner.cpp:404-434
+ *   flattening order (ids ascending)      Partitioner.cpp:98-126, 190-206
+ *
+ * The partition arithmetic itself lives in a third-party dependency that is
+ * NOT part of the reference checkout: Sandia Zoltan (Trilinos), version not
+ * pinned by the reference (spack.yaml:11 says `zoltan`; README builds Trilinos
+ * master).  orc_rcb_dots restates Zoltan's published algorithm (rcb.c rcb_fn
+ * level loop, Zoltan_Divide_Machine, par_median.c Zoltan_RB_find_median with
+ * rectilinear_blocks=1 and average_cuts=1, rcb_box.c Zoltan_RCB_Box) for the 14
+ * parameters the reference sets.  Parity is PINNED by the reference's own
+ * goldens (tests/golden/reference_goldens.json: 9 bounding-box known-answer
+ * tests + 5 integration pid maps + 5 metadata files); see DESIGN.md for what
+ * those goldens do not pin (the Q-items).
+ *
+ * Floating point: every expression that Zoltan evaluates in double is
+ * evaluated here in the same order, in IEEE double, compiled with
+ * -ffp-contract=off (no FMA).
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------- */
+/* a1: naive block decomposition (Grid.cpp:18-35,150-166)                    */
+/* ------------------------------------------------------------------------- */
+
+ORC_API void orc_find_factors(int n, int np[2])
+{
+    int fa = -1, fb = -1;
+    for (int i = 2; i * i <= n; i += 2) {
+        if (n % i == 0) {
+            fa = i;
+            fb = n / fa;
+        }
+    }
+    if (fa == -1 || fb == -1) {
+        np[0] = n;
+        np[1] = 1;
+    } else {
+        np[0] = fa;
+        np[1] = fb;
+    }
+}
+
+/* box = {x0, y0, ext_x, ext_y} of "rank" r in the naive decomposition */
+ORC_API void orc_naive_block(int P, int NX, int NY, int r, int box[4])
+{
+    int np[2];
+    int G[2] = { NX, NY };
+    int le[2];
+    orc_find_factors(P, np);
+    for (int i = 0; i < 2; i++)
+        le[i] = (int)ceil((float)G[i] / (np[i])); /* float division, as the reference */
+    int g0 = (r / np[1]) * le[0];
+    int g1 = (r % np[1]) * le[1];
+    if ((r / np[1]) == np[0] - 1)
+        le[0] = G[0] - (r / np[1]) * le[0];
+    if ((r % np[1]) == np[1] - 1)
+        le[1] = G[1] - (r % np[1]) * le[1];
+    box[0] = g0;
+    box[1] = g1;
+    box[2] = le[0];
+    box[3] = le[1];
+}
+
+/* rank whose naive block contains cell (x, y); -1 if none (degenerate blocks) */
+static int naive_rank_of_cell(int P, int NX, int NY, int x, int y)
+{
+    int np[2];
+    orc_find_factors(P, np);
+    int lx = (int)ceil((float)NX / np[0]);
+    int ly = (int)ceil((float)NY / np[1]);
+    int bx = lx > 0 ? x / lx : 0;
+    int by = ly > 0 ? y / ly : 0;
+    if (bx > np[0] - 1)
+        bx = np[0] - 1;
+    if (by > np[1] - 1)
+        by = np[1] - 1;
+    /* when ceil() over-covers, trailing blocks start beyond the extent and the
+       last block has a non-positive extent: the cell then belongs to the last
+       block that actually starts at or before it -- which is what x / lx gives. */
+    return bx * np[1] + by;
+}
+
+/* ------------------------------------------------------------------------- */
+/* a4: Zoltan RCB -- shared pieces                                           */
+/* ------------------------------------------------------------------------- */
+
+#define ORC_MAXLEV 40
+
+/* number of recursion levels for P parts and the preset (RCB_SET_DIRECTIONS=1,
+   "xyz") cut dimension of every level, from the bounding box of ALL dots
+   (Zoltan rcb.c, preset_dir).  wx > wy picks x; a tie picks y (Q1). */
+static int preset_dims(int P, double wx, double wy, int dim_of_level[ORC_MAXLEV])
+{
+    int nlev = 0;
+    for (int t = P; t > 1; t = (t + 1) / 2)
+        nlev++;
+    int ix = 0, iy = 0;
+    for (int i = 0; i < nlev; i++) {
+        if (wx > wy) {
+            ix++;
+            wx /= 2.0;
+        } else {
+            iy++;
+            wy /= 2.0;
+        }
+    }
+    for (int i = 0; i < nlev; i++)
+        dim_of_level[i] = (i < ix) ? 0 : 1;
+    (void)iy;
+    return nlev;
+}
+
+typedef struct {
+    double lo[2], hi[2]; /* cut-tree box of a part: -DBL_MAX / DBL_MAX when uncut */
+} orc_dbox;
+
+/* degenerate-cut policy (Q2, reference behaviour undefined): when a side of a
+   cut holds no dot the cut is placed half a cell beyond the populated side. */
+static double average_cut(int have_lo, double vlo, int have_hi, double vhi, double boxlo, double boxhi)
+{
+    if (have_lo && have_hi)
+        return 0.5 * (vlo + vhi);
+    if (have_lo)
+        return vlo + 0.5;
+    if (have_hi)
+        return vhi - 0.5;
+    /* no dot at all in this sub-box: split the inherited integer range in two */
+    return floor(0.5 * (boxlo + boxhi)) + 0.5;
+}
+
+/* ------------------------------------------------------------------------- */
+/* a4 (literal): dot-based RCB, one dot per ocean cell                       */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    const double* c[2]; /* coordinates of every dot, per dimension */
+    int* mark; /* dotmark scratch, indexed by dot */
+    int* list; /* dotlist scratch */
+    int* part; /* out: part of every dot */
+    orc_dbox* boxes; /* out: cut-tree box of every part */
+    int dim_of_level[ORC_MAXLEV];
+    double ext[2]; /* global extents, for the degenerate-cut policy */
+    long median_iters;
+} dots_ctx;
+
+/* Zoltan_RB_find_median restated for one MPI rank holding all dots of the set
+   (the Allreduce of `struct median` is then the identity), uniform weights,
+   rectilinear_blocks = 1, average_cuts = 1, first_guess = 0. */
+static double find_median_dots(dots_ctx* cx, const int* idx, int dotnum, int dim, double fractionlo,
+    double valuemin, double valuemax, double weight, double boxlo, double boxhi)
+{
+    const double* dots = cx->c[dim];
+    int* dotmark = cx->mark;
+    int* dotlist = cx->list;
+    int numlist = dotnum;
+    for (int i = 0; i < dotnum; i++)
+        dotlist[i] = idx[i];
+
+    const double tolerance = 1.0; /* no user weights: every dot weighs 1.0 */
+    double weightlo = 0.0, weighthi = 0.0;
+    double targetlo = fractionlo * weight;
+    double targethi = weight - targetlo;
+    double tmp_half;
+
+    for (;;) {
+        if (weight != 0.0)
+            tmp_half = valuemin
+                + (targetlo - weightlo) / (weight - weightlo - weighthi) * (valuemax - valuemin);
+        else
+            tmp_half = 0.5 * (valuemin + valuemax);
+        cx->median_iters++;
+
+        double totallo = 0.0, totalhi = 0.0;
+        double valuelo = -DBL_MAX, valuehi = DBL_MAX;
+        double wtlo = 0.0, wthi = 0.0;
+        int countlo = 0, counthi = 0;
+        int markactive;
+
+        for (int j = 0; j < numlist; j++) {
+            int i = dotlist[j];
+            if (dots[i] <= tmp_half) {
+                totallo += 1.0;
+                dotmark[i] = 0;
+                if (dots[i] > valuelo) {
+                    valuelo = dots[i];
+                    wtlo = 1.0;
+                    countlo = 1;
+                } else if (dots[i] == valuelo) {
+                    wtlo += 1.0;
+                    countlo++;
+                }
+            } else {
+                totalhi += 1.0;
+                dotmark[i] = 1;
+                if (dots[i] < valuehi) {
+                    valuehi = dots[i];
+                    wthi = 1.0;
+                    counthi = 1;
+                } else if (dots[i] == valuehi) {
+                    wthi += 1.0;
+                    counthi++;
+                }
+            }
+        }
+
+        if (weightlo + totallo < targetlo) { /* lower half TOO SMALL */
+            weightlo += totallo;
+            if (counthi == 0)
+                break; /* defensive: nothing left to move */
+            if (counthi == 1) { /* only one dot to move */
+                if (weightlo + wthi < targetlo) { /* move it, keep iterating */
+                    for (int j = 0; j < numlist; j++)
+                        if (dots[dotlist[j]] == valuehi)
+                            dotmark[dotlist[j]] = 0;
+                } else { /* only move if beneficial */
+                    if (weightlo + wthi - targetlo < targetlo - weightlo)
+                        for (int j = 0; j < numlist; j++)
+                            if (dots[dotlist[j]] == valuehi)
+                                dotmark[dotlist[j]] = 0;
+                    break;
+                }
+            } else { /* multiple dots to move */
+                int breakflag = 0;
+                double wtok = wthi;
+                if (weightlo + wthi >= targetlo) { /* all done */
+                    /* rectilinear: do not move the group if that is worse */
+                    if (weightlo + wthi - targetlo > targetlo - weightlo)
+                        wtok = 0.0;
+                    breakflag = 1;
+                }
+                double wtsum = 0.0;
+                for (int j = 0; j < numlist && wtsum < wtok; j++) {
+                    int i = dotlist[j];
+                    if (dots[i] == valuehi) {
+                        if (wtsum + 1.0 - wtok < wtok - wtsum)
+                            dotmark[i] = 0;
+                        wtsum += 1.0;
+                    }
+                }
+                if (breakflag)
+                    break;
+            }
+            weightlo += wthi;
+            if (targetlo - weightlo <= tolerance)
+                break; /* close enough */
+            valuemin = valuehi; /* iterate again */
+            markactive = 1;
+        } else if (weighthi + totalhi < targethi) { /* upper half TOO SMALL */
+            weighthi += totalhi;
+            if (countlo == 0)
+                break;
+            if (countlo == 1) {
+                if (weighthi + wtlo < targethi) {
+                    for (int j = 0; j < numlist; j++)
+                        if (dots[dotlist[j]] == valuelo)
+                            dotmark[dotlist[j]] = 1;
+                } else {
+                    if (weighthi + wtlo - targethi < targethi - weighthi)
+                        for (int j = 0; j < numlist; j++)
+                            if (dots[dotlist[j]] == valuelo)
+                                dotmark[dotlist[j]] = 1;
+                    break;
+                }
+            } else {
+                int breakflag = 0;
+                double wtok = wtlo;
+                if (weighthi + wtlo >= targethi) {
+                    if (weighthi + wtlo - targethi > targethi - weighthi)
+                        wtok = 0.0;
+                    breakflag = 1;
+                }
+                double wtsum = 0.0;
+                for (int j = 0; j < numlist && wtsum < wtok; j++) {
+                    int i = dotlist[j];
+                    if (dots[i] == valuelo) {
+                        if (wtsum + 1.0 - wtok < wtok - wtsum)
+                            dotmark[i] = 1;
+                        wtsum += 1.0;
+                    }
+                }
+                if (breakflag)
+                    break;
+            }
+            weighthi += wtlo;
+            if (targethi - weighthi <= tolerance)
+                break;
+            valuemax = valuelo;
+            markactive = 0;
+        } else /* Goldilocks result: both partitions JUST RIGHT */
+            break;
+
+        /* shrink the active list */
+        int k = 0;
+        for (int j = 0; j < numlist; j++) {
+            int i = dotlist[j];
+            if (dotmark[i] == markactive)
+                dotlist[k++] = i;
+        }
+        numlist = k;
+    }
+
+    /* AVERAGE_CUTS: halfway between the closest dots on either side, over ALL
+       dots of the set */
+    double vlo = -DBL_MAX, vhi = DBL_MAX;
+    int have_lo = 0, have_hi = 0;
+    for (int j = 0; j < dotnum; j++) {
+        int i = idx[j];
+        if (dotmark[i] == 0) {
+            have_lo = 1;
+            if (dots[i] > vlo)
+                vlo = dots[i];
+        } else {
+            have_hi = 1;
+            if (dots[i] < vhi)
+                vhi = dots[i];
+        }
+    }
+    return average_cut(have_lo, vlo, have_hi, vhi, boxlo, boxhi);
+}
+
+/* one RCB set: parts [partlower, partlower + num_parts), dots idx[0..n) */
+static void rcb_dots_recurse(dots_ctx* cx, int* idx, int n, int partlower, int num_parts, int level,
+    orc_dbox box)
+{
+    if (num_parts == 1) {
+        for (int j = 0; j < n; j++)
+            cx->part[idx[j]] = partlower;
+        cx->boxes[partlower] = box;
+        return;
+    }
+    /* Zoltan_Divide_Machine, uniform part sizes, one part per rank */
+    int partmid = partlower + (num_parts - 1) / 2 + 1;
+    double fractionlo = (double)(partmid - partlower) / (double)num_parts;
+    int dim = cx->dim_of_level[level];
+
+    /* RCB_RECOMPUTE_BOX = 1: bounding box of the dots of this set */
+    double vmin = DBL_MAX, vmax = -DBL_MAX;
+    for (int j = 0; j < n; j++) {
+        double v = cx->c[dim][idx[j]];
+        if (v < vmin)
+            vmin = v;
+        if (v > vmax)
+            vmax = v;
+    }
+    /* integer range this set inherits along dim (only used when it has no dot) */
+    double blo = (box.lo[dim] == -DBL_MAX) ? 0.0 : ceil(box.lo[dim]);
+    double bhi = (box.hi[dim] == DBL_MAX) ? cx->ext[dim] : ceil(box.hi[dim]);
+
+    double cut = find_median_dots(cx, idx, n, dim, fractionlo, vmin, vmax, (double)n, blo, bhi);
+
+    /* stable split of idx by dotmark (lower set keeps the lower part numbers) */
+    int nlo = 0;
+    for (int j = 0; j < n; j++)
+        if (cx->mark[idx[j]] == 0)
+            nlo++;
+    int* tmp = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int a = 0, b = nlo;
+    for (int j = 0; j < n; j++) {
+        if (cx->mark[idx[j]] == 0)
+            tmp[a++] = idx[j];
+        else
+            tmp[b++] = idx[j];
+    }
+    memcpy(idx, tmp, sizeof(int) * (size_t)n);
+    free(tmp);
+
+    orc_dbox lobox = box, hibox = box;
+    lobox.hi[dim] = cut;
+    hibox.lo[dim] = cut;
+    rcb_dots_recurse(cx, idx, nlo, partlower, partmid - partlower, level + 1, lobox);
+    rcb_dots_recurse(cx, idx + nlo, n - nlo, partmid, partlower + num_parts - partmid, level + 1, hibox);
+}
+
+/*
+ * Literal RCB over the ocean cells of mask[NY][NX] (x fastest).
+ *   dboxes[P*4]  : xlo, ylo, xhi, yhi doubles (+-DBL_MAX when uncut)
+ *   part_of_cell : NY*NX, part of every ocean cell, -1 on land (may be NULL)
+ * returns the number of dots, or -1 on allocation failure.
+ */
+ORC_API long orc_rcb_dots(const int32_t* mask, int NX, int NY, int P, double* dboxes,
+    int32_t* part_of_cell, long* median_iters)
+{
+    size_t ncell = (size_t)NX * (size_t)NY;
+    size_t nd = 0;
+    for (size_t i = 0; i < ncell; i++)
+        if (mask[i] > 0)
+            nd++;
+    size_t na = nd ? nd : 1;
+    double* cx0 = (double*)malloc(sizeof(double) * na);
+    double* cx1 = (double*)malloc(sizeof(double) * na);
+    int* idx = (int*)malloc(sizeof(int) * na);
+    int* mark = (int*)malloc(sizeof(int) * na);
+    int* list = (int*)malloc(sizeof(int) * na);
+    int* part = (int*)malloc(sizeof(int) * na);
+    size_t* cell = (size_t*)malloc(sizeof(size_t) * na);
+    orc_dbox* boxes = (orc_dbox*)malloc(sizeof(orc_dbox) * (size_t)P);
+    if (!cx0 || !cx1 || !idx || !mark || !list || !part || !cell || !boxes)
+        return -1;
+
+    /* Grid.cpp:176-188 (ids), ZoltanPartitioner.cpp:61-64 (coordinates) */
+    size_t k = 0;
+    double xmin = DBL_MAX, xmax = -DBL_MAX, ymin = DBL_MAX, ymax = -DBL_MAX;
+    for (size_t i = 0; i < ncell; i++) {
+        if (mask[i] > 0) {
+            long id = (long)i;
+            cx0[k] = (double)(id % NX);
+            cx1[k] = (double)(id / NX);
+            if (cx0[k] < xmin)
+                xmin = cx0[k];
+            if (cx0[k] > xmax)
+                xmax = cx0[k];
+            if (cx1[k] < ymin)
+                ymin = cx1[k];
+            if (cx1[k] > ymax)
+                ymax = cx1[k];
+            cell[k] = i;
+            idx[k] = (int)k;
+            mark[k] = 0;
+            k++;
+        }
+    }
+
+    dots_ctx cx;
+    cx.c[0] = cx0;
+    cx.c[1] = cx1;
+    cx.mark = mark;
+    cx.list = list;
+    cx.part = part;
+    cx.boxes = boxes;
+    cx.ext[0] = NX;
+    cx.ext[1] = NY;
+    cx.median_iters = 0;
+    double wx = nd ? xmax - xmin : 0.0, wy = nd ? ymax - ymin : 0.0;
+    preset_dims(P, wx, wy, cx.dim_of_level);
+
+    orc_dbox root;
+    root.lo[0] = root.lo[1] = -DBL_MAX;
+    root.hi[0] = root.hi[1] = DBL_MAX;
+    rcb_dots_recurse(&cx, idx, (int)nd, 0, P, 0, root);
+
+    for (int p = 0; p < P; p++) {
+        dboxes[4 * p + 0] = boxes[p].lo[0];
+        dboxes[4 * p + 1] = boxes[p].lo[1];
+        dboxes[4 * p + 2] = boxes[p].hi[0];
+        dboxes[4 * p + 3] = boxes[p].hi[1];
+    }
+    if (part_of_cell) {
+        for (size_t i = 0; i < ncell; i++)
+            part_of_cell[i] = -1;
+        for (size_t j = 0; j < nd; j++)
+            part_of_cell[cell[j]] = part[j];
+    }
+    if (median_iters)
+        *median_iters = cx.median_iters;
+    free(cx0);
+    free(cx1);
+    free(idx);
+    free(mark);
+    free(list);
+    free(part);
+    free(cell);
+    free(boxes);
+    return (long)nd;
+}
+
+/* ------------------------------------------------------------------------- */
+/* a4 (histogram formulation): same algorithm on counts                      */
+/* ------------------------------------------------------------------------- */
+/*
+ * Because RCB_SET_DIRECTIONS orders all x levels before all y levels and
+ * rectilinear cuts never split a column (row), the x levels only need the
+ * per-column ocean counts and the y levels only need, per vertical strip, the
+ * per-row counts.  On a histogram h[0..n) with inclusive prefix sums the
+ * median loop needs cnt(a,b), the largest non-empty bin <= t and the smallest
+ * non-empty bin > t; the active set is always a contiguous bin range.
+ */
+typedef struct {
+    const int64_t* pfx; /* pfx[i] = sum h[0..i), length n+1 */
+    int n;
+    long iters;
+} hist_t;
+
+static int64_t hcnt(const hist_t* H, int a, int b) /* bins a..b inclusive */
+{
+    if (b < a)
+        return 0;
+    return H->pfx[b + 1] - H->pfx[a];
+}
+/* largest non-empty bin in [a, b], or -1 */
+static int last_nonempty(const hist_t* H, int a, int b)
+{
+    if (b < a || hcnt(H, a, b) == 0)
+        return -1;
+    int64_t target = H->pfx[b + 1]; /* find smallest i in [a,b] with pfx[i+1] == target */
+    int lo = a, hi = b;
+    while (lo < hi) {
+        int mid = lo + (hi - lo) / 2;
+        if (H->pfx[mid + 1] >= target)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+/* smallest non-empty bin in [a, b], or -1 */
+static int first_nonempty(const hist_t* H, int a, int b)
+{
+    if (b < a || hcnt(H, a, b) == 0)
+        return -1;
+    int64_t base = H->pfx[a]; /* find smallest i in [a,b] with pfx[i+1] > base */
+    int lo = a, hi = b;
+    while (lo < hi) {
+        int mid = lo + (hi - lo) / 2;
+        if (H->pfx[mid + 1] > base)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+
+/* median of the dots in bins [c0, c1] (inclusive); returns the cut */
+static double find_median_hist(hist_t* H, int c0, int c1, double fractionlo)
+{
+    int64_t Wn = hcnt(H, c0, c1);
+    double weight = (double)Wn;
+    if (Wn == 0)
+        return average_cut(0, 0, 0, 0, (double)c0, (double)(c1 + 1));
+    int first = first_nonempty(H, c0, c1), last = last_nonempty(H, c0, c1);
+    double valuemin = (double)first, valuemax = (double)last;
+    int alo = first, ahi = last; /* active bins */
+    int B; /* bins <= B are marked 0, bins > B marked 1 */
+    const double tolerance = 1.0;
+    double weightlo = 0.0, weighthi = 0.0;
+    double targetlo = fractionlo * weight;
+    double targethi = weight - targetlo;
+
+    for (;;) {
+        double tmp_half = valuemin
+            + (targetlo - weightlo) / (weight - weightlo - weighthi) * (valuemax - valuemin);
+        H->iters++;
+        /* active bins <= tmp_half go low */
+        int t;
+        if (tmp_half < (double)alo)
+            t = alo - 1;
+        else if (tmp_half >= (double)ahi)
+            t = ahi;
+        else
+            t = (int)floor(tmp_half);
+        B = t;
+        double totallo = (double)hcnt(H, alo, t), totalhi = (double)hcnt(H, t + 1, ahi);
+        int vlo = last_nonempty(H, alo, t), vhi = first_nonempty(H, t + 1, ahi);
+        double wtlo = vlo >= 0 ? (double)hcnt(H, vlo, vlo) : 0.0;
+        double wthi = vhi >= 0 ? (double)hcnt(H, vhi, vhi) : 0.0;
+
+        if (weightlo + totallo < targetlo) {
+            weightlo += totallo;
+            if (vhi < 0)
+                break;
+            if (wthi == 1.0) {
+                if (weightlo + wthi < targetlo) {
+                    B = vhi;
+                } else {
+                    if (weightlo + wthi - targetlo < targetlo - weightlo)
+                        B = vhi;
+                    break;
+                }
+            } else {
+                if (weightlo + wthi >= targetlo) {
+                    if (!(weightlo + wthi - targetlo > targetlo - weightlo))
+                        B = vhi;
+                    break;
+                }
+                B = vhi;
+            }
+            weightlo += wthi;
+            if (targetlo - weightlo <= tolerance)
+                break;
+            valuemin = (double)vhi;
+            alo = vhi + 1;
+        } else if (weighthi + totalhi < targethi) {
+            weighthi += totalhi;
+            if (vlo < 0)
+                break;
+            if (wtlo == 1.0) {
+                if (weighthi + wtlo < targethi) {
+                    B = vlo - 1;
+                } else {
+                    if (weighthi + wtlo - targethi < targethi - weighthi)
+                        B = vlo - 1;
+                    break;
+                }
+            } else {
+                if (weighthi + wtlo >= targethi) {
+                    if (!(weighthi + wtlo - targethi > targethi - weighthi))
+                        B = vlo - 1;
+                    break;
+                }
+                B = vlo - 1;
+            }
+            weighthi += wtlo;
+            if (targethi - weighthi <= tolerance)
+                break;
+            valuemax = (double)vlo;
+            ahi = vlo - 1;
+        } else
+            break;
+    }
+    int L = last_nonempty(H, c0, B), U = first_nonempty(H, B + 1, c1);
+    return average_cut(L >= 0, (double)L, U >= 0, (double)U, (double)c0, (double)(c1 + 1));
+}
+
+typedef struct {
+    int lo, hi; /* integer cell range [lo, hi) along the cut dimension */
+    int partlower, num_parts;
+    double dlo, dhi; /* cut-tree bounds (+-DBL_MAX when uncut) */
+} hset;
+
+/* split every set of `in` with more than one part along one histogram; sets
+   with one part are passed through.  returns the number of output sets. */
+static int hist_level(hist_t* H, const hset* in, int nin, hset* out)
+{
+    int no = 0;
+    for (int s = 0; s < nin; s++) {
+        hset S = in[s];
+        if (S.num_parts == 1) {
+            out[no++] = S;
+            continue;
+        }
+        int partmid = S.partlower + (S.num_parts - 1) / 2 + 1;
+        double fractionlo = (double)(partmid - S.partlower) / (double)S.num_parts;
+        double cut = find_median_hist(H, S.lo, S.hi - 1, fractionlo);
+        int b = (int)ceil(cut);
+        hset A = S, Bs = S;
+        A.hi = b;
+        A.dhi = cut;
+        A.num_parts = partmid - S.partlower;
+        Bs.lo = b;
+        Bs.dlo = cut;
+        Bs.partlower = partmid;
+        Bs.num_parts = S.partlower + S.num_parts - partmid;
+        out[no++] = A;
+        out[no++] = Bs;
+    }
+    return no;
+}
+
+ORC_API long orc_rcb_hist(const int32_t* mask, int NX, int NY, int P, double* dboxes,
+    long* median_iters)
+{
+    size_t ncell = (size_t)NX * (size_t)NY;
+    int64_t* colpfx = (int64_t*)calloc((size_t)NX + 1, sizeof(int64_t));
+    int64_t* rowpfx = (int64_t*)calloc((size_t)NY + 1, sizeof(int64_t));
+    hset* cur = (hset*)malloc(sizeof(hset) * (size_t)(P + 1));
+    hset* nxt = (hset*)malloc(sizeof(hset) * (size_t)(P + 1));
+    if (!colpfx || !rowpfx || !cur || !nxt)
+        return -1;
+    long nd = 0;
+    int xmin = NX, xmax = -1, ymin = NY, ymax = -1;
+    for (int y = 0; y < NY; y++) {
+        const int32_t* row = mask + (size_t)y * NX;
+        for (int x = 0; x < NX; x++) {
+            if (row[x] > 0) {
+                colpfx[x + 1]++;
+                nd++;
+                if (x < xmin)
+                    xmin = x;
+                if (x > xmax)
+                    xmax = x;
+                if (y < ymin)
+                    ymin = y;
+                if (y > ymax)
+                    ymax = y;
+            }
+        }
+    }
+    (void)ncell;
+    for (int x = 0; x < NX; x++)
+        colpfx[x + 1] += colpfx[x];
+
+    int dim_of_level[ORC_MAXLEV];
+    double wx = nd ? (double)(xmax - xmin) : 0.0, wy = nd ? (double)(ymax - ymin) : 0.0;
+    int nlev = preset_dims(P, wx, wy, dim_of_level);
+
+    /* x levels on the column histogram */
+    int ns = 1;
+    cur[0].lo = 0;
+    cur[0].hi = NX;
+    cur[0].partlower = 0;
+    cur[0].num_parts = P;
+    cur[0].dlo = -DBL_MAX;
+    cur[0].dhi = DBL_MAX;
+    hist_t HX = { colpfx, NX, 0 };
+    int lev = 0;
+    for (; lev < nlev && dim_of_level[lev] == 0; lev++) {
+        ns = hist_level(&HX, cur, ns, nxt);
+        hset* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    long iters = HX.iters;
+
+    /* y levels, one vertical strip at a time, on the strip's row histogram */
+    hset* ycur = (hset*)malloc(sizeof(hset) * (size_t)(P + 1));
+    hset* ynxt = (hset*)malloc(sizeof(hset) * (size_t)(P + 1));
+    if (!ycur || !ynxt)
+        return -1;
+    for (int s = 0; s < ns; s++) {
+        hset S = cur[s];
+        memset(rowpfx, 0, sizeof(int64_t) * ((size_t)NY + 1));
+        if (S.num_parts > 1) {
+            for (int y = 0; y < NY; y++) {
+                const int32_t* row = mask + (size_t)y * NX;
+                int64_t c = 0;
+                for (int x = S.lo; x < S.hi; x++)
+                    c += row[x] > 0;
+                rowpfx[y + 1] = rowpfx[y] + c;
+            }
+        }
+        hist_t HY = { rowpfx, NY, 0 };
+        int nys = 1;
+        ycur[0].lo = 0;
+        ycur[0].hi = NY;
+        ycur[0].partlower = S.partlower;
+        ycur[0].num_parts = S.num_parts;
+        ycur[0].dlo = -DBL_MAX;
+        ycur[0].dhi = DBL_MAX;
+        for (int l = lev; l < nlev; l++) {
+            nys = hist_level(&HY, ycur, nys, ynxt);
+            hset* t = ycur;
+            ycur = ynxt;
+            ynxt = t;
+        }
+        iters += HY.iters;
+        for (int j = 0; j < nys; j++) {
+            int p = ycur[j].partlower;
+            dboxes[4 * p + 0] = S.dlo;
+            dboxes[4 * p + 1] = ycur[j].dlo;
+            dboxes[4 * p + 2] = S.dhi;
+            dboxes[4 * p + 3] = ycur[j].dhi;
+        }
+    }
+    if (median_iters)
+        *median_iters = iters;
+    free(colpfx);
+    free(rowpfx);
+    free(cur);
+    free(nxt);
+    free(ycur);
+    free(ynxt);
+    return nd;
+}
+
+/* ------------------------------------------------------------------------- */
+/* a5: RCB_Box doubles -> integer boxes (ZoltanPartitioner.cpp:172-195)      */
+/* ------------------------------------------------------------------------- */
+ORC_API void orc_boxes_to_int(const double* dboxes, int P, int NX, int NY, int32_t* boxes)
+{
+    int G[2] = { NX, NY };
+    for (int p = 0; p < P; p++) {
+        for (int d = 0; d < 2; d++) {
+            double mn = dboxes[4 * p + d], mx = dboxes[4 * p + 2 + d];
+            int g = (mn == -DBL_MAX) ? 0 : (int)ceil(mn);
+            int upper = (mx == DBL_MAX) ? G[d] : (int)ceil(mx);
+            int ext = upper - g;
+            if (g + ext > G[d]) /* "adapt to blocking" */
+                ext = G[d] - g;
+            boxes[4 * p + d] = g;
+            boxes[4 * p + 2 + d] = ext;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* full path a1-a6: boxes[P*4] = {x0,y0,ex,ey}, pid[NY*NX], *changes         */
+/* ------------------------------------------------------------------------- */
+ORC_API int orc_partition(const int32_t* mask, int NX, int NY, int P, int use_hist, int32_t* boxes,
+    int32_t* pid, int* changes_out, long* median_iters)
+{
+    size_t ncell = (size_t)NX * (size_t)NY;
+    if (P == 1) { /* ZoltanPartitioner.cpp:102-121 */
+        boxes[0] = 0;
+        boxes[1] = 0;
+        boxes[2] = NX;
+        boxes[3] = NY;
+        if (pid)
+            for (size_t i = 0; i < ncell; i++)
+                pid[i] = mask[i] > 0 ? 0 : -1;
+        if (changes_out)
+            *changes_out = 0;
+        if (median_iters)
+            *median_iters = 0;
+        return 0;
+    }
+    double* dboxes = (double*)malloc(sizeof(double) * 4 * (size_t)P);
+    int32_t* part = (int32_t*)malloc(sizeof(int32_t) * (ncell ? ncell : 1));
+    if (!dboxes || !part)
+        return -1;
+    long nd;
+    if (use_hist) {
+        nd = orc_rcb_hist(mask, NX, NY, P, dboxes, median_iters);
+        if (nd < 0)
+            return -1;
+        orc_boxes_to_int(dboxes, P, NX, NY, boxes);
+        /* label by box lookup (Q6: every dot lies inside its part's box) */
+        for (size_t i = 0; i < ncell; i++)
+            part[i] = -1;
+        for (int p = 0; p < P; p++) {
+            int x0 = boxes[4 * p], y0 = boxes[4 * p + 1], ex = boxes[4 * p + 2], ey = boxes[4 * p + 3];
+            for (int y = y0; y < y0 + ey; y++)
+                for (int x = x0; x < x0 + ex; x++)
+                    if (mask[(size_t)y * NX + x] > 0)
+                        part[(size_t)y * NX + x] = p;
+        }
+    } else {
+        nd = orc_rcb_dots(mask, NX, NY, P, dboxes, part, median_iters);
+        if (nd < 0)
+            return -1;
+        orc_boxes_to_int(dboxes, P, NX, NY, boxes);
+    }
+    /* `changes`: did any dot leave the rank that owned it in the naive layout? */
+    int changes = 0;
+    for (int y = 0; y < NY && !changes; y++)
+        for (int x = 0; x < NX; x++) {
+            int32_t q = part[(size_t)y * NX + x];
+            if (q >= 0 && q != naive_rank_of_cell(P, NX, NY, x, y)) {
+                changes = 1;
+                break;
+            }
+        }
+    if (!changes) /* ZoltanPartitioner.cpp:182-187: keep the naive blocks */
+        for (int p = 0; p < P; p++)
+            orc_naive_block(P, NX, NY, p, boxes + 4 * p);
+    if (pid)
+        memcpy(pid, part, sizeof(int32_t) * ncell);
+    if (changes_out)
+        *changes_out = changes;
+    free(dboxes);
+    free(part);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* a7-a10: neighbours and halos                                              */
+/* ------------------------------------------------------------------------- */
+enum { ORC_LEFT = 0, ORC_RIGHT = 1, ORC_BOTTOM = 2, ORC_TOP = 3 };
+typedef struct {
+    int x1, y1, x2, y2; /* p1 = (x1,y1), p2 = (x2,y2) */
+} orc_domain;
+
+/* DomainUtils.cpp:15-35 */
+ORC_API int orc_domain_overlap(int ax1, int ay1, int ax2, int ay2, int bx1, int by1, int bx2, int by2,
+    int edge)
+{
+    int overlap = 0;
+    if (edge == ORC_TOP || edge == ORC_BOTTOM) {
+        if (ax2 >= bx1 && ax1 <= bx2) {
+            int mn = ax2 < bx2 ? ax2 : bx2, mx = ax1 > bx1 ? ax1 : bx1;
+            overlap = mn - mx;
+        }
+    } else {
+        if (ay2 >= by1 && ay1 <= by2) {
+            int mn = ay2 < by2 ? ay2 : by2, mx = ay1 > by1 ? ay1 : by1;
+            overlap = mn - mx;
+        }
+    }
+    return overlap;
+}
+
+/* Partitioner.cpp:20-53 */
+static int is_neighbour(orc_domain d1, orc_domain d2, int edge, int is_px, int is_py, int NX, int NY)
+{
+    if (edge == ORC_TOP)
+        return is_py ? d1.y2 == d2.y1 + NY : d1.y2 == d2.y1;
+    if (edge == ORC_BOTTOM)
+        return is_py ? d1.y1 == d2.y2 - NY : d1.y1 == d2.y2;
+    if (edge == ORC_LEFT)
+        return is_px ? d1.x1 == d2.x2 - NX : d1.x1 == d2.x2;
+    return is_px ? d1.x2 == d2.x1 + NX : d1.x2 == d2.x1;
+}
+
+/* Partitioner.cpp:55-80 */
+static int halo_start(orc_domain d1, orc_domain d2, int edge)
+{
+    int w2 = d2.x2 - d2.x1, h2 = d2.y2 - d2.y1;
+    if (edge == ORC_TOP) {
+        int dx = (d1.x1 > d2.x1 ? d1.x1 : d2.x1) - d2.x1;
+        return dx;
+    }
+    if (edge == ORC_BOTTOM) {
+        int dx = (d1.x1 > d2.x1 ? d1.x1 : d2.x1) - d2.x1;
+        return (h2 - 1) * w2 + dx;
+    }
+    if (edge == ORC_LEFT) {
+        int dy = (d1.y1 > d2.y1 ? d1.y1 : d2.y1) - d2.y1;
+        return ((dy + 1) * w2) - 1;
+    }
+    int dy = (d1.y1 > d2.y1 ? d1.y1 : d2.y1) - d2.y1;
+    return dy * w2;
+}
+
+/*
+ * discover_neighbours for every part (Partitioner.cpp:329-435) followed by the
+ * flattening of get_neighbour_info / get_neighbour_info_periodic
+ * (Partitioner.cpp:98-126; std::map => ids ascending; the periodic getter
+ * keeps L/R only if px and B/T only if py) and the concatenation over ranks
+ * that save_metadata produces with Allreduce + Exscan (Partitioner.cpp:190-206).
+ *
+ *   counts[(periodic*4 + edge)*P + p]
+ *   two calls: with ids == NULL only counts are filled; the caller then sizes
+ *   ids/halos/starts per (periodic, edge) list with offsets[8] = exclusive
+ *   sums of the list totals, in the order interior L,R,B,T, periodic L,R,B,T.
+ */
+ORC_API void orc_neighbours(const int32_t* boxes, int P, int NX, int NY, int px, int py,
+    int32_t* counts, const int64_t* offsets, int32_t* ids, int32_t* halos, int32_t* starts)
+{
+    orc_domain* d = (orc_domain*)malloc(sizeof(orc_domain) * (size_t)P);
+    for (int p = 0; p < P; p++) {
+        d[p].x1 = boxes[4 * p];
+        d[p].y1 = boxes[4 * p + 1];
+        d[p].x2 = boxes[4 * p] + boxes[4 * p + 2];
+        d[p].y2 = boxes[4 * p + 1] + boxes[4 * p + 3];
+    }
+    int64_t fill[8];
+    for (int l = 0; l < 8; l++)
+        fill[l] = offsets ? offsets[l] : 0;
+    memset(counts, 0, sizeof(int32_t) * 8 * (size_t)P);
+    for (int me = 0; me < P; me++) {
+        for (int per = 0; per < 2; per++) {
+            for (int edge = 0; edge < 4; edge++) {
+                if (per) { /* filter of get_neighbour_info_periodic */
+                    int lr = (edge == ORC_LEFT || edge == ORC_RIGHT);
+                    if (!((lr && px) || (!lr && py)))
+                        continue;
+                }
+                int l = per * 4 + edge;
+                for (int p = 0; p < P; p++) {
+                    if (!per && p == me)
+                        continue;
+                    if (!is_neighbour(d[me], d[p], edge, per ? px : 0, per ? py : 0, NX, NY))
+                        continue;
+                    int halo = orc_domain_overlap(d[me].x1, d[me].y1, d[me].x2, d[me].y2, d[p].x1,
+                        d[p].y1, d[p].x2, d[p].y2, edge);
+                    if (halo > 0) {
+                        counts[(size_t)l * P + me]++;
+                        if (ids) {
+                            ids[fill[l]] = p;
+                            halos[fill[l]] = halo;
+                            starts[fill[l]] = halo_start(d[me], d[p], edge);
+                            fill[l]++;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    free(d);
+}
+
+/* ------------------------------------------------------------------------- */
+/* quality metrics used where bit-exactness cannot be claimed                */
+/* ------------------------------------------------------------------------- */
+/* ocean cells per part (from pid) */
+ORC_API void orc_part_loads(const int32_t* pid, size_t ncell, int P, int64_t* loads)
+{
+    memset(loads, 0, sizeof(int64_t) * (size_t)P);
+    for (size_t i = 0; i < ncell; i++)
+        if (pid[i] >= 0 && pid[i] < P)
+            loads[pid[i]]++;
+}

@@ -1,0 +1,155 @@
+"""ctypes front-end of the CPU oracle (oracle/ddc_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, by __graft_entry__.smoke() and
+by bench.py's cpu_baseline / ``--impl reference`` leg, never by the product
+package ``domain_decomp_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libddc_oracle.so")
+_REF_LIB = os.path.join(_HERE, "_ref", "libref_domainutils.so")
+
+EDGES = ("left", "right", "bottom", "top")  # DomainUtils.hpp:15 enum order L,R,B,T
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (and oracle/_ref when the reference checkout exists)."""
+    src = os.path.join(_HERE, "ddc_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_oracle.so"])
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF_LIB)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+        L.orc_find_factors.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L.orc_naive_block.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.orc_partition.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_void_p,
+                                    C.POINTER(C.c_int), C.POINTER(C.c_long)]
+        L.orc_partition.restype = C.c_int
+        L.orc_neighbours.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_domain_overlap.argtypes = [C.c_int] * 9
+        L.orc_domain_overlap.restype = C.c_int
+        L.orc_part_loads.argtypes = [i32p, C.c_size_t, C.c_int,
+                                     np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own DomainUtils.cpp compiled in oracle/_ref (None if not built)."""
+    if not os.path.exists(_REF_LIB):
+        return None
+    L = C.CDLL(_REF_LIB)
+    L.ref_domain_overlap.argtypes = [C.c_int] * 9
+    L.ref_domain_overlap.restype = C.c_int
+    return L
+
+
+def find_factors(P: int):
+    out = (C.c_int * 2)()
+    lib().orc_find_factors(P, out)
+    return [out[0], out[1]]
+
+
+def naive_block(P: int, NX: int, NY: int, r: int):
+    out = (C.c_int * 4)()
+    lib().orc_naive_block(P, NX, NY, r, out)
+    return [out[0], out[1], out[2], out[3]]
+
+
+@dataclass
+class Neighbours:
+    """counts[periodic][edge] -> int32[P]; ids/halos/starts[periodic][edge] -> flat int32 list
+    (concatenation over parts 0..P-1 of each part's id-ascending list)."""
+    counts: list
+    ids: list
+    halos: list
+    starts: list
+
+
+@dataclass
+class Decomposition:
+    NX: int
+    NY: int
+    P: int
+    boxes: np.ndarray  # int32 [P,4] = x0, y0, ext_x, ext_y
+    pid: np.ndarray | None  # int32 [NY,NX], -1 on land
+    changes: int
+    median_iters: int
+    nbr: Neighbours | None = None
+
+
+def neighbours(boxes: np.ndarray, NX: int, NY: int, px: bool, py: bool) -> Neighbours:
+    boxes = np.ascontiguousarray(boxes, dtype=np.int32)
+    P = boxes.shape[0]
+    counts = np.zeros(8 * P, dtype=np.int32)
+    lib().orc_neighbours(boxes, P, NX, NY, int(px), int(py), counts, None, None, None, None)
+    totals = counts.reshape(8, P).sum(axis=1).astype(np.int64)
+    offsets = np.zeros(8, dtype=np.int64)
+    offsets[1:] = np.cumsum(totals)[:-1]
+    n = int(totals.sum())
+    ids = np.zeros(max(n, 1), dtype=np.int32)
+    halos = np.zeros(max(n, 1), dtype=np.int32)
+    starts = np.zeros(max(n, 1), dtype=np.int32)
+    lib().orc_neighbours(boxes, P, NX, NY, int(px), int(py), counts,
+                         offsets.ctypes.data, ids.ctypes.data, halos.ctypes.data, starts.ctypes.data)
+    c = counts.reshape(2, 4, P)
+    sl = lambda a, l: a[int(offsets[l]):int(offsets[l] + totals[l])].copy()
+    return Neighbours(
+        counts=[[c[per, e].copy() for e in range(4)] for per in range(2)],
+        ids=[[sl(ids, per * 4 + e) for e in range(4)] for per in range(2)],
+        halos=[[sl(halos, per * 4 + e) for e in range(4)] for per in range(2)],
+        starts=[[sl(starts, per * 4 + e) for e in range(4)] for per in range(2)],
+    )
+
+
+def partition(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, use_hist: bool = False,
+              want_pid: bool = True, want_neighbours: bool = True) -> Decomposition:
+    """The whole reference path on the CPU: mask[NY,NX] int32 -> boxes, pid, neighbours.
+
+    P == 1 follows ZoltanPartitioner.cpp:102-121 (returns before discover_neighbours,
+    so no neighbour lists at all, quirk Q4)."""
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    NY, NX = mask.shape
+    boxes = np.zeros((P, 4), dtype=np.int32)
+    pid = np.empty((NY, NX), dtype=np.int32) if want_pid else None
+    changes = C.c_int(0)
+    iters = C.c_long(0)
+    rc = lib().orc_partition(mask, NX, NY, P, int(use_hist), boxes.reshape(-1),
+                             pid.ctypes.data if want_pid else None, C.byref(changes), C.byref(iters))
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    d = Decomposition(NX, NY, P, boxes, pid, changes.value, iters.value)
+    if want_neighbours:
+        if P == 1:
+            z = lambda: [[np.zeros(0, np.int32) for _ in range(4)] for _ in range(2)]
+            d.nbr = Neighbours([[np.zeros(1, np.int32) for _ in range(4)] for _ in range(2)], z(), z(), z())
+        else:
+            d.nbr = neighbours(boxes, NX, NY, px, py)
+    return d
+
+
+def part_loads(pid: np.ndarray, P: int) -> np.ndarray:
+    loads = np.zeros(P, dtype=np.int64)
+    flat = np.ascontiguousarray(pid, dtype=np.int32).reshape(-1)
+    lib().orc_part_loads(flat, flat.size, P, loads)
+    return loads
