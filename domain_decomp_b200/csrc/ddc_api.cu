@@ -1,0 +1,946 @@
+// ddc_api.cu -- C ABI (include/ddc.h) over the kernels in ddc_kernels.cuh.
+//
+// There is NO CPU fallback in this file: every result is produced by the kernels above; if CUDA
+// is unavailable every entry point fails with DDC_ERR_CUDA.
+#include "ddc.h"
+#include "ddc_kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+using namespace ddc;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily (only when nranks > 1) so that the library itself has no link-time
+// dependency on a particular libnccl and loads on machines without one.
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+    char internal[128];
+} ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { nccl_Int32 = 2, nccl_Uint32 = 3 }; // ncclDataType_t: ncclInt32 = 2, ncclUint32 = 3
+enum { nccl_Sum = 0, nccl_Max = 2 }; // ncclRedOp_t: ncclSum = 0, ncclProd = 1, ncclMax = 2
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+    bool load()
+    {
+        if (lib)
+            return true;
+        const char* names[] = { "libnccl.so.2", "libnccl.so" };
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib)
+                break;
+        }
+        if (!lib) {
+            err = std::string("cannot load libnccl: ") + dlerror();
+            return false;
+        }
+#define DDC_SYM(field, name)                                                                       \
+    *(void**)(&field) = dlsym(lib, name);                                                          \
+    if (!field) {                                                                                  \
+        err = std::string("libnccl lacks ") + name;                                                \
+        return false;                                                                              \
+    }
+        DDC_SYM(GetUniqueId, "ncclGetUniqueId");
+        DDC_SYM(CommInitRank, "ncclCommInitRank");
+        DDC_SYM(CommDestroy, "ncclCommDestroy");
+        DDC_SYM(AllReduce, "ncclAllReduce");
+        DDC_SYM(AllGather, "ncclAllGather");
+        DDC_SYM(GroupStart, "ncclGroupStart");
+        DDC_SYM(GroupEnd, "ncclGroupEnd");
+        DDC_SYM(GetErrorString, "ncclGetErrorString");
+#undef DDC_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess)
+            cap = n;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+} // namespace
+
+struct ddc_handle_s {
+    int device = 0, rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    // input
+    int nx = 0, ny = 0, y_begin = 0, y_count = 0;
+    const int32_t* d_mask = nullptr; // borrowed or == mask_own.p
+    bool mask_set = false;
+    DevBuf<int32_t> mask_own;
+
+    // state of the last partition
+    bool partitioned = false, have_pid = false, have_nbr = false;
+    int nparts = 0, px = 0, py = 0;
+    ddc_stats stats {};
+
+    // device buffers
+    DevBuf<uint4> bits;
+    DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx;
+    DevBuf<DevScalars> sc;
+    DevBuf<Plan> plan;
+    DevBuf<int> sets; // 6 * P : A.lo A.hi A.n B.lo B.hi B.n
+    DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
+    DevBuf<int> boxes; // x0 y0 ex ey, P each
+    DevBuf<int> strip_of_part;
+    DevBuf<long long> loads, loadmm;
+    DevBuf<int32_t> pid;
+    DevBuf<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
+    int nbr_cap = 0;
+    Plan h_plan {};
+    int h_totals[8] = { 0 };
+    bool totals_valid = false;
+    Plan* pin_plan = nullptr; // pinned staging for the plan read-back
+    cudaEvent_t ev[DDC_N_STAGES + 2] = {};
+    bool ev_ok = false;
+};
+
+namespace {
+int fail(ddc_handle_t h, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h)
+        h->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+#define CUDA_TRY(h, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, DDC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                __FILE__, __LINE__);                                                               \
+    } while (0)
+#define NCCL_TRY(h, call)                                                                          \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != ncclSuccess)                                                                     \
+            return fail(h, DDC_ERR_NCCL, "%s failed: %s (%s:%d)", #call,                           \
+                g_nccl.GetErrorString(r_), __FILE__, __LINE__);                                    \
+    } while (0)
+
+NaiveParams naive_params(int P, int NX, int NY)
+{
+    // Grid.cpp:18-35 (find_factors) and Grid.cpp:153-155 (float ceil)
+    int fa = -1, fb = -1;
+    for (int i = 2; i * i <= P; i += 2)
+        if (P % i == 0) {
+            fa = i;
+            fb = P / fa;
+        }
+    NaiveParams nv;
+    if (fa == -1 || fb == -1) {
+        nv.np0 = P;
+        nv.np1 = 1;
+    } else {
+        nv.np0 = fa;
+        nv.np1 = fb;
+    }
+    nv.lx = (int)ceilf((float)NX / (float)nv.np0);
+    nv.ly = (int)ceilf((float)NY / (float)nv.np1);
+    return nv;
+}
+
+struct Tables {
+    SetBuf A, B;
+    StripTable st;
+    BoxTable bx;
+};
+Tables tables(ddc_handle_t h, int P)
+{
+    Tables t;
+    int* s = h->sets.p;
+    t.A = { s, s + P, s + 2 * P };
+    t.B = { s + 3 * P, s + 4 * P, s + 5 * P };
+    int* q = h->strips.p;
+    t.st.x0 = q;
+    t.st.x1 = q + (P + 1);
+    t.st.p0 = q + 2 * (P + 1);
+    t.st.S = q + 3 * (P + 1) + 1;
+    t.st.always = q + 3 * (P + 1) + 2;
+    int* b = h->boxes.p;
+    t.bx = { b, b + P, b + 2 * P, b + 3 * P };
+    return t;
+}
+
+size_t max_dyn_smem(int device)
+{
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    return (size_t)v;
+}
+
+int pick_rows_per_cta(int rows, int gridx)
+{
+    // enough CTAs for ~16 per SM, but never fewer than 32 rows each (amortises the column atomics)
+    long long r = (long long)rows * gridx / (148 * 16);
+    r = (r / 8) * 8;
+    if (r < 32)
+        r = 32;
+    if (r > 512)
+        r = 512;
+    return (int)r;
+}
+
+// K7 + scans on whatever boxes / strips are in the tables
+int run_neighbours(ddc_handle_t h, int P, int nx, int ny, int px, int py)
+{
+    Tables t = tables(h, P);
+    cudaStream_t s = h->stream;
+    const int cap = 3 * P + 64;
+    CUDA_TRY(h, h->nbr_counts.ensure((size_t)8 * P));
+    CUDA_TRY(h, h->nbr_offsets.ensure((size_t)8 * P));
+    CUDA_TRY(h, h->nbr_totals.ensure(8));
+    if (h->nbr_cap < cap) {
+        CUDA_TRY(h, h->nbr_ids.ensure((size_t)8 * cap));
+        CUDA_TRY(h, h->nbr_halos.ensure((size_t)8 * cap));
+        CUDA_TRY(h, h->nbr_starts.ensure((size_t)8 * cap));
+        h->nbr_cap = cap;
+    }
+    const int warps_per_cta = 8;
+    const int grid = (P + warps_per_cta - 1) / warps_per_cta;
+    k_neighbours<false><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p, nullptr,
+        nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p);
+    k_scan_counts<<<8, 1024, 0, s>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p);
+    k_neighbours<true><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p,
+        h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
+        h->sc.p);
+    h->stats.gpu_launches += 3;
+    CUDA_TRY(h, cudaGetLastError());
+    h->totals_valid = false;
+    h->have_nbr = true;
+    return DDC_OK;
+}
+
+// make h_totals valid; re-run the fill pass with exact capacity if the bounded one overflowed
+int fetch_totals(ddc_handle_t h)
+{
+    if (h->totals_valid)
+        return DDC_OK;
+    DevScalars hs;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_totals, h->nbr_totals.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&hs, h->sc.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (hs.overflow) {
+        int need = 0;
+        for (int l = 0; l < 8; l++)
+            need = std::max(need, h->h_totals[l]);
+        CUDA_TRY(h, h->nbr_ids.ensure((size_t)8 * need));
+        CUDA_TRY(h, h->nbr_halos.ensure((size_t)8 * need));
+        CUDA_TRY(h, h->nbr_starts.ensure((size_t)8 * need));
+        h->nbr_cap = need;
+        CUDA_TRY(h, cudaMemsetAsync(&h->sc.p->overflow, 0, sizeof(int), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(&h->sc.p->edge_cut, 0, sizeof(unsigned long long), h->stream));
+        Tables t = tables(h, h->nparts);
+        const int grid = (h->nparts + 7) / 8;
+        k_neighbours<true><<<grid, 256, 0, h->stream>>>(t.bx, h->nparts, h->nx, h->ny, h->px, h->py, t.st,
+            h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p,
+            h->nbr_halos.p, h->nbr_starts.p, h->sc.p);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaMemcpyAsync(&hs, h->sc.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    h->stats.edge_cut = (int64_t)hs.edge_cut;
+    h->totals_valid = true;
+    return DDC_OK;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* ddc_version(void) { return "domain_decomp_b200 0.1 (sm_100a)"; }
+
+const char* ddc_last_error(ddc_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ddc_get_nccl_unique_id(void* out)
+{
+    if (!out)
+        return fail(nullptr, DDC_ERR_ARG, "ddc_get_nccl_unique_id: null output");
+    if (!g_nccl.load())
+        return fail(nullptr, DDC_ERR_NCCL, "%s", g_nccl.err.c_str());
+    ncclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess)
+        return fail(nullptr, DDC_ERR_NCCL, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString(r));
+    memcpy(out, &id, DDC_NCCL_ID_BYTES);
+    return DDC_OK;
+}
+
+int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* nccl_id)
+{
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(nullptr, DDC_ERR_ARG, "ddc_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, DDC_ERR_CUDA, "ddc_create: no CUDA device (%s); this library has no CPU path",
+            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, DDC_ERR_ARG, "ddc_create: device %d out of range (have %d)", device, ndev);
+    ddc_handle_t h = new ddc_handle_s();
+    h->device = device;
+    h->rank = rank;
+    h->nranks = nranks;
+#define CREATE_TRY(call)                                                                           \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            fail(nullptr, DDC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));           \
+            delete h;                                                                              \
+            return DDC_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CREATE_TRY(cudaMallocHost((void**)&h->pin_plan, sizeof(Plan)));
+    for (auto& ev : h->ev)
+        CREATE_TRY(cudaEventCreate(&ev));
+    h->ev_ok = true;
+    CREATE_TRY(h->sc.ensure(1));
+    CREATE_TRY(h->plan.ensure(1));
+#undef CREATE_TRY
+    if (nranks > 1) {
+        if (!nccl_id) {
+            delete h;
+            return fail(nullptr, DDC_ERR_ARG, "ddc_create: nranks > 1 needs a NCCL unique id");
+        }
+        if (!g_nccl.load()) {
+            delete h;
+            return fail(nullptr, DDC_ERR_NCCL, "%s", g_nccl.err.c_str());
+        }
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, DDC_NCCL_ID_BYTES);
+        int r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+        if (r != ncclSuccess) {
+            delete h;
+            return fail(nullptr, DDC_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        }
+    }
+    *out = h;
+    return DDC_OK;
+}
+
+int ddc_destroy(ddc_handle_t h)
+{
+    if (!h)
+        return DDC_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm)
+        g_nccl.CommDestroy(h->comm);
+    h->mask_own.release();
+    h->bits.release();
+    h->colcount.release();
+    h->colpfx.release();
+    h->rowcount.release();
+    h->rowcount_all.release();
+    h->ypfx.release();
+    h->sc.release();
+    h->plan.release();
+    h->sets.release();
+    h->strips.release();
+    h->boxes.release();
+    h->strip_of_part.release();
+    h->loads.release();
+    h->loadmm.release();
+    h->pid.release();
+    h->nbr_counts.release();
+    h->nbr_offsets.release();
+    h->nbr_totals.release();
+    h->nbr_ids.release();
+    h->nbr_halos.release();
+    h->nbr_starts.release();
+    if (h->pin_plan)
+        cudaFreeHost(h->pin_plan);
+    if (h->ev_ok)
+        for (auto& ev : h->ev)
+            cudaEventDestroy(ev);
+    if (h->own_stream)
+        cudaStreamDestroy(h->own_stream);
+    delete h;
+    return DDC_OK;
+}
+
+int ddc_set_stream(ddc_handle_t h, void* cuda_stream)
+{
+    if (!h)
+        return DDC_ERR_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return DDC_OK;
+}
+
+void ddc_shard_rows(int ny, int nranks, int rank, int* y_begin, int* y_count)
+{
+    const int rpr = (ny + nranks - 1) / nranks;
+    int b = std::min(ny, rank * rpr), e = std::min(ny, b + rpr);
+    if (y_begin)
+        *y_begin = b;
+    if (y_count)
+        *y_count = e - b;
+}
+
+static int check_shard(ddc_handle_t h, int nx, int ny, int y_begin, int y_count)
+{
+    if (nx < 1 || ny < 1 || (long long)nx * ny > (long long)INT_MAX)
+        return fail(h, DDC_ERR_ARG, "mask extents %d x %d out of range (the reference ids are int)", nx, ny);
+    int b, c;
+    ddc_shard_rows(ny, h->nranks, h->rank, &b, &c);
+    if (b != y_begin || c != y_count)
+        return fail(h, DDC_ERR_ARG, "rank %d/%d must hold rows [%d,%d) of %d, got [%d,%d)", h->rank,
+            h->nranks, b, b + c, ny, y_begin, y_begin + y_count);
+    return DDC_OK;
+}
+
+int ddc_set_mask_device(ddc_handle_t h, const int32_t* rows, int nx, int ny, int y_begin, int y_count)
+{
+    if (!h)
+        return DDC_ERR_ARG;
+    int rc = check_shard(h, nx, ny, y_begin, y_count);
+    if (rc)
+        return rc;
+    if (!rows && y_count > 0)
+        return fail(h, DDC_ERR_ARG, "ddc_set_mask_device: null mask");
+    h->d_mask = rows;
+    h->nx = nx;
+    h->ny = ny;
+    h->y_begin = y_begin;
+    h->y_count = y_count;
+    h->mask_set = true;
+    h->partitioned = false;
+    return DDC_OK;
+}
+
+int ddc_set_mask_host(ddc_handle_t h, const int32_t* rows, int nx, int ny, int y_begin, int y_count)
+{
+    if (!h)
+        return DDC_ERR_ARG;
+    int rc = check_shard(h, nx, ny, y_begin, y_count);
+    if (rc)
+        return rc;
+    if (!rows && y_count > 0)
+        return fail(h, DDC_ERR_ARG, "ddc_set_mask_host: null mask");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)nx * y_count;
+    CUDA_TRY(h, h->mask_own.ensure(n));
+    if (n)
+        CUDA_TRY(h, cudaMemcpyAsync(h->mask_own.p, rows, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    h->d_mask = h->mask_own.p;
+    h->nx = nx;
+    h->ny = ny;
+    h->y_begin = y_begin;
+    h->y_count = y_count;
+    h->mask_set = true;
+    h->partitioned = false;
+    return DDC_OK;
+}
+
+int ddc_synchronize(ddc_handle_t h)
+{
+    if (!h)
+        return DDC_ERR_ARG;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the hot path
+// ------------------------------------------------------------------------------------------------
+int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
+{
+    if (!h)
+        return DDC_ERR_ARG;
+    if (!h->mask_set)
+        return fail(h, DDC_ERR_STATE, "ddc_partition: no mask set");
+    if (nparts < 1)
+        return fail(h, DDC_ERR_ARG, "ddc_partition: nparts must be >= 1");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int P = nparts, NX = h->nx, NY = h->ny, rows = h->y_count, G = h->nranks;
+    const int NG = (NX + 127) / 128;
+    const bool profile = flags & DDC_PROFILE;
+    const bool want_pid = flags & DDC_WANT_PID;
+    const bool want_nbr = (flags & DDC_WANT_NEIGHBOURS) && P > 1; // P == 1 returns early (Q4)
+    cudaStream_t s = h->stream;
+    h->partitioned = false;
+    h->have_pid = false;
+    h->have_nbr = false;
+    h->totals_valid = false;
+    memset(&h->stats, 0, sizeof h->stats);
+    int launches = 0;
+    auto mark = [&](int i) {
+        if (profile)
+            cudaEventRecord(h->ev[i], s);
+    };
+
+    // buffers
+    CUDA_TRY(h, h->bits.ensure((size_t)std::max(rows, 1) * NG));
+    CUDA_TRY(h, h->colcount.ensure(NX + 4));
+    CUDA_TRY(h, h->sets.ensure((size_t)6 * P));
+    CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
+    CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
+    CUDA_TRY(h, h->strip_of_part.ensure(P));
+    CUDA_TRY(h, h->loads.ensure(P));
+    CUDA_TRY(h, h->loadmm.ensure(2));
+    if (want_pid)
+        CUDA_TRY(h, h->pid.ensure((size_t)std::max(rows, 1) * NX));
+    Tables t = tables(h, P);
+    const NaiveParams nv = naive_params(P, NX, NY);
+
+    mark(0);
+    // ---- K1: mask scan -----------------------------------------------------------------------
+    CUDA_TRY(h, cudaMemsetAsync(h->colcount.p, 0, sizeof(unsigned) * (NX + 4), s));
+    {
+        DevScalars init;
+        init.neg_ymin = INT_MIN;
+        init.ymax = -1;
+        init.changes = 0;
+        init.overflow = 0;
+        init.edge_cut = 0;
+        CUDA_TRY(h, cudaMemcpyAsync(h->sc.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    }
+    const int gridx = (NG + 7) / 8;
+    const int rpc = pick_rows_per_cta(rows, gridx);
+    const bool vec = (NX % 4 == 0) && (((uintptr_t)h->d_mask) % 16 == 0);
+    if (rows > 0) {
+        dim3 grid(gridx, (rows + rpc - 1) / rpc);
+        if (vec)
+            k_scan_mask<true><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NG, rpc, h->bits.p,
+                h->colcount.p, h->sc.p);
+        else
+            k_scan_mask<false><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NG, rpc, h->bits.p,
+                h->colcount.p, h->sc.p);
+        launches++;
+    }
+    if (G > 1) { // column histogram and dot y-range: the first exchange step
+        NCCL_TRY(h, g_nccl.GroupStart());
+        NCCL_TRY(h, g_nccl.AllReduce(h->colcount.p, h->colcount.p, NX, nccl_Uint32, nccl_Sum, h->comm, s));
+        NCCL_TRY(h, g_nccl.AllReduce(&h->sc.p->neg_ymin, &h->sc.p->neg_ymin, 2, nccl_Int32, nccl_Max, h->comm, s));
+        NCCL_TRY(h, g_nccl.GroupEnd());
+    }
+    mark(1);
+    // ---- K2: x cuts ----------------------------------------------------------------------------
+    {
+        const size_t need = sizeof(unsigned) * ((size_t)NX + 1);
+        const size_t lim = max_dyn_smem(h->device);
+        const int use_smem = need + 1024 <= lim;
+        if (!use_smem)
+            CUDA_TRY(h, h->colpfx.ensure((size_t)NX + 1));
+        if (use_smem)
+            CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        k_xcuts<<<1, 1024, use_smem ? need : 0, s>>>(h->colcount.p, NX, NY, P, h->colpfx.p, use_smem,
+            h->sc.p, h->plan.p, t.A, t.B, t.st, t.bx, h->loads.p, h->strip_of_part.p);
+        launches++;
+    }
+    // the plan decides buffer sizes and the all-gather count: read it back (one tiny D2H + sync)
+    CUDA_TRY(h, cudaMemcpyAsync(h->pin_plan, h->plan.p, sizeof(Plan), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaGetLastError());
+    h->h_plan = *h->pin_plan;
+    const Plan& pl = h->h_plan;
+    mark(2);
+    // ---- K3 + K4: strip row counts, y cuts -----------------------------------------------------
+    if (pl.iy > 0 && P > 1) {
+        const int S = pl.S;
+        const int Rmax = (NY + G - 1) / G;
+        CUDA_TRY(h, h->rowcount.ensure((size_t)S * Rmax));
+        if (rows < Rmax) // short last shard: its padding rows must read as empty
+            CUDA_TRY(h, cudaMemsetAsync(h->rowcount.p, 0, sizeof(unsigned) * (size_t)S * Rmax, s));
+        if (rows > 0) {
+            const size_t lim = max_dyn_smem(h->device) - 1024;
+            int R = 32;
+            while (R > 1 && (size_t)R * (NG + 1) * sizeof(uint4) > lim)
+                R >>= 1;
+            const size_t smem = (size_t)R * (NG + 1) * sizeof(uint4);
+            if (smem > lim)
+                return fail(h, DDC_ERR_ARG, "nx = %d too wide for the strip-row kernel", NX);
+            CUDA_TRY(h, cudaFuncSetAttribute(k_strip_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_strip_rows<<<(rows + R - 1) / R, 256, smem, s>>>(h->bits.p, NG, rows, R, t.st.x0, t.st.x1,
+                t.st.S, h->rowcount.p, Rmax);
+            launches++;
+        }
+        const unsigned* rc_all = h->rowcount.p;
+        if (G > 1) { // the second exchange step
+            CUDA_TRY(h, h->rowcount_all.ensure((size_t)G * S * Rmax));
+            NCCL_TRY(h, g_nccl.AllGather(h->rowcount.p, h->rowcount_all.p, (size_t)S * Rmax, nccl_Uint32, h->comm, s));
+            rc_all = h->rowcount_all.p;
+        }
+        mark(3);
+        const size_t need = sizeof(unsigned) * ((size_t)NY + 1);
+        const int use_smem = need + 1024 <= max_dyn_smem(h->device);
+        const int grid = std::min(S, 148 * 2);
+        if (!use_smem)
+            CUDA_TRY(h, h->ypfx.ensure((size_t)grid * (NY + 1)));
+        if (use_smem)
+            CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        k_ycuts<<<grid, 1024, use_smem ? need : 0, s>>>(rc_all, G, Rmax, NY, pl.iy, t.st, t.A, t.B,
+            h->ypfx.p, use_smem, t.bx, h->loads.p, h->plan.p);
+        launches++;
+    } else
+        mark(3);
+    mark(4);
+    // ---- K6: labels + `changes` -----------------------------------------------------------------
+    if (rows > 0 && (P > 1 || want_pid)) {
+        dim3 grid(gridx, (rows + rpc - 1) / rpc);
+        const bool vecp = want_pid && (NX % 4 == 0) && (((uintptr_t)h->pid.p) % 16 == 0);
+#define LAUNCH_LABEL(V, W)                                                                         \
+    k_label<V, W><<<grid, 256, 0, s>>>(h->bits.p, NX, rows, h->y_begin, NG, rpc, t.st.x1, t.st.p0,   \
+        t.st.S, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p)
+        if (want_pid) {
+            if (vecp)
+                LAUNCH_LABEL(true, true);
+            else
+                LAUNCH_LABEL(false, true);
+        } else
+            LAUNCH_LABEL(false, false);
+#undef LAUNCH_LABEL
+        launches++;
+    }
+    if (G > 1)
+        NCCL_TRY(h, g_nccl.AllReduce(&h->sc.p->changes, &h->sc.p->changes, 1, nccl_Int32, nccl_Max, h->comm, s));
+    mark(5);
+    // ---- K5: naive blocks when nothing moved; load statistics -----------------------------------
+    if (P > 1) {
+        k_finalize<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(P, NX, NY, nv, h->sc.p, t.st, t.bx,
+            h->strip_of_part.p);
+        launches++;
+    }
+    {
+        const long long init[2] = { LLONG_MAX, -1 };
+        CUDA_TRY(h, cudaMemcpyAsync(h->loadmm.p, init, sizeof init, cudaMemcpyHostToDevice, s));
+        k_load_minmax<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(h->loads.p, P, h->loadmm.p);
+        launches++;
+    }
+    mark(6);
+    // ---- K7: neighbours and halos ---------------------------------------------------------------
+    h->nparts = P;
+    h->px = px;
+    h->py = py;
+    h->stats.gpu_launches = launches;
+    if (want_nbr) {
+        int rc = run_neighbours(h, P, NX, NY, px, py);
+        if (rc)
+            return rc;
+    }
+    mark(7);
+    CUDA_TRY(h, cudaGetLastError());
+
+    h->stats.nx = NX;
+    h->stats.ny = NY;
+    h->stats.nparts = P;
+    h->stats.nlev = pl.nlev;
+    h->stats.n_xlev = pl.ix;
+    h->stats.n_ylev = pl.iy;
+    h->stats.nstrips = pl.S;
+    h->stats.n_ocean = pl.W;
+    h->have_pid = want_pid;
+    h->partitioned = true;
+    if (profile) {
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        for (int i = 0; i < 7; i++)
+            cudaEventElapsedTime(&h->stats.stage_ms[i], h->ev[i], h->ev[i + 1]);
+        cudaEventElapsedTime(&h->stats.stage_ms[7], h->ev[0], h->ev[7]);
+    }
+    return DDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+#define NEED_PARTITION(h)                                                                          \
+    if (!h)                                                                                        \
+        return DDC_ERR_ARG;                                                                        \
+    if (!h->partitioned)                                                                           \
+        return fail(h, DDC_ERR_STATE, "%s: call ddc_partition() first", __func__);                 \
+    CUDA_TRY(h, cudaSetDevice(h->device))
+
+int ddc_get_boxes(ddc_handle_t h, int32_t* x0, int32_t* y0, int32_t* ex, int32_t* ey)
+{
+    NEED_PARTITION(h);
+    const int P = h->nparts;
+    int32_t* dst[4] = { x0, y0, ex, ey };
+    for (int i = 0; i < 4; i++)
+        if (dst[i])
+            CUDA_TRY(h, cudaMemcpyAsync(dst[i], h->boxes.p + (size_t)i * P, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DDC_OK;
+}
+
+int ddc_get_pid_device(ddc_handle_t h, const int32_t** dev_ptr)
+{
+    NEED_PARTITION(h);
+    if (!h->have_pid)
+        return fail(h, DDC_ERR_STATE, "pid was not requested (DDC_WANT_PID)");
+    *dev_ptr = h->pid.p;
+    return DDC_OK;
+}
+
+int ddc_get_pid_host(ddc_handle_t h, int32_t* out)
+{
+    NEED_PARTITION(h);
+    if (!h->have_pid)
+        return fail(h, DDC_ERR_STATE, "pid was not requested (DDC_WANT_PID)");
+    const size_t n = (size_t)h->nx * h->y_count;
+    if (n)
+        CUDA_TRY(h, cudaMemcpyAsync(out, h->pid.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DDC_OK;
+}
+
+static int list_index(ddc_handle_t h, int edge, int periodic)
+{
+    if (edge < 0 || edge >= 4 || periodic < 0 || periodic > 1)
+        return fail(h, DDC_ERR_ARG, "edge must be 0..3 and periodic 0/1");
+    return periodic * 4 + edge;
+}
+
+int ddc_get_neighbour_counts(ddc_handle_t h, int edge, int periodic, int32_t* counts)
+{
+    NEED_PARTITION(h);
+    const int l = list_index(h, edge, periodic);
+    if (l < 0)
+        return l;
+    const int P = h->nparts;
+    if (!h->have_nbr) { // P == 1 (Q4) or neighbours not requested: empty lists
+        memset(counts, 0, sizeof(int32_t) * P);
+        return DDC_OK;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(counts, h->nbr_counts.p + (size_t)l * P, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DDC_OK;
+}
+
+int ddc_get_neighbour_total(ddc_handle_t h, int edge, int periodic, int64_t* total)
+{
+    NEED_PARTITION(h);
+    const int l = list_index(h, edge, periodic);
+    if (l < 0)
+        return l;
+    if (!h->have_nbr) {
+        *total = 0;
+        return DDC_OK;
+    }
+    int rc = fetch_totals(h);
+    if (rc)
+        return rc;
+    *total = h->h_totals[l];
+    return DDC_OK;
+}
+
+int ddc_get_neighbours(ddc_handle_t h, int edge, int periodic, int32_t* ids, int32_t* halos, int32_t* starts)
+{
+    NEED_PARTITION(h);
+    const int l = list_index(h, edge, periodic);
+    if (l < 0)
+        return l;
+    if (!h->have_nbr)
+        return DDC_OK;
+    int rc = fetch_totals(h);
+    if (rc)
+        return rc;
+    const size_t n = (size_t)h->h_totals[l], off = (size_t)l * h->nbr_cap;
+    if (n) {
+        if (ids)
+            CUDA_TRY(h, cudaMemcpyAsync(ids, h->nbr_ids.p + off, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (halos)
+            CUDA_TRY(h, cudaMemcpyAsync(halos, h->nbr_halos.p + off, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (starts)
+            CUDA_TRY(h, cudaMemcpyAsync(starts, h->nbr_starts.p + off, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DDC_OK;
+}
+
+int ddc_get_part_loads(ddc_handle_t h, int64_t* loads)
+{
+    NEED_PARTITION(h);
+    CUDA_TRY(h, cudaMemcpyAsync(loads, h->loads.p, sizeof(int64_t) * h->nparts, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DDC_OK;
+}
+
+int ddc_get_stats(ddc_handle_t h, ddc_stats* out)
+{
+    NEED_PARTITION(h);
+    DevScalars hs;
+    long long mm[2];
+    Plan pl;
+    CUDA_TRY(h, cudaMemcpyAsync(&hs, h->sc.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(mm, h->loadmm.p, sizeof mm, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&pl, h->plan.p, sizeof pl, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stats.changes = h->nparts > 1 ? hs.changes : 0;
+    h->stats.load_min = mm[0];
+    h->stats.load_max = mm[1];
+    h->stats.median_iters = pl.iters;
+    if (h->have_nbr) {
+        int rc = fetch_totals(h);
+        if (rc)
+            return rc;
+    }
+    *out = h->stats;
+    return DDC_OK;
+}
+
+int ddc_neighbours_from_boxes(ddc_handle_t h, int nparts, int nx, int ny, const int32_t* x0, const int32_t* y0,
+    const int32_t* ex, const int32_t* ey, int px, int py)
+{
+    if (!h || nparts < 1 || !x0 || !y0 || !ex || !ey)
+        return fail(h, DDC_ERR_ARG, "ddc_neighbours_from_boxes: bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int P = nparts;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
+    CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
+    CUDA_TRY(h, h->sets.ensure((size_t)6 * P));
+    Tables t = tables(h, P);
+    const int32_t* src[4] = { x0, y0, ex, ey };
+    for (int i = 0; i < 4; i++)
+        CUDA_TRY(h, cudaMemcpyAsync(h->boxes.p + (size_t)i * P, src[i], sizeof(int32_t) * P, cudaMemcpyHostToDevice, s));
+    // no strip structure is assumed for caller-supplied boxes: one always-relevant strip
+    const int zero = 0, one = 1, nx_ = nx;
+    CUDA_TRY(h, cudaMemcpyAsync(t.st.x0, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(t.st.x1, &nx_, sizeof(int), cudaMemcpyHostToDevice, s));
+    const int p0[2] = { 0, P };
+    CUDA_TRY(h, cudaMemcpyAsync(t.st.p0, p0, sizeof p0, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(t.st.S, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(t.st.always, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    DevScalars init;
+    init.neg_ymin = INT_MIN;
+    init.ymax = -1;
+    init.changes = 1;
+    init.overflow = 0;
+    init.edge_cut = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(h->sc.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s)); // the staging variables above live on this stack frame
+    memset(&h->stats, 0, sizeof h->stats);
+    h->nparts = P;
+    h->nx = nx; // also what an overflow re-run of the fill pass uses
+    h->ny = ny;
+    h->px = px;
+    h->py = py;
+    h->mask_set = false; // the mask (if any) has to be set again before the next ddc_partition
+    h->d_mask = nullptr;
+    int rc = run_neighbours(h, P, nx, ny, px, py);
+    if (rc)
+        return rc;
+    h->partitioned = true; // results (boxes + neighbour tables) are valid; pid / loads are not
+    h->have_pid = false;
+    CUDA_TRY(h, h->loads.ensure(P));
+    CUDA_TRY(h, h->loadmm.ensure(2));
+    CUDA_TRY(h, cudaMemsetAsync(h->loads.p, 0, sizeof(long long) * P, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->loadmm.p, 0, sizeof(long long) * 2, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->plan.p, 0, sizeof(Plan), s));
+    return DDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic masks
+// ------------------------------------------------------------------------------------------------
+static void synth_params(int nx, int ny, uint64_t seed, double land_frac, uint64_t* L1, uint64_t* L2, uint32_t* thresh)
+{
+    const uint64_t m = (uint64_t)std::max(nx, ny);
+    *L1 = std::max<uint64_t>(1, m / 16);
+    *L2 = std::max<uint64_t>(1, m / 64);
+    // calibrate the threshold to the requested land fraction on a fixed 128 x 128 sample lattice
+    const int K = 128;
+    std::vector<uint32_t> v;
+    v.reserve((size_t)K * K);
+    for (int j = 0; j < K; j++)
+        for (int i = 0; i < K; i++) {
+            const uint64_t x = (uint64_t)(((2 * i + 1) * (uint64_t)nx) / (2 * K));
+            const uint64_t y = (uint64_t)(((2 * j + 1) * (uint64_t)ny) / (2 * K));
+            v.push_back(synth_value(seed, *L1, *L2, x, y));
+        }
+    std::sort(v.begin(), v.end());
+    double f = land_frac < 0 ? 0 : (land_frac > 1 ? 1 : land_frac);
+    size_t k = (size_t)(f * (double)v.size());
+    if (k >= v.size())
+        *thresh = 0xffffffffu; // everything land
+    else
+        *thresh = f <= 0 ? 0u : v[k];
+}
+
+int ddc_generate_mask_device(ddc_handle_t h, int32_t* dev_rows, int nx, int ny, int y_begin, int y_count, uint64_t seed, double land_frac)
+{
+    if (!h || nx < 1 || ny < 1 || y_begin < 0 || y_count < 0 || y_begin + y_count > ny || (!dev_rows && y_count))
+        return fail(h, DDC_ERR_ARG, "ddc_generate_mask_device: bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    uint64_t L1, L2;
+    uint32_t thresh;
+    synth_params(nx, ny, seed, land_frac, &L1, &L2, &thresh);
+    if (y_count) {
+        const size_t n = (size_t)nx * y_count;
+        const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 32);
+        k_generate_mask<<<grid, 256, 0, h->stream>>>(dev_rows, nx, y_count, y_begin, seed, L1, L2, thresh);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    return DDC_OK;
+}
+
+int ddc_generate_mask_host(int32_t* rows, int nx, int ny, int y_begin, int y_count, uint64_t seed, double land_frac)
+{
+    if (nx < 1 || ny < 1 || y_begin < 0 || y_count < 0 || y_begin + y_count > ny || (!rows && y_count))
+        return DDC_ERR_ARG;
+    uint64_t L1, L2;
+    uint32_t thresh;
+    synth_params(nx, ny, seed, land_frac, &L1, &L2, &thresh);
+    for (int y = 0; y < y_count; y++)
+        for (int x = 0; x < nx; x++)
+            rows[(size_t)y * nx + x] = synth_value(seed, L1, L2, (uint64_t)x, (uint64_t)(y + y_begin)) >= thresh ? 1 : 0;
+    return DDC_OK;
+}
+
+} // extern "C"

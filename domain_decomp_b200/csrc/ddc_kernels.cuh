@@ -1,0 +1,1001 @@
+// ddc_kernels.cuh -- hand-written sm_100a kernels of the domain-decomposition hot path.
+//
+// Pipeline (one GPU; with several GPUs every rank runs it on its own block of mask rows and the
+// two histograms are combined with NCCL between the kernels, see ddc_api.cu):
+//
+//   K1 k_scan_mask     int32 mask -> 1-bit ocean map + per-column ocean counts + dot y-range
+//                      (replaces Grid.cpp:176-188 and the Zoltan geometry callbacks
+//                       ZoltanPartitioner.cpp:19-67; HBM-bound, 4 B/cell read)
+//   K2 k_xcuts         prefix sums of the column counts, preset cut directions, all x levels of
+//                      the RCB: one batched weighted-median step per level over every active set
+//   K3 k_strip_rows    per-strip per-row ocean counts from the bit map (1/32 of the mask bytes)
+//   K4 k_ycuts         all y levels, one CTA per vertical strip -> integer part boxes
+//                      (K2+K4 replace Zoltan::LB_Partition + RCB_Box + the ceil/clamp of
+//                       ZoltanPartitioner.cpp:161-195)
+//   K6 k_label         pid[y][x] = ocean ? part : -1 and Zoltan's `changes` flag
+//                      (ZoltanPartitioner.cpp:201-219; HBM-bound, 4 B/cell written)
+//   K5 k_finalize      `changes == 0` => report the naive blocks (ZoltanPartitioner.cpp:182-187)
+//   K7 k_neighbours    interval-intersection kernel: neighbour ids, halo sizes, halo starts,
+//                      interior and periodic (Partitioner.cpp:20-80,329-435, DomainUtils.cpp:15-35)
+//
+// Bit map layout: one uint4 per (row, 128-column group); word c (0..3), bit l  <=>  column
+// 128*g + 4*l + c.  That is exactly what four warp ballots over one coalesced uint4 load per lane
+// produce, so K1 never shuffles bits.  It is private to this file.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ddc {
+
+struct DevScalars {
+    int neg_ymin; // -(smallest row holding an ocean cell); max-reduced
+    int ymax; // largest row holding an ocean cell, -1 if none
+    int changes; // any ocean cell whose RCB part differs from its naive block
+    int overflow; // neighbour lists did not fit their capacity
+    unsigned long long edge_cut; // sum of interior halo lengths
+};
+
+struct Plan { // written by K2, read back by the host
+    int nlev, ix, iy, S;
+    int xmin, xmax, ymin, ymax;
+    long long W;
+    int iters; // median iterations (x levels; K4 adds its own atomically)
+    int pad;
+};
+
+struct NaiveParams { // Grid.cpp:150-166
+    int np0, np1, lx, ly;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// bits l of word c that belong to group-relative columns [a, b), 0 <= a <= b <= 128
+__device__ __forceinline__ unsigned group_word_mask(int c, int a, int b)
+{
+    int l_lo = a > c ? (a - c + 3) >> 2 : 0;
+    int l_hi = b > c ? (b - c + 3) >> 2 : 0;
+    if (l_hi <= l_lo)
+        return 0u;
+    unsigned hi = l_hi >= 32 ? 0xffffffffu : ((1u << l_hi) - 1u);
+    unsigned lo = (1u << l_lo) - 1u; // l_lo < 32 here
+    return hi & ~lo;
+}
+
+// exclusive block scan of one value per thread (blockDim.x <= 1024, multiple of 32)
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* total, T* warp_sums /* >= 33 entries */)
+{
+    unsigned lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o)
+            inc += t;
+    }
+    if (lane == 31)
+        warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < nwarp ? warp_sums[lane] : T(0);
+        T winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (unsigned)o)
+                winc += t;
+        }
+        warp_sums[lane] = winc - w; // exclusive
+        if (lane == 31)
+            warp_sums[32] = winc;
+    }
+    __syncthreads();
+    T res = warp_sums[warp] + inc - v;
+    *total = warp_sums[32];
+    __syncthreads();
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: mask scan
+// ------------------------------------------------------------------------------------------------
+// One warp owns one 128-column group for `rows_per_cta` rows; the 8 warps of a CTA own 8 adjacent
+// groups, i.e. 4 KiB contiguous per row.  Every lane issues 8 independent 16-byte loads (8 rows)
+// before using any of them.  VEC: NX % 4 == 0 and a 16-byte aligned base pointer.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ mask, int NX, int rows,
+    int y_begin, int NG, int rows_per_cta, uint4* __restrict__ bits, unsigned* __restrict__ colcount,
+    DevScalars* __restrict__ sc)
+{
+    const int lane = lane_id();
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= NG)
+        return; // whole warp leaves together
+    const int r0 = blockIdx.y * rows_per_cta;
+    const int r1 = min(rows, r0 + rows_per_cta);
+    const int x = g * 128 + lane * 4;
+    unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    int ylo = 0x7fffffff, yhi = -1;
+
+    for (int r = r0; r < r1; r += 8) {
+        int4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k] = make_int4(0, 0, 0, 0);
+            if (r + k < r1) {
+                const int32_t* p = mask + (size_t)(r + k) * NX + x;
+                if (VEC) {
+                    if (x < NX)
+                        v[k] = __ldcs(reinterpret_cast<const int4*>(p));
+                } else {
+                    if (x < NX)
+                        v[k].x = __ldcs(p);
+                    if (x + 1 < NX)
+                        v[k].y = __ldcs(p + 1);
+                    if (x + 2 < NX)
+                        v[k].z = __ldcs(p + 2);
+                    if (x + 3 < NX)
+                        v[k].w = __ldcs(p + 3);
+                }
+            }
+        }
+        uint4 mine = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const bool o0 = v[k].x > 0, o1 = v[k].y > 0, o2 = v[k].z > 0, o3 = v[k].w > 0;
+            const unsigned b0 = __ballot_sync(0xffffffffu, o0);
+            const unsigned b1 = __ballot_sync(0xffffffffu, o1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, o2);
+            const unsigned b3 = __ballot_sync(0xffffffffu, o3);
+            c0 += o0;
+            c1 += o1;
+            c2 += o2;
+            c3 += o3;
+            if (lane == k)
+                mine = make_uint4(b0, b1, b2, b3);
+            if (b0 | b1 | b2 | b3) {
+                ylo = min(ylo, r + k);
+                yhi = max(yhi, r + k);
+            }
+        }
+        if (lane < 8 && r + lane < r1)
+            bits[(size_t)(r + lane) * NG + g] = mine;
+    }
+    if (c0)
+        atomicAdd(colcount + x, c0);
+    if (c1)
+        atomicAdd(colcount + x + 1, c1);
+    if (c2)
+        atomicAdd(colcount + x + 2, c2);
+    if (c3)
+        atomicAdd(colcount + x + 3, c3);
+    if (lane == 0 && yhi >= 0) {
+        const int ny0 = -(y_begin + ylo), y1 = y_begin + yhi;
+        if (ny0 > sc->neg_ymin)
+            atomicMax(&sc->neg_ymin, ny0);
+        if (y1 > sc->ymax)
+            atomicMax(&sc->ymax, y1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Zoltan_RB_find_median on a histogram (device restatement; see DESIGN.md "median")
+// ------------------------------------------------------------------------------------------------
+// pfx[i] = number of dots in bins [0, i).  All doubles are combined with explicit
+// round-to-nearest intrinsics so that no FMA contraction can change Zoltan's arithmetic.
+__device__ __forceinline__ unsigned hcnt(const unsigned* pfx, int a, int b)
+{
+    return b < a ? 0u : pfx[b + 1] - pfx[a];
+}
+__device__ inline int last_nonempty(const unsigned* pfx, int a, int b)
+{
+    if (b < a || pfx[b + 1] == pfx[a])
+        return -1;
+    const unsigned target = pfx[b + 1];
+    int lo = a, hi = b;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (pfx[mid + 1] >= target)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+__device__ inline int first_nonempty(const unsigned* pfx, int a, int b)
+{
+    if (b < a || pfx[b + 1] == pfx[a])
+        return -1;
+    const unsigned base = pfx[a];
+    int lo = a, hi = b;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (pfx[mid + 1] > base)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+
+// Integer boundary ceil(cut) of the weighted-median cut of bins [c0, c1] for a set of num_parts
+// parts whose lower child receives nlo parts.  *iters += median iterations.
+__device__ inline int median_boundary(const unsigned* pfx, int c0, int c1, int nlo, int num_parts,
+    int* iters)
+{
+    const unsigned Wn = hcnt(pfx, c0, c1);
+    if (Wn == 0u) { // no dot at all: integer midpoint of the inherited range (policy Q2)
+        *iters += 1;
+        return c0 + ((c1 + 1 - c0) >> 1);
+    }
+    const double weight = (double)Wn;
+    const double fractionlo = __ddiv_rn((double)nlo, (double)num_parts);
+    const int first = first_nonempty(pfx, c0, c1), last = last_nonempty(pfx, c0, c1);
+    double valuemin = (double)first, valuemax = (double)last;
+    int alo = first, ahi = last;
+    int B;
+    double weightlo = 0.0, weighthi = 0.0;
+    const double targetlo = __dmul_rn(fractionlo, weight);
+    const double targethi = __dsub_rn(weight, targetlo);
+    int it = 0;
+    for (;;) {
+        // tmp_half = valuemin + (targetlo - weightlo) / (weight - weightlo - weighthi) * (valuemax - valuemin)
+        const double num = __dsub_rn(targetlo, weightlo);
+        const double den = __dsub_rn(__dsub_rn(weight, weightlo), weighthi);
+        const double tmp_half
+            = __dadd_rn(valuemin, __dmul_rn(__ddiv_rn(num, den), __dsub_rn(valuemax, valuemin)));
+        it++;
+        int t;
+        if (tmp_half < (double)alo)
+            t = alo - 1;
+        else if (tmp_half >= (double)ahi)
+            t = ahi;
+        else
+            t = (int)floor(tmp_half);
+        B = t;
+        const double totallo = (double)hcnt(pfx, alo, t), totalhi = (double)hcnt(pfx, t + 1, ahi);
+        const int vlo = last_nonempty(pfx, alo, t), vhi = first_nonempty(pfx, t + 1, ahi);
+        const double wtlo = vlo >= 0 ? (double)hcnt(pfx, vlo, vlo) : 0.0;
+        const double wthi = vhi >= 0 ? (double)hcnt(pfx, vhi, vhi) : 0.0;
+
+        if (__dadd_rn(weightlo, totallo) < targetlo) { // lower half TOO SMALL
+            weightlo = __dadd_rn(weightlo, totallo);
+            if (vhi < 0)
+                break;
+            const double moved = __dadd_rn(weightlo, wthi);
+            if (wthi == 1.0) { // a single dot: move only if strictly better
+                if (moved < targetlo) {
+                    B = vhi;
+                } else {
+                    if (__dsub_rn(moved, targetlo) < __dsub_rn(targetlo, weightlo))
+                        B = vhi;
+                    break;
+                }
+            } else { // a whole column: move unless strictly worse
+                if (moved >= targetlo) {
+                    if (!(__dsub_rn(moved, targetlo) > __dsub_rn(targetlo, weightlo)))
+                        B = vhi;
+                    break;
+                }
+                B = vhi;
+            }
+            weightlo = moved;
+            if (__dsub_rn(targetlo, weightlo) <= 1.0) // tolerance = weight of one dot
+                break;
+            valuemin = (double)vhi;
+            alo = vhi + 1;
+        } else if (__dadd_rn(weighthi, totalhi) < targethi) { // upper half TOO SMALL
+            weighthi = __dadd_rn(weighthi, totalhi);
+            if (vlo < 0)
+                break;
+            const double moved = __dadd_rn(weighthi, wtlo);
+            if (wtlo == 1.0) {
+                if (moved < targethi) {
+                    B = vlo - 1;
+                } else {
+                    if (__dsub_rn(moved, targethi) < __dsub_rn(targethi, weighthi))
+                        B = vlo - 1;
+                    break;
+                }
+            } else {
+                if (moved >= targethi) {
+                    if (!(__dsub_rn(moved, targethi) > __dsub_rn(targethi, weighthi)))
+                        B = vlo - 1;
+                    break;
+                }
+                B = vlo - 1;
+            }
+            weighthi = moved;
+            if (__dsub_rn(targethi, weighthi) <= 1.0)
+                break;
+            valuemax = (double)vlo;
+            ahi = vlo - 1;
+        } else
+            break; // both halves just right
+    }
+    *iters += it;
+    // AVERAGE_CUTS over all dots of the set, then ceil() (ZoltanPartitioner.cpp:177-180)
+    const int L = last_nonempty(pfx, c0, B), U = first_nonempty(pfx, B + 1, c1);
+    if (L >= 0 && U >= 0)
+        return (L + U + 1) >> 1; // ceil(0.5 * (L + U))
+    if (L >= 0)
+        return L + 1; // policy Q2
+    return U; // policy Q2 (U >= 0 because Wn > 0)
+}
+
+// One RCB level over the sets [p_begin, p_end): sets live at the index of their lowest part.
+// Reads buffer `in`, writes buffer `out` (double buffered: all reads precede all writes).
+struct SetBuf {
+    int* lo;
+    int* hi;
+    int* n;
+};
+__device__ inline void rcb_level(const unsigned* pfx, SetBuf in, SetBuf out, int p_begin, int p_end,
+    int* iters)
+{
+    for (int p = p_begin + threadIdx.x; p < p_end; p += blockDim.x) {
+        const int n = in.n[p];
+        if (n == 0)
+            continue;
+        const int lo = in.lo[p], hi = in.hi[p];
+        if (n == 1) {
+            out.lo[p] = lo;
+            out.hi[p] = hi;
+            out.n[p] = 1;
+            continue;
+        }
+        // Zoltan_Divide_Machine: lower child gets ceil(n/2) parts
+        const int nlo = (n - 1) / 2 + 1;
+        const int b = median_boundary(pfx, lo, hi - 1, nlo, n, iters);
+        out.lo[p] = lo;
+        out.hi[p] = b;
+        out.n[p] = nlo;
+        out.lo[p + nlo] = b;
+        out.hi[p + nlo] = hi;
+        out.n[p + nlo] = n - nlo;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: column prefix sums, preset directions, all x levels, strip table
+// ------------------------------------------------------------------------------------------------
+struct StripTable {
+    int* x0; // [cap]
+    int* x1; // [cap]
+    int* p0; // [cap + 1]  first part of every strip, p0[S] = P
+    int* S; // [1]
+    int* always; // [1] != 0: no x structure, treat every strip as relevant (brute force)
+};
+struct BoxTable { // final boxes, SoA
+    int* x0;
+    int* y0;
+    int* ex;
+    int* ey;
+};
+
+// dynamic shared memory: (NX + 1) unsigned when use_smem
+__global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ colcount, int NX, int NY,
+    int P, unsigned* pfx_g, int use_smem, const DevScalars* __restrict__ sc, Plan* plan, SetBuf A,
+    SetBuf Bf, StripTable st, BoxTable bx, long long* loads, int* strip_of_part)
+{
+    extern __shared__ unsigned smem_dyn[];
+    __shared__ unsigned long long wsum64[33];
+    __shared__ int wsum32[33];
+    __shared__ int s_ix, s_iters;
+    unsigned* pfx = use_smem ? smem_dyn : pfx_g;
+    const int tid = threadIdx.x;
+
+    // 1. pfx[i] = ocean cells in columns [0, i)
+    {
+        const int chunk = (NX + blockDim.x - 1) / blockDim.x;
+        const int b = min(NX, tid * chunk), e = min(NX, b + chunk);
+        unsigned long long sum = 0;
+        for (int i = b; i < e; i++)
+            sum += colcount[i];
+        unsigned long long total;
+        unsigned long long run = block_exclusive_scan<unsigned long long>(sum, &total, wsum64);
+        for (int i = b; i < e; i++) {
+            pfx[i] = (unsigned)run;
+            run += colcount[i];
+        }
+        if (tid == 0)
+            pfx[NX] = (unsigned)total;
+    }
+    // sets: everything invalid, then the root set
+    for (int p = tid; p < P; p += blockDim.x) {
+        A.n[p] = 0;
+        Bf.n[p] = 0;
+    }
+    __syncthreads();
+
+    // 2. the plan: bounding box of all dots -> preset direction of every level
+    if (tid == 0) {
+        const long long W = pfx[NX];
+        int xmin = 0, xmax = 0, ymin = 0, ymax = 0;
+        if (W > 0) {
+            xmin = first_nonempty(pfx, 0, NX - 1);
+            xmax = last_nonempty(pfx, 0, NX - 1);
+            ymin = -sc->neg_ymin;
+            ymax = sc->ymax;
+        }
+        double wx = (double)(xmax - xmin), wy = (double)(ymax - ymin);
+        int nlev = 0;
+        for (int t = P; t > 1; t = (t + 1) / 2)
+            nlev++;
+        int ix = 0, iy = 0;
+        for (int i = 0; i < nlev; i++) {
+            if (wx > wy) { // a tie cuts y (Q1)
+                ix++;
+                wx = __ddiv_rn(wx, 2.0);
+            } else {
+                iy++;
+                wy = __ddiv_rn(wy, 2.0);
+            }
+        }
+        plan->nlev = nlev;
+        plan->ix = ix;
+        plan->iy = iy;
+        plan->xmin = xmin;
+        plan->xmax = xmax;
+        plan->ymin = ymin;
+        plan->ymax = ymax;
+        plan->W = W;
+        s_ix = ix;
+        s_iters = 0;
+        A.lo[0] = 0;
+        A.hi[0] = NX;
+        A.n[0] = P;
+    }
+    __syncthreads();
+
+    // 3. the x levels
+    const int ix = s_ix;
+    int my_iters = 0;
+    SetBuf cur = A, nxt = Bf;
+    for (int l = 0; l < ix; l++) {
+        rcb_level(pfx, cur, nxt, 0, P, &my_iters);
+        __syncthreads();
+        SetBuf t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    if (my_iters)
+        atomicAdd(&s_iters, my_iters);
+
+    // 4. strips = valid sets in ascending part order
+    {
+        const int chunk = (P + blockDim.x - 1) / blockDim.x;
+        const int b = min(P, tid * chunk), e = min(P, b + chunk);
+        int cnt = 0;
+        for (int p = b; p < e; p++)
+            cnt += cur.n[p] != 0;
+        int total;
+        int pos = block_exclusive_scan<int>(cnt, &total, wsum32);
+        for (int p = b; p < e; p++) {
+            const int n = cur.n[p];
+            if (n != 0) {
+                const int lo = cur.lo[p], hi = cur.hi[p];
+                st.x0[pos] = lo;
+                st.x1[pos] = hi;
+                st.p0[pos] = p;
+                for (int q = p; q < p + n; q++)
+                    strip_of_part[q] = pos;
+                if (n == 1) { // a leaf already: uncut in y
+                    bx.x0[p] = lo;
+                    bx.ex[p] = hi - lo;
+                    bx.y0[p] = 0;
+                    bx.ey[p] = NY;
+                    loads[p] = (long long)hcnt(pfx, lo, hi - 1);
+                }
+                pos++;
+            }
+        }
+        if (tid == 0) {
+            st.p0[total] = P;
+            *st.S = total;
+            *st.always = 0;
+            plan->S = total;
+        }
+    }
+    __syncthreads();
+    if (tid == 0)
+        plan->iters = s_iters;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: per-strip row counts from the bit map
+// ------------------------------------------------------------------------------------------------
+// A CTA stages R rows of the bit map in shared memory (row pitch NG + 1 uint4: conflict-free
+// 16-byte reads when the lanes of a warp are consecutive rows), then thread (strip, row) sums the
+// popcounts of its strip.  rowcount layout [S][Rmax], rows local to this rank.
+__global__ void __launch_bounds__(256) k_strip_rows(const uint4* __restrict__ bits, int NG, int rows,
+    int R, const int* __restrict__ st_x0, const int* __restrict__ st_x1, const int* __restrict__ st_S,
+    unsigned* __restrict__ rowcount, int Rmax)
+{
+    extern __shared__ uint4 tile[];
+    const int pitch = NG + 1;
+    const int r0 = blockIdx.x * R;
+    for (int i = threadIdx.x; i < R * NG; i += blockDim.x) {
+        const int row = i / NG, g = i - row * NG;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r0 + row < rows)
+            v = bits[(size_t)(r0 + row) * NG + g];
+        tile[row * pitch + g] = v;
+    }
+    __syncthreads();
+    const int S = *st_S;
+    for (int t = threadIdx.x; t < S * R; t += blockDim.x) {
+        const int s = t / R, row = t - s * R;
+        if (r0 + row >= rows)
+            continue;
+        const int x0 = st_x0[s], x1 = st_x1[s];
+        unsigned cnt = 0;
+        if (x1 > x0) {
+            const int g0 = x0 >> 7, g1 = (x1 - 1) >> 7;
+            for (int g = g0; g <= g1; g++) {
+                const uint4 w = tile[row * pitch + g];
+                const int a = max(x0 - g * 128, 0), b = min(x1 - g * 128, 128);
+                if (a == 0 && b == 128)
+                    cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+                else
+                    cnt += __popc(w.x & group_word_mask(0, a, b)) + __popc(w.y & group_word_mask(1, a, b))
+                        + __popc(w.z & group_word_mask(2, a, b)) + __popc(w.w & group_word_mask(3, a, b));
+            }
+        }
+        rowcount[(size_t)s * Rmax + r0 + row] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: y levels, one CTA per strip (grid-stride), boxes out
+// ------------------------------------------------------------------------------------------------
+// rowcount_all layout [G][S][Rmax] (the NCCL all-gather of every rank's [S][Rmax]); global row y
+// lives at rank y / Rmax, local row y % Rmax.  dynamic smem: (NY + 1) unsigned when use_smem,
+// otherwise pfx_g holds gridDim.x slices of NY + 1.
+__global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ rowcount_all, int G,
+    int Rmax, int NY, int ylevels, StripTable st, SetBuf A, SetBuf Bf, unsigned* pfx_g, int use_smem,
+    BoxTable bx, long long* loads, Plan* plan)
+{
+    extern __shared__ unsigned smem_dyn[];
+    __shared__ unsigned long long wsum64[33];
+    unsigned* pfx = use_smem ? smem_dyn : pfx_g + (size_t)blockIdx.x * (NY + 1);
+    const int tid = threadIdx.x;
+    const int S = *st.S;
+    int my_iters = 0;
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const int plo = st.p0[s], n = st.p0[s + 1] - plo;
+        if (n <= 1)
+            continue; // K2 already wrote the box of a leaf strip
+        __syncthreads(); // previous strip done with pfx
+        {
+            const int chunk = (NY + blockDim.x - 1) / blockDim.x;
+            const int b = min(NY, tid * chunk), e = min(NY, b + chunk);
+            unsigned long long sum = 0;
+            for (int y = b; y < e; y++) {
+                const int g = y / Rmax, yl = y - g * Rmax;
+                sum += rowcount_all[((size_t)g * S + s) * Rmax + yl];
+            }
+            unsigned long long total;
+            unsigned long long run = block_exclusive_scan<unsigned long long>(sum, &total, wsum64);
+            for (int y = b; y < e; y++) {
+                const int g = y / Rmax, yl = y - g * Rmax;
+                pfx[y] = (unsigned)run;
+                run += rowcount_all[((size_t)g * S + s) * Rmax + yl];
+            }
+            if (tid == 0)
+                pfx[NY] = (unsigned)total;
+        }
+        for (int p = plo + tid; p < plo + n; p += blockDim.x) {
+            A.n[p] = 0;
+            Bf.n[p] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            A.lo[plo] = 0;
+            A.hi[plo] = NY;
+            A.n[plo] = n;
+        }
+        __syncthreads();
+        SetBuf cur = A, nxt = Bf;
+        for (int l = 0; l < ylevels; l++) {
+            rcb_level(pfx, cur, nxt, plo, plo + n, &my_iters);
+            __syncthreads();
+            SetBuf t = cur;
+            cur = nxt;
+            nxt = t;
+        }
+        const int sx0 = st.x0[s], sx1 = st.x1[s];
+        for (int p = plo + tid; p < plo + n; p += blockDim.x) {
+            const int lo = cur.lo[p], hi = cur.hi[p];
+            bx.x0[p] = sx0;
+            bx.ex[p] = sx1 - sx0;
+            bx.y0[p] = lo;
+            bx.ey[p] = hi - lo;
+            loads[p] = (long long)hcnt(pfx, lo, hi - 1);
+        }
+    }
+    if (my_iters)
+        atomicAdd(&plan->iters, my_iters);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: owner labelling + Zoltan's `changes`
+// ------------------------------------------------------------------------------------------------
+// Same thread mapping as K1.  Every thread keeps, for each of its 4 columns, a cursor into the
+// (y-sorted) parts of the column's strip; rows are walked in order so a cursor only ever advances.
+template <bool VEC, bool WRITE>
+__global__ void __launch_bounds__(256) k_label(const uint4* __restrict__ bits, int NX, int rows,
+    int y_begin, int NG, int rows_per_cta, const int* __restrict__ st_x1, const int* __restrict__ st_p0,
+    const int* __restrict__ st_S, const int* __restrict__ box_y0, const int* __restrict__ box_ey,
+    NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc)
+{
+    const int lane = lane_id();
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= NG)
+        return;
+    const int r0 = blockIdx.y * rows_per_cta;
+    const int r1 = min(rows, r0 + rows_per_cta);
+    const int x = g * 128 + lane * 4;
+    const int S = *st_S;
+
+    int pcur[4], plast[4], yend[4], nbx[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int xc = min(x + c, NX - 1);
+        // strip of column xc: first s with xc < x1[s]
+        int lo = 0, hi = S - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (xc < st_x1[mid])
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        const int pb = st_p0[lo], pe = st_p0[lo + 1];
+        // part of row y_begin + r0 inside the strip: first p with y < y0[p] + ey[p]
+        const int y = y_begin + r0;
+        int a = pb, b = pe - 1;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (y < box_y0[mid] + box_ey[mid])
+                b = mid;
+            else
+                a = mid + 1;
+        }
+        pcur[c] = a;
+        plast[c] = pe - 1;
+        yend[c] = box_y0[a] + box_ey[a];
+        nbx[c] = min(xc / nv.lx, nv.np0 - 1) * nv.np1;
+    }
+    int by = min((y_begin + r0) / nv.ly, nv.np1 - 1);
+    int by_next = (by == nv.np1 - 1) ? 0x7fffffff : (by + 1) * nv.ly;
+    bool changed = false;
+
+    for (int r = r0; r < r1; r += 8) {
+        uint4 b[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            b[k] = make_uint4(0, 0, 0, 0);
+            if (r + k < r1)
+                b[k] = __ldg(bits + (size_t)(r + k) * NG + g);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (r + k < r1) {
+                const int y = y_begin + r + k;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    while (y >= yend[c] && pcur[c] < plast[c]) {
+                        pcur[c]++;
+                        yend[c] = box_y0[pcur[c]] + box_ey[pcur[c]];
+                    }
+                }
+                if (y >= by_next) {
+                    by++;
+                    by_next = (by == nv.np1 - 1) ? 0x7fffffff : by_next + nv.ly;
+                }
+                const bool o0 = (b[k].x >> lane) & 1u, o1 = (b[k].y >> lane) & 1u;
+                const bool o2 = (b[k].z >> lane) & 1u, o3 = (b[k].w >> lane) & 1u;
+                changed |= (o0 && pcur[0] != nbx[0] + by) | (o1 && pcur[1] != nbx[1] + by)
+                    | (o2 && pcur[2] != nbx[2] + by) | (o3 && pcur[3] != nbx[3] + by);
+                if (WRITE) {
+                    int4 out = make_int4(o0 ? pcur[0] : -1, o1 ? pcur[1] : -1, o2 ? pcur[2] : -1,
+                        o3 ? pcur[3] : -1);
+                    int32_t* q = pid + (size_t)(r + k) * NX + x;
+                    if (VEC) {
+                        if (x < NX)
+                            __stcs(reinterpret_cast<int4*>(q), out);
+                    } else {
+                        if (x < NX)
+                            q[0] = out.x;
+                        if (x + 1 < NX)
+                            q[1] = out.y;
+                        if (x + 2 < NX)
+                            q[2] = out.z;
+                        if (x + 3 < NX)
+                            q[3] = out.w;
+                    }
+                }
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, changed) && lane == 0 && sc->changes == 0)
+        atomicOr(&sc->changes, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: `changes == 0`  =>  report the naive blocks (ZoltanPartitioner.cpp:182-187)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(int P, int NX, int NY, NaiveParams nv,
+    const DevScalars* __restrict__ sc, StripTable st, BoxTable bx, int* strip_of_part)
+{
+    if (sc->changes != 0)
+        return;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const int bxi = p / nv.np1, byi = p % nv.np1; // Grid.cpp:158-159
+        int ex = nv.lx, ey = nv.ly;
+        if (bxi == nv.np0 - 1)
+            ex = NX - bxi * nv.lx;
+        if (byi == nv.np1 - 1)
+            ey = NY - byi * nv.ly;
+        bx.x0[p] = bxi * nv.lx;
+        bx.y0[p] = byi * nv.ly;
+        bx.ex[p] = ex;
+        bx.ey[p] = ey;
+        strip_of_part[p] = bxi;
+        if (byi == 0) {
+            st.x0[bxi] = bxi * nv.lx;
+            st.x1[bxi] = bxi * nv.lx + ex;
+            st.p0[bxi] = p;
+        }
+        if (p == 0) {
+            st.p0[nv.np0] = P;
+            *st.S = nv.np0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: neighbours and halos (interval intersection), count pass and fill pass
+// ------------------------------------------------------------------------------------------------
+struct Dom {
+    int x1, y1, x2, y2;
+};
+// DomainUtils.cpp:15-35
+__device__ __forceinline__ int domain_overlap(const Dom& d1, const Dom& d2, int edge)
+{
+    int overlap = 0;
+    if (edge >= 2) { // BOTTOM, TOP: overlap along x
+        if (d1.x2 >= d2.x1 && d1.x1 <= d2.x2)
+            overlap = min(d1.x2, d2.x2) - max(d1.x1, d2.x1);
+    } else { // LEFT, RIGHT: overlap along y
+        if (d1.y2 >= d2.y1 && d1.y1 <= d2.y2)
+            overlap = min(d1.y2, d2.y2) - max(d1.y1, d2.y1);
+    }
+    return overlap;
+}
+// Partitioner.cpp:20-53
+__device__ __forceinline__ bool is_neighbour(const Dom& d1, const Dom& d2, int edge, bool is_px,
+    bool is_py, int NX, int NY)
+{
+    if (edge == 3)
+        return is_py ? d1.y2 == d2.y1 + NY : d1.y2 == d2.y1;
+    if (edge == 2)
+        return is_py ? d1.y1 == d2.y2 - NY : d1.y1 == d2.y2;
+    if (edge == 0)
+        return is_px ? d1.x1 == d2.x2 - NX : d1.x1 == d2.x2;
+    return is_px ? d1.x2 == d2.x1 + NX : d1.x2 == d2.x1;
+}
+// Partitioner.cpp:55-80
+__device__ __forceinline__ int halo_start(const Dom& d1, const Dom& d2, int edge)
+{
+    const int w2 = d2.x2 - d2.x1, h2 = d2.y2 - d2.y1;
+    if (edge == 3)
+        return max(d1.x1, d2.x1) - d2.x1;
+    if (edge == 2)
+        return (h2 - 1) * w2 + (max(d1.x1, d2.x1) - d2.x1);
+    const int dy = max(d1.y1, d2.y1) - d2.y1;
+    if (edge == 0)
+        return (dy + 1) * w2 - 1;
+    return dy * w2;
+}
+
+// One warp per part.  Candidate parts are pruned by strip: every edge test needs either a shared
+// x coordinate or a positive x overlap, so only strips whose closed x range touches mine (or
+// wraps around when periodic in x) can contribute; inside a candidate strip the reference's tests
+// are evaluated literally.  Lists come out id-ascending because strips and the parts inside a
+// strip are visited in ascending order and compacted with ballots.
+// list l = periodic * 4 + edge; counts/offsets [8][P]; ids/halos/starts [8][cap].
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, int NY, int px, int py,
+    StripTable st, int* __restrict__ counts, const int* __restrict__ offsets,
+    const int* __restrict__ totals, int cap, int* __restrict__ ids, int* __restrict__ halos,
+    int* __restrict__ starts, DevScalars* sc)
+{
+    const int lane = lane_id();
+    const int me = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (me >= P)
+        return;
+    if (FILL) {
+        bool over = false;
+#pragma unroll
+        for (int l = 0; l < 8; l++)
+            over |= totals[l] > cap;
+        if (over) {
+            if (me == 0 && lane == 0)
+                sc->overflow = 1;
+            return;
+        }
+    }
+    Dom d1;
+    d1.x1 = bx.x0[me];
+    d1.y1 = bx.y0[me];
+    d1.x2 = d1.x1 + bx.ex[me];
+    d1.y2 = d1.y1 + bx.ey[me];
+    const int S = *st.S;
+    const bool always = *st.always != 0 || d1.x2 <= d1.x1;
+    int cnt[8];
+    int base[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        cnt[l] = 0;
+        base[l] = FILL ? offsets[l * P + me] : 0;
+    }
+    unsigned long long cut = 0;
+
+    for (int sb = 0; sb < S; sb += 32) {
+        const int s = sb + lane;
+        bool rel = false;
+        if (s < S) {
+            const int sx0 = st.x0[s], sx1 = st.x1[s];
+            rel = always || sx1 <= sx0 || (sx0 <= d1.x2 && d1.x1 <= sx1)
+                || (px && (d1.x1 == sx1 - NX || d1.x2 == sx0 + NX)); // periodic L / R edge match
+        }
+        unsigned m = __ballot_sync(0xffffffffu, rel);
+        while (m) {
+            const int t = sb + __ffs(m) - 1;
+            m &= m - 1;
+            const int q0 = st.p0[t], q1 = st.p0[t + 1];
+            for (int qb = q0; qb < q1; qb += 32) {
+                const int q = qb + lane;
+                const bool valid = q < q1;
+                Dom d2 = { 0, 0, 0, 0 };
+                if (valid) {
+                    d2.x1 = bx.x0[q];
+                    d2.y1 = bx.y0[q];
+                    d2.x2 = d2.x1 + bx.ex[q];
+                    d2.y2 = d2.y1 + bx.ey[q];
+                }
+#pragma unroll
+                for (int l = 0; l < 8; l++) {
+                    const int per = l >> 2, edge = l & 3;
+                    const bool lr = edge < 2;
+                    bool pass = valid;
+                    if (per) // filter of get_neighbour_info_periodic (Partitioner.cpp:116)
+                        pass = pass && ((lr && px) || (!lr && py));
+                    else // a subdomain is not its own interior neighbour (Partitioner.cpp:408)
+                        pass = pass && q != me;
+                    int halo = 0;
+                    if (pass) {
+                        pass = is_neighbour(d1, d2, edge, per && px, per && py, NX, NY);
+                        if (pass) {
+                            halo = domain_overlap(d1, d2, edge);
+                            pass = halo > 0;
+                        }
+                    }
+                    const unsigned b = __ballot_sync(0xffffffffu, pass);
+                    if (FILL && pass) {
+                        const int pos = base[l] + cnt[l] + __popc(b & ((1u << lane) - 1u));
+                        ids[(size_t)l * cap + pos] = q;
+                        halos[(size_t)l * cap + pos] = halo;
+                        starts[(size_t)l * cap + pos] = halo_start(d1, d2, edge);
+                        if (!per)
+                            cut += (unsigned long long)halo;
+                    }
+                    cnt[l] += __popc(b);
+                }
+            }
+        }
+    }
+    if (!FILL) {
+        if (lane == 0) {
+#pragma unroll
+            for (int l = 0; l < 8; l++)
+                counts[l * P + me] = cnt[l];
+        }
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            cut += __shfl_xor_sync(0xffffffffu, cut, o);
+        if (lane == 0 && cut)
+            atomicAdd(&sc->edge_cut, cut);
+    }
+}
+
+// exclusive scan of each of the 8 count lists (one CTA per list)
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, int P,
+    int* __restrict__ offsets, int* __restrict__ totals)
+{
+    __shared__ int wsum[33];
+    const int l = blockIdx.x;
+    const int* c = counts + (size_t)l * P;
+    int* o = offsets + (size_t)l * P;
+    const int chunk = (P + blockDim.x - 1) / blockDim.x;
+    const int b = min(P, (int)threadIdx.x * chunk), e = min(P, b + chunk);
+    int sum = 0;
+    for (int i = b; i < e; i++)
+        sum += c[i];
+    int total;
+    int run = block_exclusive_scan<int>(sum, &total, wsum);
+    for (int i = b; i < e; i++) {
+        o[i] = run;
+        run += c[i];
+    }
+    if (threadIdx.x == 0)
+        totals[l] = total;
+}
+
+// min / max of the part loads
+__global__ void __launch_bounds__(256) k_load_minmax(const long long* __restrict__ loads, int P,
+    long long* out /* [2] = min, max; pre-set to LLONG_MAX, -1 */)
+{
+    long long mn = 0x7fffffffffffffffLL, mx = -1;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const long long v = loads[p];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if (lane_id() == 0) {
+        atomicMin(out, mn);
+        atomicMax(out + 1, mx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic land-sea mask: two octaves of integer value noise (bit-identical on host and device)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline uint64_t lattice16(uint64_t seed, uint64_t oct, uint64_t ix, uint64_t iy)
+{
+    return splitmix64(seed ^ splitmix64((oct << 60) ^ (ix << 30) ^ iy)) >> 48;
+}
+__host__ __device__ inline uint64_t octave16(uint64_t seed, uint64_t oct, uint64_t L, uint64_t x, uint64_t y)
+{
+    const uint64_t cx = x / L, fx = x % L, cy = y / L, fy = y % L;
+    const uint64_t v00 = lattice16(seed, oct, cx, cy), v10 = lattice16(seed, oct, cx + 1, cy);
+    const uint64_t v01 = lattice16(seed, oct, cx, cy + 1), v11 = lattice16(seed, oct, cx + 1, cy + 1);
+    const uint64_t top = v00 * (L - fx) + v10 * fx, bot = v01 * (L - fx) + v11 * fx;
+    return (top * (L - fy) + bot * fy) / (L * L); // < 65536
+}
+// value in [0, 4 * 65536): ocean <=> value >= threshold
+__host__ __device__ inline uint32_t synth_value(uint64_t seed, uint64_t L1, uint64_t L2, uint64_t x, uint64_t y)
+{
+    return (uint32_t)(3 * octave16(seed, 1, L1, x, y) + octave16(seed, 2, L2, x, y));
+}
+
+__global__ void __launch_bounds__(256) k_generate_mask(int32_t* __restrict__ out, int NX, int rows,
+    int y_begin, uint64_t seed, uint64_t L1, uint64_t L2, uint32_t thresh)
+{
+    const size_t n = (size_t)NX * rows;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t y = i / NX + y_begin, x = i % NX;
+        out[i] = synth_value(seed, L1, L2, x, y) >= thresh ? 1 : 0;
+    }
+}
+
+} // namespace ddc

@@ -29,7 +29,7 @@
  * level loop, Zoltan_Divide_Machine, par_median.c Zoltan_RB_find_median with
  * rectilinear_blocks=1 and average_cuts=1, rcb_box.c Zoltan_RCB_Box) for the 14
  * parameters the reference sets.  Parity is PINNED by the reference's own
- * goldens (tests/golden/reference_goldens.json: 9 bounding-box known-answer
+ * goldens (tests/golden/reference_goldens.json: 8 bounding-box known-answer
  * tests + 5 integration pid maps + 5 metadata files); see DESIGN.md for what
  * those goldens do not pin (the Q-items).
  *
@@ -141,8 +141,13 @@ typedef struct {
     double lo[2], hi[2]; /* cut-tree box of a part: -DBL_MAX / DBL_MAX when uncut */
 } orc_dbox;
 
-/* degenerate-cut policy (Q2, reference behaviour undefined): when a side of a
-   cut holds no dot the cut is placed half a cell beyond the populated side. */
+/* degenerate-cut policy (Q2; the reference's behaviour is undefined there: it
+   would feed +-DBL_MAX/2 through ceil() into an int).  [boxlo, boxhi) is the
+   integer cell range the set inherits from its ancestors along the cut
+   dimension.  The cut is placed so that ceil(cut) stays inside that range:
+     only the low side populated  -> boundary just above its last dot
+     only the high side populated -> boundary at its first dot
+     no dot at all                -> integer midpoint of the inherited range */
 static double average_cut(int have_lo, double vlo, int have_hi, double vhi, double boxlo, double boxhi)
 {
     if (have_lo && have_hi)
@@ -151,8 +156,7 @@ static double average_cut(int have_lo, double vlo, int have_hi, double vhi, doub
         return vlo + 0.5;
     if (have_hi)
         return vhi - 0.5;
-    /* no dot at all in this sub-box: split the inherited integer range in two */
-    return floor(0.5 * (boxlo + boxhi)) + 0.5;
+    return boxlo + floor(0.5 * (boxhi - boxlo)) - 0.5;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -551,8 +555,10 @@ static double find_median_hist(hist_t* H, int c0, int c1, double fractionlo)
 {
     int64_t Wn = hcnt(H, c0, c1);
     double weight = (double)Wn;
-    if (Wn == 0)
+    if (Wn == 0) {
+        H->iters++; /* the dot version runs one (empty) iteration too */
         return average_cut(0, 0, 0, 0, (double)c0, (double)(c1 + 1));
+    }
     int first = first_nonempty(H, c0, c1), last = last_nonempty(H, c0, c1);
     double valuemin = (double)first, valuemax = (double)last;
     int alo = first, ahi = last; /* active bins */
