@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: land-sea mask -> RCB boxes + pid labels + neighbours / halos.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one complete decomposition (ddc_partition with pid + neighbour tables) of the
+workload's synthetic mask.  With N > 1 (torchrun, one rank per GPU) the SAME mask is row-sharded
+over the ranks (strong scaling) and the histograms are combined with NCCL inside the step.
+
+  value       whole-job mask cells partitioned per second, mask already resident in HBM
+  e2e         same metric through the C ABI with HOST buffers: pinned-host -> device copy of the
+              int32 mask and device -> host read-back of pid, boxes and neighbour tables inside
+              the timed region
+  roofline    the dominant kernel against the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (a port of the reference algorithm) on a bounded sample
+
+`--impl reference` times the reference algorithm's CPU port (oracle/, OpenMP tasks over all host
+cores) on a bounded sample of the same workload; the reference binary itself needs MPI + Zoltan +
+parallel netCDF + Boost, none of which exist in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name -> nx, ny, parts, land fraction, seed, periodic x, periodic y   (SURVEY 8d / BASELINE.json configs)
+WORKLOADS = {
+    "C5_32768x32768_p16384": (32768, 32768, 16384, 0.45, 32, 1, 0),
+    "C4_8192x8192_p4096": (8192, 8192, 4096, 0.60, 1, 0, 0),
+    "C3_4096x4096_p1024": (4096, 4096, 1024, 0.45, 3, 0, 0),
+    "C2_528x522_p64": (528, 522, 64, 0.45, 25, 1, 1),
+}
+DEFAULT_WORKLOAD = "C5_32768x32768_p16384"
+L2_BYTES = 126 * 1000 * 1000
+ALGO_BYTES_PER_CELL = 8  # 4 B int32 mask read + 4 B int32 pid write
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str, workload: str):
+    """dram bytes per launch of `kernel` from the committed ncu capture, if one exists"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[workload][kernel]
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """polls SM clock and throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index: int, period_s: float = 0.002):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # NVML missing: report it rather than invent numbers
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                r = get_reasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "note": "NVML unavailable" if not self.ok else "no sample fell inside the timed region"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_sample(workload, threads: int):
+    """a bounded sample of the workload for the CPU legs: the top-left 1/8 x 1/8 window of the SAME
+    mask into 1/64 of the parts (same cells per part), or the whole mask when it is small"""
+    nx, ny, P, land, seed, px, py = WORKLOADS[workload]
+    from domain_decomp_b200 import capi
+    if nx * ny > 4096 * 4096:
+        f = 8
+        sx, sy, sp = nx // f, ny // f, max(2, P // (f * f))
+        desc = ("top-left %dx%d window of the %dx%d mask into %d parts (same cells per part; %d RCB levels "
+                "instead of %d, which favours the CPU)" % (sx, sy, nx, ny, sp, (sp - 1).bit_length(), (P - 1).bit_length()))
+    else:
+        sx, sy, sp, desc = nx, ny, P, "the whole %dx%d mask into %d parts" % (nx, ny, P)
+    full = capi.generate_mask_host(nx, ny, seed, land, 0, sy)  # rows [0, sy) of the global mask
+    import numpy as np
+    mask = np.ascontiguousarray(full[:, :sx])
+    return mask, sp, px, py, desc
+
+
+def run_cpu(mask, P, px, py, threads, steps, warmup):
+    from oracle import oracle as orc
+    orc.set_threads(threads)
+    times = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        orc.partition(mask, P, bool(px), bool(py), use_hist=False, want_pid=True, want_neighbours=True)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.max_threads()
+    mask, sp, px, py, desc = cpu_sample(args.workload, threads)
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    # keep the whole run within a few minutes whatever K is
+    t0 = time.perf_counter()
+    sec = run_cpu(mask, sp, px, py, threads, 1, 0)
+    budget = 150.0
+    steps = max(1, min(steps, int(budget / max(sec, 1e-3))))
+    sec = run_cpu(mask, sp, px, py, threads, steps, warmup) if steps > 1 else sec
+    value = mask.size / sec
+    nx, ny, P, land, seed, _, _ = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "mask cells partitioned/sec", "value": value, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": {"workload": args.workload, "nx": nx, "ny": ny, "parts": P, "land_frac": land, "seed": seed,
+                   "periodic_x": px, "periodic_y": py},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": desc,
+                         "note": "CPU port of the reference algorithm (oracle/ddc_oracle.c, dot-based Zoltan RCB "
+                                 "restatement + labelling + O(P^2) neighbour discovery); the reference binary "
+                                 "needs MPI+Zoltan+netCDF+Boost which this image lacks"},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from domain_decomp_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torchrun --nproc-per-node N)" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    nccl_id = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        ids = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nx, ny, P, land, seed, px, py = WORKLOADS[args.workload]
+    cells = nx * ny
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    h = capi.Handle(local_rank, rank, world, nccl_id)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    y_begin, y_count = capi.shard_rows(ny, world, rank)
+    d_mask = torch.empty((max(y_count, 1), nx), dtype=torch.int32, device=dev)
+    h.generate_mask_device(d_mask.data_ptr(), nx, ny, seed, land, y_begin, y_count)
+    h.set_mask_device(d_mask.data_ptr(), nx, ny, y_begin, y_count)
+    flags = capi.WANT_PID | capi.WANT_NEIGHBOURS
+    shard_bytes = y_count * nx * 4
+    need_flush = shard_bytes * 2 < 2 * L2_BYTES  # mask + pid of this rank could sit in the 126 MB L2
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if need_flush else None
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(W):
+        h.partition(P, px, py, flags)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    if not need_flush:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            h.partition(P, px, py, flags)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        total_ms = e0.elapsed_time(e1)
+    else:
+        total_ms = 0.0
+        for _ in range(K):
+            flush_buf.fill_(1)  # evict mask / bit map / pid from L2 (outside the timed events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            h.partition(P, px, py, flags)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+    barrier()
+    clocks = sampler.stop()
+    ms_per_step = max_over_ranks(total_ms / K)
+    value = cells / (ms_per_step * 1e-3)
+    st = h.stats()
+
+    # ---- per-kernel timing (CUDA events on the launching stream, inside ddc_partition) --------
+    stage = {k: 0.0 for k in capi.STAGE_NAMES}
+    nprof = 5
+    for _ in range(nprof):
+        if flush_buf is not None:
+            flush_buf.fill_(1)
+        h.partition(P, px, py, flags | capi.PROFILE)
+        s = h.stats()["stage_ms"]
+        for k in stage:
+            stage[k] += s[k] / nprof
+    peak, peak_src = measured_peak_gbs()
+    local_cells = y_count * nx
+    kern = {"mask_scan": "k_scan_mask", "label": "k_label"}
+    dom = max(kern, key=lambda k: stage[k])
+    dom_ms = max_over_ranks(stage[dom])
+    achieved = (4.0 * local_cells) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": kern[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": ncu_traffic(kern[dom], args.workload), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": 4 * local_cells, "kernel_ms": dom_ms,
+        "pipeline": {"achieved": ALGO_BYTES_PER_CELL * cells / (ms_per_step * 1e-3) / 1e9,
+                     "frac_of_aggregate_peak": ALGO_BYTES_PER_CELL * cells / (ms_per_step * 1e-3) / 1e9 / (peak * world),
+                     "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL},
+        "stage_ms": {k: round(v, 4) for k, v in stage.items()},
+    }
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_mask = torch.empty((max(y_count, 1), nx), dtype=torch.int32, pin_memory=True)
+        h_pid = torch.empty((max(y_count, 1), nx), dtype=torch.int32, pin_memory=True)
+        h_mask.copy_(d_mask)  # the same synthetic mask, now living in pinned host memory
+        torch.cuda.synchronize()
+        ke = max(1, min(K, 10))
+
+        def e2e_step():
+            h.set_mask_host_ptr(h_mask.data_ptr(), nx, ny, y_begin, y_count)  # H2D
+            h.partition(P, px, py, flags)
+            h.pid_host_into(h_pid.data_ptr())  # D2H, 4 B / cell
+            b = h.boxes()
+            n = b.nbytes
+            for per in range(2):
+                for e in range(4):
+                    n += h.neighbour_counts(e, per).nbytes
+                    n += sum(a.nbytes for a in h.neighbours(e, per))
+            return n
+
+        small = e2e_step()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(ke):
+            e2e_step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3 / ke
+        ev_ms = e0.elapsed_time(e1) / ke
+        barrier()
+        e2e_ms = max_over_ranks(max(wall, ev_ms))
+        e2e = {"value": cells / (e2e_ms * 1e-3), "unit": "cells/s", "ms_per_step": e2e_ms, "steps": ke,
+               "h2d_bytes_per_step": shard_bytes * world if world > 1 else shard_bytes,
+               "d2h_bytes_per_step": (shard_bytes + small) * world if world > 1 else shard_bytes + small,
+               "note": "pinned host int32 mask -> device, partition, pid + boxes + neighbour tables -> host"}
+        h.set_mask_device(d_mask.data_ptr(), nx, ny, y_begin, y_count)
+        del h_mask, h_pid
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        orc.build()
+        mask, sp, spx, spy, desc = cpu_sample(args.workload, 1)
+        sec = run_cpu(mask, sp, spx, spy, 1, 1, 0)
+        cpu = {"value": mask.size / sec, "unit": "cells/s", "cores": 1, "kind": "port", "sample": desc,
+               "seconds": sec, "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": "mask cells partitioned/sec", "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": {"workload": args.workload, "nx": nx, "ny": ny, "parts": P, "land_frac_target": land,
+                       "ocean_frac_measured": st["n_ocean"] / cells, "seed": seed, "periodic_x": px,
+                       "periodic_y": py, "sharding": "rows over %d GPU(s), NCCL allreduce + allgather" % world,
+                       "outputs": "boxes + pid + neighbour/halo tables",
+                       "l2": ("L2 flushed between timed iterations (256 MiB write)" if need_flush else
+                              "inputs larger than L2 (%.0f MiB int32 mask + %.0f MiB pid per GPU vs 126 MB L2)"
+                              % (shard_bytes / 2**20, shard_bytes / 2**20))},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": st["gpu_launches"] * K * world,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "result": {"n_ocean": st["n_ocean"], "strips": st["nstrips"], "x_levels": st["n_xlev"],
+                       "y_levels": st["n_ylev"], "changes": st["changes"], "median_iters": st["median_iters"],
+                       "imbalance": st["load_max"] / max(st["n_ocean"] / P, 1e-9), "edge_cut": st["edge_cut"],
+                       "launches_per_step": st["gpu_launches"]},
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

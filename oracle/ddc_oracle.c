@@ -42,6 +42,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define ORC_API __attribute__((visibility("default")))
 
@@ -88,23 +91,32 @@ ORC_API void orc_naive_block(int P, int NX, int NY, int r, int box[4])
     box[3] = le[1];
 }
 
-/* rank whose naive block contains cell (x, y); -1 if none (degenerate blocks) */
-static int naive_rank_of_cell(int P, int NX, int NY, int x, int y)
+/* rank whose naive block contains cell (x, y) */
+typedef struct {
+    int np0, np1, lx, ly;
+} naive_t;
+static naive_t naive_setup(int P, int NX, int NY)
 {
     int np[2];
+    naive_t nv;
     orc_find_factors(P, np);
-    int lx = (int)ceil((float)NX / np[0]);
-    int ly = (int)ceil((float)NY / np[1]);
-    int bx = lx > 0 ? x / lx : 0;
-    int by = ly > 0 ? y / ly : 0;
-    if (bx > np[0] - 1)
-        bx = np[0] - 1;
-    if (by > np[1] - 1)
-        by = np[1] - 1;
-    /* when ceil() over-covers, trailing blocks start beyond the extent and the
-       last block has a non-positive extent: the cell then belongs to the last
-       block that actually starts at or before it -- which is what x / lx gives. */
-    return bx * np[1] + by;
+    nv.np0 = np[0];
+    nv.np1 = np[1];
+    nv.lx = (int)ceil((float)NX / np[0]);
+    nv.ly = (int)ceil((float)NY / np[1]);
+    return nv;
+}
+static inline int naive_rank_of_cell(const naive_t* nv, int x, int y)
+{
+    int bx = nv->lx > 0 ? x / nv->lx : 0;
+    int by = nv->ly > 0 ? y / nv->ly : 0;
+    /* when ceil() over-covers, trailing blocks start beyond the extent: the cell
+       belongs to the last block that starts at or before it, which x / lx gives */
+    if (bx > nv->np0 - 1)
+        bx = nv->np0 - 1;
+    if (by > nv->np1 - 1)
+        by = nv->np1 - 1;
+    return bx * nv->np1 + by;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -166,7 +178,8 @@ static double average_cut(int have_lo, double vlo, int have_hi, double vhi, doub
 typedef struct {
     const double* c[2]; /* coordinates of every dot, per dimension */
     int* mark; /* dotmark scratch, indexed by dot */
-    int* list; /* dotlist scratch */
+    int* list; /* dotlist scratch (a set uses the slice that mirrors its slice of idx) */
+    const int* idx0; /* base of the index array, to locate that slice */
     int* part; /* out: part of every dot */
     orc_dbox* boxes; /* out: cut-tree box of every part */
     int dim_of_level[ORC_MAXLEV];
@@ -182,8 +195,9 @@ static double find_median_dots(dots_ctx* cx, const int* idx, int dotnum, int dim
 {
     const double* dots = cx->c[dim];
     int* dotmark = cx->mark;
-    int* dotlist = cx->list;
+    int* dotlist = cx->list + (idx - cx->idx0);
     int numlist = dotnum;
+    long my_iters = 0;
     for (int i = 0; i < dotnum; i++)
         dotlist[i] = idx[i];
 
@@ -199,7 +213,7 @@ static double find_median_dots(dots_ctx* cx, const int* idx, int dotnum, int dim
                 + (targetlo - weightlo) / (weight - weightlo - weighthi) * (valuemax - valuemin);
         else
             tmp_half = 0.5 * (valuemin + valuemax);
-        cx->median_iters++;
+        my_iters++;
 
         double totallo = 0.0, totalhi = 0.0;
         double valuelo = -DBL_MAX, valuehi = DBL_MAX;
@@ -330,6 +344,8 @@ static double find_median_dots(dots_ctx* cx, const int* idx, int dotnum, int dim
         numlist = k;
     }
 
+#pragma omp atomic
+    cx->median_iters += my_iters;
     /* AVERAGE_CUTS: halfway between the closest dots on either side, over ALL
        dots of the set */
     double vlo = -DBL_MAX, vhi = DBL_MAX;
@@ -398,8 +414,24 @@ static void rcb_dots_recurse(dots_ctx* cx, int* idx, int n, int partlower, int n
     orc_dbox lobox = box, hibox = box;
     lobox.hi[dim] = cut;
     hibox.lo[dim] = cut;
+    /* The two halves are independent (Zoltan hands them to the two halves of the
+       processor set); with orc_set_threads(T > 1) they run as OpenMP tasks. */
+#pragma omp task default(shared) if (n > 50000)
     rcb_dots_recurse(cx, idx, nlo, partlower, partmid - partlower, level + 1, lobox);
     rcb_dots_recurse(cx, idx + nlo, n - nlo, partmid, partlower + num_parts - partmid, level + 1, hibox);
+#pragma omp taskwait
+}
+
+static int g_threads = 1;
+/* threads used by orc_rcb_dots (default 1 = the plain serial restatement) */
+ORC_API void orc_set_threads(int t) { g_threads = t < 1 ? 1 : t; }
+ORC_API int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
 }
 
 /*
@@ -456,6 +488,7 @@ ORC_API long orc_rcb_dots(const int32_t* mask, int NX, int NY, int P, double* db
     cx.c[1] = cx1;
     cx.mark = mark;
     cx.list = list;
+    cx.idx0 = idx;
     cx.part = part;
     cx.boxes = boxes;
     cx.ext[0] = NX;
@@ -467,6 +500,8 @@ ORC_API long orc_rcb_dots(const int32_t* mask, int NX, int NY, int P, double* db
     orc_dbox root;
     root.lo[0] = root.lo[1] = -DBL_MAX;
     root.hi[0] = root.hi[1] = DBL_MAX;
+#pragma omp parallel num_threads(g_threads)
+#pragma omp single
     rcb_dots_recurse(&cx, idx, (int)nd, 0, P, 0, root);
 
     for (int p = 0; p < P; p++) {
@@ -550,9 +585,20 @@ static int first_nonempty(const hist_t* H, int a, int b)
     return lo;
 }
 
+/* diagnostics: the largest iteration count any single median needed */
+static long g_max_single_iters = 0;
+ORC_API long orc_max_single_iters(int reset)
+{
+    long v = g_max_single_iters;
+    if (reset)
+        g_max_single_iters = 0;
+    return v;
+}
+
 /* median of the dots in bins [c0, c1] (inclusive); returns the cut */
 static double find_median_hist(hist_t* H, int c0, int c1, double fractionlo)
 {
+    long iters0 = H->iters;
     int64_t Wn = hcnt(H, c0, c1);
     double weight = (double)Wn;
     if (Wn == 0) {
@@ -639,6 +685,8 @@ static double find_median_hist(hist_t* H, int c0, int c1, double fractionlo)
         } else
             break;
     }
+    if (H->iters - iters0 > g_max_single_iters)
+        g_max_single_iters = H->iters - iters0;
     int L = last_nonempty(H, c0, B), U = first_nonempty(H, B + 1, c1);
     return average_cut(L >= 0, (double)L, U >= 0, (double)U, (double)c0, (double)(c1 + 1));
 }
@@ -853,10 +901,11 @@ ORC_API int orc_partition(const int32_t* mask, int NX, int NY, int P, int use_hi
     }
     /* `changes`: did any dot leave the rank that owned it in the naive layout? */
     int changes = 0;
+    const naive_t nv = naive_setup(P, NX, NY);
     for (int y = 0; y < NY && !changes; y++)
         for (int x = 0; x < NX; x++) {
             int32_t q = part[(size_t)y * NX + x];
-            if (q >= 0 && q != naive_rank_of_cell(P, NX, NY, x, y)) {
+            if (q >= 0 && q != naive_rank_of_cell(&nv, x, y)) {
                 changes = 1;
                 break;
             }

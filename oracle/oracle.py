@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_domain_overlap.argtypes = [C.c_int] * 9
         L.orc_domain_overlap.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_max_threads.restype = C.c_int
         L.orc_part_loads.argtypes = [i32p, C.c_size_t, C.c_int,
                                      np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
         _lib = L
@@ -62,6 +64,15 @@ def ref_lib():
     L.ref_domain_overlap.argtypes = [C.c_int] * 9
     L.ref_domain_overlap.restype = C.c_int
     return L
+
+
+def set_threads(t: int) -> None:
+    """threads for the dot-based RCB (OpenMP tasks over the independent halves); default 1"""
+    lib().orc_set_threads(int(t))
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
 
 
 def find_factors(P: int):
