@@ -121,14 +121,14 @@ struct ddc_handle_s {
     ddc_stats stats {};
 
     // device buffers
-    DevBuf<uint4> bits;
+    DevBuf<uint8_t> bits;
     DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx;
     DevBuf<DevScalars> sc;
     DevBuf<Plan> plan;
     DevBuf<int> sets; // 6 * P : A.lo A.hi A.n B.lo B.hi B.n
     DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
     DevBuf<int> boxes; // x0 y0 ex ey, P each
-    DevBuf<int> strip_of_part;
+    DevBuf<int> strip_of_part, strip_of_col, rowpart;
     DevBuf<long long> loads, loadmm;
     DevBuf<int32_t> pid;
     DevBuf<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
@@ -221,16 +221,21 @@ size_t max_dyn_smem(int device)
     return (size_t)v;
 }
 
-int pick_rows_per_cta(int rows, int gridx)
+// K1 / K6 run as ONE wave: every CTA owns one 1024-column block and a contiguous row range sized so
+// that the whole grid is co-resident (no tail wave) and the per-CTA column atomics are paid once.
+template <typename K>
+int pick_rows_per_cta(K kernel, int rows, int gridx)
 {
-    // enough CTAs for ~16 per SM, but never fewer than 32 rows each (amortises the column atomics)
-    long long r = (long long)rows * gridx / (148 * 16);
-    r = (r / 8) * 8;
-    if (r < 32)
-        r = 32;
-    if (r > 512)
-        r = 512;
-    return (int)r;
+    int per_sm = 0, sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const int slots = per_sm * sms;
+    const int gy = std::max(1, slots / std::max(gridx, 1));
+    int rpc = (rows + gy - 1) / gy;
+    rpc = ((rpc + 7) / 8) * 8;
+    return std::max(rpc, 8);
 }
 
 // K7 + scans on whatever boxes / strips are in the tables
@@ -395,6 +400,8 @@ int ddc_destroy(ddc_handle_t h)
     h->strips.release();
     h->boxes.release();
     h->strip_of_part.release();
+    h->strip_of_col.release();
+    h->rowpart.release();
     h->loads.release();
     h->loadmm.release();
     h->pid.release();
@@ -526,12 +533,14 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     };
 
     // buffers
-    CUDA_TRY(h, h->bits.ensure((size_t)std::max(rows, 1) * NG));
+    const int NB = NG * 16; // bytes per bit-map row
+    CUDA_TRY(h, h->bits.ensure((size_t)std::max(rows, 1) * NB));
     CUDA_TRY(h, h->colcount.ensure(NX + 4));
     CUDA_TRY(h, h->sets.ensure((size_t)6 * P));
     CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
     CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
     CUDA_TRY(h, h->strip_of_part.ensure(P));
+    CUDA_TRY(h, h->strip_of_col.ensure(NX));
     CUDA_TRY(h, h->loads.ensure(P));
     CUDA_TRY(h, h->loadmm.ensure(2));
     if (want_pid)
@@ -552,15 +561,16 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         CUDA_TRY(h, cudaMemcpyAsync(h->sc.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
     }
     const int gridx = (NG + 7) / 8;
-    const int rpc = pick_rows_per_cta(rows, gridx);
     const bool vec = (NX % 4 == 0) && (((uintptr_t)h->d_mask) % 16 == 0);
     if (rows > 0) {
+        const int rpc = vec ? pick_rows_per_cta(k_scan_mask<true>, rows, gridx)
+                            : pick_rows_per_cta(k_scan_mask<false>, rows, gridx);
         dim3 grid(gridx, (rows + rpc - 1) / rpc);
         if (vec)
-            k_scan_mask<true><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NG, rpc, h->bits.p,
+            k_scan_mask<true><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
                 h->colcount.p, h->sc.p);
         else
-            k_scan_mask<false><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NG, rpc, h->bits.p,
+            k_scan_mask<false><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
                 h->colcount.p, h->sc.p);
         launches++;
     }
@@ -581,7 +591,7 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         if (use_smem)
             CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         k_xcuts<<<1, 1024, use_smem ? need : 0, s>>>(h->colcount.p, NX, NY, P, h->colpfx.p, use_smem,
-            h->sc.p, h->plan.p, t.A, t.B, t.st, t.bx, h->loads.p, h->strip_of_part.p);
+            h->sc.p, h->plan.p, t.A, t.B, t.st, t.bx, h->loads.p, h->strip_of_part.p, h->strip_of_col.p);
         launches++;
     }
     // the plan decides buffer sizes and the all-gather count: read it back (one tiny D2H + sync)
@@ -599,16 +609,9 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         if (rows < Rmax) // short last shard: its padding rows must read as empty
             CUDA_TRY(h, cudaMemsetAsync(h->rowcount.p, 0, sizeof(unsigned) * (size_t)S * Rmax, s));
         if (rows > 0) {
-            const size_t lim = max_dyn_smem(h->device) - 1024;
-            int R = 32;
-            while (R > 1 && (size_t)R * (NG + 1) * sizeof(uint4) > lim)
-                R >>= 1;
-            const size_t smem = (size_t)R * (NG + 1) * sizeof(uint4);
-            if (smem > lim)
-                return fail(h, DDC_ERR_ARG, "nx = %d too wide for the strip-row kernel", NX);
-            CUDA_TRY(h, cudaFuncSetAttribute(k_strip_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_strip_rows<<<(rows + R - 1) / R, 256, smem, s>>>(h->bits.p, NG, rows, R, t.st.x0, t.st.x1,
-                t.st.S, h->rowcount.p, Rmax);
+            dim3 grid((rows + 31) / 32, (S + 7) / 8);
+            k_strip_rows<<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0, S,
+                h->rowcount.p, Rmax);
             launches++;
         }
         const unsigned* rc_all = h->rowcount.p;
@@ -625,19 +628,23 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             CUDA_TRY(h, h->ypfx.ensure((size_t)grid * (NY + 1)));
         if (use_smem)
             CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        CUDA_TRY(h, h->rowpart.ensure((size_t)S * NY));
         k_ycuts<<<grid, 1024, use_smem ? need : 0, s>>>(rc_all, G, Rmax, NY, pl.iy, t.st, t.A, t.B,
-            h->ypfx.p, use_smem, t.bx, h->loads.p, h->plan.p);
+            h->ypfx.p, use_smem, t.bx, h->loads.p, h->plan.p, h->rowpart.p);
         launches++;
     } else
         mark(3);
     mark(4);
     // ---- K6: labels + `changes` -----------------------------------------------------------------
     if (rows > 0 && (P > 1 || want_pid)) {
-        dim3 grid(gridx, (rows + rpc - 1) / rpc);
         const bool vecp = want_pid && (NX % 4 == 0) && (((uintptr_t)h->pid.p) % 16 == 0);
 #define LAUNCH_LABEL(V, W)                                                                         \
-    k_label<V, W><<<grid, 256, 0, s>>>(h->bits.p, NX, rows, h->y_begin, NG, rpc, t.st.x1, t.st.p0,   \
-        t.st.S, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p)
+    do {                                                                                           \
+        const int rpc = 128; /* no per-CTA epilogue: many small CTAs keep more stores in flight */ \
+        dim3 grid(gridx, (rows + rpc - 1) / rpc);                                                  \
+        k_label<V, W><<<grid, 256, 0, s>>>(h->bits.p, NX, NY, rows, h->y_begin, NB, rpc,           \
+            h->strip_of_col.p, t.st.p0, h->rowpart.p, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p);    \
+    } while (0)
         if (want_pid) {
             if (vecp)
                 LAUNCH_LABEL(true, true);

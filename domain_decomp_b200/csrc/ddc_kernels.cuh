@@ -18,9 +18,9 @@
 //   K7 k_neighbours    interval-intersection kernel: neighbour ids, halo sizes, halo starts,
 //                      interior and periodic (Partitioner.cpp:20-80,329-435, DomainUtils.cpp:15-35)
 //
-// Bit map layout: one uint4 per (row, 128-column group); word c (0..3), bit l  <=>  column
-// 128*g + 4*l + c.  That is exactly what four warp ballots over one coalesced uint4 load per lane
-// produce, so K1 never shuffles bits.  It is private to this file.
+// Bit map layout: plain row-major little-endian bit map, bit (x & 7) of byte x >> 3 of a row is
+// column x; rows are padded to NB = 16 * ceil(NX / 128) bytes so that every row is 16-byte aligned.
+// Columns >= NX read as land.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -52,16 +52,15 @@ struct NaiveParams { // Grid.cpp:150-166
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
-// bits l of word c that belong to group-relative columns [a, b), 0 <= a <= b <= 128
-__device__ __forceinline__ unsigned group_word_mask(int c, int a, int b)
+// bits of a 32-column word that belong to word-relative columns [a, b), clipped to [0, 32]
+__device__ __forceinline__ unsigned word_range_mask(int a, int b)
 {
-    int l_lo = a > c ? (a - c + 3) >> 2 : 0;
-    int l_hi = b > c ? (b - c + 3) >> 2 : 0;
-    if (l_hi <= l_lo)
+    a = max(a, 0);
+    b = min(b, 32);
+    if (b <= a)
         return 0u;
-    unsigned hi = l_hi >= 32 ? 0xffffffffu : ((1u << l_hi) - 1u);
-    unsigned lo = (1u << l_lo) - 1u; // l_lo < 32 here
-    return hi & ~lo;
+    const unsigned hi = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+    return hi & ~((1u << a) - 1u);
 }
 
 // exclusive block scan of one value per thread (blockDim.x <= 1024, multiple of 32)
@@ -99,70 +98,135 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* total, T* warp_sums /*
     return res;
 }
 
+// dst[i] = sum of src(0..i-1) for i in [0, n] (exclusive prefix, n + 1 outputs); every thread of the
+// block calls it.  4 consecutive elements per thread and tile, so a warp reads 512 contiguous bytes.
+// INCL_M1: write (inclusive prefix - 1 + bias) into dst[0..n) instead (used to turn "start flags"
+// into "index of the last interval starting at or before i").
+template <bool INCL_M1, typename F>
+__device__ inline unsigned long long block_prefix(F src, int n, unsigned* dst, int bias,
+    unsigned long long* wsum /* >= 33 */)
+{
+    unsigned long long carry = 0;
+    const int tile = blockDim.x * 4;
+    for (int base = 0; base < n; base += tile) {
+        const int i0 = base + threadIdx.x * 4;
+        unsigned v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            v[k] = i0 + k < n ? src(i0 + k) : 0u;
+        unsigned long long total;
+        unsigned long long run
+            = carry + block_exclusive_scan<unsigned long long>((unsigned long long)v[0] + v[1] + v[2] + v[3], &total, wsum);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (INCL_M1) {
+                run += v[k];
+                if (i0 + k < n)
+                    dst[i0 + k] = (unsigned)((long long)run - 1 + bias);
+            } else {
+                if (i0 + k < n)
+                    dst[i0 + k] = (unsigned)run;
+                run += v[k];
+            }
+        }
+        carry += total;
+    }
+    if (!INCL_M1 && threadIdx.x == 0)
+        dst[n] = (unsigned)carry;
+    __syncthreads();
+    return carry;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: mask scan
 // ------------------------------------------------------------------------------------------------
 // One warp owns one 128-column group for `rows_per_cta` rows; the 8 warps of a CTA own 8 adjacent
 // groups, i.e. 4 KiB contiguous per row.  Every lane issues 8 independent 16-byte loads (8 rows)
-// before using any of them.  VEC: NX % 4 == 0 and a 16-byte aligned base pointer.
+// before using any of them, then packs its 4 x 8 ocean flags into ONE register (nibble k = row k).
+// Everything else is derived from that register once per 8 rows: the column counts (4 popcounts),
+// the bit-map bytes (one shuffle pairs the nibbles of neighbouring lanes) and the rows that hold
+// any ocean cell (one warp OR-reduction).  VEC: NX % 4 == 0 and a 16-byte aligned base pointer.
+__device__ __forceinline__ unsigned ocean_nibble(const int4& v)
+{
+    return (unsigned)(v.x > 0) | ((unsigned)(v.y > 0) << 1) | ((unsigned)(v.z > 0) << 2)
+        | ((unsigned)(v.w > 0) << 3);
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ mask, int NX, int rows,
-    int y_begin, int NG, int rows_per_cta, uint4* __restrict__ bits, unsigned* __restrict__ colcount,
+    int y_begin, int NB, int rows_per_cta, uint8_t* __restrict__ bits, unsigned* __restrict__ colcount,
     DevScalars* __restrict__ sc)
 {
     const int lane = lane_id();
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (g >= NG)
+    if (g * 128 >= NX)
         return; // whole warp leaves together
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(rows, r0 + rows_per_cta);
     const int x = g * 128 + lane * 4;
     unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     int ylo = 0x7fffffff, yhi = -1;
+    uint8_t* brow = bits + (size_t)g * 16 + (lane >> 1);
 
+    // VEC: out-of-range lanes (x >= NX, only in the last group) re-read the last valid 16 bytes of
+    // the row and are masked off below, so the main loop is branch-free: 8 unconditional loads.
+    const int xl = VEC ? min(x, NX - 4) : x;
+    const unsigned lane_valid = (VEC && x >= NX) ? 0u : 0xffffffffu;
     for (int r = r0; r < r1; r += 8) {
         int4 v[8];
+        const bool full = r + 8 <= r1;
+        if (VEC && full) {
+            const int4* p = reinterpret_cast<const int4*>(mask + (size_t)r * NX + xl);
+            const size_t pitch4 = (size_t)NX >> 2;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            v[k] = make_int4(0, 0, 0, 0);
-            if (r + k < r1) {
-                const int32_t* p = mask + (size_t)(r + k) * NX + x;
-                if (VEC) {
-                    if (x < NX)
+            for (int k = 0; k < 8; k++)
+                v[k] = __ldcs(p + k * pitch4);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                v[k] = make_int4(0, 0, 0, 0);
+                if (r + k < r1) {
+                    const int32_t* p = mask + (size_t)(r + k) * NX + xl;
+                    if (VEC) {
                         v[k] = __ldcs(reinterpret_cast<const int4*>(p));
-                } else {
-                    if (x < NX)
-                        v[k].x = __ldcs(p);
-                    if (x + 1 < NX)
-                        v[k].y = __ldcs(p + 1);
-                    if (x + 2 < NX)
-                        v[k].z = __ldcs(p + 2);
-                    if (x + 3 < NX)
-                        v[k].w = __ldcs(p + 3);
+                    } else {
+                        if (x < NX)
+                            v[k].x = __ldcs(p);
+                        if (x + 1 < NX)
+                            v[k].y = __ldcs(p + 1);
+                        if (x + 2 < NX)
+                            v[k].z = __ldcs(p + 2);
+                        if (x + 3 < NX)
+                            v[k].w = __ldcs(p + 3);
+                    }
                 }
             }
         }
-        uint4 mine = make_uint4(0, 0, 0, 0);
+        unsigned packed = 0; // nibble k = the ocean flags of my 4 columns in row r + k
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const bool o0 = v[k].x > 0, o1 = v[k].y > 0, o2 = v[k].z > 0, o3 = v[k].w > 0;
-            const unsigned b0 = __ballot_sync(0xffffffffu, o0);
-            const unsigned b1 = __ballot_sync(0xffffffffu, o1);
-            const unsigned b2 = __ballot_sync(0xffffffffu, o2);
-            const unsigned b3 = __ballot_sync(0xffffffffu, o3);
-            c0 += o0;
-            c1 += o1;
-            c2 += o2;
-            c3 += o3;
-            if (lane == k)
-                mine = make_uint4(b0, b1, b2, b3);
-            if (b0 | b1 | b2 | b3) {
-                ylo = min(ylo, r + k);
-                yhi = max(yhi, r + k);
-            }
+        for (int k = 0; k < 8; k++)
+            packed |= ocean_nibble(v[k]) << (4 * k);
+        packed &= lane_valid;
+        c0 += __popc(packed & 0x11111111u);
+        c1 += __popc(packed & 0x22222222u);
+        c2 += __popc(packed & 0x44444444u);
+        c3 += __popc(packed & 0x88888888u);
+        // bit-map bytes: even lanes store [nibble of lane + 1 : own nibble]
+        const unsigned other = __shfl_down_sync(0xffffffffu, packed, 1);
+        const unsigned even = (packed & 0x0f0f0f0fu) | ((other & 0x0f0f0f0fu) << 4); // rows 0,2,4,6
+        const unsigned odd = ((packed >> 4) & 0x0f0f0f0fu) | (other & 0xf0f0f0f0u); // rows 1,3,5,7
+        if (!(lane & 1)) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (full || r + k < r1)
+                    brow[(size_t)(r + k) * NB] = (uint8_t)(((k & 1) ? odd : even) >> (8 * (k >> 1)));
         }
-        if (lane < 8 && r + lane < r1)
-            bits[(size_t)(r + lane) * NG + g] = mine;
+        // rows of this batch that hold an ocean cell in my 128 columns
+        const unsigned any = __reduce_or_sync(0xffffffffu, packed);
+        if (any) {
+            ylo = min(ylo, r + ((__ffs(any) - 1) >> 2));
+            yhi = r + ((31 - __clz(any)) >> 2);
+        }
     }
     if (c0)
         atomicAdd(colcount + x, c0);
@@ -195,6 +259,8 @@ __device__ inline int last_nonempty(const unsigned* pfx, int a, int b)
     if (b < a || pfx[b + 1] == pfx[a])
         return -1;
     const unsigned target = pfx[b + 1];
+    if (pfx[b] != target)
+        return b; // bin b itself holds a dot (the common case on a real coastline)
     int lo = a, hi = b;
     while (lo < hi) {
         const int mid = lo + ((hi - lo) >> 1);
@@ -210,6 +276,8 @@ __device__ inline int first_nonempty(const unsigned* pfx, int a, int b)
     if (b < a || pfx[b + 1] == pfx[a])
         return -1;
     const unsigned base = pfx[a];
+    if (pfx[a + 1] != base)
+        return a; // bin a itself holds a dot
     int lo = a, hi = b;
     while (lo < hi) {
         const int mid = lo + ((hi - lo) >> 1);
@@ -379,7 +447,7 @@ struct BoxTable { // final boxes, SoA
 // dynamic shared memory: (NX + 1) unsigned when use_smem
 __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ colcount, int NX, int NY,
     int P, unsigned* pfx_g, int use_smem, const DevScalars* __restrict__ sc, Plan* plan, SetBuf A,
-    SetBuf Bf, StripTable st, BoxTable bx, long long* loads, int* strip_of_part)
+    SetBuf Bf, StripTable st, BoxTable bx, long long* loads, int* strip_of_part, int* strip_of_col)
 {
     extern __shared__ unsigned smem_dyn[];
     __shared__ unsigned long long wsum64[33];
@@ -389,21 +457,7 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
     const int tid = threadIdx.x;
 
     // 1. pfx[i] = ocean cells in columns [0, i)
-    {
-        const int chunk = (NX + blockDim.x - 1) / blockDim.x;
-        const int b = min(NX, tid * chunk), e = min(NX, b + chunk);
-        unsigned long long sum = 0;
-        for (int i = b; i < e; i++)
-            sum += colcount[i];
-        unsigned long long total;
-        unsigned long long run = block_exclusive_scan<unsigned long long>(sum, &total, wsum64);
-        for (int i = b; i < e; i++) {
-            pfx[i] = (unsigned)run;
-            run += colcount[i];
-        }
-        if (tid == 0)
-            pfx[NX] = (unsigned)total;
-    }
+    block_prefix<false>([&](int i) { return colcount[i]; }, NX, pfx, 0, wsum64);
     // sets: everything invalid, then the root set
     for (int p = tid; p < P; p += blockDim.x) {
         A.n[p] = 0;
@@ -466,14 +520,14 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
         atomicAdd(&s_iters, my_iters);
 
     // 4. strips = valid sets in ascending part order
+    int nstrips;
     {
         const int chunk = (P + blockDim.x - 1) / blockDim.x;
         const int b = min(P, tid * chunk), e = min(P, b + chunk);
         int cnt = 0;
         for (int p = b; p < e; p++)
             cnt += cur.n[p] != 0;
-        int total;
-        int pos = block_exclusive_scan<int>(cnt, &total, wsum32);
+        int pos = block_exclusive_scan<int>(cnt, &nstrips, wsum32);
         for (int p = b; p < e; p++) {
             const int n = cur.n[p];
             if (n != 0) {
@@ -481,8 +535,6 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
                 st.x0[pos] = lo;
                 st.x1[pos] = hi;
                 st.p0[pos] = p;
-                for (int q = p; q < p + n; q++)
-                    strip_of_part[q] = pos;
                 if (n == 1) { // a leaf already: uncut in y
                     bx.x0[p] = lo;
                     bx.ex[p] = hi - lo;
@@ -494,13 +546,32 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
             }
         }
         if (tid == 0) {
-            st.p0[total] = P;
-            *st.S = total;
+            st.p0[nstrips] = P;
+            *st.S = nstrips;
             *st.always = 0;
-            plan->S = total;
+            plan->S = nstrips;
         }
     }
     __syncthreads();
+    // 5. strip of every part and of every column.  Column table: count the strips that start at
+    //    each column, inclusive prefix - 1 = last strip starting at or before the column (a
+    //    zero-width strip shares its start with the strip that follows it, which wins).
+    for (int s = tid; s < nstrips; s += blockDim.x) {
+        const int p0 = st.p0[s], p1 = st.p0[s + 1];
+        for (int q = p0; q < p1; q++)
+            strip_of_part[q] = s;
+    }
+    unsigned* cnt = pfx; // the column prefix sums are no longer needed
+    for (int x = tid; x < NX; x += blockDim.x)
+        cnt[x] = 0;
+    __syncthreads();
+    for (int s = tid; s < nstrips; s += blockDim.x) {
+        const int x0 = st.x0[s];
+        if (x0 < NX)
+            atomicAdd(&cnt[x0], 1u);
+    }
+    __syncthreads();
+    block_prefix<true>([&](int i) { return cnt[i]; }, NX, reinterpret_cast<unsigned*>(strip_of_col), 0, wsum64);
     if (tid == 0)
         plan->iters = s_iters;
 }
@@ -508,45 +579,36 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
 // ------------------------------------------------------------------------------------------------
 // K3: per-strip row counts from the bit map
 // ------------------------------------------------------------------------------------------------
-// A CTA stages R rows of the bit map in shared memory (row pitch NG + 1 uint4: conflict-free
-// 16-byte reads when the lanes of a warp are consecutive rows), then thread (strip, row) sums the
-// popcounts of its strip.  rowcount layout [S][Rmax], rows local to this rank.
-__global__ void __launch_bounds__(256) k_strip_rows(const uint4* __restrict__ bits, int NG, int rows,
-    int R, const int* __restrict__ st_x0, const int* __restrict__ st_x1, const int* __restrict__ st_S,
+// One warp = 32 consecutive rows of one strip; lane = row.  A lane reads the few 16-byte groups its
+// strip overlaps straight from global memory (neighbouring strips share the boundary group, which
+// L1 / L2 serve) and the warp writes 32 consecutive counts.  rowcount layout [S][Rmax], rows local
+// to this rank.  Leaf strips (one part, never cut in y) are skipped.
+__global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ bits, int NB, int rows,
+    const int* __restrict__ st_x0, const int* __restrict__ st_x1, const int* __restrict__ st_p0, int S,
     unsigned* __restrict__ rowcount, int Rmax)
 {
-    extern __shared__ uint4 tile[];
-    const int pitch = NG + 1;
-    const int r0 = blockIdx.x * R;
-    for (int i = threadIdx.x; i < R * NG; i += blockDim.x) {
-        const int row = i / NG, g = i - row * NG;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (r0 + row < rows)
-            v = bits[(size_t)(r0 + row) * NG + g];
-        tile[row * pitch + g] = v;
-    }
-    __syncthreads();
-    const int S = *st_S;
-    for (int t = threadIdx.x; t < S * R; t += blockDim.x) {
-        const int s = t / R, row = t - s * R;
-        if (r0 + row >= rows)
-            continue;
-        const int x0 = st_x0[s], x1 = st_x1[s];
-        unsigned cnt = 0;
-        if (x1 > x0) {
-            const int g0 = x0 >> 7, g1 = (x1 - 1) >> 7;
-            for (int g = g0; g <= g1; g++) {
-                const uint4 w = tile[row * pitch + g];
-                const int a = max(x0 - g * 128, 0), b = min(x1 - g * 128, 128);
-                if (a == 0 && b == 128)
-                    cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-                else
-                    cnt += __popc(w.x & group_word_mask(0, a, b)) + __popc(w.y & group_word_mask(1, a, b))
-                        + __popc(w.z & group_word_mask(2, a, b)) + __popc(w.w & group_word_mask(3, a, b));
-            }
+    const int s = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (s >= S || st_p0[s + 1] - st_p0[s] <= 1)
+        return;
+    const int row = blockIdx.x * 32 + lane_id();
+    if (row >= rows)
+        return;
+    const int x0 = st_x0[s], x1 = st_x1[s];
+    unsigned cnt = 0;
+    if (x1 > x0) {
+        const int g0 = x0 >> 7, g1 = (x1 - 1) >> 7;
+        const uint4* rp = reinterpret_cast<const uint4*>(bits + (size_t)row * NB);
+        for (int g = g0; g <= g1; g++) {
+            const uint4 w = __ldg(rp + g);
+            const int a = x0 - g * 128, b = x1 - g * 128; // group-relative column range
+            if (a <= 0 && b >= 128)
+                cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+            else
+                cnt += __popc(w.x & word_range_mask(a, b)) + __popc(w.y & word_range_mask(a - 32, b - 32))
+                    + __popc(w.z & word_range_mask(a - 64, b - 64)) + __popc(w.w & word_range_mask(a - 96, b - 96));
         }
-        rowcount[(size_t)s * Rmax + r0 + row] = cnt;
     }
+    rowcount[(size_t)s * Rmax + row] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -554,10 +616,11 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint4* __restrict__ bi
 // ------------------------------------------------------------------------------------------------
 // rowcount_all layout [G][S][Rmax] (the NCCL all-gather of every rank's [S][Rmax]); global row y
 // lives at rank y / Rmax, local row y % Rmax.  dynamic smem: (NY + 1) unsigned when use_smem,
-// otherwise pfx_g holds gridDim.x slices of NY + 1.
+// otherwise pfx_g holds gridDim.x slices of NY + 1.  Also writes rowpart[s][y] = part owning row y
+// of strip s, the lookup table of the label kernel.
 __global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ rowcount_all, int G,
     int Rmax, int NY, int ylevels, StripTable st, SetBuf A, SetBuf Bf, unsigned* pfx_g, int use_smem,
-    BoxTable bx, long long* loads, Plan* plan)
+    BoxTable bx, long long* loads, Plan* plan, int* __restrict__ rowpart)
 {
     extern __shared__ unsigned smem_dyn[];
     __shared__ unsigned long long wsum64[33];
@@ -570,24 +633,12 @@ __global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ row
         if (n <= 1)
             continue; // K2 already wrote the box of a leaf strip
         __syncthreads(); // previous strip done with pfx
-        {
-            const int chunk = (NY + blockDim.x - 1) / blockDim.x;
-            const int b = min(NY, tid * chunk), e = min(NY, b + chunk);
-            unsigned long long sum = 0;
-            for (int y = b; y < e; y++) {
+        block_prefix<false>(
+            [&](int y) {
                 const int g = y / Rmax, yl = y - g * Rmax;
-                sum += rowcount_all[((size_t)g * S + s) * Rmax + yl];
-            }
-            unsigned long long total;
-            unsigned long long run = block_exclusive_scan<unsigned long long>(sum, &total, wsum64);
-            for (int y = b; y < e; y++) {
-                const int g = y / Rmax, yl = y - g * Rmax;
-                pfx[y] = (unsigned)run;
-                run += rowcount_all[((size_t)g * S + s) * Rmax + yl];
-            }
-            if (tid == 0)
-                pfx[NY] = (unsigned)total;
-        }
+                return rowcount_all[((size_t)g * S + s) * Rmax + yl];
+            },
+            NY, pfx, 0, wsum64);
         for (int p = plo + tid; p < plo + n; p += blockDim.x) {
             A.n[p] = 0;
             Bf.n[p] = 0;
@@ -616,6 +667,21 @@ __global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ row
             bx.ey[p] = hi - lo;
             loads[p] = (long long)hcnt(pfx, lo, hi - 1);
         }
+        __syncthreads();
+        // rowpart: count the parts starting at each row; inclusive prefix - 1 + plo = last part
+        // starting at or before the row (zero-height parts lose against their successor)
+        unsigned* cnt = pfx;
+        for (int y = tid; y < NY; y += blockDim.x)
+            cnt[y] = 0;
+        __syncthreads();
+        for (int p = plo + tid; p < plo + n; p += blockDim.x) {
+            const int lo = cur.lo[p];
+            if (lo < NY)
+                atomicAdd(&cnt[lo], 1u);
+        }
+        __syncthreads();
+        block_prefix<true>([&](int y) { return cnt[y]; }, NY,
+            reinterpret_cast<unsigned*>(rowpart) + (size_t)s * NY, plo, wsum64);
     }
     if (my_iters)
         atomicAdd(&plan->iters, my_iters);
@@ -624,86 +690,164 @@ __global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ row
 // ------------------------------------------------------------------------------------------------
 // K6: owner labelling + Zoltan's `changes`
 // ------------------------------------------------------------------------------------------------
-// Same thread mapping as K1.  Every thread keeps, for each of its 4 columns, a cursor into the
-// (y-sorted) parts of the column's strip; rows are walked in order so a cursor only ever advances.
+// Same thread mapping as K1: one warp = one 128-column group, walking down the rows 8 at a time.
+// The part of a cell is strip_of_col[x] -> strip, then the part of that strip owning row y.  Parts
+// of a strip are y-sorted and ~hundreds of rows tall, so a thread keeps a cursor (part, last row)
+// for the strip of its first and of its last column (two cursors cover every thread that spans at
+// most two strips; they coincide for the ~97 % of threads inside one strip).  While all 8 rows of
+// a batch stay inside both cursor parts -- the common case -- no table is touched at all; otherwise
+// the rows are resolved through the rowpart[strip][y] table that K4 wrote and the cursors re-seat.
+__device__ __forceinline__ int part_lookup(const int* __restrict__ st_p0, const int* __restrict__ rowpart,
+    int NY, int s, int y)
+{
+    const int p0 = st_p0[s];
+    return (st_p0[s + 1] - p0 <= 1) ? p0 : __ldg(rowpart + (size_t)s * NY + y);
+}
+
+struct LabelCursor {
+    int part; // part owning the current rows
+    int yend; // first row that no longer belongs to it
+};
+__device__ __forceinline__ LabelCursor seat_cursor(const int* __restrict__ st_p0,
+    const int* __restrict__ rowpart, const int* __restrict__ box_y0, const int* __restrict__ box_ey, int NY,
+    int s, int y)
+{
+    LabelCursor c;
+    const int p0 = st_p0[s];
+    if (st_p0[s + 1] - p0 <= 1) {
+        c.part = p0;
+        c.yend = 0x7fffffff;
+    } else {
+        c.part = __ldg(rowpart + (size_t)s * NY + y);
+        c.yend = box_y0[c.part] + box_ey[c.part];
+    }
+    return c;
+}
+
 template <bool VEC, bool WRITE>
-__global__ void __launch_bounds__(256) k_label(const uint4* __restrict__ bits, int NX, int rows,
-    int y_begin, int NG, int rows_per_cta, const int* __restrict__ st_x1, const int* __restrict__ st_p0,
-    const int* __restrict__ st_S, const int* __restrict__ box_y0, const int* __restrict__ box_ey,
-    NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc)
+__global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bits, int NX, int NY, int rows,
+    int y_begin, int NB, int rows_per_cta, const int* __restrict__ strip_of_col,
+    const int* __restrict__ st_p0, const int* __restrict__ rowpart, const int* __restrict__ box_y0,
+    const int* __restrict__ box_ey, NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc)
 {
     const int lane = lane_id();
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (g >= NG)
+    if (g * 128 >= NX)
         return;
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(rows, r0 + rows_per_cta);
+    if (r0 >= r1)
+        return;
     const int x = g * 128 + lane * 4;
-    const int S = *st_S;
 
-    int pcur[4], plast[4], yend[4], nbx[4];
+    int sc4[4], nbx[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const int xc = min(x + c, NX - 1);
-        // strip of column xc: first s with xc < x1[s]
-        int lo = 0, hi = S - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (xc < st_x1[mid])
-                hi = mid;
-            else
-                lo = mid + 1;
-        }
-        const int pb = st_p0[lo], pe = st_p0[lo + 1];
-        // part of row y_begin + r0 inside the strip: first p with y < y0[p] + ey[p]
-        const int y = y_begin + r0;
-        int a = pb, b = pe - 1;
-        while (a < b) {
-            const int mid = (a + b) >> 1;
-            if (y < box_y0[mid] + box_ey[mid])
-                b = mid;
-            else
-                a = mid + 1;
-        }
-        pcur[c] = a;
-        plast[c] = pe - 1;
-        yend[c] = box_y0[a] + box_ey[a];
+        sc4[c] = strip_of_col[xc];
         nbx[c] = min(xc / nv.lx, nv.np0 - 1) * nv.np1;
     }
+    // columns 1, 2 belong to the strip of column 0 or of column 3 unless the thread spans > 2 strips
+    const bool two = (sc4[1] == sc4[0] || sc4[1] == sc4[3]) && (sc4[2] == sc4[0] || sc4[2] == sc4[3]);
+    const bool b1 = sc4[1] != sc4[0], b2 = sc4[2] != sc4[0], b3 = sc4[3] != sc4[0];
+    LabelCursor A = seat_cursor(st_p0, rowpart, box_y0, box_ey, NY, sc4[0], y_begin + r0);
+    LabelCursor B = seat_cursor(st_p0, rowpart, box_y0, box_ey, NY, sc4[3], y_begin + r0);
+    const uint8_t* brow = bits + (size_t)g * 16 + (lane >> 1);
+    const int sh = (lane & 1) * 4;
     int by = min((y_begin + r0) / nv.ly, nv.np1 - 1);
     int by_next = (by == nv.np1 - 1) ? 0x7fffffff : (by + 1) * nv.ly;
-    bool changed = false;
+    // `changes` only ever goes 0 -> 1: stop looking as soon as anyone has found a moved cell
+    bool check = *reinterpret_cast<volatile int*>(&sc->changes) == 0;
 
     for (int r = r0; r < r1; r += 8) {
-        uint4 b[8];
+        const int y = y_begin + r;
+        const int nrow = min(8, r1 - r);
+        unsigned packed = 0; // nibble k = ocean flags of my 4 columns in row r + k
+        {
+            unsigned nb[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            b[k] = make_uint4(0, 0, 0, 0);
-            if (r + k < r1)
-                b[k] = __ldg(bits + (size_t)(r + k) * NG + g);
+            for (int k = 0; k < 8; k++)
+                nb[k] = k < nrow ? (unsigned)__ldg(brow + (size_t)(r + k) * NB) : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                packed |= ((nb[k] >> sh) & 15u) << (4 * k);
         }
+        const int ylast = y + nrow - 1;
+        if (two && ylast < A.yend && ylast < B.yend) {
+            // fast path: one part per column for the whole batch
+            const int p0 = A.part, p1 = b1 ? B.part : A.part, p2 = b2 ? B.part : A.part, p3 = b3 ? B.part : A.part;
+            if (check) {
+                bool changed;
+                if (ylast < by_next) {
+                    const unsigned dm = (unsigned)(p0 != nbx[0] + by) | ((unsigned)(p1 != nbx[1] + by) << 1)
+                        | ((unsigned)(p2 != nbx[2] + by) << 2) | ((unsigned)(p3 != nbx[3] + by) << 3);
+                    changed = (packed & (dm * 0x11111111u)) != 0;
+                } else { // the naive block row changes inside the batch: row by row
+                    changed = false;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (r + k < r1) {
-                const int y = y_begin + r + k;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    while (y >= yend[c] && pcur[c] < plast[c]) {
-                        pcur[c]++;
-                        yend[c] = box_y0[pcur[c]] + box_ey[pcur[c]];
+                    for (int k = 0; k < 8; k++) {
+                        if (k < nrow) {
+                            if (y + k >= by_next) {
+                                by++;
+                                by_next = (by == nv.np1 - 1) ? 0x7fffffff : by_next + nv.ly;
+                            }
+                            const unsigned nib = packed >> (4 * k);
+                            changed |= ((nib & 1u) && p0 != nbx[0] + by) | ((nib & 2u) && p1 != nbx[1] + by)
+                                | ((nib & 4u) && p2 != nbx[2] + by) | ((nib & 8u) && p3 != nbx[3] + by);
+                        }
                     }
                 }
-                if (y >= by_next) {
-                    by++;
-                    by_next = (by == nv.np1 - 1) ? 0x7fffffff : by_next + nv.ly;
+                if (__any_sync(__activemask(), changed)) {
+                    if (changed)
+                        atomicOr(&sc->changes, 1);
+                    check = false;
                 }
-                const bool o0 = (b[k].x >> lane) & 1u, o1 = (b[k].y >> lane) & 1u;
-                const bool o2 = (b[k].z >> lane) & 1u, o3 = (b[k].w >> lane) & 1u;
-                changed |= (o0 && pcur[0] != nbx[0] + by) | (o1 && pcur[1] != nbx[1] + by)
-                    | (o2 && pcur[2] != nbx[2] + by) | (o3 && pcur[3] != nbx[3] + by);
+            }
+            if (WRITE) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (k < nrow) {
+                        const unsigned nib = packed >> (4 * k);
+                        const int4 out = make_int4((nib & 1u) ? p0 : -1, (nib & 2u) ? p1 : -1,
+                            (nib & 4u) ? p2 : -1, (nib & 8u) ? p3 : -1);
+                        int32_t* q = pid + (size_t)(r + k) * NX + x;
+                        if (VEC) {
+                            if (x < NX)
+                                __stcs(reinterpret_cast<int4*>(q), out);
+                        } else {
+                            if (x < NX)
+                                q[0] = out.x;
+                            if (x + 1 < NX)
+                                q[1] = out.y;
+                            if (x + 2 < NX)
+                                q[2] = out.z;
+                            if (x + 3 < NX)
+                                q[3] = out.w;
+                        }
+                    }
+                }
+            }
+        } else {
+            // slow path: a part boundary crosses the batch (or the thread spans > 2 strips)
+            bool changed = false;
+            for (int k = 0; k < nrow; k++) {
+                const int yy = y + k;
+                const int p0 = part_lookup(st_p0, rowpart, NY, sc4[0], yy);
+                const int p1 = part_lookup(st_p0, rowpart, NY, sc4[1], yy);
+                const int p2 = part_lookup(st_p0, rowpart, NY, sc4[2], yy);
+                const int p3 = part_lookup(st_p0, rowpart, NY, sc4[3], yy);
+                const unsigned nib = packed >> (4 * k);
+                if (check) {
+                    if (yy >= by_next) {
+                        by++;
+                        by_next = (by == nv.np1 - 1) ? 0x7fffffff : by_next + nv.ly;
+                    }
+                    changed |= ((nib & 1u) && p0 != nbx[0] + by) | ((nib & 2u) && p1 != nbx[1] + by)
+                        | ((nib & 4u) && p2 != nbx[2] + by) | ((nib & 8u) && p3 != nbx[3] + by);
+                }
                 if (WRITE) {
-                    int4 out = make_int4(o0 ? pcur[0] : -1, o1 ? pcur[1] : -1, o2 ? pcur[2] : -1,
-                        o3 ? pcur[3] : -1);
+                    const int4 out = make_int4((nib & 1u) ? p0 : -1, (nib & 2u) ? p1 : -1,
+                        (nib & 4u) ? p2 : -1, (nib & 8u) ? p3 : -1);
                     int32_t* q = pid + (size_t)(r + k) * NX + x;
                     if (VEC) {
                         if (x < NX)
@@ -720,10 +864,18 @@ __global__ void __launch_bounds__(256) k_label(const uint4* __restrict__ bits, i
                     }
                 }
             }
+            if (check && changed) {
+                atomicOr(&sc->changes, 1);
+                check = false;
+            }
+            if (r + 8 < r1) { // re-seat the cursors on the first row of the next batch
+                A = seat_cursor(st_p0, rowpart, box_y0, box_ey, NY, sc4[0], y + 8);
+                B = seat_cursor(st_p0, rowpart, box_y0, box_ey, NY, sc4[3], y + 8);
+            }
         }
+        if (check && (r & 63) == 0)
+            check = *reinterpret_cast<volatile int*>(&sc->changes) == 0;
     }
-    if (__any_sync(0xffffffffu, changed) && lane == 0 && sc->changes == 0)
-        atomicOr(&sc->changes, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
