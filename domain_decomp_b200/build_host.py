@@ -1,0 +1,43 @@
+"""Builds the C++ host library (libdomain_decomp.so: Grid, Partitioner, DomainUtils,
+CudaRcbPartitioner over the C ABI), the `decomp` CLI and the host test executable."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+from . import build as b
+
+HOST_LIB = os.path.join(b.PKG, "libdomain_decomp.so")
+DECOMP = os.path.join(b.PKG, "decomp")
+HOST_TESTS = os.path.join(b.PKG, "host_tests")
+
+LIB_SRCS = ["CdlIO.cpp", "DomainUtils.cpp", "Grid.cpp", "Partitioner.cpp", "CudaRcbPartitioner.cpp"]
+
+
+def _cxx() -> str:
+    for cand in ("/usr/bin/g++", shutil.which("g++")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("g++ not found")
+
+
+def build_host(force: bool = False, verbose: bool = False) -> None:
+    inc = ["-I", os.path.join(b.INCLUDE, "domain_decomp"), "-I", b.INCLUDE, "-I", b.HOST]
+    flags = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra", "-pedantic"]
+    srcs = [os.path.join(b.HOST, s) for s in LIB_SRCS]
+    hdrs = [os.path.join(b.INCLUDE, "domain_decomp", h) for h in os.listdir(os.path.join(b.INCLUDE, "domain_decomp")) if h.endswith(".hpp")]
+    hdrs += [os.path.join(b.HOST, "CdlIO.hpp"), os.path.join(b.INCLUDE, "ddc.h"), __file__]
+    rpath = "-Wl,-rpath,$ORIGIN"
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+
+    if force or b._stale(HOST_LIB, srcs + hdrs + [b.CUDA_LIB]):
+        run([_cxx()] + flags + inc + ["-shared", "-o", HOST_LIB] + srcs + ["-L", b.PKG, "-lddc_cuda", rpath])
+    for exe, src in ((DECOMP, "main.cpp"), (HOST_TESTS, "host_tests.cpp")):
+        s = os.path.join(b.HOST, src)
+        if force or b._stale(exe, [s, HOST_LIB] + hdrs):
+            run([_cxx()] + flags + inc + ["-o", exe, s, "-L", b.PKG, "-ldomain_decomp", "-lddc_cuda", rpath])
