@@ -125,10 +125,10 @@ struct ddc_handle_s {
     DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx;
     DevBuf<DevScalars> sc;
     DevBuf<Plan> plan;
-    DevBuf<int> sets; // 6 * P : A.lo A.hi A.n B.lo B.hi B.n
+    DevBuf<int4> sets; // 2 * P set records {lo, hi, plo, n}: list A, list B
     DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
     DevBuf<int> boxes; // x0 y0 ex ey, P each
-    DevBuf<int> strip_of_part, strip_of_col, rowpart;
+    DevBuf<int> strip_of_col;
     DevBuf<long long> loads, loadmm;
     DevBuf<int32_t> pid;
     DevBuf<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
@@ -193,16 +193,15 @@ NaiveParams naive_params(int P, int NX, int NY)
 }
 
 struct Tables {
-    SetBuf A, B;
+    int4 *A, *B;
     StripTable st;
     BoxTable bx;
 };
 Tables tables(ddc_handle_t h, int P)
 {
     Tables t;
-    int* s = h->sets.p;
-    t.A = { s, s + P, s + 2 * P };
-    t.B = { s + 3 * P, s + 4 * P, s + 5 * P };
+    t.A = h->sets.p;
+    t.B = h->sets.p + P;
     int* q = h->strips.p;
     t.st.x0 = q;
     t.st.x1 = q + (P + 1);
@@ -245,7 +244,7 @@ int run_neighbours(ddc_handle_t h, int P, int nx, int ny, int px, int py)
     cudaStream_t s = h->stream;
     const int cap = 3 * P + 64;
     CUDA_TRY(h, h->nbr_counts.ensure((size_t)8 * P));
-    CUDA_TRY(h, h->nbr_offsets.ensure((size_t)8 * P));
+    CUDA_TRY(h, h->nbr_offsets.ensure((size_t)8 * (P + 1)));
     CUDA_TRY(h, h->nbr_totals.ensure(8));
     if (h->nbr_cap < cap) {
         CUDA_TRY(h, h->nbr_ids.ensure((size_t)8 * cap));
@@ -254,7 +253,7 @@ int run_neighbours(ddc_handle_t h, int P, int nx, int ny, int px, int py)
         h->nbr_cap = cap;
     }
     const int warps_per_cta = 8;
-    const int grid = (P + warps_per_cta - 1) / warps_per_cta;
+    const int grid = (std::max(P, 8) + warps_per_cta - 1) / warps_per_cta; // >= 8 * pad32(P) threads
     k_neighbours<false><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p, nullptr,
         nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p);
     k_scan_counts<<<8, 1024, 0, s>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p);
@@ -288,7 +287,7 @@ int fetch_totals(ddc_handle_t h)
         CUDA_TRY(h, cudaMemsetAsync(&h->sc.p->overflow, 0, sizeof(int), h->stream));
         CUDA_TRY(h, cudaMemsetAsync(&h->sc.p->edge_cut, 0, sizeof(unsigned long long), h->stream));
         Tables t = tables(h, h->nparts);
-        const int grid = (h->nparts + 7) / 8;
+        const int grid = (std::max(h->nparts, 8) + 7) / 8;
         k_neighbours<true><<<grid, 256, 0, h->stream>>>(t.bx, h->nparts, h->nx, h->ny, h->px, h->py, t.st,
             h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p,
             h->nbr_halos.p, h->nbr_starts.p, h->sc.p);
@@ -399,9 +398,7 @@ int ddc_destroy(ddc_handle_t h)
     h->sets.release();
     h->strips.release();
     h->boxes.release();
-    h->strip_of_part.release();
     h->strip_of_col.release();
-    h->rowpart.release();
     h->loads.release();
     h->loadmm.release();
     h->pid.release();
@@ -536,10 +533,9 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const int NB = NG * 16; // bytes per bit-map row
     CUDA_TRY(h, h->bits.ensure((size_t)std::max(rows, 1) * NB));
     CUDA_TRY(h, h->colcount.ensure(NX + 4));
-    CUDA_TRY(h, h->sets.ensure((size_t)6 * P));
+    CUDA_TRY(h, h->sets.ensure((size_t)2 * P));
     CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
     CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
-    CUDA_TRY(h, h->strip_of_part.ensure(P));
     CUDA_TRY(h, h->strip_of_col.ensure(NX));
     CUDA_TRY(h, h->loads.ensure(P));
     CUDA_TRY(h, h->loadmm.ensure(2));
@@ -591,7 +587,7 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         if (use_smem)
             CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         k_xcuts<<<1, 1024, use_smem ? need : 0, s>>>(h->colcount.p, NX, NY, P, h->colpfx.p, use_smem,
-            h->sc.p, h->plan.p, t.A, t.B, t.st, t.bx, h->loads.p, h->strip_of_part.p, h->strip_of_col.p);
+            h->sc.p, h->plan.p, t.A, t.B, t.st, t.bx, h->loads.p, h->strip_of_col.p);
         launches++;
     }
     // the plan decides buffer sizes and the all-gather count: read it back (one tiny D2H + sync)
@@ -628,9 +624,8 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             CUDA_TRY(h, h->ypfx.ensure((size_t)grid * (NY + 1)));
         if (use_smem)
             CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        CUDA_TRY(h, h->rowpart.ensure((size_t)S * NY));
         k_ycuts<<<grid, 1024, use_smem ? need : 0, s>>>(rc_all, G, Rmax, NY, pl.iy, t.st, t.A, t.B,
-            h->ypfx.p, use_smem, t.bx, h->loads.p, h->plan.p, h->rowpart.p);
+            h->ypfx.p, use_smem, t.bx, h->loads.p, h->plan.p);
         launches++;
     } else
         mark(3);
@@ -642,8 +637,8 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     do {                                                                                           \
         const int rpc = 128; /* no per-CTA epilogue: many small CTAs keep more stores in flight */ \
         dim3 grid(gridx, (rows + rpc - 1) / rpc);                                                  \
-        k_label<V, W><<<grid, 256, 0, s>>>(h->bits.p, NX, NY, rows, h->y_begin, NB, rpc,           \
-            h->strip_of_col.p, t.st.p0, h->rowpart.p, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p);    \
+        k_label<V, W><<<grid, 256, 0, s>>>(h->bits.p, NX, rows, h->y_begin, NB, rpc,               \
+            h->strip_of_col.p, t.st.p0, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p);                  \
     } while (0)
         if (want_pid) {
             if (vecp)
@@ -660,8 +655,7 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     mark(5);
     // ---- K5: naive blocks when nothing moved; load statistics -----------------------------------
     if (P > 1) {
-        k_finalize<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(P, NX, NY, nv, h->sc.p, t.st, t.bx,
-            h->strip_of_part.p);
+        k_finalize<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(P, NX, NY, nv, h->sc.p, t.st, t.bx);
         launches++;
     }
     {
@@ -851,7 +845,7 @@ int ddc_neighbours_from_boxes(ddc_handle_t h, int nparts, int nx, int ny, const 
     cudaStream_t s = h->stream;
     CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
     CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
-    CUDA_TRY(h, h->sets.ensure((size_t)6 * P));
+    CUDA_TRY(h, h->sets.ensure((size_t)2 * P));
     Tables t = tables(h, P);
     const int32_t* src[4] = { x0, y0, ex, ey };
     for (int i = 0; i < 4; i++)

@@ -394,37 +394,42 @@ __device__ inline int median_boundary(const unsigned* pfx, int c0, int c1, int n
     return U; // policy Q2 (U >= 0 because Wn > 0)
 }
 
-// One RCB level over the sets [p_begin, p_end): sets live at the index of their lowest part.
-// Reads buffer `in`, writes buffer `out` (double buffered: all reads precede all writes).
-struct SetBuf {
-    int* lo;
-    int* hi;
-    int* n;
-};
-__device__ inline void rcb_level(const unsigned* pfx, SetBuf in, SetBuf out, int p_begin, int p_end,
-    int* iters)
+// One RCB level over a compact, order-preserving list of sets.  A set is {lo, hi, plo, n}: the cell
+// range [lo, hi) along the cut dimension and the parts [plo, plo + n) it still has to produce.
+// Every set with n > 1 is split by the weighted median into two children, sets with n == 1 are
+// copied; the output list keeps ascending part order (children positions come from a block scan),
+// so after the last level the list IS the strip table / the y-sorted part list.
+// All threads of the block must call it.  Returns the length of the output list.
+__device__ inline int rcb_level(const unsigned* pfx, const int4* __restrict__ in, int nin, int4* __restrict__ out,
+    int* iters, int* wsum32 /* >= 33 */)
 {
-    for (int p = p_begin + threadIdx.x; p < p_end; p += blockDim.x) {
-        const int n = in.n[p];
-        if (n == 0)
-            continue;
-        const int lo = in.lo[p], hi = in.hi[p];
-        if (n == 1) {
-            out.lo[p] = lo;
-            out.hi[p] = hi;
-            out.n[p] = 1;
-            continue;
+    int carry = 0;
+    for (int base = 0; base < nin; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
+        int nout = 0;
+        if (i < nin) {
+            a = in[i];
+            nout = 1;
+            if (a.w > 1) {
+                // Zoltan_Divide_Machine: the lower child gets ceil(n / 2) parts
+                const int nlo = (a.w - 1) / 2 + 1;
+                const int cut = median_boundary(pfx, a.x, a.y - 1, nlo, a.w, iters);
+                b = make_int4(cut, a.y, a.z + nlo, a.w - nlo);
+                a = make_int4(a.x, cut, a.z, nlo);
+                nout = 2;
+            }
         }
-        // Zoltan_Divide_Machine: lower child gets ceil(n/2) parts
-        const int nlo = (n - 1) / 2 + 1;
-        const int b = median_boundary(pfx, lo, hi - 1, nlo, n, iters);
-        out.lo[p] = lo;
-        out.hi[p] = b;
-        out.n[p] = nlo;
-        out.lo[p + nlo] = b;
-        out.hi[p + nlo] = hi;
-        out.n[p + nlo] = n - nlo;
+        int total;
+        const int pos = carry + block_exclusive_scan<int>(nout, &total, wsum32);
+        if (nout >= 1)
+            out[pos] = a;
+        if (nout == 2)
+            out[pos + 1] = b;
+        carry += total;
     }
+    __syncthreads();
+    return carry;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -446,8 +451,8 @@ struct BoxTable { // final boxes, SoA
 
 // dynamic shared memory: (NX + 1) unsigned when use_smem
 __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ colcount, int NX, int NY,
-    int P, unsigned* pfx_g, int use_smem, const DevScalars* __restrict__ sc, Plan* plan, SetBuf A,
-    SetBuf Bf, StripTable st, BoxTable bx, long long* loads, int* strip_of_part, int* strip_of_col)
+    int P, unsigned* pfx_g, int use_smem, const DevScalars* __restrict__ sc, Plan* plan, int4* listA,
+    int4* listB, StripTable st, BoxTable bx, long long* loads, int* strip_of_col)
 {
     extern __shared__ unsigned smem_dyn[];
     __shared__ unsigned long long wsum64[33];
@@ -458,12 +463,6 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
 
     // 1. pfx[i] = ocean cells in columns [0, i)
     block_prefix<false>([&](int i) { return colcount[i]; }, NX, pfx, 0, wsum64);
-    // sets: everything invalid, then the root set
-    for (int p = tid; p < P; p += blockDim.x) {
-        A.n[p] = 0;
-        Bf.n[p] = 0;
-    }
-    __syncthreads();
 
     // 2. the plan: bounding box of all dots -> preset direction of every level
     if (tid == 0) {
@@ -499,74 +498,55 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
         plan->W = W;
         s_ix = ix;
         s_iters = 0;
-        A.lo[0] = 0;
-        A.hi[0] = NX;
-        A.n[0] = P;
+        listA[0] = make_int4(0, NX, 0, P); // the root set
     }
     __syncthreads();
 
     // 3. the x levels
     const int ix = s_ix;
     int my_iters = 0;
-    SetBuf cur = A, nxt = Bf;
+    int4 *cur = listA, *nxt = listB;
+    int ncur = 1;
     for (int l = 0; l < ix; l++) {
-        rcb_level(pfx, cur, nxt, 0, P, &my_iters);
-        __syncthreads();
-        SetBuf t = cur;
+        ncur = rcb_level(pfx, cur, ncur, nxt, &my_iters, wsum32);
+        int4* t = cur;
         cur = nxt;
         nxt = t;
     }
     if (my_iters)
         atomicAdd(&s_iters, my_iters);
 
-    // 4. strips = valid sets in ascending part order
-    int nstrips;
-    {
-        const int chunk = (P + blockDim.x - 1) / blockDim.x;
-        const int b = min(P, tid * chunk), e = min(P, b + chunk);
-        int cnt = 0;
-        for (int p = b; p < e; p++)
-            cnt += cur.n[p] != 0;
-        int pos = block_exclusive_scan<int>(cnt, &nstrips, wsum32);
-        for (int p = b; p < e; p++) {
-            const int n = cur.n[p];
-            if (n != 0) {
-                const int lo = cur.lo[p], hi = cur.hi[p];
-                st.x0[pos] = lo;
-                st.x1[pos] = hi;
-                st.p0[pos] = p;
-                if (n == 1) { // a leaf already: uncut in y
-                    bx.x0[p] = lo;
-                    bx.ex[p] = hi - lo;
-                    bx.y0[p] = 0;
-                    bx.ey[p] = NY;
-                    loads[p] = (long long)hcnt(pfx, lo, hi - 1);
-                }
-                pos++;
-            }
+    // 4. the list is the strip table, in ascending part order
+    const int nstrips = ncur;
+    for (int i = tid; i < nstrips; i += blockDim.x) {
+        const int4 r = cur[i];
+        st.x0[i] = r.x;
+        st.x1[i] = r.y;
+        st.p0[i] = r.z;
+        if (r.w == 1) { // a leaf already: uncut in y
+            bx.x0[r.z] = r.x;
+            bx.ex[r.z] = r.y - r.x;
+            bx.y0[r.z] = 0;
+            bx.ey[r.z] = NY;
+            loads[r.z] = (long long)hcnt(pfx, r.x, r.y - 1);
         }
-        if (tid == 0) {
-            st.p0[nstrips] = P;
-            *st.S = nstrips;
-            *st.always = 0;
-            plan->S = nstrips;
-        }
+    }
+    if (tid == 0) {
+        st.p0[nstrips] = P;
+        *st.S = nstrips;
+        *st.always = 0;
+        plan->S = nstrips;
     }
     __syncthreads();
-    // 5. strip of every part and of every column.  Column table: count the strips that start at
-    //    each column, inclusive prefix - 1 = last strip starting at or before the column (a
-    //    zero-width strip shares its start with the strip that follows it, which wins).
-    for (int s = tid; s < nstrips; s += blockDim.x) {
-        const int p0 = st.p0[s], p1 = st.p0[s + 1];
-        for (int q = p0; q < p1; q++)
-            strip_of_part[q] = s;
-    }
+    // 5. strip of every column: count the strips that start at each column, inclusive prefix - 1 =
+    //    last strip starting at or before the column (a zero-width strip shares its start with
+    //    the strip that follows it, which wins).
     unsigned* cnt = pfx; // the column prefix sums are no longer needed
     for (int x = tid; x < NX; x += blockDim.x)
         cnt[x] = 0;
     __syncthreads();
-    for (int s = tid; s < nstrips; s += blockDim.x) {
-        const int x0 = st.x0[s];
+    for (int i = tid; i < nstrips; i += blockDim.x) {
+        const int x0 = cur[i].x;
         if (x0 < NX)
             atomicAdd(&cnt[x0], 1u);
     }
@@ -616,14 +596,15 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // rowcount_all layout [G][S][Rmax] (the NCCL all-gather of every rank's [S][Rmax]); global row y
 // lives at rank y / Rmax, local row y % Rmax.  dynamic smem: (NY + 1) unsigned when use_smem,
-// otherwise pfx_g holds gridDim.x slices of NY + 1.  Also writes rowpart[s][y] = part owning row y
-// of strip s, the lookup table of the label kernel.
+// otherwise pfx_g holds gridDim.x slices of NY + 1.  The set lists of strip s live in
+// listA/listB[p0[s] .. p0[s+1]) (strips own disjoint part ranges).
 __global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ rowcount_all, int G,
-    int Rmax, int NY, int ylevels, StripTable st, SetBuf A, SetBuf Bf, unsigned* pfx_g, int use_smem,
-    BoxTable bx, long long* loads, Plan* plan, int* __restrict__ rowpart)
+    int Rmax, int NY, int ylevels, StripTable st, int4* listA, int4* listB, unsigned* pfx_g, int use_smem,
+    BoxTable bx, long long* loads, Plan* plan)
 {
     extern __shared__ unsigned smem_dyn[];
     __shared__ unsigned long long wsum64[33];
+    __shared__ int wsum32[33];
     unsigned* pfx = use_smem ? smem_dyn : pfx_g + (size_t)blockIdx.x * (NY + 1);
     const int tid = threadIdx.x;
     const int S = *st.S;
@@ -639,49 +620,27 @@ __global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ row
                 return rowcount_all[((size_t)g * S + s) * Rmax + yl];
             },
             NY, pfx, 0, wsum64);
-        for (int p = plo + tid; p < plo + n; p += blockDim.x) {
-            A.n[p] = 0;
-            Bf.n[p] = 0;
-        }
+        int4 *cur = listA + plo, *nxt = listB + plo;
+        if (tid == 0)
+            cur[0] = make_int4(0, NY, plo, n);
         __syncthreads();
-        if (tid == 0) {
-            A.lo[plo] = 0;
-            A.hi[plo] = NY;
-            A.n[plo] = n;
-        }
-        __syncthreads();
-        SetBuf cur = A, nxt = Bf;
+        int ncur = 1;
         for (int l = 0; l < ylevels; l++) {
-            rcb_level(pfx, cur, nxt, plo, plo + n, &my_iters);
-            __syncthreads();
-            SetBuf t = cur;
+            ncur = rcb_level(pfx, cur, ncur, nxt, &my_iters, wsum32);
+            int4* t = cur;
             cur = nxt;
             nxt = t;
         }
+        // ncur == n: one leaf set per part, y-sorted
         const int sx0 = st.x0[s], sx1 = st.x1[s];
-        for (int p = plo + tid; p < plo + n; p += blockDim.x) {
-            const int lo = cur.lo[p], hi = cur.hi[p];
-            bx.x0[p] = sx0;
-            bx.ex[p] = sx1 - sx0;
-            bx.y0[p] = lo;
-            bx.ey[p] = hi - lo;
-            loads[p] = (long long)hcnt(pfx, lo, hi - 1);
+        for (int j = tid; j < ncur; j += blockDim.x) {
+            const int4 r = cur[j];
+            bx.x0[r.z] = sx0;
+            bx.ex[r.z] = sx1 - sx0;
+            bx.y0[r.z] = r.x;
+            bx.ey[r.z] = r.y - r.x;
+            loads[r.z] = (long long)hcnt(pfx, r.x, r.y - 1);
         }
-        __syncthreads();
-        // rowpart: count the parts starting at each row; inclusive prefix - 1 + plo = last part
-        // starting at or before the row (zero-height parts lose against their successor)
-        unsigned* cnt = pfx;
-        for (int y = tid; y < NY; y += blockDim.x)
-            cnt[y] = 0;
-        __syncthreads();
-        for (int p = plo + tid; p < plo + n; p += blockDim.x) {
-            const int lo = cur.lo[p];
-            if (lo < NY)
-                atomicAdd(&cnt[lo], 1u);
-        }
-        __syncthreads();
-        block_prefix<true>([&](int y) { return cnt[y]; }, NY,
-            reinterpret_cast<unsigned*>(rowpart) + (size_t)s * NY, plo, wsum64);
     }
     if (my_iters)
         atomicAdd(&plan->iters, my_iters);
@@ -692,43 +651,67 @@ __global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ row
 // ------------------------------------------------------------------------------------------------
 // Same thread mapping as K1: one warp = one 128-column group, walking down the rows 8 at a time.
 // The part of a cell is strip_of_col[x] -> strip, then the part of that strip owning row y.  Parts
-// of a strip are y-sorted and ~hundreds of rows tall, so a thread keeps a cursor (part, last row)
-// for the strip of its first and of its last column (two cursors cover every thread that spans at
-// most two strips; they coincide for the ~97 % of threads inside one strip).  While all 8 rows of
-// a batch stay inside both cursor parts -- the common case -- no table is touched at all; otherwise
-// the rows are resolved through the rowpart[strip][y] table that K4 wrote and the cursors re-seat.
-__device__ __forceinline__ int part_lookup(const int* __restrict__ st_p0, const int* __restrict__ rowpart,
-    int NY, int s, int y)
-{
-    const int p0 = st_p0[s];
-    return (st_p0[s + 1] - p0 <= 1) ? p0 : __ldg(rowpart + (size_t)s * NY + y);
-}
-
+// of a strip are y-sorted and ~hundreds of rows tall, so a thread keeps a cursor (part, first row
+// after it) for the strip of its first and of its last column (two cursors cover every thread that
+// spans at most two strips; they coincide for the ~97 % of threads inside one strip).  While all 8
+// rows of a batch stay inside both cursor parts -- the common case -- nothing is looked up at all;
+// when a part boundary crosses the batch the cursors step forward row by row.
 struct LabelCursor {
-    int part; // part owning the current rows
+    int part; // part owning the current row
     int yend; // first row that no longer belongs to it
+    int last; // last part of the strip
 };
-__device__ __forceinline__ LabelCursor seat_cursor(const int* __restrict__ st_p0,
-    const int* __restrict__ rowpart, const int* __restrict__ box_y0, const int* __restrict__ box_ey, int NY,
-    int s, int y)
+// first part of strip s whose rows end after y (binary search over the y-sorted parts)
+__device__ __forceinline__ LabelCursor seat_cursor(const int* __restrict__ st_p0, const int* __restrict__ box_y0,
+    const int* __restrict__ box_ey, int s, int y)
 {
     LabelCursor c;
-    const int p0 = st_p0[s];
-    if (st_p0[s + 1] - p0 <= 1) {
-        c.part = p0;
-        c.yend = 0x7fffffff;
-    } else {
-        c.part = __ldg(rowpart + (size_t)s * NY + y);
+    int lo = st_p0[s];
+    c.last = st_p0[s + 1] - 1;
+    int hi = c.last;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (y < box_y0[mid] + box_ey[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    c.part = lo;
+    c.yend = box_y0[lo] + box_ey[lo];
+    return c;
+}
+__device__ __forceinline__ void advance_cursor(LabelCursor& c, const int* __restrict__ box_y0,
+    const int* __restrict__ box_ey, int y)
+{
+    while (y >= c.yend && c.part < c.last) { // zero-height parts are stepped over
+        c.part++;
         c.yend = box_y0[c.part] + box_ey[c.part];
     }
-    return c;
+}
+
+template <bool VEC>
+__device__ __forceinline__ void store_pid_row(int32_t* __restrict__ q, int x, int NX, const int4& out)
+{
+    if (VEC) {
+        if (x < NX)
+            __stcs(reinterpret_cast<int4*>(q), out);
+    } else {
+        if (x < NX)
+            q[0] = out.x;
+        if (x + 1 < NX)
+            q[1] = out.y;
+        if (x + 2 < NX)
+            q[2] = out.z;
+        if (x + 3 < NX)
+            q[3] = out.w;
+    }
 }
 
 template <bool VEC, bool WRITE>
-__global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bits, int NX, int NY, int rows,
+__global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bits, int NX, int rows,
     int y_begin, int NB, int rows_per_cta, const int* __restrict__ strip_of_col,
-    const int* __restrict__ st_p0, const int* __restrict__ rowpart, const int* __restrict__ box_y0,
-    const int* __restrict__ box_ey, NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc)
+    const int* __restrict__ st_p0, const int* __restrict__ box_y0, const int* __restrict__ box_ey,
+    NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc)
 {
     const int lane = lane_id();
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -750,8 +733,8 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
     // columns 1, 2 belong to the strip of column 0 or of column 3 unless the thread spans > 2 strips
     const bool two = (sc4[1] == sc4[0] || sc4[1] == sc4[3]) && (sc4[2] == sc4[0] || sc4[2] == sc4[3]);
     const bool b1 = sc4[1] != sc4[0], b2 = sc4[2] != sc4[0], b3 = sc4[3] != sc4[0];
-    LabelCursor A = seat_cursor(st_p0, rowpart, box_y0, box_ey, NY, sc4[0], y_begin + r0);
-    LabelCursor B = seat_cursor(st_p0, rowpart, box_y0, box_ey, NY, sc4[3], y_begin + r0);
+    LabelCursor A = seat_cursor(st_p0, box_y0, box_ey, sc4[0], y_begin + r0);
+    LabelCursor B = b3 ? seat_cursor(st_p0, box_y0, box_ey, sc4[3], y_begin + r0) : A;
     const uint8_t* brow = bits + (size_t)g * 16 + (lane >> 1);
     const int sh = (lane & 1) * 4;
     int by = min((y_begin + r0) / nv.ly, nv.np1 - 1);
@@ -808,22 +791,9 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
                 for (int k = 0; k < 8; k++) {
                     if (k < nrow) {
                         const unsigned nib = packed >> (4 * k);
-                        const int4 out = make_int4((nib & 1u) ? p0 : -1, (nib & 2u) ? p1 : -1,
-                            (nib & 4u) ? p2 : -1, (nib & 8u) ? p3 : -1);
-                        int32_t* q = pid + (size_t)(r + k) * NX + x;
-                        if (VEC) {
-                            if (x < NX)
-                                __stcs(reinterpret_cast<int4*>(q), out);
-                        } else {
-                            if (x < NX)
-                                q[0] = out.x;
-                            if (x + 1 < NX)
-                                q[1] = out.y;
-                            if (x + 2 < NX)
-                                q[2] = out.z;
-                            if (x + 3 < NX)
-                                q[3] = out.w;
-                        }
+                        store_pid_row<VEC>(pid + (size_t)(r + k) * NX + x, x, NX,
+                            make_int4((nib & 1u) ? p0 : -1, (nib & 2u) ? p1 : -1, (nib & 4u) ? p2 : -1,
+                                (nib & 8u) ? p3 : -1));
                     }
                 }
             }
@@ -832,10 +802,13 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
             bool changed = false;
             for (int k = 0; k < nrow; k++) {
                 const int yy = y + k;
-                const int p0 = part_lookup(st_p0, rowpart, NY, sc4[0], yy);
-                const int p1 = part_lookup(st_p0, rowpart, NY, sc4[1], yy);
-                const int p2 = part_lookup(st_p0, rowpart, NY, sc4[2], yy);
-                const int p3 = part_lookup(st_p0, rowpart, NY, sc4[3], yy);
+                advance_cursor(A, box_y0, box_ey, yy);
+                advance_cursor(B, box_y0, box_ey, yy);
+                int p0 = A.part, p1 = b1 ? B.part : A.part, p2 = b2 ? B.part : A.part, p3 = b3 ? B.part : A.part;
+                if (!two) { // > 2 strips under one thread (strips narrower than 3 columns)
+                    p1 = seat_cursor(st_p0, box_y0, box_ey, sc4[1], yy).part;
+                    p2 = seat_cursor(st_p0, box_y0, box_ey, sc4[2], yy).part;
+                }
                 const unsigned nib = packed >> (4 * k);
                 if (check) {
                     if (yy >= by_next) {
@@ -845,32 +818,14 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
                     changed |= ((nib & 1u) && p0 != nbx[0] + by) | ((nib & 2u) && p1 != nbx[1] + by)
                         | ((nib & 4u) && p2 != nbx[2] + by) | ((nib & 8u) && p3 != nbx[3] + by);
                 }
-                if (WRITE) {
-                    const int4 out = make_int4((nib & 1u) ? p0 : -1, (nib & 2u) ? p1 : -1,
-                        (nib & 4u) ? p2 : -1, (nib & 8u) ? p3 : -1);
-                    int32_t* q = pid + (size_t)(r + k) * NX + x;
-                    if (VEC) {
-                        if (x < NX)
-                            __stcs(reinterpret_cast<int4*>(q), out);
-                    } else {
-                        if (x < NX)
-                            q[0] = out.x;
-                        if (x + 1 < NX)
-                            q[1] = out.y;
-                        if (x + 2 < NX)
-                            q[2] = out.z;
-                        if (x + 3 < NX)
-                            q[3] = out.w;
-                    }
-                }
+                if (WRITE)
+                    store_pid_row<VEC>(pid + (size_t)(r + k) * NX + x, x, NX,
+                        make_int4((nib & 1u) ? p0 : -1, (nib & 2u) ? p1 : -1, (nib & 4u) ? p2 : -1,
+                            (nib & 8u) ? p3 : -1));
             }
             if (check && changed) {
                 atomicOr(&sc->changes, 1);
                 check = false;
-            }
-            if (r + 8 < r1) { // re-seat the cursors on the first row of the next batch
-                A = seat_cursor(st_p0, rowpart, box_y0, box_ey, NY, sc4[0], y + 8);
-                B = seat_cursor(st_p0, rowpart, box_y0, box_ey, NY, sc4[3], y + 8);
             }
         }
         if (check && (r & 63) == 0)
@@ -882,7 +837,7 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
 // K5: `changes == 0`  =>  report the naive blocks (ZoltanPartitioner.cpp:182-187)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_finalize(int P, int NX, int NY, NaiveParams nv,
-    const DevScalars* __restrict__ sc, StripTable st, BoxTable bx, int* strip_of_part)
+    const DevScalars* __restrict__ sc, StripTable st, BoxTable bx)
 {
     if (sc->changes != 0)
         return;
@@ -897,7 +852,6 @@ __global__ void __launch_bounds__(256) k_finalize(int P, int NX, int NY, NaivePa
         bx.y0[p] = byi * nv.ly;
         bx.ex[p] = ex;
         bx.ey[p] = ey;
-        strip_of_part[p] = bxi;
         if (byi == 0) {
             st.x0[bxi] = bxi * nv.lx;
             st.x1[bxi] = bxi * nv.lx + ex;
@@ -906,6 +860,10 @@ __global__ void __launch_bounds__(256) k_finalize(int P, int NX, int NY, NaivePa
         if (p == 0) {
             st.p0[nv.np0] = P;
             *st.S = nv.np0;
+            // ceil() over-covering makes trailing blocks start beyond the extent (non-positive
+            // extents, y no longer sorted): let the neighbour kernel test all pairs then
+            if ((nv.np0 - 1) * nv.lx >= NX || (nv.np1 - 1) * nv.ly >= NY)
+                *st.always = 1;
         }
     }
 }
@@ -955,101 +913,71 @@ __device__ __forceinline__ int halo_start(const Dom& d1, const Dom& d2, int edge
     return dy * w2;
 }
 
-// One warp per part.  Candidate parts are pruned by strip: every edge test needs either a shared
-// x coordinate or a positive x overlap, so only strips whose closed x range touches mine (or
-// wraps around when periodic in x) can contribute; inside a candidate strip the reference's tests
-// are evaluated literally.  Lists come out id-ascending because strips and the parts inside a
-// strip are visited in ascending order and compacted with ballots.
+// Two search strategies, same literal edge tests:
+//  * structured (the normal case): the boxes are vertical strips, each holding y-sorted parts that
+//    tile [0, NY).  One THREAD per (list, part): walk the strips in ascending order, keep those
+//    whose x range satisfies the edge's x condition (exact at strip level, every part of a strip
+//    has the strip's x range), binary-search the first part whose y range can match and scan the
+//    short run that does.  ids come out ascending by construction.
+//  * unstructured (`always`: caller-supplied boxes, degenerate naive blocks): one WARP per part,
+//    all pairs, ballot compaction keeps ids ascending.
 // list l = periodic * 4 + edge; counts/offsets [8][P]; ids/halos/starts [8][cap].
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, int NY, int px, int py,
-    StripTable st, int* __restrict__ counts, const int* __restrict__ offsets,
-    const int* __restrict__ totals, int cap, int* __restrict__ ids, int* __restrict__ halos,
-    int* __restrict__ starts, DevScalars* sc)
+__device__ __forceinline__ void neighbours_all_pairs(const BoxTable& bx, int P, int NX, int NY, int px, int py,
+    int me, int* __restrict__ counts, const int* __restrict__ offsets, int cap, int* __restrict__ ids,
+    int* __restrict__ halos, int* __restrict__ starts, DevScalars* sc)
 {
     const int lane = lane_id();
-    const int me = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (me >= P)
-        return;
-    if (FILL) {
-        bool over = false;
-#pragma unroll
-        for (int l = 0; l < 8; l++)
-            over |= totals[l] > cap;
-        if (over) {
-            if (me == 0 && lane == 0)
-                sc->overflow = 1;
-            return;
-        }
-    }
     Dom d1;
     d1.x1 = bx.x0[me];
     d1.y1 = bx.y0[me];
     d1.x2 = d1.x1 + bx.ex[me];
     d1.y2 = d1.y1 + bx.ey[me];
-    const int S = *st.S;
-    const bool always = *st.always != 0 || d1.x2 <= d1.x1;
     int cnt[8];
     int base[8];
 #pragma unroll
     for (int l = 0; l < 8; l++) {
         cnt[l] = 0;
-        base[l] = FILL ? offsets[l * P + me] : 0;
+        base[l] = FILL ? offsets[l * (P + 1) + me] : 0;
     }
     unsigned long long cut = 0;
-
-    for (int sb = 0; sb < S; sb += 32) {
-        const int s = sb + lane;
-        bool rel = false;
-        if (s < S) {
-            const int sx0 = st.x0[s], sx1 = st.x1[s];
-            rel = always || sx1 <= sx0 || (sx0 <= d1.x2 && d1.x1 <= sx1)
-                || (px && (d1.x1 == sx1 - NX || d1.x2 == sx0 + NX)); // periodic L / R edge match
+    for (int qb = 0; qb < P; qb += 32) {
+        const int q = qb + lane;
+        const bool valid = q < P;
+        Dom d2 = { 0, 0, 0, 0 };
+        if (valid) {
+            d2.x1 = bx.x0[q];
+            d2.y1 = bx.y0[q];
+            d2.x2 = d2.x1 + bx.ex[q];
+            d2.y2 = d2.y1 + bx.ey[q];
         }
-        unsigned m = __ballot_sync(0xffffffffu, rel);
-        while (m) {
-            const int t = sb + __ffs(m) - 1;
-            m &= m - 1;
-            const int q0 = st.p0[t], q1 = st.p0[t + 1];
-            for (int qb = q0; qb < q1; qb += 32) {
-                const int q = qb + lane;
-                const bool valid = q < q1;
-                Dom d2 = { 0, 0, 0, 0 };
-                if (valid) {
-                    d2.x1 = bx.x0[q];
-                    d2.y1 = bx.y0[q];
-                    d2.x2 = d2.x1 + bx.ex[q];
-                    d2.y2 = d2.y1 + bx.ey[q];
-                }
 #pragma unroll
-                for (int l = 0; l < 8; l++) {
-                    const int per = l >> 2, edge = l & 3;
-                    const bool lr = edge < 2;
-                    bool pass = valid;
-                    if (per) // filter of get_neighbour_info_periodic (Partitioner.cpp:116)
-                        pass = pass && ((lr && px) || (!lr && py));
-                    else // a subdomain is not its own interior neighbour (Partitioner.cpp:408)
-                        pass = pass && q != me;
-                    int halo = 0;
-                    if (pass) {
-                        pass = is_neighbour(d1, d2, edge, per && px, per && py, NX, NY);
-                        if (pass) {
-                            halo = domain_overlap(d1, d2, edge);
-                            pass = halo > 0;
-                        }
-                    }
-                    const unsigned b = __ballot_sync(0xffffffffu, pass);
-                    if (FILL && pass) {
-                        const int pos = base[l] + cnt[l] + __popc(b & ((1u << lane) - 1u));
-                        ids[(size_t)l * cap + pos] = q;
-                        halos[(size_t)l * cap + pos] = halo;
-                        starts[(size_t)l * cap + pos] = halo_start(d1, d2, edge);
-                        if (!per)
-                            cut += (unsigned long long)halo;
-                    }
-                    cnt[l] += __popc(b);
+        for (int l = 0; l < 8; l++) {
+            const int per = l >> 2, edge = l & 3;
+            const bool lr = edge < 2;
+            bool pass = valid;
+            if (per) // filter of get_neighbour_info_periodic (Partitioner.cpp:116)
+                pass = pass && ((lr && px) || (!lr && py));
+            else // a subdomain is not its own interior neighbour (Partitioner.cpp:408)
+                pass = pass && q != me;
+            int halo = 0;
+            if (pass) {
+                pass = is_neighbour(d1, d2, edge, per && px, per && py, NX, NY);
+                if (pass) {
+                    halo = domain_overlap(d1, d2, edge);
+                    pass = halo > 0;
                 }
             }
+            const unsigned b = __ballot_sync(0xffffffffu, pass);
+            if (FILL && pass) {
+                const int pos = base[l] + cnt[l] + __popc(b & ((1u << lane) - 1u));
+                ids[(size_t)l * cap + pos] = q;
+                halos[(size_t)l * cap + pos] = halo;
+                starts[(size_t)l * cap + pos] = halo_start(d1, d2, edge);
+                if (!per)
+                    cut += (unsigned long long)halo;
+            }
+            cnt[l] += __popc(b);
         }
     }
     if (!FILL) {
@@ -1067,27 +995,145 @@ __global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, 
     }
 }
 
+template <bool FILL>
+__device__ __forceinline__ void neighbours_structured(const BoxTable& bx, int P, int NX, int NY, int px, int py,
+    const StripTable& st, int l, int me, int* __restrict__ counts, const int* __restrict__ offsets, int cap,
+    int* __restrict__ ids, int* __restrict__ halos, int* __restrict__ starts, DevScalars* sc)
+{
+    const int per = l >> 2, edge = l & 3;
+    const bool lr = edge < 2;
+    int cnt = 0;
+    unsigned long long cut = 0;
+    const bool listed = me < P && (!per || (lr && px) || (!lr && py)); // get_neighbour_info_periodic's filter
+    if (listed) {
+        Dom d1;
+        d1.x1 = bx.x0[me];
+        d1.y1 = bx.y0[me];
+        d1.x2 = d1.x1 + bx.ex[me];
+        d1.y2 = d1.y1 + bx.ey[me];
+        const bool wx = per && px, wy = per && py;
+        const int base = FILL ? offsets[l * (P + 1) + me] : 0;
+        const int S = *st.S;
+        // strips are x-sorted and tile [0, NX): binary-search the first strip that can satisfy the
+        // edge's x condition, then walk the (short) run of strips that do
+        //   LEFT   strips ending   at xt = d1.x1 (+ NX)      RIGHT  strips starting at xt = d1.x2 (- NX)
+        //   BOTTOM / TOP  strips with a positive x overlap: the first one ending after d1.x1
+        const int xt = edge == 0 ? (wx ? d1.x1 + NX : d1.x1) : (wx ? d1.x2 - NX : d1.x2);
+        int s = 0, hi = S;
+        while (s < hi) {
+            const int mid = (s + hi) >> 1;
+            const bool ge = edge == 0 ? st.x1[mid] >= xt : (edge == 1 ? st.x0[mid] >= xt : st.x1[mid] > d1.x1);
+            if (ge)
+                hi = mid;
+            else
+                s = mid + 1;
+        }
+        for (; s < S; s++) {
+            const int sx0 = st.x0[s], sx1 = st.x1[s];
+            if (edge == 0 ? sx1 != xt : (edge == 1 ? sx0 != xt : sx0 >= d1.x2))
+                break;
+            if (!lr && !(d1.x2 >= sx0 && d1.x1 <= sx1 && min(d1.x2, sx1) - max(d1.x1, sx0) > 0))
+                continue;
+            const int q0 = st.p0[s], q1 = st.p0[s + 1];
+            // first part of the strip whose y range can satisfy the y condition (parts are y-sorted)
+            const int yt = edge == 3 ? (wy ? d1.y2 - NY : d1.y2) : (wy ? d1.y1 + NY : d1.y1);
+            int lo = q0, qh = q1;
+            while (lo < qh) {
+                const int mid = (lo + qh) >> 1;
+                const int y1m = bx.y0[mid], y2m = y1m + bx.ey[mid];
+                // LEFT/RIGHT: first part ending above my first row; TOP: first part starting at or
+                // above yt (d1.y2 == d2.y1); BOTTOM: first part ending at or above yt (d1.y1 == d2.y2)
+                const bool ge = lr ? y2m > d1.y1 : (edge == 3 ? y1m >= yt : y2m >= yt);
+                if (ge)
+                    qh = mid;
+                else
+                    lo = mid + 1;
+            }
+            for (int q = lo; q < q1; q++) {
+                Dom d2;
+                d2.x1 = sx0;
+                d2.x2 = sx1;
+                d2.y1 = bx.y0[q];
+                d2.y2 = d2.y1 + bx.ey[q];
+                if (lr ? d2.y1 >= d1.y2 : (edge == 3 ? d2.y1 > yt : d2.y2 > yt))
+                    break; // past the run that can match
+                if (!per && q == me)
+                    continue;
+                if (!is_neighbour(d1, d2, edge, wx, wy, NX, NY))
+                    continue;
+                const int halo = domain_overlap(d1, d2, edge);
+                if (halo <= 0)
+                    continue;
+                if (FILL) {
+                    const size_t pos = (size_t)l * cap + base + cnt;
+                    ids[pos] = q;
+                    halos[pos] = halo;
+                    starts[pos] = halo_start(d1, d2, edge);
+                    if (!per)
+                        cut += (unsigned long long)halo;
+                }
+                cnt++;
+            }
+        }
+    }
+    if (!FILL) {
+        if (me < P)
+            counts[l * P + me] = cnt;
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            cut += __shfl_xor_sync(0xffffffffu, cut, o);
+        if (lane_id() == 0 && cut)
+            atomicAdd(&sc->edge_cut, cut);
+    }
+}
+
+// launched with enough threads for one warp per part (P * 32); the structured mode only uses the
+// first 8 * P of them (thread = list * P + part, so a warp works on 32 consecutive parts of one list)
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, int NY, int px, int py,
+    StripTable st, int* __restrict__ counts, const int* __restrict__ offsets,
+    const int* __restrict__ totals, int cap, int* __restrict__ ids, int* __restrict__ halos,
+    int* __restrict__ starts, DevScalars* sc)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (FILL) {
+        bool over = false;
+#pragma unroll
+        for (int l = 0; l < 8; l++)
+            over |= totals[l] > cap;
+        if (over) {
+            if (t == 0)
+                sc->overflow = 1;
+            return;
+        }
+    }
+    if (*st.always) {
+        const int me = (int)(t >> 5);
+        if (me < P)
+            neighbours_all_pairs<FILL>(bx, P, NX, NY, px, py, me, counts, offsets, cap, ids, halos, starts, sc);
+    } else {
+        // thread = list * Ppad + part with Ppad a multiple of 32: a warp works on 32 consecutive
+        // parts of ONE list (uniform control flow, coalesced box loads)
+        const int Ppad = (P + 31) & ~31;
+        if (t < 8LL * Ppad)
+            neighbours_structured<FILL>(bx, P, NX, NY, px, py, st, (int)(t / Ppad), (int)(t % Ppad), counts,
+                offsets, cap, ids, halos, starts, sc);
+    }
+}
+
 // exclusive scan of each of the 8 count lists (one CTA per list)
 __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, int P,
     int* __restrict__ offsets, int* __restrict__ totals)
 {
-    __shared__ int wsum[33];
+    __shared__ unsigned long long wsum64[33];
     const int l = blockIdx.x;
     const int* c = counts + (size_t)l * P;
-    int* o = offsets + (size_t)l * P;
-    const int chunk = (P + blockDim.x - 1) / blockDim.x;
-    const int b = min(P, (int)threadIdx.x * chunk), e = min(P, b + chunk);
-    int sum = 0;
-    for (int i = b; i < e; i++)
-        sum += c[i];
-    int total;
-    int run = block_exclusive_scan<int>(sum, &total, wsum);
-    for (int i = b; i < e; i++) {
-        o[i] = run;
-        run += c[i];
-    }
+    // writes P + 1 values; offsets has one spare slot after every list
+    const unsigned long long total = block_prefix<false>([&](int i) { return (unsigned)c[i]; }, P,
+        reinterpret_cast<unsigned*>(offsets) + (size_t)l * (P + 1), 0, wsum64);
     if (threadIdx.x == 0)
-        totals[l] = total;
+        totals[l] = (int)total;
 }
 
 // min / max of the part loads
