@@ -220,8 +220,10 @@ size_t max_dyn_smem(int device)
     return (size_t)v;
 }
 
-// K1 / K6 run as ONE wave: every CTA owns one 1024-column block and a contiguous row range sized so
-// that the whole grid is co-resident (no tail wave) and the per-CTA column atomics are paid once.
+// Rows per CTA of the mask scan.  Measured on B200 (scripts/kernel_probe.cu): many small CTAs beat
+// one fat wave (more independent load streams in flight, no tail), and the per-CTA epilogue of 1024
+// column atomics is cheap; 128 rows keeps the atomics at 8 per 1024 mask cells.  Smaller shards
+// (multi-GPU, small grids) step down so that the grid still covers the SMs a few times.
 template <typename K>
 int pick_rows_per_cta(K kernel, int rows, int gridx)
 {
@@ -230,11 +232,11 @@ int pick_rows_per_cta(K kernel, int rows, int gridx)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
         per_sm = 1;
-    const int slots = per_sm * sms;
-    const int gy = std::max(1, slots / std::max(gridx, 1));
-    int rpc = (rows + gy - 1) / gy;
-    rpc = ((rpc + 7) / 8) * 8;
-    return std::max(rpc, 8);
+    const long long want = 2LL * per_sm * sms; // CTAs for two full waves
+    int rpc = 128;
+    while (rpc > 8 && (long long)gridx * ((rows + rpc - 1) / rpc) < want)
+        rpc >>= 1;
+    return rpc;
 }
 
 // K7 + scans on whatever boxes / strips are in the tables
@@ -546,16 +548,8 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
 
     mark(0);
     // ---- K1: mask scan -----------------------------------------------------------------------
-    CUDA_TRY(h, cudaMemsetAsync(h->colcount.p, 0, sizeof(unsigned) * (NX + 4), s));
-    {
-        DevScalars init;
-        init.neg_ymin = INT_MIN;
-        init.ymax = -1;
-        init.changes = 0;
-        init.overflow = 0;
-        init.edge_cut = 0;
-        CUDA_TRY(h, cudaMemcpyAsync(h->sc.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
-    }
+    k_init<<<(NX + 4 + 255) / 256, 256, 0, s>>>(h->colcount.p, NX + 4, h->sc.p, h->loadmm.p);
+    launches++;
     const int gridx = (NG + 7) / 8;
     const bool vec = (NX % 4 == 0) && (((uintptr_t)h->d_mask) % 16 == 0);
     if (rows > 0) {
@@ -635,7 +629,7 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         const bool vecp = want_pid && (NX % 4 == 0) && (((uintptr_t)h->pid.p) % 16 == 0);
 #define LAUNCH_LABEL(V, W)                                                                         \
     do {                                                                                           \
-        const int rpc = 128; /* no per-CTA epilogue: many small CTAs keep more stores in flight */ \
+        const int rpc = 32; /* no per-CTA epilogue: many small CTAs keep more stores in flight */  \
         dim3 grid(gridx, (rows + rpc - 1) / rpc);                                                  \
         k_label<V, W><<<grid, 256, 0, s>>>(h->bits.p, NX, rows, h->y_begin, NB, rpc,               \
             h->strip_of_col.p, t.st.p0, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p);                  \
@@ -659,8 +653,6 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         launches++;
     }
     {
-        const long long init[2] = { LLONG_MAX, -1 };
-        CUDA_TRY(h, cudaMemcpyAsync(h->loadmm.p, init, sizeof init, cudaMemcpyHostToDevice, s));
         k_load_minmax<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(h->loads.p, P, h->loadmm.p);
         launches++;
     }

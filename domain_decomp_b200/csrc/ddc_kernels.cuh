@@ -152,36 +152,61 @@ __device__ __forceinline__ unsigned ocean_nibble(const int4& v)
         | ((unsigned)(v.w > 0) << 3);
 }
 
+constexpr int SCAN_STAGE_ROWS = 64; // bit-map rows staged in shared memory between flushes (power of 2)
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ mask, int NX, int rows,
     int y_begin, int NB, int rows_per_cta, uint8_t* __restrict__ bits, unsigned* __restrict__ colcount,
     DevScalars* __restrict__ sc)
 {
-    const int lane = lane_id();
-    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (g * 128 >= NX)
-        return; // whole warp leaves together
+    __shared__ __align__(16) uint8_t sbits[SCAN_STAGE_ROWS][128];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    // warps beyond the last 128-column group (last column block only) have no columns: they
+    // load nothing (clamped, masked addresses below) but take part in the CTA barriers
+    const int g = min(blockIdx.x * 8 + warp, NB / 16 - 1);
+    const bool warp_valid = blockIdx.x * 8 + warp < NB / 16;
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(rows, r0 + rows_per_cta);
     const int x = g * 128 + lane * 4;
     unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     int ylo = 0x7fffffff, yhi = -1;
-    uint8_t* brow = bits + (size_t)g * 16 + (lane >> 1);
 
     // VEC: out-of-range lanes (x >= NX, only in the last group) re-read the last valid 16 bytes of
-    // the row and are masked off below, so the main loop is branch-free: 8 unconditional loads.
+    // the row and are masked off below, so the main loop is branch-free.  The 8 rows of a batch
+    // are loaded as two halves of 4; the next half is always requested before the current one
+    // is consumed, so every lane keeps 4 to 8 independent 16-byte loads in flight at all times.
     const int xl = VEC ? min(x, NX - 4) : x;
-    const unsigned lane_valid = (VEC && x >= NX) ? 0u : 0xffffffffu;
+    const unsigned lane_valid = ((VEC && x >= NX) || !warp_valid) ? 0u : 0xffffffffu;
+    const size_t pitch4 = (size_t)NX >> 2;
+    int4 h0[4], h1[4];
+    const int4* pv = reinterpret_cast<const int4*>(mask + (size_t)r0 * NX + xl);
+    const bool vec_first = VEC && r0 + 8 <= r1;
+    if (vec_first) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            h0[k] = __ldcs(pv + k * pitch4);
+    }
     for (int r = r0; r < r1; r += 8) {
-        int4 v[8];
         const bool full = r + 8 <= r1;
+        unsigned packed = 0; // nibble k = the ocean flags of my 4 columns in row r + k
         if (VEC && full) {
             const int4* p = reinterpret_cast<const int4*>(mask + (size_t)r * NX + xl);
-            const size_t pitch4 = (size_t)NX >> 2;
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                v[k] = __ldcs(p + k * pitch4);
+            for (int k = 0; k < 4; k++)
+                h1[k] = __ldcs(p + (4 + k) * pitch4);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                packed |= ocean_nibble(h0[k]) << (4 * k);
+            if (r + 16 <= r1) { // first half of the next batch
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    h0[k] = __ldcs(p + (8 + k) * pitch4);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                packed |= ocean_nibble(h1[k]) << (16 + 4 * k);
         } else {
+            int4 v[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 v[k] = make_int4(0, 0, 0, 0);
@@ -201,11 +226,10 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
                     }
                 }
             }
-        }
-        unsigned packed = 0; // nibble k = the ocean flags of my 4 columns in row r + k
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            packed |= ocean_nibble(v[k]) << (4 * k);
+            for (int k = 0; k < 8; k++)
+                packed |= ocean_nibble(v[k]) << (4 * k);
+        }
         packed &= lane_valid;
         c0 += __popc(packed & 0x11111111u);
         c1 += __popc(packed & 0x22222222u);
@@ -215,11 +239,25 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
         const unsigned other = __shfl_down_sync(0xffffffffu, packed, 1);
         const unsigned even = (packed & 0x0f0f0f0fu) | ((other & 0x0f0f0f0fu) << 4); // rows 0,2,4,6
         const unsigned odd = ((packed >> 4) & 0x0f0f0f0fu) | (other & 0xf0f0f0f0u); // rows 1,3,5,7
+        // bit-map bytes go through shared memory so that the CTA writes whole 128-byte lines
         if (!(lane & 1)) {
+            uint8_t* sp = &sbits[(r - r0) & (SCAN_STAGE_ROWS - 1)][warp * 16 + (lane >> 1)];
 #pragma unroll
             for (int k = 0; k < 8; k++)
-                if (full || r + k < r1)
-                    brow[(size_t)(r + k) * NB] = (uint8_t)(((k & 1) ? odd : even) >> (8 * (k >> 1)));
+                sp[k * 128] = (uint8_t)(((k & 1) ? odd : even) >> (8 * (k >> 1)));
+        }
+        if ((((r - r0) + 8) & (SCAN_STAGE_ROWS - 1)) == 0 || r + 8 >= r1) {
+            // flush the staged rows [rs, r + 8) as 16-byte chunks, 8 chunks (one line) per row
+            const int rs = r0 + ((r - r0) & ~(SCAN_STAGE_ROWS - 1));
+            const int nr = min(r + 8, r1) - rs;
+            __syncthreads();
+            for (int i = threadIdx.x; i < nr * 8; i += blockDim.x) {
+                const int row = i >> 3, c = i & 7;
+                if (blockIdx.x * 8 + c < NB / 16)
+                    *reinterpret_cast<uint4*>(bits + (size_t)(rs + row) * NB + (size_t)blockIdx.x * 128 + c * 16)
+                        = *reinterpret_cast<const uint4*>(&sbits[row][c * 16]);
+            }
+            __syncthreads();
         }
         // rows of this batch that hold an ocean cell in my 128 columns
         const unsigned any = __reduce_or_sync(0xffffffffu, packed);
@@ -742,18 +780,22 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
     // `changes` only ever goes 0 -> 1: stop looking as soon as anyone has found a moved cell
     bool check = *reinterpret_cast<volatile int*>(&sc->changes) == 0;
 
+    // the bit-map bytes of the next batch are requested before the current batch is stored
+    unsigned nb[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        nb[k] = r0 + k < r1 ? (unsigned)__ldg(brow + (size_t)(r0 + k) * NB) : 0u;
     for (int r = r0; r < r1; r += 8) {
         const int y = y_begin + r;
         const int nrow = min(8, r1 - r);
         unsigned packed = 0; // nibble k = ocean flags of my 4 columns in row r + k
-        {
-            unsigned nb[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            packed |= ((nb[k] >> sh) & 15u) << (4 * k);
+        if (r + 8 < r1) {
 #pragma unroll
             for (int k = 0; k < 8; k++)
-                nb[k] = k < nrow ? (unsigned)__ldg(brow + (size_t)(r + k) * NB) : 0u;
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                packed |= ((nb[k] >> sh) & 15u) << (4 * k);
+                nb[k] = r + 8 + k < r1 ? (unsigned)__ldg(brow + (size_t)(r + 8 + k) * NB) : 0u;
         }
         const int ylast = y + nrow - 1;
         if (two && ylast < A.yend && ylast < B.yend) {
@@ -1134,6 +1176,25 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
         reinterpret_cast<unsigned*>(offsets) + (size_t)l * (P + 1), 0, wsum64);
     if (threadIdx.x == 0)
         totals[l] = (int)total;
+}
+
+// resets the per-call accumulators: column counts, scalars, load min / max (one launch instead of
+// a memset plus two host-to-device copies)
+__global__ void __launch_bounds__(256) k_init(unsigned* __restrict__ colcount, int n, DevScalars* __restrict__ sc,
+    long long* __restrict__ loadmm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        colcount[i] = 0u;
+    if (i == 0) {
+        sc->neg_ymin = (int)0x80000000;
+        sc->ymax = -1;
+        sc->changes = 0;
+        sc->overflow = 0;
+        sc->edge_cut = 0ull;
+        loadmm[0] = 0x7fffffffffffffffLL;
+        loadmm[1] = -1;
+    }
 }
 
 // min / max of the part loads
