@@ -289,7 +289,7 @@ def main():
     achieved = (4.0 * local_cells) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {
         "bound": "hbm", "kernel": kern[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": ncu_traffic(kern[dom], args.workload), "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": ncu_traffic(kern[dom], args.workload) if world == 1 else None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": 4 * local_cells, "kernel_ms": dom_ms,
         "pipeline": {"achieved": ALGO_BYTES_PER_CELL * cells / (ms_per_step * 1e-3) / 1e9,
                      "frac_of_aggregate_peak": ALGO_BYTES_PER_CELL * cells / (ms_per_step * 1e-3) / 1e9 / (peak * world),
