@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libddc_cuda.so")
 
 LEFT, RIGHT, BOTTOM, TOP = 0, 1, 2, 3
 EDGE_NAMES = ("left", "right", "bottom", "top")
-WANT_PID, WANT_NEIGHBOURS, PROFILE = 1, 2, 4
+WANT_PID, WANT_NEIGHBOURS, PROFILE, ASYNC = 1, 2, 4, 8
 NCCL_ID_BYTES = 128
 N_STAGES = 8
 STAGE_NAMES = ("mask_scan", "x_cuts", "strip_rows", "y_cuts", "label", "finalize", "neighbours", "total")

@@ -125,7 +125,6 @@ struct ddc_handle_s {
     DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx;
     DevBuf<DevScalars> sc;
     DevBuf<Plan> plan;
-    DevBuf<int4> sets; // 2 * P set records {lo, hi, plo, n}: list A, list B
     DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
     DevBuf<int> boxes; // x0 y0 ex ey, P each
     DevBuf<int> strip_of_col;
@@ -133,7 +132,13 @@ struct ddc_handle_s {
     DevBuf<int32_t> pid;
     DevBuf<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
     int nbr_cap = 0;
-    Plan h_plan {};
+    // the plan the launches were sized for, and what it was assumed for (see enqueue_partition)
+    int plan_nx = 0, plan_ny = 0, plan_P = 0, aix = 0, aiy = 0;
+    bool pending = false, profiled = false; // a step is enqueued but not yet validated
+    int last_flags = 0;
+    size_t xcuts_smem = 0, ycuts16_smem = 0, ycuts32_smem = 0; // dynamic smem opt-ins already made
+    cudaStream_t side_stream = nullptr; // speculative neighbour tables run beside the labelling
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int h_totals[8] = { 0 };
     bool totals_valid = false;
     Plan* pin_plan = nullptr; // pinned staging for the plan read-back
@@ -193,15 +198,12 @@ NaiveParams naive_params(int P, int NX, int NY)
 }
 
 struct Tables {
-    int4 *A, *B;
     StripTable st;
     BoxTable bx;
 };
 Tables tables(ddc_handle_t h, int P)
 {
     Tables t;
-    t.A = h->sets.p;
-    t.B = h->sets.p + P;
     int* q = h->strips.p;
     t.st.x0 = q;
     t.st.x1 = q + (P + 1);
@@ -257,11 +259,11 @@ int run_neighbours(ddc_handle_t h, int P, int nx, int ny, int px, int py)
     const int warps_per_cta = 8;
     const int grid = (std::max(P, 8) + warps_per_cta - 1) / warps_per_cta; // >= 8 * pad32(P) threads
     k_neighbours<false><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p, nullptr,
-        nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p);
-    k_scan_counts<<<8, 1024, 0, s>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p);
+        nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, nullptr, 0);
+    k_scan_counts<<<8, 1024, 0, s>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p, h->sc.p, nullptr, 0);
     k_neighbours<true><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p,
         h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
-        h->sc.p);
+        h->sc.p, nullptr, 0);
     h->stats.gpu_launches += 3;
     CUDA_TRY(h, cudaGetLastError());
     h->totals_valid = false;
@@ -292,7 +294,7 @@ int fetch_totals(ddc_handle_t h)
         const int grid = (std::max(h->nparts, 8) + 7) / 8;
         k_neighbours<true><<<grid, 256, 0, h->stream>>>(t.bx, h->nparts, h->nx, h->ny, h->px, h->py, t.st,
             h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p,
-            h->nbr_halos.p, h->nbr_starts.p, h->sc.p);
+            h->nbr_halos.p, h->nbr_starts.p, h->sc.p, nullptr, 0);
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaMemcpyAsync(&hs, h->sc.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -352,6 +354,15 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     CREATE_TRY(cudaSetDevice(device));
     CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    {
+        // highest priority: the small neighbour kernels must get SM slots while the labelling
+        // kernel still has tens of thousands of CTAs queued
+        int least = 0, greatest = 0;
+        CREATE_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CREATE_TRY(cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, greatest));
+    }
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CREATE_TRY(cudaMallocHost((void**)&h->pin_plan, sizeof(Plan)));
     for (auto& ev : h->ev)
         CREATE_TRY(cudaEventCreate(&ev));
@@ -386,6 +397,8 @@ int ddc_destroy(ddc_handle_t h)
         return DDC_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->side_stream)
+        cudaStreamSynchronize(h->side_stream);
     if (h->comm)
         g_nccl.CommDestroy(h->comm);
     h->mask_own.release();
@@ -397,7 +410,6 @@ int ddc_destroy(ddc_handle_t h)
     h->ypfx.release();
     h->sc.release();
     h->plan.release();
-    h->sets.release();
     h->strips.release();
     h->boxes.release();
     h->strip_of_col.release();
@@ -415,6 +427,12 @@ int ddc_destroy(ddc_handle_t h)
     if (h->ev_ok)
         for (auto& ev : h->ev)
             cudaEventDestroy(ev);
+    if (h->ev_fork)
+        cudaEventDestroy(h->ev_fork);
+    if (h->ev_join)
+        cudaEventDestroy(h->ev_join);
+    if (h->side_stream)
+        cudaStreamDestroy(h->side_stream);
     if (h->own_stream)
         cudaStreamDestroy(h->own_stream);
     delete h;
@@ -494,10 +512,17 @@ int ddc_set_mask_host(ddc_handle_t h, const int32_t* rows, int nx, int ny, int y
     return DDC_OK;
 }
 
+namespace {
+int validate(ddc_handle_t h);
+}
+
 int ddc_synchronize(ddc_handle_t h)
 {
     if (!h)
         return DDC_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->partitioned && h->pending)
+        return validate(h); // waits for the step and settles the plan
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DDC_OK;
 }
@@ -505,14 +530,30 @@ int ddc_synchronize(ddc_handle_t h)
 // ------------------------------------------------------------------------------------------------
 // the hot path
 // ------------------------------------------------------------------------------------------------
-int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
+namespace {
+// The numbers of x / y levels depend on the bounding box of the dots, i.e. on the data, and they
+// size the launches after K2 (strip count, row-count buffers, the all-gather).  Instead of reading
+// the plan back in the middle of the pipeline, the host ASSUMES a plan -- the one of the previous
+// call on the same geometry, else the one of a full-extent bounding box -- K2 compares it with the
+// real one, and on a mismatch every later kernel does nothing; the step is then run again with the
+// real plan (validate(), at the end of ddc_partition or, with DDC_ASYNC, in the first getter).
+void guess_plan(int P, int NX, int NY, int* ix, int* iy)
 {
-    if (!h)
-        return DDC_ERR_ARG;
-    if (!h->mask_set)
-        return fail(h, DDC_ERR_STATE, "ddc_partition: no mask set");
-    if (nparts < 1)
-        return fail(h, DDC_ERR_ARG, "ddc_partition: nparts must be >= 1");
+    double wx = (double)(NX - 1), wy = (double)(NY - 1);
+    *ix = *iy = 0;
+    for (int t = P; t > 1; t = (t + 1) / 2) {
+        if (wx > wy) {
+            (*ix)++;
+            wx /= 2.0;
+        } else {
+            (*iy)++;
+            wy /= 2.0;
+        }
+    }
+}
+
+int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
+{
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int P = nparts, NX = h->nx, NY = h->ny, rows = h->y_count, G = h->nranks;
     const int NG = (NX + 127) / 128;
@@ -531,11 +572,25 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             cudaEventRecord(h->ev[i], s);
     };
 
+    // the assumed plan
+    if (h->plan_nx != NX || h->plan_ny != NY || h->plan_P != P) {
+        guess_plan(P, NX, NY, &h->aix, &h->aiy);
+        h->plan_nx = NX;
+        h->plan_ny = NY;
+        h->plan_P = P;
+    }
+    const int aix = h->aix, aiy = h->aiy;
+    const int Scap = (int)std::min<long long>(P, 1LL << std::min(aix, 30)); // strips after aix levels
+    const bool ycuts = aiy > 0 && P > 1;
+    const bool narrow = NX < 65536; // a strip row holds < 65536 cells: 16-bit row counts
+
     // buffers
     const int NB = NG * 16; // bytes per bit-map row
+    const int yr_off = (NX + 3) & ~3; // per-rank y-range pairs follow the column counts
+    const int ncol = yr_off + 2 * G;
+    const int Rmax = (NY + G - 1) / G;
     CUDA_TRY(h, h->bits.ensure((size_t)std::max(rows, 1) * NB));
-    CUDA_TRY(h, h->colcount.ensure(NX + 4));
-    CUDA_TRY(h, h->sets.ensure((size_t)2 * P));
+    CUDA_TRY(h, h->colcount.ensure(ncol));
     CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
     CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
     CUDA_TRY(h, h->strip_of_col.ensure(NX));
@@ -543,87 +598,130 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     CUDA_TRY(h, h->loadmm.ensure(2));
     if (want_pid)
         CUDA_TRY(h, h->pid.ensure((size_t)std::max(rows, 1) * NX));
+    const size_t rc_elems = (size_t)Scap * Rmax; // per rank
+    const size_t rc_words = narrow ? (rc_elems + 1) / 2 : rc_elems; // 32-bit words per rank
+    const size_t rank_stride = narrow ? rc_words * 2 : rc_words; // elements between two ranks' blocks
+    if (ycuts) {
+        CUDA_TRY(h, h->rowcount.ensure(rc_words + 4));
+        if (G > 1)
+            CUDA_TRY(h, h->rowcount_all.ensure(rc_words * G + 4));
+    }
+    const size_t xneed = sizeof(unsigned) * ((size_t)NX + 1), yneed = sizeof(unsigned) * ((size_t)NY + 1);
+    const size_t lim = max_dyn_smem(h->device);
+    const int x_smem = xneed + 1024 <= lim, y_smem = yneed + 1024 <= lim;
+    const int ygrid = std::max(1, std::min(Scap, 148 * 2));
+    if (!x_smem)
+        CUDA_TRY(h, h->colpfx.ensure((size_t)NX + 1));
+    if (ycuts && !y_smem)
+        CUDA_TRY(h, h->ypfx.ensure((size_t)ygrid * (((size_t)NY + 1 + 3) & ~(size_t)3)));
+    if (want_nbr) {
+        const int cap = 3 * P + 64;
+        CUDA_TRY(h, h->nbr_counts.ensure((size_t)8 * P));
+        CUDA_TRY(h, h->nbr_offsets.ensure((size_t)8 * (P + 1)));
+        CUDA_TRY(h, h->nbr_totals.ensure(8));
+        if (h->nbr_cap < cap) {
+            CUDA_TRY(h, h->nbr_ids.ensure((size_t)8 * cap));
+            CUDA_TRY(h, h->nbr_halos.ensure((size_t)8 * cap));
+            CUDA_TRY(h, h->nbr_starts.ensure((size_t)8 * cap));
+            h->nbr_cap = cap;
+        }
+    }
     Tables t = tables(h, P);
     const NaiveParams nv = naive_params(P, NX, NY);
 
     mark(0);
     // ---- K1: mask scan -----------------------------------------------------------------------
-    k_init<<<(NX + 4 + 255) / 256, 256, 0, s>>>(h->colcount.p, NX + 4, h->sc.p, h->loadmm.p);
+    k_init<<<(ncol + 255) / 256, 256, 0, s>>>(h->colcount.p, ncol, yr_off, h->rank, h->sc.p, h->loadmm.p);
     launches++;
     const int gridx = (NG + 7) / 8;
     const bool vec = (NX % 4 == 0) && (((uintptr_t)h->d_mask) % 16 == 0);
+    int* yr = reinterpret_cast<int*>(h->colcount.p + yr_off + 2 * h->rank);
     if (rows > 0) {
         const int rpc = vec ? pick_rows_per_cta(k_scan_mask<true>, rows, gridx)
                             : pick_rows_per_cta(k_scan_mask<false>, rows, gridx);
         dim3 grid(gridx, (rows + rpc - 1) / rpc);
         if (vec)
             k_scan_mask<true><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
-                h->colcount.p, h->sc.p);
+                h->colcount.p, yr);
         else
             k_scan_mask<false><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
-                h->colcount.p, h->sc.p);
+                h->colcount.p, yr);
         launches++;
     }
-    if (G > 1) { // column histogram and dot y-range: the first exchange step
-        NCCL_TRY(h, g_nccl.GroupStart());
-        NCCL_TRY(h, g_nccl.AllReduce(h->colcount.p, h->colcount.p, NX, nccl_Uint32, nccl_Sum, h->comm, s));
-        NCCL_TRY(h, g_nccl.AllReduce(&h->sc.p->neg_ymin, &h->sc.p->neg_ymin, 2, nccl_Int32, nccl_Max, h->comm, s));
-        NCCL_TRY(h, g_nccl.GroupEnd());
-    }
+    if (G > 1) // the first exchange step: column histogram and every rank's dot y-range in one sum
+        NCCL_TRY(h, g_nccl.AllReduce(h->colcount.p, h->colcount.p, ncol, nccl_Uint32, nccl_Sum, h->comm, s));
     mark(1);
     // ---- K2: x cuts ----------------------------------------------------------------------------
-    {
-        const size_t need = sizeof(unsigned) * ((size_t)NX + 1);
-        const size_t lim = max_dyn_smem(h->device);
-        const int use_smem = need + 1024 <= lim;
-        if (!use_smem)
-            CUDA_TRY(h, h->colpfx.ensure((size_t)NX + 1));
-        if (use_smem)
-            CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        k_xcuts<<<1, 1024, use_smem ? need : 0, s>>>(h->colcount.p, NX, NY, P, h->colpfx.p, use_smem,
-            h->sc.p, h->plan.p, t.A, t.B, t.st, t.bx, h->loads.p, h->strip_of_col.p);
-        launches++;
+    if (x_smem && h->xcuts_smem < xneed) {
+        CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xneed));
+        h->xcuts_smem = xneed;
     }
-    // the plan decides buffer sizes and the all-gather count: read it back (one tiny D2H + sync)
-    CUDA_TRY(h, cudaMemcpyAsync(h->pin_plan, h->plan.p, sizeof(Plan), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaStreamSynchronize(s));
-    CUDA_TRY(h, cudaGetLastError());
-    h->h_plan = *h->pin_plan;
-    const Plan& pl = h->h_plan;
+    k_xcuts<<<1, 1024, x_smem ? xneed : 0, s>>>(h->colcount.p, NX, NY, P, h->colpfx.p, x_smem,
+        reinterpret_cast<const int*>(h->colcount.p + yr_off), G, aix, aiy, h->plan.p, t.st, t.bx,
+        h->loads.p, h->strip_of_col.p);
+    launches++;
     mark(2);
     // ---- K3 + K4: strip row counts, y cuts -----------------------------------------------------
-    if (pl.iy > 0 && P > 1) {
-        const int S = pl.S;
-        const int Rmax = (NY + G - 1) / G;
-        CUDA_TRY(h, h->rowcount.ensure((size_t)S * Rmax));
+    if (ycuts) {
         if (rows < Rmax) // short last shard: its padding rows must read as empty
-            CUDA_TRY(h, cudaMemsetAsync(h->rowcount.p, 0, sizeof(unsigned) * (size_t)S * Rmax, s));
+            CUDA_TRY(h, cudaMemsetAsync(h->rowcount.p, 0, sizeof(unsigned) * rc_words, s));
         if (rows > 0) {
-            dim3 grid((rows + 31) / 32, (S + 7) / 8);
-            k_strip_rows<<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0, S,
-                h->rowcount.p, Rmax);
+            dim3 grid((rows + 31) / 32, (Scap + 7) / 8);
+            if (narrow)
+                k_strip_rows<uint16_t><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
+                    h->plan.p, Scap, reinterpret_cast<uint16_t*>(h->rowcount.p), Rmax);
+            else
+                k_strip_rows<unsigned><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
+                    h->plan.p, Scap, h->rowcount.p, Rmax);
             launches++;
         }
         const unsigned* rc_all = h->rowcount.p;
         if (G > 1) { // the second exchange step
-            CUDA_TRY(h, h->rowcount_all.ensure((size_t)G * S * Rmax));
-            NCCL_TRY(h, g_nccl.AllGather(h->rowcount.p, h->rowcount_all.p, (size_t)S * Rmax, nccl_Uint32, h->comm, s));
+            NCCL_TRY(h, g_nccl.AllGather(h->rowcount.p, h->rowcount_all.p, rc_words, nccl_Uint32, h->comm, s));
             rc_all = h->rowcount_all.p;
         }
         mark(3);
-        const size_t need = sizeof(unsigned) * ((size_t)NY + 1);
-        const int use_smem = need + 1024 <= max_dyn_smem(h->device);
-        const int grid = std::min(S, 148 * 2);
-        if (!use_smem)
-            CUDA_TRY(h, h->ypfx.ensure((size_t)grid * (NY + 1)));
-        if (use_smem)
-            CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        k_ycuts<<<grid, 1024, use_smem ? need : 0, s>>>(rc_all, G, Rmax, NY, pl.iy, t.st, t.A, t.B,
-            h->ypfx.p, use_smem, t.bx, h->loads.p, h->plan.p);
+        if (narrow) {
+            if (y_smem && h->ycuts16_smem < yneed) {
+                CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed));
+                h->ycuts16_smem = yneed;
+            }
+            k_ycuts<uint16_t><<<ygrid, 1024, y_smem ? yneed : 0, s>>>(reinterpret_cast<const uint16_t*>(rc_all),
+                rank_stride, Rmax, NY, t.st, h->ypfx.p, y_smem, t.bx, h->loads.p, h->plan.p);
+        } else {
+            if (y_smem && h->ycuts32_smem < yneed) {
+                CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed));
+                h->ycuts32_smem = yneed;
+            }
+            k_ycuts<unsigned><<<ygrid, 1024, y_smem ? yneed : 0, s>>>(rc_all, rank_stride, Rmax, NY, t.st,
+                h->ypfx.p, y_smem, t.bx, h->loads.p, h->plan.p);
+        }
         launches++;
     } else
         mark(3);
     mark(4);
+    // ---- K7 (speculative): the neighbour tables of the RCB boxes are built on a second stream while
+    //      K6 labels the cells; they are final unless K6 finds `changes == 0` (see the redo below)
+    h->nparts = P;
+    h->px = px;
+    h->py = py;
+    const int ngrid = (std::max(P, 8) + 7) / 8; // >= 8 * pad32(P) threads
+    auto neighbours = [&](cudaStream_t q, int redo) {
+        k_neighbours<false><<<ngrid, 256, 0, q>>>(t.bx, P, NX, NY, px, py, t.st, h->nbr_counts.p, nullptr,
+            nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p, redo);
+        k_scan_counts<<<8, 1024, 0, q>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p, h->sc.p,
+            h->plan.p, redo);
+        k_neighbours<true><<<ngrid, 256, 0, q>>>(t.bx, P, NX, NY, px, py, t.st, h->nbr_counts.p,
+            h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
+            h->sc.p, h->plan.p, redo);
+        launches += 3;
+    };
+    if (want_nbr) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_fork, s));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        neighbours(h->side_stream, 0);
+        CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+    }
     // ---- K6: labels + `changes` -----------------------------------------------------------------
     if (rows > 0 && (P > 1 || want_pid)) {
         const bool vecp = want_pid && (NX % 4 == 0) && (((uintptr_t)h->pid.p) % 16 == 0);
@@ -632,7 +730,7 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         const int rpc = 32; /* no per-CTA epilogue: many small CTAs keep more stores in flight */  \
         dim3 grid(gridx, (rows + rpc - 1) / rpc);                                                  \
         k_label<V, W><<<grid, 256, 0, s>>>(h->bits.p, NX, rows, h->y_begin, NB, rpc,               \
-            h->strip_of_col.p, t.st.p0, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p);                  \
+            h->strip_of_col.p, t.st.p0, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p, h->plan.p);       \
     } while (0)
         if (want_pid) {
             if (vecp)
@@ -648,45 +746,88 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         NCCL_TRY(h, g_nccl.AllReduce(&h->sc.p->changes, &h->sc.p->changes, 1, nccl_Int32, nccl_Max, h->comm, s));
     mark(5);
     // ---- K5: naive blocks when nothing moved; load statistics -----------------------------------
-    if (P > 1) {
-        k_finalize<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(P, NX, NY, nv, h->sc.p, t.st, t.bx);
-        launches++;
-    }
-    {
-        k_load_minmax<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(h->loads.p, P, h->loadmm.p);
-        launches++;
-    }
+    if (want_nbr)
+        CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0)); // K5 rewrites the boxes K7 is reading
+    k_finalize<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(P, NX, NY, nv, h->sc.p, h->plan.p, t.st, t.bx,
+        h->loads.p, h->loadmm.p);
+    launches++;
     mark(6);
-    // ---- K7: neighbours and halos ---------------------------------------------------------------
-    h->nparts = P;
-    h->px = px;
-    h->py = py;
-    h->stats.gpu_launches = launches;
+    // ---- K7 again, only if the naive blocks replaced the RCB boxes (the kernels return at once otherwise)
     if (want_nbr) {
-        int rc = run_neighbours(h, P, NX, NY, px, py);
-        if (rc)
-            return rc;
+        neighbours(s, 1);
+        h->have_nbr = true;
     }
     mark(7);
+    CUDA_TRY(h, cudaMemcpyAsync(h->pin_plan, h->plan.p, sizeof(Plan), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaGetLastError());
 
+    h->stats.gpu_launches = launches;
     h->stats.nx = NX;
     h->stats.ny = NY;
     h->stats.nparts = P;
+    h->have_pid = want_pid;
+    h->last_flags = flags;
+    h->profiled = profile;
+    h->partitioned = true;
+    h->pending = true;
+    return DDC_OK;
+}
+
+// wait for the step, check the assumed plan against the real one, run the step again if they differ
+int validate(ddc_handle_t h)
+{
+    if (!h->pending)
+        return DDC_OK;
+    for (int attempt = 0;; attempt++) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        h->pending = false;
+        const Plan& pl = *h->pin_plan;
+        if (!pl.mismatch)
+            break;
+        if (attempt >= 2) {
+            h->partitioned = false;
+            return fail(h, DDC_ERR_STATE, "the RCB plan did not settle (x/y levels %d/%d)", pl.ix, pl.iy);
+        }
+        h->aix = pl.ix;
+        h->aiy = pl.iy;
+        const int launches = h->stats.gpu_launches;
+        int rc = enqueue_partition(h, h->nparts, h->px, h->py, h->last_flags);
+        if (rc) {
+            h->partitioned = false;
+            return rc;
+        }
+        h->stats.gpu_launches += launches;
+    }
+    const Plan& pl = *h->pin_plan;
     h->stats.nlev = pl.nlev;
     h->stats.n_xlev = pl.ix;
     h->stats.n_ylev = pl.iy;
     h->stats.nstrips = pl.S;
     h->stats.n_ocean = pl.W;
-    h->have_pid = want_pid;
-    h->partitioned = true;
-    if (profile) {
-        CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (h->profiled) {
         for (int i = 0; i < 7; i++)
             cudaEventElapsedTime(&h->stats.stage_ms[i], h->ev[i], h->ev[i + 1]);
         cudaEventElapsedTime(&h->stats.stage_ms[7], h->ev[0], h->ev[7]);
     }
     return DDC_OK;
+}
+} // namespace
+
+int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
+{
+    if (!h)
+        return DDC_ERR_ARG;
+    if (!h->mask_set)
+        return fail(h, DDC_ERR_STATE, "ddc_partition: no mask set");
+    if (nparts < 1)
+        return fail(h, DDC_ERR_ARG, "ddc_partition: nparts must be >= 1");
+    // (an earlier DDC_ASYNC step that nobody looked at is simply superseded)
+    int rc = enqueue_partition(h, nparts, px, py, flags);
+    if (rc)
+        return rc;
+    if (flags & DDC_ASYNC)
+        return DDC_OK;
+    return validate(h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -697,7 +838,9 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         return DDC_ERR_ARG;                                                                        \
     if (!h->partitioned)                                                                           \
         return fail(h, DDC_ERR_STATE, "%s: call ddc_partition() first", __func__);                 \
-    CUDA_TRY(h, cudaSetDevice(h->device))
+    CUDA_TRY(h, cudaSetDevice(h->device));                                                         \
+    if (int vrc_ = validate(h))                                                                    \
+        return vrc_
 
 int ddc_get_boxes(ddc_handle_t h, int32_t* x0, int32_t* y0, int32_t* ex, int32_t* ey)
 {
@@ -812,7 +955,7 @@ int ddc_get_stats(ddc_handle_t h, ddc_stats* out)
     Plan pl;
     CUDA_TRY(h, cudaMemcpyAsync(&hs, h->sc.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(mm, h->loadmm.p, sizeof mm, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(&pl, h->plan.p, sizeof pl, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&pl, h->plan.p, sizeof pl, cudaMemcpyDeviceToHost, h->stream)); // iters: K4 adds late
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->stats.changes = h->nparts > 1 ? hs.changes : 0;
     h->stats.load_min = mm[0];
@@ -837,7 +980,6 @@ int ddc_neighbours_from_boxes(ddc_handle_t h, int nparts, int nx, int ny, const 
     cudaStream_t s = h->stream;
     CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
     CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
-    CUDA_TRY(h, h->sets.ensure((size_t)2 * P));
     Tables t = tables(h, P);
     const int32_t* src[4] = { x0, y0, ex, ey };
     for (int i = 0; i < 4; i++)
@@ -851,8 +993,6 @@ int ddc_neighbours_from_boxes(ddc_handle_t h, int nparts, int nx, int ny, const 
     CUDA_TRY(h, cudaMemcpyAsync(t.st.S, &one, sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(t.st.always, &one, sizeof(int), cudaMemcpyHostToDevice, s));
     DevScalars init;
-    init.neg_ymin = INT_MIN;
-    init.ymax = -1;
     init.changes = 1;
     init.overflow = 0;
     init.edge_cut = 0;
@@ -866,6 +1006,7 @@ int ddc_neighbours_from_boxes(ddc_handle_t h, int nparts, int nx, int ny, const 
     h->py = py;
     h->mask_set = false; // the mask (if any) has to be set again before the next ddc_partition
     h->d_mask = nullptr;
+    h->pending = false;
     int rc = run_neighbours(h, P, nx, ny, px, py);
     if (rc)
         return rc;

@@ -28,8 +28,6 @@
 namespace ddc {
 
 struct DevScalars {
-    int neg_ymin; // -(smallest row holding an ocean cell); max-reduced
-    int ymax; // largest row holding an ocean cell, -1 if none
     int changes; // any ocean cell whose RCB part differs from its naive block
     int overflow; // neighbour lists did not fit their capacity
     unsigned long long edge_cut; // sum of interior halo lengths
@@ -40,7 +38,8 @@ struct Plan { // written by K2, read back by the host
     int xmin, xmax, ymin, ymax;
     long long W;
     int iters; // median iterations (x levels; K4 adds its own atomically)
-    int pad;
+    int mismatch; // (ix, iy) differ from what the host assumed when it sized the launches: the
+                  // kernels after K2 do nothing and the host runs the step again with the real plan
 };
 
 struct NaiveParams { // Grid.cpp:150-166
@@ -137,6 +136,59 @@ __device__ inline unsigned long long block_prefix(F src, int n, unsigned* dst, i
     return carry;
 }
 
+// Same result as block_prefix<false> (dst[i] = sum of the first i elements, n + 1 outputs, 32-bit
+// sums), but every thread owns E CONSECUTIVE elements: a 1024-thread block covers 1024 * E elements
+// with ONE block scan instead of one per 4096, which is what the latency of the cut kernels is made
+// of.  load(i0, v) fills v[k] = element i0 + k (0 beyond n); dst may be shared or global memory.
+template <int E, typename F>
+__device__ inline unsigned block_prefix_wide(F load, int n, unsigned* dst, unsigned* wsum /* >= 33 */)
+{
+    static_assert(E % 4 == 0, "E must be a multiple of 4");
+    unsigned carry = 0;
+    const int tile = blockDim.x * E;
+    for (int base = 0; base < n; base += tile) {
+        const int i0 = base + threadIdx.x * E;
+        unsigned v[E];
+        if (i0 < n)
+            load(i0, v);
+        else {
+#pragma unroll
+            for (int k = 0; k < E; k++)
+                v[k] = 0u;
+        }
+        unsigned sum = 0;
+#pragma unroll
+        for (int k = 0; k < E; k++)
+            sum += v[k];
+        unsigned total;
+        unsigned run = carry + block_exclusive_scan<unsigned>(sum, &total, wsum);
+        if (i0 + E <= n && ((uintptr_t)(dst + i0) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < E / 4; q++) {
+                uint4 o;
+                o.x = run;
+                o.y = o.x + v[4 * q];
+                o.z = o.y + v[4 * q + 1];
+                o.w = o.z + v[4 * q + 2];
+                run = o.w + v[4 * q + 3];
+                *reinterpret_cast<uint4*>(dst + i0 + 4 * q) = o;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                if (i0 + k < n)
+                    dst[i0 + k] = run;
+                run += v[k];
+            }
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0)
+        dst[n] = carry;
+    __syncthreads();
+    return carry;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: mask scan
 // ------------------------------------------------------------------------------------------------
@@ -157,7 +209,7 @@ constexpr int SCAN_STAGE_ROWS = 64; // bit-map rows staged in shared memory betw
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ mask, int NX, int rows,
     int y_begin, int NB, int rows_per_cta, uint8_t* __restrict__ bits, unsigned* __restrict__ colcount,
-    DevScalars* __restrict__ sc)
+    int* __restrict__ yr /* this rank's {-(first ocean row), last ocean row}, max-reduced */)
 {
     __shared__ __align__(16) uint8_t sbits[SCAN_STAGE_ROWS][128];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -276,10 +328,10 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
         atomicAdd(colcount + x + 3, c3);
     if (lane == 0 && yhi >= 0) {
         const int ny0 = -(y_begin + ylo), y1 = y_begin + yhi;
-        if (ny0 > sc->neg_ymin)
-            atomicMax(&sc->neg_ymin, ny0);
-        if (y1 > sc->ymax)
-            atomicMax(&sc->ymax, y1);
+        if (ny0 > yr[0])
+            atomicMax(&yr[0], ny0);
+        if (y1 > yr[1])
+            atomicMax(&yr[1], y1);
     }
 }
 
@@ -432,42 +484,45 @@ __device__ inline int median_boundary(const unsigned* pfx, int c0, int c1, int n
     return U; // policy Q2 (U >= 0 because Wn > 0)
 }
 
-// One RCB level over a compact, order-preserving list of sets.  A set is {lo, hi, plo, n}: the cell
-// range [lo, hi) along the cut dimension and the parts [plo, plo + n) it still has to produce.
-// Every set with n > 1 is split by the weighted median into two children, sets with n == 1 are
-// copied; the output list keeps ascending part order (children positions come from a block scan),
-// so after the last level the list IS the strip table / the y-sorted part list.
-// All threads of the block must call it.  Returns the length of the output list.
-__device__ inline int rcb_level(const unsigned* pfx, const int4* __restrict__ in, int nin, int4* __restrict__ out,
-    int* iters, int* wsum32 /* >= 33 */)
+// The RCB recursion without level barriers.  A set is the cell range [lo, hi) along the cut
+// dimension plus the parts [plo, plo + n) it still has to produce; a set with n > 1 is split by the
+// weighted median into a lower child with ceil(n / 2) parts (Zoltan_Divide_Machine) and an upper
+// child with the rest, a set with n == 1 is final.  Because a set of n parts has min(n, 2^l) leaves
+// l levels further down (the part counts of one level differ by at most one), the path from the root
+// to the k-th leaf can be walked WITHOUT knowing the other branches: every thread walks the path
+// of its own leaf and evaluates the medians along it.  Threads whose paths share a set evaluate the
+// same median redundantly (same instructions, same result), nothing is exchanged, and no thread
+// waits for the slowest median of a level -- Zoltan's interpolation search needs 2-3 iterations on
+// average but tens for an occasional set, and with per-level barriers every level paid for its worst.
+struct RcbSet {
+    int lo, hi, plo, n;
+};
+__device__ __forceinline__ int leaves_below(int n, int levels)
 {
-    int carry = 0;
-    for (int base = 0; base < nin; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
-        int nout = 0;
-        if (i < nin) {
-            a = in[i];
-            nout = 1;
-            if (a.w > 1) {
-                // Zoltan_Divide_Machine: the lower child gets ceil(n / 2) parts
-                const int nlo = (a.w - 1) / 2 + 1;
-                const int cut = median_boundary(pfx, a.x, a.y - 1, nlo, a.w, iters);
-                b = make_int4(cut, a.y, a.z + nlo, a.w - nlo);
-                a = make_int4(a.x, cut, a.z, nlo);
-                nout = 2;
-            }
+    return levels >= 31 ? n : min(n, 1 << levels);
+}
+// walk `levels` levels down from `set` towards leaf number k (0-based among the leaves below
+// `set`); iterations of a median are counted by the thread whose leaf is the first of its upper child
+__device__ inline RcbSet rcb_walk(const unsigned* pfx, RcbSet set, int levels, int k, int* iters)
+{
+    for (int l = levels; l > 0 && set.n > 1; l--) {
+        const int nlo = (set.n - 1) / 2 + 1;
+        int it = 0;
+        const int cut = median_boundary(pfx, set.lo, set.hi - 1, nlo, set.n, &it);
+        const int below = leaves_below(nlo, l - 1);
+        if (k < below) {
+            set.hi = cut;
+            set.n = nlo;
+        } else {
+            if (k == below)
+                *iters += it;
+            k -= below;
+            set.lo = cut;
+            set.plo += nlo;
+            set.n -= nlo;
         }
-        int total;
-        const int pos = carry + block_exclusive_scan<int>(nout, &total, wsum32);
-        if (nout >= 1)
-            out[pos] = a;
-        if (nout == 2)
-            out[pos + 1] = b;
-        carry += total;
     }
-    __syncthreads();
-    return carry;
+    return set;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -487,20 +542,42 @@ struct BoxTable { // final boxes, SoA
     int* ey;
 };
 
-// dynamic shared memory: (NX + 1) unsigned when use_smem
-__global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ colcount, int NX, int NY,
-    int P, unsigned* pfx_g, int use_smem, const DevScalars* __restrict__ sc, Plan* plan, int4* listA,
-    int4* listB, StripTable st, BoxTable bx, long long* loads, int* strip_of_col)
+constexpr int PFX_E = 32; // elements per thread of the wide prefix scans (1024 threads: 32768 per tile)
+
+// 32 consecutive unsigned counts, vector loads when the chunk is whole and 16-byte aligned
+__device__ __forceinline__ void load_counts_u32(const unsigned* __restrict__ src, int i0, int n, unsigned (&v)[PFX_E])
 {
-    extern __shared__ unsigned smem_dyn[];
-    __shared__ unsigned long long wsum64[33];
-    __shared__ int wsum32[33];
+    if (i0 + PFX_E <= n && ((uintptr_t)(src + i0) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < PFX_E / 4; q++) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(src + i0) + q);
+            v[4 * q] = t.x;
+            v[4 * q + 1] = t.y;
+            v[4 * q + 2] = t.z;
+            v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < PFX_E; k++)
+            v[k] = i0 + k < n ? __ldg(src + i0 + k) : 0u;
+    }
+}
+
+// dynamic shared memory: (NX + 1) unsigned when use_smem.  yr_all: G pairs {-(first ocean row),
+// last ocean row}, one per rank (summed into place by the all-reduce of the column counts).
+// aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
+__global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ colcount, int NX, int NY,
+    int P, unsigned* pfx_g, int use_smem, const int* __restrict__ yr_all, int G, int aix, int aiy, Plan* plan,
+    StripTable st, BoxTable bx, long long* loads, int* strip_of_col)
+{
+    extern __shared__ __align__(16) unsigned smem_dyn[];
+    __shared__ unsigned wsum[33];
     __shared__ int s_ix, s_iters;
     unsigned* pfx = use_smem ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
 
     // 1. pfx[i] = ocean cells in columns [0, i)
-    block_prefix<false>([&](int i) { return colcount[i]; }, NX, pfx, 0, wsum64);
+    block_prefix_wide<PFX_E>([&](int i0, unsigned (&v)[PFX_E]) { load_counts_u32(colcount, i0, NX, v); }, NX, pfx, wsum);
 
     // 2. the plan: bounding box of all dots -> preset direction of every level
     if (tid == 0) {
@@ -509,8 +586,13 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
         if (W > 0) {
             xmin = first_nonempty(pfx, 0, NX - 1);
             xmax = last_nonempty(pfx, 0, NX - 1);
-            ymin = -sc->neg_ymin;
-            ymax = sc->ymax;
+            int a = (int)0x80000000, b = -1;
+            for (int g = 0; g < G; g++) {
+                a = max(a, yr_all[2 * g]);
+                b = max(b, yr_all[2 * g + 1]);
+            }
+            ymin = -a;
+            ymax = b;
         }
         double wx = (double)(xmax - xmin), wy = (double)(ymax - ymin);
         int nlev = 0;
@@ -534,62 +616,60 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
         plan->ymin = ymin;
         plan->ymax = ymax;
         plan->W = W;
+        plan->mismatch = (ix != aix || iy != aiy) ? 1 : 0;
         s_ix = ix;
         s_iters = 0;
-        listA[0] = make_int4(0, NX, 0, P); // the root set
     }
     __syncthreads();
 
-    // 3. the x levels
+    // 3. the x levels: thread i walks to strip i
     const int ix = s_ix;
+    const int nstrips = leaves_below(P, ix);
     int my_iters = 0;
-    int4 *cur = listA, *nxt = listB;
-    int ncur = 1;
-    for (int l = 0; l < ix; l++) {
-        ncur = rcb_level(pfx, cur, ncur, nxt, &my_iters, wsum32);
-        int4* t = cur;
-        cur = nxt;
-        nxt = t;
+    for (int i = tid; i < nstrips; i += blockDim.x) {
+        const RcbSet root = { 0, NX, 0, P };
+        const RcbSet r = rcb_walk(pfx, root, ix, i, &my_iters);
+        // 4. the strip table, in ascending part order
+        st.x0[i] = r.lo;
+        st.x1[i] = r.hi;
+        st.p0[i] = r.plo;
+        if (r.n == 1) { // a leaf already: uncut in y
+            bx.x0[r.plo] = r.lo;
+            bx.ex[r.plo] = r.hi - r.lo;
+            bx.y0[r.plo] = 0;
+            bx.ey[r.plo] = NY;
+            loads[r.plo] = (long long)hcnt(pfx, r.lo, r.hi - 1);
+        }
     }
     if (my_iters)
         atomicAdd(&s_iters, my_iters);
-
-    // 4. the list is the strip table, in ascending part order
-    const int nstrips = ncur;
-    for (int i = tid; i < nstrips; i += blockDim.x) {
-        const int4 r = cur[i];
-        st.x0[i] = r.x;
-        st.x1[i] = r.y;
-        st.p0[i] = r.z;
-        if (r.w == 1) { // a leaf already: uncut in y
-            bx.x0[r.z] = r.x;
-            bx.ex[r.z] = r.y - r.x;
-            bx.y0[r.z] = 0;
-            bx.ey[r.z] = NY;
-            loads[r.z] = (long long)hcnt(pfx, r.x, r.y - 1);
-        }
-    }
     if (tid == 0) {
         st.p0[nstrips] = P;
         *st.S = nstrips;
         *st.always = 0;
         plan->S = nstrips;
     }
-    __syncthreads();
-    // 5. strip of every column: count the strips that start at each column, inclusive prefix - 1 =
-    //    last strip starting at or before the column (a zero-width strip shares its start with
-    //    the strip that follows it, which wins).
-    unsigned* cnt = pfx; // the column prefix sums are no longer needed
-    for (int x = tid; x < NX; x += blockDim.x)
-        cnt[x] = 0;
-    __syncthreads();
-    for (int i = tid; i < nstrips; i += blockDim.x) {
-        const int x0 = cur[i].x;
-        if (x0 < NX)
-            atomicAdd(&cnt[x0], 1u);
+    __syncthreads(); // the strip table is complete (this block wrote it: visible after the barrier)
+    // 5. strip of every column: the strips tile [0, NX) in order, so every warp paints the column
+    //    ranges of its strips (a zero-width strip paints nothing: the strip that follows it owns
+    //    the shared start column).
+    {
+        const int lane = lane_id(), warp = tid >> 5, nwarp = blockDim.x >> 5;
+        if (nstrips < nwarp) { // few wide strips: the whole block paints each of them
+            for (int i = 0; i < nstrips; i++) {
+                const int x0 = st.x0[i], x1 = st.x1[i];
+                for (int x = x0 + tid; x < x1; x += blockDim.x)
+                    strip_of_col[x] = i;
+            }
+        } else {
+            for (int i = warp; i < nstrips; i += nwarp) {
+                const int x0 = st.x0[i], x1 = st.x1[i];
+                for (int x = x0 + lane; x < x1; x += 32)
+                    strip_of_col[x] = i;
+            }
+        }
     }
     __syncthreads();
-    block_prefix<true>([&](int i) { return cnt[i]; }, NX, reinterpret_cast<unsigned*>(strip_of_col), 0, wsum64);
     if (tid == 0)
         plan->iters = s_iters;
 }
@@ -601,12 +681,16 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
 // strip overlaps straight from global memory (neighbouring strips share the boundary group, which
 // L1 / L2 serve) and the warp writes 32 consecutive counts.  rowcount layout [S][Rmax], rows local
 // to this rank.  Leaf strips (one part, never cut in y) are skipped.
+template <typename CT /* uint16_t when NX < 65536, else unsigned */>
 __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ bits, int NB, int rows,
-    const int* __restrict__ st_x0, const int* __restrict__ st_x1, const int* __restrict__ st_p0, int S,
-    unsigned* __restrict__ rowcount, int Rmax)
+    const int* __restrict__ st_x0, const int* __restrict__ st_x1, const int* __restrict__ st_p0,
+    const Plan* __restrict__ plan, int Scap, CT* __restrict__ rowcount, int Rmax)
 {
+    if (plan->mismatch)
+        return;
+    const int S = plan->S;
     const int s = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (s >= S || st_p0[s + 1] - st_p0[s] <= 1)
+    if (s >= S || s >= Scap || st_p0[s + 1] - st_p0[s] <= 1)
         return;
     const int row = blockIdx.x * 32 + lane_id();
     if (row >= rows)
@@ -626,58 +710,92 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
                     + __popc(w.z & word_range_mask(a - 64, b - 64)) + __popc(w.w & word_range_mask(a - 96, b - 96));
         }
     }
-    rowcount[(size_t)s * Rmax + row] = cnt;
+    rowcount[(size_t)s * Rmax + row] = (CT)cnt;
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4: y levels, one CTA per strip (grid-stride), boxes out
 // ------------------------------------------------------------------------------------------------
-// rowcount_all layout [G][S][Rmax] (the NCCL all-gather of every rank's [S][Rmax]); global row y
+// rowcount_all layout [G][rank_stride >= Scap * Rmax] (the NCCL all-gather of every rank's [Scap][Rmax]); global row y
 // lives at rank y / Rmax, local row y % Rmax.  dynamic smem: (NY + 1) unsigned when use_smem,
 // otherwise pfx_g holds gridDim.x slices of NY + 1.  The set lists of strip s live in
 // listA/listB[p0[s] .. p0[s+1]) (strips own disjoint part ranges).
-__global__ void __launch_bounds__(1024) k_ycuts(const unsigned* __restrict__ rowcount_all, int G,
-    int Rmax, int NY, int ylevels, StripTable st, int4* listA, int4* listB, unsigned* pfx_g, int use_smem,
-    BoxTable bx, long long* loads, Plan* plan)
+template <typename CT>
+__device__ __forceinline__ void load_row_counts(const CT* __restrict__ base /* [G][Scap][Rmax] + s * Rmax */,
+    size_t rank_stride, int Rmax, int i0, int NY, unsigned (&v)[PFX_E])
 {
-    extern __shared__ unsigned smem_dyn[];
-    __shared__ unsigned long long wsum64[33];
-    __shared__ int wsum32[33];
-    unsigned* pfx = use_smem ? smem_dyn : pfx_g + (size_t)blockIdx.x * (NY + 1);
+    const int g = i0 / Rmax, yl = i0 - g * Rmax;
+    const CT* src = base + (size_t)g * rank_stride + yl;
+    if (i0 + PFX_E <= NY && yl + PFX_E <= Rmax && ((uintptr_t)src & 15) == 0) {
+        // the chunk lies inside one rank's rows: vector loads
+        if (sizeof(CT) == 4) {
+#pragma unroll
+            for (int q = 0; q < PFX_E / 4; q++) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                v[4 * q] = t.x;
+                v[4 * q + 1] = t.y;
+                v[4 * q + 2] = t.z;
+                v[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < PFX_E / 8; q++) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                v[8 * q] = t.x & 0xffffu;
+                v[8 * q + 1] = t.x >> 16;
+                v[8 * q + 2] = t.y & 0xffffu;
+                v[8 * q + 3] = t.y >> 16;
+                v[8 * q + 4] = t.z & 0xffffu;
+                v[8 * q + 5] = t.z >> 16;
+                v[8 * q + 6] = t.w & 0xffffu;
+                v[8 * q + 7] = t.w >> 16;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < PFX_E; k++) {
+            const int y = i0 + k;
+            unsigned c = 0u;
+            if (y < NY) {
+                const int gg = y / Rmax;
+                c = (unsigned)__ldg(base + (size_t)gg * rank_stride + (y - gg * Rmax));
+            }
+            v[k] = c;
+        }
+    }
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(1024) k_ycuts(const CT* __restrict__ rowcount_all, size_t rank_stride,
+    int Rmax, int NY, StripTable st, unsigned* pfx_g, int use_smem, BoxTable bx, long long* loads, Plan* plan)
+{
+    extern __shared__ __align__(16) unsigned smem_dyn[];
+    __shared__ unsigned wsum[33];
+    if (plan->mismatch)
+        return;
+    unsigned* pfx = use_smem ? smem_dyn : pfx_g + (size_t)blockIdx.x * (((size_t)NY + 1 + 3) & ~(size_t)3);
     const int tid = threadIdx.x;
     const int S = *st.S;
+    const int ylevels = plan->iy;
     int my_iters = 0;
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
         const int plo = st.p0[s], n = st.p0[s + 1] - plo;
         if (n <= 1)
             continue; // K2 already wrote the box of a leaf strip
         __syncthreads(); // previous strip done with pfx
-        block_prefix<false>(
-            [&](int y) {
-                const int g = y / Rmax, yl = y - g * Rmax;
-                return rowcount_all[((size_t)g * S + s) * Rmax + yl];
-            },
-            NY, pfx, 0, wsum64);
-        int4 *cur = listA + plo, *nxt = listB + plo;
-        if (tid == 0)
-            cur[0] = make_int4(0, NY, plo, n);
-        __syncthreads();
-        int ncur = 1;
-        for (int l = 0; l < ylevels; l++) {
-            ncur = rcb_level(pfx, cur, ncur, nxt, &my_iters, wsum32);
-            int4* t = cur;
-            cur = nxt;
-            nxt = t;
-        }
-        // ncur == n: one leaf set per part, y-sorted
+        const CT* base = rowcount_all + (size_t)s * Rmax;
+        block_prefix_wide<PFX_E>(
+            [&](int i0, unsigned (&v)[PFX_E]) { load_row_counts<CT>(base, rank_stride, Rmax, i0, NY, v); }, NY, pfx, wsum);
+        // thread j walks to the j-th part of the strip (parts come out y-sorted)
         const int sx0 = st.x0[s], sx1 = st.x1[s];
-        for (int j = tid; j < ncur; j += blockDim.x) {
-            const int4 r = cur[j];
-            bx.x0[r.z] = sx0;
-            bx.ex[r.z] = sx1 - sx0;
-            bx.y0[r.z] = r.x;
-            bx.ey[r.z] = r.y - r.x;
-            loads[r.z] = (long long)hcnt(pfx, r.x, r.y - 1);
+        for (int j = tid; j < n; j += blockDim.x) {
+            const RcbSet root = { 0, NY, plo, n };
+            const RcbSet r = rcb_walk(pfx, root, ylevels, j, &my_iters);
+            bx.x0[r.plo] = sx0;
+            bx.ex[r.plo] = sx1 - sx0;
+            bx.y0[r.plo] = r.lo;
+            bx.ey[r.plo] = r.hi - r.lo;
+            loads[r.plo] = (long long)hcnt(pfx, r.lo, r.hi - 1);
         }
     }
     if (my_iters)
@@ -749,8 +867,10 @@ template <bool VEC, bool WRITE>
 __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bits, int NX, int rows,
     int y_begin, int NB, int rows_per_cta, const int* __restrict__ strip_of_col,
     const int* __restrict__ st_p0, const int* __restrict__ box_y0, const int* __restrict__ box_ey,
-    NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc)
+    NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc, const Plan* __restrict__ plan)
 {
+    if (plan->mismatch)
+        return;
     const int lane = lane_id();
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (g * 128 >= NX)
@@ -878,10 +998,30 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
 // ------------------------------------------------------------------------------------------------
 // K5: `changes == 0`  =>  report the naive blocks (ZoltanPartitioner.cpp:182-187)
 // ------------------------------------------------------------------------------------------------
+// Also reduces the part loads to their min / max (loadmm pre-set to LLONG_MAX, -1 by k_init).
 __global__ void __launch_bounds__(256) k_finalize(int P, int NX, int NY, NaiveParams nv,
-    const DevScalars* __restrict__ sc, StripTable st, BoxTable bx)
+    const DevScalars* __restrict__ sc, const Plan* __restrict__ plan, StripTable st, BoxTable bx,
+    const long long* __restrict__ loads, long long* __restrict__ loadmm)
 {
-    if (sc->changes != 0)
+    if (plan->mismatch)
+        return;
+    long long mn = 0x7fffffffffffffffLL, mx = -1;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const long long v = loads[p];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if (lane_id() == 0) {
+        atomicMin(loadmm, mn);
+        atomicMax(loadmm + 1, mx);
+    }
+    if (P == 1 || sc->changes != 0)
         return;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         const int bxi = p / nv.np1, byi = p % nv.np1; // Grid.cpp:158-159
@@ -1136,9 +1276,17 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, int NY, int px, int py,
     StripTable st, int* __restrict__ counts, const int* __restrict__ offsets,
     const int* __restrict__ totals, int cap, int* __restrict__ ids, int* __restrict__ halos,
-    int* __restrict__ starts, DevScalars* sc)
+    int* __restrict__ starts, DevScalars* sc, const Plan* __restrict__ plan, int redo)
 {
+    // redo: the tables were built speculatively from the RCB boxes while the labelling kernel was
+    // still looking for `changes`; they are only built again when the naive blocks replaced them
+    if ((plan && plan->mismatch) || (redo && sc->changes != 0))
+        return;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (redo && !FILL && t == 0) { // the count pass of a redo resets what the speculative fill left
+        sc->edge_cut = 0ull;
+        sc->overflow = 0;
+    }
     if (FILL) {
         bool over = false;
 #pragma unroll
@@ -1166,9 +1314,12 @@ __global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, 
 
 // exclusive scan of each of the 8 count lists (one CTA per list)
 __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, int P,
-    int* __restrict__ offsets, int* __restrict__ totals)
+    int* __restrict__ offsets, int* __restrict__ totals, const DevScalars* __restrict__ sc,
+    const Plan* __restrict__ plan, int redo)
 {
     __shared__ unsigned long long wsum64[33];
+    if ((plan && plan->mismatch) || (redo && sc->changes != 0))
+        return;
     const int l = blockIdx.x;
     const int* c = counts + (size_t)l * P;
     // writes P + 1 values; offsets has one spare slot after every list
@@ -1178,44 +1329,27 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
         totals[l] = (int)total;
 }
 
-// resets the per-call accumulators: column counts, scalars, load min / max (one launch instead of
-// a memset plus two host-to-device copies)
-__global__ void __launch_bounds__(256) k_init(unsigned* __restrict__ colcount, int n, DevScalars* __restrict__ sc,
-    long long* __restrict__ loadmm)
+// resets the per-call accumulators: column counts, the per-rank y-range slots that follow them
+// (this rank's slot to "no dot yet", the others to 0 so that the SUM all-reduce of the whole
+// buffer delivers every rank's pair), scalars, load min / max
+__global__ void __launch_bounds__(256) k_init(unsigned* __restrict__ colcount, int n, int yr_off, int rank,
+    DevScalars* __restrict__ sc, long long* __restrict__ loadmm)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n)
-        colcount[i] = 0u;
+    if (i < n) {
+        unsigned v = 0u;
+        if (i == yr_off + 2 * rank)
+            v = 0x80000000u; // -(first ocean row) = INT_MIN
+        if (i == yr_off + 2 * rank + 1)
+            v = 0xffffffffu; // last ocean row = -1
+        colcount[i] = v;
+    }
     if (i == 0) {
-        sc->neg_ymin = (int)0x80000000;
-        sc->ymax = -1;
         sc->changes = 0;
         sc->overflow = 0;
         sc->edge_cut = 0ull;
         loadmm[0] = 0x7fffffffffffffffLL;
         loadmm[1] = -1;
-    }
-}
-
-// min / max of the part loads
-__global__ void __launch_bounds__(256) k_load_minmax(const long long* __restrict__ loads, int P,
-    long long* out /* [2] = min, max; pre-set to LLONG_MAX, -1 */)
-{
-    long long mn = 0x7fffffffffffffffLL, mx = -1;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-        const long long v = loads[p];
-        mn = v < mn ? v : mn;
-        mx = v > mx ? v : mx;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
-        mn = a < mn ? a : mn;
-        mx = b > mx ? b : mx;
-    }
-    if (lane_id() == 0) {
-        atomicMin(out, mn);
-        atomicMax(out + 1, mx);
     }
 }
 

@@ -56,7 +56,10 @@ enum { DDC_LEFT = 0, DDC_RIGHT = 1, DDC_BOTTOM = 2, DDC_TOP = 3, DDC_N_EDGE = 4 
 enum {
     DDC_WANT_PID = 1, /* write the pid map (owner labelling, ZoltanPartitioner.cpp:201-219) */
     DDC_WANT_NEIGHBOURS = 2, /* neighbour / halo tables (Partitioner.cpp:329-435) */
-    DDC_PROFILE = 4 /* record per-stage CUDA-event timings into ddc_stats */
+    DDC_PROFILE = 4, /* record per-stage CUDA-event timings into ddc_stats */
+    DDC_ASYNC = 8 /* only enqueue the step on the stream; the first result getter (or
+                     ddc_synchronize) waits for it.  Without it ddc_partition() returns when the
+                     step is complete.  With nranks > 1 all ranks must then call the same first getter. */
 };
 
 #define DDC_NCCL_ID_BYTES 128

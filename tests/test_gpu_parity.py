@@ -203,3 +203,35 @@ def test_repeatability_and_flags(capi, handle, oracle):
     with pytest.raises(capi.DdcError):
         handle.pid_host()
     assert handle.neighbour_counts(0, 0).sum() == 0
+
+
+def test_async_steps_and_plan_mismatch(capi, handle, oracle):
+    """DDC_ASYNC only enqueues; the getters settle the step.  A mask whose dots sit in a narrow
+    band has other x / y level counts than the full-extent guess the launches were sized for:
+    the step must notice and run again with the real plan."""
+    for shape, band in (((96, 200), (slice(None), slice(90, 101))), ((200, 96), (slice(90, 101), slice(None)))):
+        m = np.zeros(shape, dtype=np.int32)
+        m[band] = 1
+        for P in (8, 13):
+            o = oracle.partition(m, P, True, True)
+            handle.set_mask_host(m)
+            for _ in range(3):  # back-to-back enqueues, nobody looks in between
+                handle.partition(P, True, True, flags=capi.WANT_PID | capi.WANT_NEIGHBOURS | capi.ASYNC)
+            g = {
+                "boxes": handle.boxes(), "pid": handle.pid_host(), "stats": handle.stats(),
+                "counts": [[handle.neighbour_counts(e, per) for e in range(4)] for per in range(2)],
+                "nbr": [[handle.neighbours(e, per) for e in range(4)] for per in range(2)],
+            }
+            assert_same(g, o, "band %s P=%d" % (shape, P))
+            # and the synchronous call on the now-cached plan
+            assert_same(run_gpu(handle, m, P, True, True), o, "band %s P=%d again" % (shape, P))
+
+
+@pytest.mark.parametrize("n,P", [(64, 4), (96, 16), (60, 6)])
+def test_nothing_moved_reports_naive_blocks(handle, oracle, n, P):
+    """all ocean, RCB == the naive blocks: `changes == 0`, boxes AND neighbour tables are the
+    naive blocks' (the speculative tables of the RCB boxes are rebuilt)"""
+    m = np.ones((n, n), dtype=np.int32)
+    for px, py in ((False, False), (True, True)):
+        o = oracle.partition(m, P, px, py)
+        assert_same(run_gpu(handle, m, P, px, py), o, "all ocean n=%d P=%d" % (n, P))
