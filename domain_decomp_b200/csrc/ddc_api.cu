@@ -259,11 +259,11 @@ int run_neighbours(ddc_handle_t h, int P, int nx, int ny, int px, int py)
     const int warps_per_cta = 8;
     const int grid = (std::max(P, 8) + warps_per_cta - 1) / warps_per_cta; // >= 8 * pad32(P) threads
     k_neighbours<false><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p, nullptr,
-        nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, nullptr, 0);
-    k_scan_counts<<<8, 1024, 0, s>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p, h->sc.p, nullptr, 0);
+        nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, nullptr);
+    k_scan_counts<<<8, 1024, 0, s>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p, nullptr);
     k_neighbours<true><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p,
         h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
-        h->sc.p, nullptr, 0);
+        h->sc.p, nullptr);
     h->stats.gpu_launches += 3;
     CUDA_TRY(h, cudaGetLastError());
     h->totals_valid = false;
@@ -294,7 +294,7 @@ int fetch_totals(ddc_handle_t h)
         const int grid = (std::max(h->nparts, 8) + 7) / 8;
         k_neighbours<true><<<grid, 256, 0, h->stream>>>(t.bx, h->nparts, h->nx, h->ny, h->px, h->py, t.st,
             h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p,
-            h->nbr_halos.p, h->nbr_starts.p, h->sc.p, nullptr, 0);
+            h->nbr_halos.p, h->nbr_starts.p, h->sc.p, nullptr);
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaMemcpyAsync(&hs, h->sc.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -706,20 +706,19 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     h->px = px;
     h->py = py;
     const int ngrid = (std::max(P, 8) + 7) / 8; // >= 8 * pad32(P) threads
-    auto neighbours = [&](cudaStream_t q, int redo) {
+    auto neighbours = [&](cudaStream_t q) {
         k_neighbours<false><<<ngrid, 256, 0, q>>>(t.bx, P, NX, NY, px, py, t.st, h->nbr_counts.p, nullptr,
-            nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p, redo);
-        k_scan_counts<<<8, 1024, 0, q>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p, h->sc.p,
-            h->plan.p, redo);
+            nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p);
+        k_scan_counts<<<8, 1024, 0, q>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p, h->plan.p);
         k_neighbours<true><<<ngrid, 256, 0, q>>>(t.bx, P, NX, NY, px, py, t.st, h->nbr_counts.p,
             h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
-            h->sc.p, h->plan.p, redo);
+            h->sc.p, h->plan.p);
         launches += 3;
     };
     if (want_nbr) {
         CUDA_TRY(h, cudaEventRecord(h->ev_fork, s));
         CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-        neighbours(h->side_stream, 0);
+        neighbours(h->side_stream);
         CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
     }
     // ---- K6: labels + `changes` -----------------------------------------------------------------
@@ -754,7 +753,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     mark(6);
     // ---- K7 again, only if the naive blocks replaced the RCB boxes (the kernels return at once otherwise)
     if (want_nbr) {
-        neighbours(s, 1);
+        k_neighbours_redo<<<1, 1024, 0, s>>>(t.bx, P, NX, NY, px, py, t.st, h->nbr_counts.p, h->nbr_offsets.p,
+            h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p, h->sc.p, h->plan.p);
+        launches++;
         h->have_nbr = true;
     }
     mark(7);

@@ -1276,17 +1276,11 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, int NY, int px, int py,
     StripTable st, int* __restrict__ counts, const int* __restrict__ offsets,
     const int* __restrict__ totals, int cap, int* __restrict__ ids, int* __restrict__ halos,
-    int* __restrict__ starts, DevScalars* sc, const Plan* __restrict__ plan, int redo)
+    int* __restrict__ starts, DevScalars* sc, const Plan* __restrict__ plan)
 {
-    // redo: the tables were built speculatively from the RCB boxes while the labelling kernel was
-    // still looking for `changes`; they are only built again when the naive blocks replaced them
-    if ((plan && plan->mismatch) || (redo && sc->changes != 0))
+    if (plan && plan->mismatch)
         return;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (redo && !FILL && t == 0) { // the count pass of a redo resets what the speculative fill left
-        sc->edge_cut = 0ull;
-        sc->overflow = 0;
-    }
     if (FILL) {
         bool over = false;
 #pragma unroll
@@ -1314,11 +1308,10 @@ __global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, 
 
 // exclusive scan of each of the 8 count lists (one CTA per list)
 __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, int P,
-    int* __restrict__ offsets, int* __restrict__ totals, const DevScalars* __restrict__ sc,
-    const Plan* __restrict__ plan, int redo)
+    int* __restrict__ offsets, int* __restrict__ totals, const Plan* __restrict__ plan)
 {
     __shared__ unsigned long long wsum64[33];
-    if ((plan && plan->mismatch) || (redo && sc->changes != 0))
+    if (plan && plan->mismatch)
         return;
     const int l = blockIdx.x;
     const int* c = counts + (size_t)l * P;
@@ -1327,6 +1320,63 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
         reinterpret_cast<unsigned*>(offsets) + (size_t)l * (P + 1), 0, wsum64);
     if (threadIdx.x == 0)
         totals[l] = (int)total;
+}
+
+// The tables above are built speculatively from the RCB boxes, beside the labelling kernel that is
+// still looking for `changes`.  In the rare case that nothing moved (`changes == 0`) K5 replaced the
+// boxes by the naive blocks and the tables are built again here: count, scan and fill in ONE block,
+// so that the common case costs a single launch that returns at once.
+__global__ void __launch_bounds__(1024) k_neighbours_redo(BoxTable bx, int P, int NX, int NY, int px, int py,
+    StripTable st, int* __restrict__ counts, int* __restrict__ offsets, int* __restrict__ totals, int cap,
+    int* __restrict__ ids, int* __restrict__ halos, int* __restrict__ starts, DevScalars* sc,
+    const Plan* __restrict__ plan)
+{
+    __shared__ unsigned long long wsum64[33];
+    __shared__ int s_over;
+    if (plan->mismatch || sc->changes != 0)
+        return;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        sc->edge_cut = 0ull;
+        sc->overflow = 0;
+        s_over = 0;
+    }
+    __syncthreads();
+    const bool all = *st.always != 0;
+    const int Ppad = (P + 31) & ~31;
+    if (all) {
+        for (int me = tid >> 5; me < P; me += blockDim.x >> 5)
+            neighbours_all_pairs<false>(bx, P, NX, NY, px, py, me, counts, offsets, cap, ids, halos, starts, sc);
+    } else {
+        for (int t = tid; t < 8 * Ppad; t += blockDim.x)
+            neighbours_structured<false>(bx, P, NX, NY, px, py, st, t / Ppad, t % Ppad, counts, offsets, cap, ids,
+                halos, starts, sc);
+    }
+    __syncthreads();
+    for (int l = 0; l < 8; l++) {
+        const int* c = counts + (size_t)l * P;
+        const unsigned long long total = block_prefix<false>([&](int i) { return (unsigned)c[i]; }, P,
+            reinterpret_cast<unsigned*>(offsets) + (size_t)l * (P + 1), 0, wsum64);
+        if (tid == 0) {
+            totals[l] = (int)total;
+            if ((long long)total > cap)
+                s_over = 1;
+        }
+    }
+    __syncthreads();
+    if (s_over) {
+        if (tid == 0)
+            sc->overflow = 1;
+        return;
+    }
+    if (all) {
+        for (int me = tid >> 5; me < P; me += blockDim.x >> 5)
+            neighbours_all_pairs<true>(bx, P, NX, NY, px, py, me, counts, offsets, cap, ids, halos, starts, sc);
+    } else {
+        for (int t = tid; t < 8 * Ppad; t += blockDim.x)
+            neighbours_structured<true>(bx, P, NX, NY, px, py, st, t / Ppad, t % Ppad, counts, offsets, cap, ids,
+                halos, starts, sc);
+    }
 }
 
 // resets the per-call accumulators: column counts, the per-rank y-range slots that follow them
