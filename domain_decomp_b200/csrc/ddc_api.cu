@@ -606,7 +606,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         if (G > 1)
             CUDA_TRY(h, h->rowcount_all.ensure(rc_words * G + 4));
     }
-    const size_t xneed = sizeof(unsigned) * ((size_t)NX + 1), yneed = sizeof(unsigned) * ((size_t)NY + 1);
+    // prefix sums + the bit map of the non-empty bins (ddc_kernels.cuh: Hist)
+    const size_t xneed = sizeof(unsigned) * ((((size_t)NX + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NX));
+    const size_t yneed = sizeof(unsigned) * ((((size_t)NY + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NY));
     const size_t lim = max_dyn_smem(h->device);
     const int x_smem = xneed + 1024 <= lim, y_smem = yneed + 1024 <= lim;
     const int ygrid = std::max(1, std::min(Scap, 148 * 2));

@@ -136,16 +136,102 @@ __device__ inline unsigned long long block_prefix(F src, int n, unsigned* dst, i
     return carry;
 }
 
+// A histogram as the median search sees it: pfx[i] = number of dots in bins [0, i), plus an optional
+// three-level bit map of the non-empty bins (l0: one bit per bin, l1: one bit per l0 word, l2: one
+// bit per l1 word) that answers "nearest non-empty bin at or below / above" in a handful of
+// dependent loads instead of a binary search over the prefix sums.  On a land-sea mask whole runs
+// of rows of a strip are land, so these queries are most of what Zoltan's median loop does.
+struct Hist {
+    const unsigned* pfx;
+    const unsigned *l0, *l1, *l2; // l0 == nullptr: no bit map, search the prefix sums
+    int nl2; // words of l2
+};
+__device__ __forceinline__ Hist make_hist(const unsigned* pfx, const unsigned* bitmap, int n)
+{
+    Hist H;
+    H.pfx = pfx;
+    const int tiles = (n + 32767) / 32768;
+    H.l0 = bitmap;
+    H.l1 = bitmap ? bitmap + tiles * 1024 : nullptr;
+    H.l2 = bitmap ? bitmap + tiles * (1024 + 32) : nullptr;
+    H.nl2 = tiles;
+    return H;
+}
+constexpr int HIST_TILE = 32768; // bins per tile of block_prefix_wide<32> with 1024 threads
+__host__ __device__ inline size_t hist_bitmap_words(int n) // words behind pfx for n bins
+{
+    const size_t tiles = ((size_t)n + HIST_TILE - 1) / HIST_TILE;
+    return tiles * (1024 + 32 + 1);
+}
+// largest non-empty bin in [a, t], -1 if none
+__device__ __forceinline__ int bitmap_prev(const Hist& H, int a, int t)
+{
+    if (t < a)
+        return -1;
+    int w = t >> 5;
+    unsigned m = H.l0[w] & (0xffffffffu >> (31 - (t & 31)));
+    if (!m) {
+        int w1 = w >> 5;
+        m = H.l1[w1] & ((1u << (w & 31)) - 1u);
+        if (!m) {
+            int w2 = w1 >> 5;
+            unsigned m2 = H.l2[w2] & ((1u << (w1 & 31)) - 1u);
+            while (!m2) {
+                if (w2 == 0)
+                    return -1;
+                m2 = H.l2[--w2];
+            }
+            w1 = (w2 << 5) + 31 - __clz(m2);
+            m = H.l1[w1];
+        }
+        w = (w1 << 5) + 31 - __clz(m);
+        m = H.l0[w];
+    }
+    const int j = (w << 5) + 31 - __clz(m);
+    return j >= a ? j : -1;
+}
+// smallest non-empty bin in [t, b], -1 if none
+__device__ __forceinline__ int bitmap_next(const Hist& H, int t, int b)
+{
+    if (t > b)
+        return -1;
+    int w = t >> 5;
+    unsigned m = H.l0[w] & (0xffffffffu << (t & 31));
+    if (!m) {
+        int w1 = w >> 5;
+        m = (w & 31) == 31 ? 0u : H.l1[w1] & (0xffffffffu << ((w & 31) + 1));
+        if (!m) {
+            int w2 = w1 >> 5;
+            unsigned m2 = (w1 & 31) == 31 ? 0u : H.l2[w2] & (0xffffffffu << ((w1 & 31) + 1));
+            while (!m2) {
+                if (++w2 >= H.nl2)
+                    return -1;
+                m2 = H.l2[w2];
+            }
+            w1 = (w2 << 5) + __ffs(m2) - 1;
+            m = H.l1[w1];
+        }
+        w = (w1 << 5) + __ffs(m) - 1;
+        m = H.l0[w];
+    }
+    const int j = (w << 5) + __ffs(m) - 1;
+    return j <= b ? j : -1;
+}
+
 // Same result as block_prefix<false> (dst[i] = sum of the first i elements, n + 1 outputs, 32-bit
 // sums), but every thread owns E CONSECUTIVE elements: a 1024-thread block covers 1024 * E elements
 // with ONE block scan instead of one per 4096, which is what the latency of the cut kernels is made
 // of.  load(i0, v) fills v[k] = element i0 + k (0 beyond n); dst may be shared or global memory.
+// bitmap != nullptr (needs E == 32 and 1024 threads): also writes the three-level bit map of the
+// non-empty elements, l0 / l1 / l2 = bitmap + 0 / tiles * 1024 / tiles * (1024 + 32).
 template <int E, typename F>
-__device__ inline unsigned block_prefix_wide(F load, int n, unsigned* dst, unsigned* wsum /* >= 33 */)
+__device__ inline unsigned block_prefix_wide(F load, int n, unsigned* dst, unsigned* wsum /* >= 33 */,
+    unsigned* bitmap = nullptr)
 {
     static_assert(E % 4 == 0, "E must be a multiple of 4");
     unsigned carry = 0;
     const int tile = blockDim.x * E;
+    const int tiles = (n + tile - 1) / tile;
     for (int base = 0; base < n; base += tile) {
         const int i0 = base + threadIdx.x * E;
         unsigned v[E];
@@ -155,6 +241,24 @@ __device__ inline unsigned block_prefix_wide(F load, int n, unsigned* dst, unsig
 #pragma unroll
             for (int k = 0; k < E; k++)
                 v[k] = 0u;
+        }
+        if (E == 32 && bitmap) {
+            unsigned word = 0;
+#pragma unroll
+            for (int k = 0; k < E; k++)
+                word |= (unsigned)(v[k] != 0u) << (k & 31);
+            const int t = base / tile;
+            bitmap[t * 1024 + threadIdx.x] = word; // l0
+            const unsigned b1 = __ballot_sync(0xffffffffu, word != 0u);
+            if (lane_id() == 0)
+                bitmap[tiles * 1024 + t * 32 + (threadIdx.x >> 5)] = b1; // l1
+            // l2 word t = the non-zero l1 words of this tile
+            __syncthreads(); // the l1 words of the tile are written
+            if (threadIdx.x < 32) {
+                const unsigned b2 = __ballot_sync(0xffffffffu, bitmap[tiles * 1024 + t * 32 + threadIdx.x] != 0u);
+                if (threadIdx.x == 0)
+                    bitmap[tiles * (1024 + 32) + t] = b2; // l2
+            }
         }
         unsigned sum = 0;
 #pragma unroll
@@ -378,105 +482,140 @@ __device__ inline int first_nonempty(const unsigned* pfx, int a, int b)
     }
     return lo;
 }
+// the same two queries on a Hist: the bit map when there is one
+__device__ __forceinline__ int last_nonempty(const Hist& H, int a, int b)
+{
+    return H.l0 ? bitmap_prev(H, a, b) : last_nonempty(H.pfx, a, b);
+}
+__device__ __forceinline__ int first_nonempty(const Hist& H, int a, int b)
+{
+    return H.l0 ? bitmap_next(H, a, b) : first_nonempty(H.pfx, a, b);
+}
+
+// floor() of Zoltan's interpolated guess
+//     tmp_half = valuemin + (targetlo - weightlo) / (weight - weightlo - weighthi) * (valuemax - valuemin)
+// clamped to [alo - 1, ahi].  Only floor(tmp_half) matters, so the quotient is first formed with a
+// reciprocal approximation refined by two Newton steps (relative error < 2^-48, i.e. < 2^-17 bins
+// for any range below 2^31); unless that value lies within 2^-10 of an integer -- where the
+// rounding of the real IEEE sequence could matter -- its floor IS the floor of the exact sequence.
+// Otherwise the exact sequence (correctly rounded division, multiplication, addition) is evaluated.
+__device__ __forceinline__ int guess_bin(int vmin, double num, double den, int range, int alo, int ahi)
+{
+    const double dvmin = (double)vmin, drange = (double)range;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    double tmp = fma(num * r, drange, dvmin);
+    const double fl = floor(tmp), fr = tmp - fl;
+    if (!(den >= 1.0 && fr > 0x1p-10 && fr < 1.0 - 0x1p-10))
+        tmp = __dadd_rn(dvmin, __dmul_rn(__ddiv_rn(num, den), drange));
+    // tmp < alo -> alo - 1;  tmp >= ahi -> ahi;  else floor(tmp)
+    if (tmp < (double)alo)
+        return alo - 1;
+    if (tmp >= (double)ahi)
+        return ahi;
+    return (int)floor(tmp);
+}
 
 // Integer boundary ceil(cut) of the weighted-median cut of bins [c0, c1] for a set of num_parts
 // parts whose lower child receives nlo parts.  *iters += median iterations.
-__device__ inline int median_boundary(const unsigned* pfx, int c0, int c1, int nlo, int num_parts,
+//
+// Zoltan keeps weightlo / weighthi / totallo / totalhi as doubles, but with unit weights they are
+// exact integers: here they are integers read off the prefix sums (dots in [c0, t] = weightlo +
+// totallo, dots in (t, c1] = weighthi + totalhi), converted to double exactly where Zoltan
+// compares them with the (non-integer) targets or forms the tie-rule differences.  One iteration
+// is then one guess, one prefix-sum load, one bit-map query and one more prefix-sum load.
+__device__ inline int median_boundary(const Hist& H, int c0, int c1, int nlo, int num_parts,
     int* iters)
 {
-    const unsigned Wn = hcnt(pfx, c0, c1);
+    const unsigned* pfx = H.pfx;
+    const unsigned base = pfx[c0];
+    const unsigned Wn = c1 < c0 ? 0u : pfx[c1 + 1] - base;
     if (Wn == 0u) { // no dot at all: integer midpoint of the inherited range (policy Q2)
         *iters += 1;
         return c0 + ((c1 + 1 - c0) >> 1);
     }
     const double weight = (double)Wn;
     const double fractionlo = __ddiv_rn((double)nlo, (double)num_parts);
-    const int first = first_nonempty(pfx, c0, c1), last = last_nonempty(pfx, c0, c1);
-    double valuemin = (double)first, valuemax = (double)last;
-    int alo = first, ahi = last;
+    const int first = first_nonempty(H, c0, c1), last = last_nonempty(H, c0, c1);
+    int vmin = first, vmax = last; // valuemin, valuemax (always bin indices)
+    int alo = first, ahi = last; // the active bins
     int B;
-    double weightlo = 0.0, weighthi = 0.0;
+    unsigned wlo = 0, whi = 0; // weightlo, weighthi
     const double targetlo = __dmul_rn(fractionlo, weight);
     const double targethi = __dsub_rn(weight, targetlo);
     int it = 0;
     for (;;) {
-        // tmp_half = valuemin + (targetlo - weightlo) / (weight - weightlo - weighthi) * (valuemax - valuemin)
-        const double num = __dsub_rn(targetlo, weightlo);
-        const double den = __dsub_rn(__dsub_rn(weight, weightlo), weighthi);
-        const double tmp_half
-            = __dadd_rn(valuemin, __dmul_rn(__ddiv_rn(num, den), __dsub_rn(valuemax, valuemin)));
+        const int t = guess_bin(vmin, __dsub_rn(targetlo, (double)wlo), (double)(Wn - wlo - whi), vmax - vmin, alo, ahi);
         it++;
-        int t;
-        if (tmp_half < (double)alo)
-            t = alo - 1;
-        else if (tmp_half >= (double)ahi)
-            t = ahi;
-        else
-            t = (int)floor(tmp_half);
         B = t;
-        const double totallo = (double)hcnt(pfx, alo, t), totalhi = (double)hcnt(pfx, t + 1, ahi);
-        const int vlo = last_nonempty(pfx, alo, t), vhi = first_nonempty(pfx, t + 1, ahi);
-        const double wtlo = vlo >= 0 ? (double)hcnt(pfx, vlo, vlo) : 0.0;
-        const double wthi = vhi >= 0 ? (double)hcnt(pfx, vhi, vhi) : 0.0;
-
-        if (__dadd_rn(weightlo, totallo) < targetlo) { // lower half TOO SMALL
-            weightlo = __dadd_rn(weightlo, totallo);
+        const unsigned cum = pfx[t + 1] - base; // dots in [c0, t]
+        const double dcum = (double)cum;
+        if (dcum < targetlo) { // lower half TOO SMALL (weightlo + totallo < targetlo)
+            const int vhi = first_nonempty(H, t + 1, ahi);
             if (vhi < 0)
                 break;
-            const double moved = __dadd_rn(weightlo, wthi);
-            if (wthi == 1.0) { // a single dot: move only if strictly better
+            const unsigned moved_n = pfx[vhi + 1] - base; // weightlo + wthi
+            const double moved = (double)moved_n;
+            if (moved_n - cum == 1u) { // a single dot: move only if strictly better
                 if (moved < targetlo) {
                     B = vhi;
                 } else {
-                    if (__dsub_rn(moved, targetlo) < __dsub_rn(targetlo, weightlo))
+                    if (__dsub_rn(moved, targetlo) < __dsub_rn(targetlo, dcum))
                         B = vhi;
                     break;
                 }
             } else { // a whole column: move unless strictly worse
                 if (moved >= targetlo) {
-                    if (!(__dsub_rn(moved, targetlo) > __dsub_rn(targetlo, weightlo)))
+                    if (!(__dsub_rn(moved, targetlo) > __dsub_rn(targetlo, dcum)))
                         B = vhi;
                     break;
                 }
                 B = vhi;
             }
-            weightlo = moved;
-            if (__dsub_rn(targetlo, weightlo) <= 1.0) // tolerance = weight of one dot
+            wlo = moved_n;
+            if (__dsub_rn(targetlo, moved) <= 1.0) // tolerance = weight of one dot
                 break;
-            valuemin = (double)vhi;
+            vmin = vhi;
             alo = vhi + 1;
-        } else if (__dadd_rn(weighthi, totalhi) < targethi) { // upper half TOO SMALL
-            weighthi = __dadd_rn(weighthi, totalhi);
+        } else {
+            const unsigned above = Wn - cum; // dots in (t, c1] = weighthi + totalhi
+            const double dabove = (double)above;
+            if (!(dabove < targethi))
+                break; // both halves just right
+            // upper half TOO SMALL
+            const int vlo = last_nonempty(H, alo, t);
             if (vlo < 0)
                 break;
-            const double moved = __dadd_rn(weighthi, wtlo);
-            if (wtlo == 1.0) {
+            const unsigned moved_n = Wn - (pfx[vlo] - base); // weighthi + wtlo = dots in [vlo, c1]
+            const double moved = (double)moved_n;
+            if (moved_n - above == 1u) {
                 if (moved < targethi) {
                     B = vlo - 1;
                 } else {
-                    if (__dsub_rn(moved, targethi) < __dsub_rn(targethi, weighthi))
+                    if (__dsub_rn(moved, targethi) < __dsub_rn(targethi, dabove))
                         B = vlo - 1;
                     break;
                 }
             } else {
                 if (moved >= targethi) {
-                    if (!(__dsub_rn(moved, targethi) > __dsub_rn(targethi, weighthi)))
+                    if (!(__dsub_rn(moved, targethi) > __dsub_rn(targethi, dabove)))
                         B = vlo - 1;
                     break;
                 }
                 B = vlo - 1;
             }
-            weighthi = moved;
-            if (__dsub_rn(targethi, weighthi) <= 1.0)
+            whi = moved_n;
+            if (__dsub_rn(targethi, moved) <= 1.0)
                 break;
-            valuemax = (double)vlo;
+            vmax = vlo;
             ahi = vlo - 1;
-        } else
-            break; // both halves just right
+        }
     }
     *iters += it;
     // AVERAGE_CUTS over all dots of the set, then ceil() (ZoltanPartitioner.cpp:177-180)
-    const int L = last_nonempty(pfx, c0, B), U = first_nonempty(pfx, B + 1, c1);
+    const int L = last_nonempty(H, c0, B), U = first_nonempty(H, B + 1, c1);
     if (L >= 0 && U >= 0)
         return (L + U + 1) >> 1; // ceil(0.5 * (L + U))
     if (L >= 0)
@@ -503,12 +642,12 @@ __device__ __forceinline__ int leaves_below(int n, int levels)
 }
 // walk `levels` levels down from `set` towards leaf number k (0-based among the leaves below
 // `set`); iterations of a median are counted by the thread whose leaf is the first of its upper child
-__device__ inline RcbSet rcb_walk(const unsigned* pfx, RcbSet set, int levels, int k, int* iters)
+__device__ inline RcbSet rcb_walk(const Hist& H, RcbSet set, int levels, int k, int* iters)
 {
     for (int l = levels; l > 0 && set.n > 1; l--) {
         const int nlo = (set.n - 1) / 2 + 1;
         int it = 0;
-        const int cut = median_boundary(pfx, set.lo, set.hi - 1, nlo, set.n, &it);
+        const int cut = median_boundary(H, set.lo, set.hi - 1, nlo, set.n, &it);
         const int below = leaves_below(nlo, l - 1);
         if (k < below) {
             set.hi = cut;
@@ -563,7 +702,7 @@ __device__ __forceinline__ void load_counts_u32(const unsigned* __restrict__ src
     }
 }
 
-// dynamic shared memory: (NX + 1) unsigned when use_smem.  yr_all: G pairs {-(first ocean row),
+// dynamic shared memory when use_smem: (NX + 1) unsigned, rounded up to 4, + hist_bitmap_words(NX).  yr_all: G pairs {-(first ocean row),
 // last ocean row}, one per rank (summed into place by the all-reduce of the column counts).
 // aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
 __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ colcount, int NX, int NY,
@@ -577,15 +716,18 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
     const int tid = threadIdx.x;
 
     // 1. pfx[i] = ocean cells in columns [0, i)
-    block_prefix_wide<PFX_E>([&](int i0, unsigned (&v)[PFX_E]) { load_counts_u32(colcount, i0, NX, v); }, NX, pfx, wsum);
+    unsigned* bitmap = use_smem ? smem_dyn + (((size_t)NX + 1 + 3) & ~(size_t)3) : nullptr;
+    block_prefix_wide<PFX_E>([&](int i0, unsigned (&v)[PFX_E]) { load_counts_u32(colcount, i0, NX, v); }, NX, pfx, wsum,
+        bitmap);
+    const Hist H = make_hist(pfx, bitmap, NX);
 
     // 2. the plan: bounding box of all dots -> preset direction of every level
     if (tid == 0) {
         const long long W = pfx[NX];
         int xmin = 0, xmax = 0, ymin = 0, ymax = 0;
         if (W > 0) {
-            xmin = first_nonempty(pfx, 0, NX - 1);
-            xmax = last_nonempty(pfx, 0, NX - 1);
+            xmin = first_nonempty(H, 0, NX - 1);
+            xmax = last_nonempty(H, 0, NX - 1);
             int a = (int)0x80000000, b = -1;
             for (int g = 0; g < G; g++) {
                 a = max(a, yr_all[2 * g]);
@@ -628,7 +770,7 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
     int my_iters = 0;
     for (int i = tid; i < nstrips; i += blockDim.x) {
         const RcbSet root = { 0, NX, 0, P };
-        const RcbSet r = rcb_walk(pfx, root, ix, i, &my_iters);
+        const RcbSet r = rcb_walk(H, root, ix, i, &my_iters);
         // 4. the strip table, in ascending part order
         st.x0[i] = r.lo;
         st.x1[i] = r.hi;
@@ -774,6 +916,8 @@ __global__ void __launch_bounds__(1024) k_ycuts(const CT* __restrict__ rowcount_
     if (plan->mismatch)
         return;
     unsigned* pfx = use_smem ? smem_dyn : pfx_g + (size_t)blockIdx.x * (((size_t)NY + 1 + 3) & ~(size_t)3);
+    unsigned* bitmap = use_smem ? smem_dyn + (((size_t)NY + 1 + 3) & ~(size_t)3) : nullptr;
+    const Hist H = make_hist(pfx, bitmap, NY);
     const int tid = threadIdx.x;
     const int S = *st.S;
     const int ylevels = plan->iy;
@@ -785,12 +929,13 @@ __global__ void __launch_bounds__(1024) k_ycuts(const CT* __restrict__ rowcount_
         __syncthreads(); // previous strip done with pfx
         const CT* base = rowcount_all + (size_t)s * Rmax;
         block_prefix_wide<PFX_E>(
-            [&](int i0, unsigned (&v)[PFX_E]) { load_row_counts<CT>(base, rank_stride, Rmax, i0, NY, v); }, NY, pfx, wsum);
+            [&](int i0, unsigned (&v)[PFX_E]) { load_row_counts<CT>(base, rank_stride, Rmax, i0, NY, v); }, NY, pfx, wsum,
+            bitmap);
         // thread j walks to the j-th part of the strip (parts come out y-sorted)
         const int sx0 = st.x0[s], sx1 = st.x1[s];
         for (int j = tid; j < n; j += blockDim.x) {
             const RcbSet root = { 0, NY, plo, n };
-            const RcbSet r = rcb_walk(pfx, root, ylevels, j, &my_iters);
+            const RcbSet r = rcb_walk(H, root, ylevels, j, &my_iters);
             bx.x0[r.plo] = sx0;
             bx.ex[r.plo] = sx1 - sx0;
             bx.y0[r.plo] = r.lo;
