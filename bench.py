@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU exchange: loads from peer memory inside the kernels (default) or NCCL collectives")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -228,6 +230,10 @@ def main():
     cells = nx * ny
     W, K = max(args.warmup, 3), max(args.steps, 1)
     h = capi.Handle(local_rank, rank, world, nccl_id)
+    if world > 1 and args.exchange == "peer":
+        handles = [None] * world
+        dist.all_gather_object(handles, h.peer_export(nx, ny, P))
+        h.peer_import(handles)
     # a real (non-default) stream: the handle launches on it and the timing events are recorded on it
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -360,7 +366,9 @@ def main():
             "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": {"workload": args.workload, "nx": nx, "ny": ny, "parts": P, "land_frac_target": land,
                        "ocean_frac_measured": st["n_ocean"] / cells, "seed": seed, "periodic_x": px,
-                       "periodic_y": py, "sharding": "rows over %d GPU(s), NCCL allreduce + allgather" % world,
+                       "periodic_y": py, "sharding": "rows over %d GPU(s)%s" % (world, "" if world == 1 else (
+                           ", histograms read from peer memory over NVLink inside the cut kernels" if st["exchange"] == 2
+                           else ", NCCL allreduce + allgather")),
                        "outputs": "boxes + pid + neighbour/halo tables",
                        "l2": ("L2 flushed between timed iterations (256 MiB write)" if need_flush else
                               "inputs larger than L2 (%.0f MiB int32 mask + %.0f MiB pid per GPU vs 126 MB L2)"
@@ -376,6 +384,9 @@ def main():
                        "launches_per_step": st["gpu_launches"]},
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        h.peer_close()
+        dist.barrier()
     h.close()
     if world > 1:
         dist.destroy_process_group()

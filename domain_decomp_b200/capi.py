@@ -18,6 +18,7 @@ LEFT, RIGHT, BOTTOM, TOP = 0, 1, 2, 3
 EDGE_NAMES = ("left", "right", "bottom", "top")
 WANT_PID, WANT_NEIGHBOURS, PROFILE, ASYNC = 1, 2, 4, 8
 NCCL_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 N_STAGES = 8
 STAGE_NAMES = ("mask_scan", "x_cuts", "strip_rows", "y_cuts", "label", "finalize", "neighbours", "total")
 
@@ -28,6 +29,7 @@ SYMBOLS = (
     "ddc_get_boxes", "ddc_get_pid_host", "ddc_get_pid_device", "ddc_get_neighbour_counts",
     "ddc_get_neighbour_total", "ddc_get_neighbours", "ddc_get_part_loads", "ddc_get_stats",
     "ddc_neighbours_from_boxes", "ddc_generate_mask_device", "ddc_generate_mask_host", "ddc_version",
+    "ddc_peer_export", "ddc_peer_import", "ddc_peer_close",
 )
 
 
@@ -40,6 +42,7 @@ class Stats(C.Structure):
         ("edge_cut", C.c_int64),
         ("median_iters", C.c_int32), ("gpu_launches", C.c_int32),
         ("stage_ms", C.c_float * N_STAGES),
+        ("exchange", C.c_int32),
     ]
 
     def as_dict(self):
@@ -73,6 +76,9 @@ def load() -> C.CDLL:
     L.ddc_create.argtypes = [C.POINTER(vp), i32, i32, i32, vp]
     L.ddc_destroy.argtypes = [vp]
     L.ddc_set_stream.argtypes = [vp, vp]
+    L.ddc_peer_export.argtypes = [vp, i32, i32, i32, vp]
+    L.ddc_peer_import.argtypes = [vp, vp]
+    L.ddc_peer_close.argtypes = [vp]
     L.ddc_set_mask_host.argtypes = [vp, vp, i32, i32, i32, i32]
     L.ddc_set_mask_device.argtypes = [vp, vp, i32, i32, i32, i32]
     L.ddc_shard_rows.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
@@ -154,6 +160,20 @@ class Handle:
 
     def __exit__(self, *a):
         self.close()
+
+    def peer_export(self, nx: int, ny: int, nparts: int) -> bytes:
+        """allocate this rank's exchange buffer; returns its CUDA IPC handle (IPC_HANDLE_BYTES bytes)"""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._ck(self.L.ddc_peer_export(self.h, nx, ny, nparts, buf), "ddc_peer_export")
+        return buf.raw
+
+    def peer_import(self, handles: list[bytes]):
+        """handles: the ddc_peer_export() result of every rank, in rank order"""
+        blob = b"".join(handles)
+        self._ck(self.L.ddc_peer_import(self.h, blob), "ddc_peer_import")
+
+    def peer_close(self):
+        self._ck(self.L.ddc_peer_close(self.h), "ddc_peer_close")
 
     def set_stream(self, cuda_stream: int | None):
         self._ck(self.L.ddc_set_stream(self.h, cuda_stream), "ddc_set_stream")

@@ -139,6 +139,13 @@ struct ddc_handle_s {
     size_t xcuts_smem = 0, ycuts16_smem = 0, ycuts32_smem = 0; // dynamic smem opt-ins already made
     cudaStream_t side_stream = nullptr; // speculative neighbour tables run beside the labelling
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // peer exchange (CUDA IPC): one buffer per rank, mapped by all ranks
+    //   [flags: PEER_STAGES * MAX_PEERS u32, padded to 256 B][col 0][col 1][row 0][row 1]
+    unsigned* xbuf = nullptr; // this rank's buffer
+    unsigned* xpeer[MAX_PEERS] = {}; // every rank's buffer as mapped here (xpeer[rank] == xbuf)
+    size_t x_colcap = 0, x_rowcap = 0; // capacity of one col / row copy, in 32-bit words
+    bool p2p = false;
+    unsigned step = 0; // decompositions enqueued so far (the flag value of the exchange barriers)
     int h_totals[8] = { 0 };
     bool totals_valid = false;
     Plan* pin_plan = nullptr; // pinned staging for the plan read-back
@@ -401,6 +408,11 @@ int ddc_destroy(ddc_handle_t h)
         cudaStreamSynchronize(h->side_stream);
     if (h->comm)
         g_nccl.CommDestroy(h->comm);
+    for (int q = 0; q < h->nranks && q < MAX_PEERS; q++)
+        if (h->xpeer[q] && q != h->rank)
+            cudaIpcCloseMemHandle(h->xpeer[q]);
+    if (h->xbuf)
+        cudaFree(h->xbuf);
     h->mask_own.release();
     h->bits.release();
     h->colcount.release();
@@ -436,6 +448,75 @@ int ddc_destroy(ddc_handle_t h)
     if (h->own_stream)
         cudaStreamDestroy(h->own_stream);
     delete h;
+    return DDC_OK;
+}
+
+static void guess_plan_public(int P, int NX, int NY, int* ix, int* iy);
+static void peer_capacity(int nx, int ny, int nparts, int G, size_t* colcap, size_t* rowcap)
+{
+    int ix, iy;
+    guess_plan_public(nparts, nx, ny, &ix, &iy);
+    const size_t Scap = (size_t)std::min<long long>(nparts, 1LL << std::min(ix, 30));
+    const size_t Rmax = ((size_t)ny + G - 1) / G;
+    const size_t elems = iy > 0 ? Scap * Rmax : 0;
+    *colcap = ((((size_t)nx + 3) & ~(size_t)3) + 2 * (size_t)G + 4 + 3) & ~(size_t)3;
+    *rowcap = ((nx < 65536 ? (elems + 1) / 2 : elems) + 4 + 3) & ~(size_t)3;
+}
+
+int ddc_peer_export(ddc_handle_t h, int nx, int ny, int nparts, void* ipc_handle_out)
+{
+    if (!h || !ipc_handle_out || nx < 1 || ny < 1 || nparts < 1)
+        return fail(h, DDC_ERR_ARG, "ddc_peer_export: bad arguments");
+    if (h->nranks > MAX_PEERS)
+        return fail(h, DDC_ERR_ARG, "ddc_peer_export: at most %d ranks", MAX_PEERS);
+    if (h->xbuf)
+        return fail(h, DDC_ERR_STATE, "ddc_peer_export: already exported");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    peer_capacity(nx, ny, nparts, h->nranks, &h->x_colcap, &h->x_rowcap);
+    const size_t words = 64 + 2 * h->x_colcap + 2 * h->x_rowcap;
+    CUDA_TRY(h, cudaMalloc((void**)&h->xbuf, words * sizeof(unsigned)));
+    CUDA_TRY(h, cudaMemset(h->xbuf, 0, words * sizeof(unsigned)));
+    cudaIpcMemHandle_t ipc;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&ipc, h->xbuf));
+    static_assert(sizeof(cudaIpcMemHandle_t) == DDC_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(ipc_handle_out, &ipc, sizeof ipc);
+    return DDC_OK;
+}
+
+int ddc_peer_import(ddc_handle_t h, const void* all_handles)
+{
+    if (!h || !all_handles)
+        return fail(h, DDC_ERR_ARG, "ddc_peer_import: bad arguments");
+    if (!h->xbuf)
+        return fail(h, DDC_ERR_STATE, "ddc_peer_import: call ddc_peer_export() first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (int q = 0; q < h->nranks; q++) {
+        if (q == h->rank) {
+            h->xpeer[q] = h->xbuf;
+            continue;
+        }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char*)all_handles + (size_t)q * DDC_IPC_HANDLE_BYTES, sizeof ipc);
+        void* p = nullptr;
+        CUDA_TRY(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->xpeer[q] = (unsigned*)p;
+    }
+    h->p2p = true;
+    return DDC_OK;
+}
+
+int ddc_peer_close(ddc_handle_t h)
+{
+    if (!h)
+        return DDC_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < h->nranks && q < MAX_PEERS; q++) {
+        if (h->xpeer[q] && q != h->rank)
+            CUDA_TRY(h, cudaIpcCloseMemHandle(h->xpeer[q]));
+        h->xpeer[q] = nullptr;
+    }
+    h->p2p = false;
     return DDC_OK;
 }
 
@@ -552,6 +633,9 @@ void guess_plan(int P, int NX, int NY, int* ix, int* iy)
     }
 }
 
+} // namespace
+static void guess_plan_public(int P, int NX, int NY, int* ix, int* iy) { guess_plan(P, NX, NY, ix, iy); }
+namespace {
 int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
 {
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -631,73 +715,112 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     Tables t = tables(h, P);
     const NaiveParams nv = naive_params(P, NX, NY);
 
+    // exchange mode: peer memory when the buffers were exchanged and are large enough, else NCCL
+    h->step++;
+    const bool p2p = G > 1 && h->p2p && (size_t)ncol <= h->x_colcap && (!ycuts || rc_words + 4 <= h->x_rowcap);
+    const int par = (int)(h->step & 1u);
+    constexpr size_t XFLAGS = 64; // words reserved for the flags at the head of an exchange buffer
+    auto xcol = [&](int q) { return h->xpeer[q] + XFLAGS + (size_t)par * h->x_colcap; };
+    auto xrow = [&](int q) { return h->xpeer[q] + XFLAGS + 2 * h->x_colcap + (size_t)par * h->x_rowcap; };
+    unsigned* colcount = p2p ? xcol(h->rank) : h->colcount.p;
+    unsigned* rowcount = p2p ? xrow(h->rank) : h->rowcount.p;
+    PeerSync ps {};
+    ps.rank = h->rank;
+    ps.G = G;
+    ps.enabled = p2p ? 1 : 0;
+    ps.step = h->step;
+    PeerCols pc {};
+    PeerRows pr {};
+    if (p2p) {
+        for (int q = 0; q < G; q++) {
+            ps.flags[q] = h->xpeer[q];
+            pc.col[q] = xcol(q);
+            pr.row[q] = xrow(q);
+        }
+        pc.n = pr.n = G;
+    } else {
+        pc.col[0] = colcount;
+        pc.n = pr.n = 1;
+    }
+
     mark(0);
     // ---- K1: mask scan -----------------------------------------------------------------------
-    k_init<<<(ncol + 255) / 256, 256, 0, s>>>(h->colcount.p, ncol, yr_off, h->rank, h->sc.p, h->loadmm.p);
+    k_init<<<(ncol + 255) / 256, 256, 0, s>>>(colcount, ncol, yr_off, h->rank, h->sc.p, h->loadmm.p);
     launches++;
     const int gridx = (NG + 7) / 8;
     const bool vec = (NX % 4 == 0) && (((uintptr_t)h->d_mask) % 16 == 0);
-    int* yr = reinterpret_cast<int*>(h->colcount.p + yr_off + 2 * h->rank);
+    int* yr = reinterpret_cast<int*>(colcount + yr_off + 2 * h->rank);
     if (rows > 0) {
         const int rpc = vec ? pick_rows_per_cta(k_scan_mask<true>, rows, gridx)
                             : pick_rows_per_cta(k_scan_mask<false>, rows, gridx);
         dim3 grid(gridx, (rows + rpc - 1) / rpc);
         if (vec)
             k_scan_mask<true><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
-                h->colcount.p, yr);
+                colcount, yr);
         else
             k_scan_mask<false><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
-                h->colcount.p, yr);
+                colcount, yr);
         launches++;
     }
-    if (G > 1) // the first exchange step: column histogram and every rank's dot y-range in one sum
-        NCCL_TRY(h, g_nccl.AllReduce(h->colcount.p, h->colcount.p, ncol, nccl_Uint32, nccl_Sum, h->comm, s));
+    if (G > 1 && !p2p) // the first exchange step: column histogram and every rank's dot y-range in one sum
+        NCCL_TRY(h, g_nccl.AllReduce(colcount, colcount, ncol, nccl_Uint32, nccl_Sum, h->comm, s));
     mark(1);
     // ---- K2: x cuts ----------------------------------------------------------------------------
-    if (x_smem && h->xcuts_smem < xneed) {
-        CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xneed));
-        h->xcuts_smem = xneed;
-    }
-    k_xcuts<<<1, 1024, x_smem ? xneed : 0, s>>>(h->colcount.p, NX, NY, P, h->colpfx.p, x_smem,
-        reinterpret_cast<const int*>(h->colcount.p + yr_off), G, aix, aiy, h->plan.p, t.st, t.bx,
-        h->loads.p, h->strip_of_col.p);
+    if (x_smem) {
+        if (h->xcuts_smem < xneed) {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xneed));
+            h->xcuts_smem = xneed;
+        }
+        k_xcuts<true><<<1, 1024, xneed, s>>>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, h->plan.p, t.st, t.bx,
+            h->loads.p, h->strip_of_col.p);
+    } else
+        k_xcuts<false><<<1, 1024, 0, s>>>(pc, ps, NX, NY, P, h->colpfx.p, yr_off, G, aix, aiy, h->plan.p, t.st,
+            t.bx, h->loads.p, h->strip_of_col.p);
     launches++;
     mark(2);
     // ---- K3 + K4: strip row counts, y cuts -----------------------------------------------------
     if (ycuts) {
         if (rows < Rmax) // short last shard: its padding rows must read as empty
-            CUDA_TRY(h, cudaMemsetAsync(h->rowcount.p, 0, sizeof(unsigned) * rc_words, s));
+            CUDA_TRY(h, cudaMemsetAsync(rowcount, 0, sizeof(unsigned) * rc_words, s));
         if (rows > 0) {
             dim3 grid((rows + 31) / 32, (Scap + 7) / 8);
             if (narrow)
                 k_strip_rows<uint16_t><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
-                    h->plan.p, Scap, reinterpret_cast<uint16_t*>(h->rowcount.p), Rmax);
+                    h->plan.p, Scap, reinterpret_cast<uint16_t*>(rowcount), Rmax);
             else
                 k_strip_rows<unsigned><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
-                    h->plan.p, Scap, h->rowcount.p, Rmax);
+                    h->plan.p, Scap, rowcount, Rmax);
             launches++;
         }
-        const unsigned* rc_all = h->rowcount.p;
-        if (G > 1) { // the second exchange step
-            NCCL_TRY(h, g_nccl.AllGather(h->rowcount.p, h->rowcount_all.p, rc_words, nccl_Uint32, h->comm, s));
-            rc_all = h->rowcount_all.p;
+        if (!p2p) {
+            pr.row[0] = rowcount;
+            if (G > 1) { // the second exchange step
+                NCCL_TRY(h, g_nccl.AllGather(rowcount, h->rowcount_all.p, rc_words, nccl_Uint32, h->comm, s));
+                pr.row[0] = h->rowcount_all.p;
+            }
         }
         mark(3);
+#define LAUNCH_YCUTS(CT, SM, opted)                                                                \
+    do {                                                                                           \
+        if (SM && opted < yneed) {                                                                 \
+            CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<CT, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed)); \
+            opted = yneed;                                                                         \
+        }                                                                                          \
+        k_ycuts<CT, SM><<<ygrid, 1024, SM ? yneed : 0, s>>>(pr, ps, rank_stride, Rmax, NY, t.st, h->ypfx.p, t.bx, \
+            h->loads.p, h->plan.p);                                                                \
+    } while (0)
         if (narrow) {
-            if (y_smem && h->ycuts16_smem < yneed) {
-                CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed));
-                h->ycuts16_smem = yneed;
-            }
-            k_ycuts<uint16_t><<<ygrid, 1024, y_smem ? yneed : 0, s>>>(reinterpret_cast<const uint16_t*>(rc_all),
-                rank_stride, Rmax, NY, t.st, h->ypfx.p, y_smem, t.bx, h->loads.p, h->plan.p);
+            if (y_smem)
+                LAUNCH_YCUTS(uint16_t, true, h->ycuts16_smem);
+            else
+                LAUNCH_YCUTS(uint16_t, false, h->ycuts16_smem);
         } else {
-            if (y_smem && h->ycuts32_smem < yneed) {
-                CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed));
-                h->ycuts32_smem = yneed;
-            }
-            k_ycuts<unsigned><<<ygrid, 1024, y_smem ? yneed : 0, s>>>(rc_all, rank_stride, Rmax, NY, t.st,
-                h->ypfx.p, y_smem, t.bx, h->loads.p, h->plan.p);
+            if (y_smem)
+                LAUNCH_YCUTS(unsigned, true, h->ycuts32_smem);
+            else
+                LAUNCH_YCUTS(unsigned, false, h->ycuts32_smem);
         }
+#undef LAUNCH_YCUTS
         launches++;
     } else
         mark(3);
@@ -743,13 +866,13 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
 #undef LAUNCH_LABEL
         launches++;
     }
-    if (G > 1)
+    if (G > 1 && !p2p)
         NCCL_TRY(h, g_nccl.AllReduce(&h->sc.p->changes, &h->sc.p->changes, 1, nccl_Int32, nccl_Max, h->comm, s));
     mark(5);
     // ---- K5: naive blocks when nothing moved; load statistics -----------------------------------
     if (want_nbr)
         CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0)); // K5 rewrites the boxes K7 is reading
-    k_finalize<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(P, NX, NY, nv, h->sc.p, h->plan.p, t.st, t.bx,
+    k_finalize<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(ps, P, NX, NY, nv, h->sc.p, h->plan.p, t.st, t.bx,
         h->loads.p, h->loadmm.p);
     launches++;
     mark(6);
@@ -765,6 +888,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     CUDA_TRY(h, cudaGetLastError());
 
     h->stats.gpu_launches = launches;
+    h->stats.exchange = G == 1 ? 0 : (p2p ? 2 : 1);
     h->stats.nx = NX;
     h->stats.ny = NY;
     h->stats.nparts = P;
@@ -787,6 +911,11 @@ int validate(ddc_handle_t h)
         const Plan& pl = *h->pin_plan;
         if (!pl.mismatch)
             break;
+        if (pl.mismatch == 3) {
+            h->partitioned = false;
+            return fail(h, DDC_ERR_PEER, "peer exchange timed out: a rank did not reach the step within %.1f s",
+                (double)PEER_TIMEOUT_NS * 1e-9);
+        }
         if (attempt >= 2) {
             h->partitioned = false;
             return fail(h, DDC_ERR_STATE, "the RCB plan did not settle (x/y levels %d/%d)", pl.ix, pl.iy);
@@ -960,7 +1089,7 @@ int ddc_get_stats(ddc_handle_t h, ddc_stats* out)
     CUDA_TRY(h, cudaMemcpyAsync(mm, h->loadmm.p, sizeof mm, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(&pl, h->plan.p, sizeof pl, cudaMemcpyDeviceToHost, h->stream)); // iters: K4 adds late
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    h->stats.changes = h->nparts > 1 ? hs.changes : 0;
+    h->stats.changes = h->nparts > 1 ? hs.changes_all : 0;
     h->stats.load_min = mm[0];
     h->stats.load_max = mm[1];
     h->stats.median_iters = pl.iters;
@@ -997,6 +1126,7 @@ int ddc_neighbours_from_boxes(ddc_handle_t h, int nparts, int nx, int ny, const 
     CUDA_TRY(h, cudaMemcpyAsync(t.st.always, &one, sizeof(int), cudaMemcpyHostToDevice, s));
     DevScalars init;
     init.changes = 1;
+    init.changes_all = 1;
     init.overflow = 0;
     init.edge_cut = 0;
     CUDA_TRY(h, cudaMemcpyAsync(h->sc.p, &init, sizeof init, cudaMemcpyHostToDevice, s));

@@ -28,7 +28,8 @@
 namespace ddc {
 
 struct DevScalars {
-    int changes; // any ocean cell whose RCB part differs from its naive block
+    int changes; // any ocean cell OF THIS RANK whose RCB part differs from its naive block
+    int changes_all; // the same over all ranks (written by K5)
     int overflow; // neighbour lists did not fit their capacity
     unsigned long long edge_cut; // sum of interior halo lengths
 };
@@ -45,6 +46,68 @@ struct Plan { // written by K2, read back by the host
 struct NaiveParams { // Grid.cpp:150-166
     int np0, np1, lx, ly;
 };
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU exchange over peer memory (NVLink / NVSwitch)
+// ------------------------------------------------------------------------------------------------
+// With several GPUs the three exchange steps of a decomposition (column counts, strip row counts,
+// the `changes` flag) are not separate collectives: the kernel that consumes the data reads it
+// straight out of the peers' buffers (mapped with CUDA IPC), after a flag barrier in its prologue.
+//   signal  every rank stores 2 * step + bit into slot [stage][own rank] of EVERY rank's flag array
+//           (st.release.sys over NVLink) once the producing kernel before it on the stream is done;
+//   wait    it then polls its OWN flag array (local memory) until all G slots of the stage have
+//           reached 2 * step.  Steps only grow, so flags are never reset, and the data buffers
+//           alternate between two copies by step parity, so a rank may run ahead into the next
+//           step without overwriting what a slower peer is still reading.
+// Each rank runs on its own GPU; a rank that does not show up within PEER_TIMEOUT_NS makes the
+// others give up (Plan::mismatch = 3) instead of hanging.
+constexpr int MAX_PEERS = 16;
+constexpr int PEER_STAGES = 3; // 0 column counts, 1 strip row counts, 2 changes
+constexpr unsigned long long PEER_TIMEOUT_NS = 2000000000ull;
+struct PeerSync {
+    unsigned* flags[MAX_PEERS]; // rank q's flag array [PEER_STAGES][MAX_PEERS], as mapped here
+    int rank, G, enabled;
+    unsigned step;
+};
+struct PeerCols { // the column-count buffer of every rank; n == 1: col[0] already holds global counts
+    const unsigned* col[MAX_PEERS];
+    int n;
+};
+struct PeerRows { // the strip-row-count block of every rank; n == 1: row[0] is the gathered [G][rank_stride]
+    const void* row[MAX_PEERS];
+    int n;
+};
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Called by the first G threads of a block (thread q talks to rank q).  do_signal: exactly one
+// block per rank sends.  Returns false on timeout; *seen = the flag value read from rank q.
+__device__ __forceinline__ bool peer_barrier(const PeerSync& ps, int stage, unsigned bit, bool do_signal,
+    unsigned* seen)
+{
+    const int q = threadIdx.x;
+    const unsigned want = 2u * ps.step;
+    if (do_signal) {
+        __threadfence_system();
+        unsigned* dst = ps.flags[q] + stage * MAX_PEERS + ps.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(want + bit) : "memory");
+    }
+    const unsigned* src = ps.flags[ps.rank] + stage * MAX_PEERS + q;
+    const unsigned long long t0 = global_ns();
+    unsigned v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+        if (v >= want)
+            break;
+        if (global_ns() - t0 > PEER_TIMEOUT_NS)
+            return false;
+    }
+    *seen = v;
+    return true;
+}
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -640,6 +703,14 @@ __device__ __forceinline__ int leaves_below(int n, int levels)
 {
     return levels >= 31 ? n : min(n, 1 << levels);
 }
+// threads that share one leaf's walk: the largest power of two <= 32 with lanes * leaves <= threads
+__device__ __forceinline__ int walk_lanes(int leaves, int threads)
+{
+    int lanes = 32;
+    while (lanes > 1 && (long long)lanes * leaves > threads)
+        lanes >>= 1;
+    return lanes;
+}
 // walk `levels` levels down from `set` towards leaf number k (0-based among the leaves below
 // `set`); iterations of a median are counted by the thread whose leaf is the first of its upper child
 __device__ inline RcbSet rcb_walk(const Hist& H, RcbSet set, int levels, int k, int* iters)
@@ -683,41 +754,62 @@ struct BoxTable { // final boxes, SoA
 
 constexpr int PFX_E = 32; // elements per thread of the wide prefix scans (1024 threads: 32768 per tile)
 
-// 32 consecutive unsigned counts, vector loads when the chunk is whole and 16-byte aligned
-__device__ __forceinline__ void load_counts_u32(const unsigned* __restrict__ src, int i0, int n, unsigned (&v)[PFX_E])
+// 32 consecutive column counts summed over the ranks' buffers (one buffer when the counts are
+// already global); vector loads when the chunk is whole and 16-byte aligned.  ld.global.cg: the
+// buffers of the peers are written by other GPUs.
+__device__ __forceinline__ void load_counts_u32(const PeerCols& pc, int i0, int n, unsigned (&v)[PFX_E])
 {
-    if (i0 + PFX_E <= n && ((uintptr_t)(src + i0) & 15) == 0) {
 #pragma unroll
-        for (int q = 0; q < PFX_E / 4; q++) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4*>(src + i0) + q);
-            v[4 * q] = t.x;
-            v[4 * q + 1] = t.y;
-            v[4 * q + 2] = t.z;
-            v[4 * q + 3] = t.w;
+    for (int k = 0; k < PFX_E; k++)
+        v[k] = 0u;
+    for (int g = 0; g < pc.n; g++) {
+        const unsigned* src = pc.col[g];
+        if (i0 + PFX_E <= n && ((uintptr_t)(src + i0) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < PFX_E / 4; q++) {
+                const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src + i0) + q);
+                v[4 * q] += t.x;
+                v[4 * q + 1] += t.y;
+                v[4 * q + 2] += t.z;
+                v[4 * q + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < PFX_E; k++)
+                v[k] += i0 + k < n ? __ldcg(src + i0 + k) : 0u;
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < PFX_E; k++)
-            v[k] = i0 + k < n ? __ldg(src + i0 + k) : 0u;
     }
 }
 
-// dynamic shared memory when use_smem: (NX + 1) unsigned, rounded up to 4, + hist_bitmap_words(NX).  yr_all: G pairs {-(first ocean row),
-// last ocean row}, one per rank (summed into place by the all-reduce of the column counts).
+// dynamic shared memory when SMEM: (NX + 1) unsigned, rounded up to 4, + hist_bitmap_words(NX).
 // aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
-__global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ colcount, int NX, int NY,
-    int P, unsigned* pfx_g, int use_smem, const int* __restrict__ yr_all, int G, int aix, int aiy, Plan* plan,
-    StripTable st, BoxTable bx, long long* loads, int* strip_of_col)
+template <bool SMEM>
+__global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
+    int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads,
+    int* strip_of_col)
 {
     extern __shared__ __align__(16) unsigned smem_dyn[];
     __shared__ unsigned wsum[33];
     __shared__ int s_ix, s_iters;
-    unsigned* pfx = use_smem ? smem_dyn : pfx_g;
+    unsigned* pfx = SMEM ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
 
+    // 0. exchange step 1: every rank's mask scan is done and its column counts can be read
+    if (ps.enabled) {
+        bool ok = true;
+        unsigned seen;
+        if (tid < ps.G)
+            ok = peer_barrier(ps, 0, 0u, true, &seen);
+        if (__syncthreads_or(!ok)) {
+            if (tid == 0)
+                plan->mismatch = 3;
+            return;
+        }
+    }
+
     // 1. pfx[i] = ocean cells in columns [0, i)
-    unsigned* bitmap = use_smem ? smem_dyn + (((size_t)NX + 1 + 3) & ~(size_t)3) : nullptr;
-    block_prefix_wide<PFX_E>([&](int i0, unsigned (&v)[PFX_E]) { load_counts_u32(colcount, i0, NX, v); }, NX, pfx, wsum,
+    unsigned* bitmap = SMEM ? smem_dyn + (((size_t)NX + 1 + 3) & ~(size_t)3) : nullptr;
+    block_prefix_wide<PFX_E>([&](int i0, unsigned (&v)[PFX_E]) { load_counts_u32(pc, i0, NX, v); }, NX, pfx, wsum,
         bitmap);
     const Hist H = make_hist(pfx, bitmap, NX);
 
@@ -728,10 +820,13 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
         if (W > 0) {
             xmin = first_nonempty(H, 0, NX - 1);
             xmax = last_nonempty(H, 0, NX - 1);
+            // every rank's {-(first ocean row), last ocean row} sits in slot g behind its column
+            // counts (and, after an all-reduce, in slot g of the one global buffer)
             int a = (int)0x80000000, b = -1;
             for (int g = 0; g < G; g++) {
-                a = max(a, yr_all[2 * g]);
-                b = max(b, yr_all[2 * g + 1]);
+                const unsigned* src = (pc.n == 1 ? pc.col[0] : pc.col[g]) + yr_off + 2 * g;
+                a = max(a, (int)__ldcg(src));
+                b = max(b, (int)__ldcg(src + 1));
             }
             ymin = -a;
             ymax = b;
@@ -764,13 +859,20 @@ __global__ void __launch_bounds__(1024) k_xcuts(const unsigned* __restrict__ col
     }
     __syncthreads();
 
-    // 3. the x levels: thread i walks to strip i
+    // 3. the x levels: a group of `lanes` adjacent threads walks to strip i, all of them evaluating
+    //    the same medians (the block has more threads than strips; the fewer different medians the
+    //    lanes of a warp work on, the less a warp waits for the slowest of them)
     const int ix = s_ix;
     const int nstrips = leaves_below(P, ix);
+    const int lanes = walk_lanes(nstrips, blockDim.x);
     int my_iters = 0;
-    for (int i = tid; i < nstrips; i += blockDim.x) {
+    for (int i = tid / lanes; i < nstrips; i += blockDim.x / lanes) {
         const RcbSet root = { 0, NX, 0, P };
-        const RcbSet r = rcb_walk(H, root, ix, i, &my_iters);
+        int it = 0;
+        const RcbSet r = rcb_walk(H, root, ix, i, &it);
+        if (tid % lanes)
+            continue;
+        my_iters += it;
         // 4. the strip table, in ascending part order
         st.x0[i] = r.lo;
         st.x1[i] = r.hi;
@@ -863,17 +965,24 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
 // otherwise pfx_g holds gridDim.x slices of NY + 1.  The set lists of strip s live in
 // listA/listB[p0[s] .. p0[s+1]) (strips own disjoint part ranges).
 template <typename CT>
-__device__ __forceinline__ void load_row_counts(const CT* __restrict__ base /* [G][Scap][Rmax] + s * Rmax */,
-    size_t rank_stride, int Rmax, int i0, int NY, unsigned (&v)[PFX_E])
+__device__ __forceinline__ const CT* row_segment(const PeerRows& pr, size_t rank_stride, int g)
+{
+    return pr.n == 1 ? reinterpret_cast<const CT*>(pr.row[0]) + (size_t)g * rank_stride
+                     : reinterpret_cast<const CT*>(pr.row[g]);
+}
+// 32 consecutive row counts of strip s starting at global row i0 (rank g = y / Rmax holds row y)
+template <typename CT>
+__device__ __forceinline__ void load_row_counts(const PeerRows& pr, size_t rank_stride, size_t strip_off, int Rmax,
+    int i0, int NY, unsigned (&v)[PFX_E])
 {
     const int g = i0 / Rmax, yl = i0 - g * Rmax;
-    const CT* src = base + (size_t)g * rank_stride + yl;
+    const CT* src = row_segment<CT>(pr, rank_stride, g) + strip_off + yl;
     if (i0 + PFX_E <= NY && yl + PFX_E <= Rmax && ((uintptr_t)src & 15) == 0) {
         // the chunk lies inside one rank's rows: vector loads
         if (sizeof(CT) == 4) {
 #pragma unroll
             for (int q = 0; q < PFX_E / 4; q++) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src) + q);
                 v[4 * q] = t.x;
                 v[4 * q + 1] = t.y;
                 v[4 * q + 2] = t.z;
@@ -882,7 +991,7 @@ __device__ __forceinline__ void load_row_counts(const CT* __restrict__ base /* [
         } else {
 #pragma unroll
             for (int q = 0; q < PFX_E / 8; q++) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src) + q);
                 v[8 * q] = t.x & 0xffffu;
                 v[8 * q + 1] = t.x >> 16;
                 v[8 * q + 2] = t.y & 0xffffu;
@@ -900,23 +1009,35 @@ __device__ __forceinline__ void load_row_counts(const CT* __restrict__ base /* [
             unsigned c = 0u;
             if (y < NY) {
                 const int gg = y / Rmax;
-                c = (unsigned)__ldg(base + (size_t)gg * rank_stride + (y - gg * Rmax));
+                c = (unsigned)__ldcg(row_segment<CT>(pr, rank_stride, gg) + strip_off + (y - gg * Rmax));
             }
             v[k] = c;
         }
     }
 }
 
-template <typename CT>
-__global__ void __launch_bounds__(1024) k_ycuts(const CT* __restrict__ rowcount_all, size_t rank_stride,
-    int Rmax, int NY, StripTable st, unsigned* pfx_g, int use_smem, BoxTable bx, long long* loads, Plan* plan)
+template <typename CT, bool SMEM>
+__global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t rank_stride,
+    int Rmax, int NY, StripTable st, unsigned* pfx_g, BoxTable bx, long long* loads, Plan* plan)
 {
     extern __shared__ __align__(16) unsigned smem_dyn[];
     __shared__ unsigned wsum[33];
     if (plan->mismatch)
         return;
-    unsigned* pfx = use_smem ? smem_dyn : pfx_g + (size_t)blockIdx.x * (((size_t)NY + 1 + 3) & ~(size_t)3);
-    unsigned* bitmap = use_smem ? smem_dyn + (((size_t)NY + 1 + 3) & ~(size_t)3) : nullptr;
+    // exchange step 2: every rank's strip row counts are written (block 0 says so for this rank)
+    if (ps.enabled) {
+        bool ok = true;
+        unsigned seen;
+        if (threadIdx.x < ps.G)
+            ok = peer_barrier(ps, 1, 0u, blockIdx.x == 0, &seen);
+        if (__syncthreads_or(!ok)) {
+            if (threadIdx.x == 0)
+                plan->mismatch = 3;
+            return;
+        }
+    }
+    unsigned* pfx = SMEM ? smem_dyn : pfx_g + (size_t)blockIdx.x * (((size_t)NY + 1 + 3) & ~(size_t)3);
+    unsigned* bitmap = SMEM ? smem_dyn + (((size_t)NY + 1 + 3) & ~(size_t)3) : nullptr;
     const Hist H = make_hist(pfx, bitmap, NY);
     const int tid = threadIdx.x;
     const int S = *st.S;
@@ -927,15 +1048,20 @@ __global__ void __launch_bounds__(1024) k_ycuts(const CT* __restrict__ rowcount_
         if (n <= 1)
             continue; // K2 already wrote the box of a leaf strip
         __syncthreads(); // previous strip done with pfx
-        const CT* base = rowcount_all + (size_t)s * Rmax;
+        const size_t strip_off = (size_t)s * Rmax;
         block_prefix_wide<PFX_E>(
-            [&](int i0, unsigned (&v)[PFX_E]) { load_row_counts<CT>(base, rank_stride, Rmax, i0, NY, v); }, NY, pfx, wsum,
-            bitmap);
-        // thread j walks to the j-th part of the strip (parts come out y-sorted)
+            [&](int i0, unsigned (&v)[PFX_E]) { load_row_counts<CT>(pr, rank_stride, strip_off, Rmax, i0, NY, v); }, NY,
+            pfx, wsum, bitmap);
+        // a group of `lanes` threads walks to the j-th part of the strip (parts come out y-sorted)
         const int sx0 = st.x0[s], sx1 = st.x1[s];
-        for (int j = tid; j < n; j += blockDim.x) {
+        const int lanes = walk_lanes(n, blockDim.x);
+        for (int j = tid / lanes; j < n; j += blockDim.x / lanes) {
             const RcbSet root = { 0, NY, plo, n };
-            const RcbSet r = rcb_walk(H, root, ylevels, j, &my_iters);
+            int it = 0;
+            const RcbSet r = rcb_walk(H, root, ylevels, j, &it);
+            if (tid % lanes)
+                continue;
+            my_iters += it;
             bx.x0[r.plo] = sx0;
             bx.ex[r.plo] = sx1 - sx0;
             bx.y0[r.plo] = r.lo;
@@ -1144,12 +1270,26 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
 // K5: `changes == 0`  =>  report the naive blocks (ZoltanPartitioner.cpp:182-187)
 // ------------------------------------------------------------------------------------------------
 // Also reduces the part loads to their min / max (loadmm pre-set to LLONG_MAX, -1 by k_init).
-__global__ void __launch_bounds__(256) k_finalize(int P, int NX, int NY, NaiveParams nv,
-    const DevScalars* __restrict__ sc, const Plan* __restrict__ plan, StripTable st, BoxTable bx,
+__global__ void __launch_bounds__(256) k_finalize(PeerSync ps, int P, int NX, int NY, NaiveParams nv,
+    DevScalars* __restrict__ sc, Plan* __restrict__ plan, StripTable st, BoxTable bx,
     const long long* __restrict__ loads, long long* __restrict__ loadmm)
 {
     if (plan->mismatch)
         return;
+    // exchange step 3: `changes` of every rank rides in the low bit of its flag
+    int changes = sc->changes;
+    if (ps.enabled) {
+        bool ok = true;
+        unsigned seen = 0u;
+        if (threadIdx.x < ps.G)
+            ok = peer_barrier(ps, 2, changes ? 1u : 0u, blockIdx.x == 0, &seen);
+        if (__syncthreads_or(!ok)) {
+            if (threadIdx.x == 0)
+                plan->mismatch = 3;
+            return;
+        }
+        changes = __syncthreads_or(threadIdx.x < ps.G && (seen & 1u));
+    }
     long long mn = 0x7fffffffffffffffLL, mx = -1;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         const long long v = loads[p];
@@ -1166,7 +1306,11 @@ __global__ void __launch_bounds__(256) k_finalize(int P, int NX, int NY, NaivePa
         atomicMin(loadmm, mn);
         atomicMax(loadmm + 1, mx);
     }
-    if (P == 1 || sc->changes != 0)
+    if (ps.enabled && blockIdx.x == 0 && threadIdx.x == 0)
+        sc->changes_all = changes; // only this block reads sc->changes (above); later kernels read changes_all
+    if (!ps.enabled && blockIdx.x == 0 && threadIdx.x == 0)
+        sc->changes_all = changes;
+    if (P == 1 || changes != 0)
         return;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         const int bxi = p / nv.np1, byi = p % nv.np1; // Grid.cpp:158-159
@@ -1478,7 +1622,7 @@ __global__ void __launch_bounds__(1024) k_neighbours_redo(BoxTable bx, int P, in
 {
     __shared__ unsigned long long wsum64[33];
     __shared__ int s_over;
-    if (plan->mismatch || sc->changes != 0)
+    if (plan->mismatch || sc->changes_all != 0)
         return;
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -1541,6 +1685,7 @@ __global__ void __launch_bounds__(256) k_init(unsigned* __restrict__ colcount, i
     }
     if (i == 0) {
         sc->changes = 0;
+        sc->changes_all = 0;
         sc->overflow = 0;
         sc->edge_cut = 0ull;
         loadmm[0] = 0x7fffffffffffffffLL;

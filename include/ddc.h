@@ -47,7 +47,8 @@ typedef enum {
     DDC_ERR_CUDA = -2, /* CUDA runtime error (message has the detail) */
     DDC_ERR_NCCL = -3, /* NCCL error */
     DDC_ERR_NOMEM = -4,
-    DDC_ERR_STATE = -5 /* result requested before ddc_partition() */
+    DDC_ERR_STATE = -5, /* result requested before ddc_partition() */
+    DDC_ERR_PEER = -6 /* a rank did not reach an exchange step in time (peer-memory exchange) */
 } ddc_status;
 
 enum { DDC_LEFT = 0, DDC_RIGHT = 1, DDC_BOTTOM = 2, DDC_TOP = 3, DDC_N_EDGE = 4 };
@@ -63,6 +64,7 @@ enum {
 };
 
 #define DDC_NCCL_ID_BYTES 128
+#define DDC_IPC_HANDLE_BYTES 64
 #define DDC_N_STAGES 8
 
 typedef struct {
@@ -78,6 +80,8 @@ typedef struct {
     /* DDC_PROFILE: milliseconds per stage on this rank (0 when not profiled)
        0 mask scan, 1 x cuts, 2 strip rows, 3 y cuts, 4 label, 5 finalize, 6 neighbours, 7 total */
     float stage_ms[DDC_N_STAGES];
+    int32_t exchange; /* how the ranks exchanged their histograms: 0 single GPU, 1 NCCL collectives,
+                         2 peer memory (loads from the other ranks' buffers inside the kernels) */
 } ddc_stats;
 
 /* ---- life cycle ---------------------------------------------------------------------------- */
@@ -90,6 +94,21 @@ DDC_API int ddc_get_nccl_unique_id(void* out /* DDC_NCCL_ID_BYTES */);
 DDC_API int ddc_create(ddc_handle_t* h, int device, int rank, int nranks, const void* nccl_id);
 DDC_API int ddc_destroy(ddc_handle_t h);
 DDC_API const char* ddc_last_error(ddc_handle_t h);
+
+/* Peer-memory exchange (nranks > 1, all GPUs of one NVLink / NVSwitch box, one process per GPU).
+   The reference exchanges through MPI inside Zoltan and with four MPI_Allgather calls in
+   discover_neighbours (Partitioner.cpp:378-388).  Here the kernels that consume the exchanged
+   histograms read them straight out of the other ranks' buffers: ddc_peer_export() allocates this
+   rank's exchange buffer for masks up to nx * ny into nparts parts and returns its CUDA IPC
+   handle; the host gathers the handles of all ranks (MPI_Allgather / torch.distributed) and hands
+   them, in rank order, to ddc_peer_import().  Without these two calls -- or for a decomposition
+   that does not fit the exported capacity -- the exchange steps are NCCL collectives. */
+DDC_API int ddc_peer_export(ddc_handle_t h, int nx, int ny, int nparts, void* ipc_handle_out /* DDC_IPC_HANDLE_BYTES */);
+DDC_API int ddc_peer_import(ddc_handle_t h, const void* all_handles /* nranks * DDC_IPC_HANDLE_BYTES */);
+/* unmap the other ranks' buffers (back to NCCL).  Shutdown order: every rank calls ddc_peer_close(),
+   the host synchronises the ranks (a barrier), then every rank calls ddc_destroy(), which frees its
+   own buffer -- so that no buffer is freed while another rank still has it mapped. */
+DDC_API int ddc_peer_close(ddc_handle_t h);
 
 /* launch everything on this CUDA stream (a cudaStream_t; NULL = the handle's own stream) */
 DDC_API int ddc_set_stream(ddc_handle_t h, void* cuda_stream);

@@ -40,31 +40,43 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     h = capi.Handle(local, rank, world, ids[0])
     failures = 0
-    for (nx, ny, P, land, seed, px, py) in CASES:
-        mask = capi.generate_mask_host(nx, ny, seed, land)
-        yb, yc = capi.shard_rows(ny, world, rank)
-        shard = np.ascontiguousarray(mask[yb:yb + yc])
-        if yc == 0:
-            shard = np.zeros((0, nx), dtype=np.int32)
-        h.set_mask_host(shard, ny=ny, y_begin=yb)
-        h.partition(P, bool(px), bool(py))
-        o = orc.partition(mask, P, bool(px), bool(py), use_hist=True)
-        ok = h.boxes().tolist() == o.boxes.tolist()
-        ok &= np.array_equal(h.pid_host(), o.pid[yb:yb + yc])
-        st = h.stats()
-        ok &= st["changes"] == o.changes and st["n_ocean"] == int((mask > 0).sum())
-        ok &= st["median_iters"] == o.median_iters
-        for per in range(2):
-            for e in range(4):
-                ok &= h.neighbour_counts(e, per).tolist() == o.nbr.counts[per][e].tolist()
-                a, b, c = h.neighbours(e, per)
-                ok &= a.tolist() == o.nbr.ids[per][e].tolist() and b.tolist() == o.nbr.halos[per][e].tolist()
-                ok &= c.tolist() == o.nbr.starts[per][e].tolist()
-        ok &= h.part_loads().tolist() == orc.part_loads(o.pid, P).tolist()
-        print("rank %d/%d case %dx%d P=%d: %s" % (rank, world, nx, ny, P, "ok" if ok else "MISMATCH"), flush=True)
-        failures += 0 if ok else 1
+    for mode in ("nccl", "peer"):
+        if mode == "peer":
+            # hand every rank's exchange buffer to every other rank (CUDA IPC handles through the host)
+            mine = h.peer_export(4096, 4096, 1024)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            h.peer_import(handles)
+        for (nx, ny, P, land, seed, px, py) in CASES:
+            mask = capi.generate_mask_host(nx, ny, seed, land)
+            yb, yc = capi.shard_rows(ny, world, rank)
+            shard = np.ascontiguousarray(mask[yb:yb + yc])
+            if yc == 0:
+                shard = np.zeros((0, nx), dtype=np.int32)
+            h.set_mask_host(shard, ny=ny, y_begin=yb)
+            for rep in range(2):  # twice: both parities of the double-buffered exchange
+                h.partition(P, bool(px), bool(py))
+            o = orc.partition(mask, P, bool(px), bool(py), use_hist=True)
+            ok = h.boxes().tolist() == o.boxes.tolist()
+            ok &= np.array_equal(h.pid_host(), o.pid[yb:yb + yc])
+            st = h.stats()
+            ok &= st["exchange"] == (1 if mode == "nccl" else 2)
+            ok &= st["changes"] == o.changes and st["n_ocean"] == int((mask > 0).sum())
+            ok &= st["median_iters"] == o.median_iters
+            for per in range(2):
+                for e in range(4):
+                    ok &= h.neighbour_counts(e, per).tolist() == o.nbr.counts[per][e].tolist()
+                    a, b, c = h.neighbours(e, per)
+                    ok &= a.tolist() == o.nbr.ids[per][e].tolist() and b.tolist() == o.nbr.halos[per][e].tolist()
+                    ok &= c.tolist() == o.nbr.starts[per][e].tolist()
+            ok &= h.part_loads().tolist() == orc.part_loads(o.pid, P).tolist()
+            print("rank %d/%d %s case %dx%d P=%d: %s" % (rank, world, mode, nx, ny, P, "ok" if ok else "MISMATCH"),
+                  flush=True)
+            failures += 0 if ok else 1
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
+    h.peer_close()
+    dist.barrier()  # nobody frees its exchange buffer while a peer still has it mapped
     h.close()
     dist.destroy_process_group()
     if int(t.item()):
