@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -374,6 +375,10 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     for (auto& ev : h->ev)
         CREATE_TRY(cudaEventCreate(&ev));
     h->ev_ok = true;
+    if (const char* e = getenv("DDC_WALK_LANES")) { // tuning knob of the cut kernels
+        const int v = std::max(1, std::min(32, atoi(e)));
+        CREATE_TRY(cudaMemcpyToSymbol(g_walk_lanes, &v, sizeof v));
+    }
     CREATE_TRY(h->sc.ensure(1));
     CREATE_TRY(h->plan.ensure(1));
 #undef CREATE_TRY
@@ -783,13 +788,24 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         if (rows < Rmax) // short last shard: its padding rows must read as empty
             CUDA_TRY(h, cudaMemsetAsync(rowcount, 0, sizeof(unsigned) * rc_words, s));
         if (rows > 0) {
-            dim3 grid((rows + 31) / 32, (Scap + 7) / 8);
-            if (narrow)
-                k_strip_rows<uint16_t><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
-                    h->plan.p, Scap, reinterpret_cast<uint16_t*>(rowcount), Rmax);
-            else
-                k_strip_rows<unsigned><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
-                    h->plan.p, Scap, rowcount, Rmax);
+            const size_t scan_smem = sizeof(int) * strip_scan_smem_words(NG, Scap);
+            if (scan_smem <= 48 * 1024) { // the streaming kernel: boundary table in shared memory
+                const int grid = (rows + 31) / 32;
+                if (narrow)
+                    k_strip_rows_scan<uint16_t><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0,
+                        h->plan.p, Scap, reinterpret_cast<uint16_t*>(rowcount), Rmax);
+                else
+                    k_strip_rows_scan<unsigned><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0,
+                        h->plan.p, Scap, rowcount, Rmax);
+            } else {
+                dim3 grid((rows + 31) / 32, (Scap + 7) / 8);
+                if (narrow)
+                    k_strip_rows<uint16_t><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
+                        h->plan.p, Scap, reinterpret_cast<uint16_t*>(rowcount), Rmax);
+                else
+                    k_strip_rows<unsigned><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
+                        h->plan.p, Scap, rowcount, Rmax);
+            }
             launches++;
         }
         if (!p2p) {
@@ -931,6 +947,13 @@ int validate(ddc_handle_t h)
         h->stats.gpu_launches += launches;
     }
     const Plan& pl = *h->pin_plan;
+    if (getenv("DDC_DEBUG_TS")) {
+        const unsigned long long* t = pl.ts;
+        fprintf(stderr, "[ddc] K2 ns: barrier %llu prefix %llu plan %llu walks %llu paint %llu | K4 block 0 ns: barrier %llu "
+                        "prefix %llu walks %llu, longest block %llu | K2 end -> K4 start %llu\n",
+            t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[7] - t[6], t[8] - t[7], t[9] - t[8], t[10],
+            t[6] - t[5]);
+    }
     h->stats.nlev = pl.nlev;
     h->stats.n_xlev = pl.ix;
     h->stats.n_ylev = pl.iy;

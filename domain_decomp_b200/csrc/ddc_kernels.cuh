@@ -41,6 +41,10 @@ struct Plan { // written by K2, read back by the host
     int iters; // median iterations (x levels; K4 adds its own atomically)
     int mismatch; // (ix, iy) differ from what the host assumed when it sized the launches: the
                   // kernels after K2 do nothing and the host runs the step again with the real plan
+    // diagnostics (printed by the host when DDC_DEBUG_TS is set): %globaltimer stamps of the phases
+    // of the two cut kernels.  0-5: K2 start, after the exchange barrier, prefix, plan, walks, end;
+    // 6-9: K4 block 0 start, after the barrier, after the prefix, end; 10: longest K4 block (ns)
+    unsigned long long ts[12];
 };
 
 struct NaiveParams { // Grid.cpp:150-166
@@ -557,28 +561,38 @@ __device__ __forceinline__ int first_nonempty(const Hist& H, int a, int b)
 
 // floor() of Zoltan's interpolated guess
 //     tmp_half = valuemin + (targetlo - weightlo) / (weight - weightlo - weighthi) * (valuemax - valuemin)
-// clamped to [alo - 1, ahi].  Only floor(tmp_half) matters, so the quotient is first formed with a
-// reciprocal approximation refined by two Newton steps (relative error < 2^-48, i.e. < 2^-17 bins
-// for any range below 2^31); unless that value lies within 2^-10 of an integer -- where the
-// rounding of the real IEEE sequence could matter -- its floor IS the floor of the exact sequence.
-// Otherwise the exact sequence (correctly rounded division, multiplication, addition) is evaluated.
-__device__ __forceinline__ int guess_bin(int vmin, double num, double den, int range, int alo, int ahi)
+// clamped to [alo - 1, ahi].  Only floor(tmp_half) matters, and FP64 instructions have a long
+// latency on this part, so the offset from valuemin is first formed in FP32 from exact integers
+// (targetlo = Ti + Tfrac with Ti an integer, so targetlo - weightlo starts from an exact integer
+// difference): its relative error is below 2^-21, i.e. below range * 2^-21 bins.  Unless the result
+// lies that close to an integer -- where the rounding of the real IEEE sequence could matter -- its
+// floor IS the floor of the exact sequence.  Otherwise (and for ranges FP32 cannot hold) the exact
+// sequence is evaluated in FP64: correctly rounded subtraction, division, multiplication, addition.
+__device__ __forceinline__ int guess_bin(int vmin, int range, unsigned Ti, float Tfrac, double T, unsigned wlo,
+    unsigned den, int alo, int ahi)
 {
-    const double dvmin = (double)vmin, drange = (double)range;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-    r = fma(r, fma(-den, r, 1.0), r);
-    r = fma(r, fma(-den, r, 1.0), r);
-    double tmp = fma(num * r, drange, dvmin);
-    const double fl = floor(tmp), fr = tmp - fl;
-    if (!(den >= 1.0 && fr > 0x1p-10 && fr < 1.0 - 0x1p-10))
-        tmp = __dadd_rn(dvmin, __dmul_rn(__ddiv_rn(num, den), drange));
+    int t;
+    bool sure = false;
+    if (range < (1 << 22) && den != 0u) {
+        const float numf = (float)(Ti - wlo) + Tfrac;
+        const float rangef = (float)range;
+        const float off = __fdividef(numf, (float)den) * rangef;
+        const float fl = floorf(off), fr = off - fl;
+        const float guard = rangef * 0x1p-20f + 0x1p-18f;
+        sure = fr > guard && fr < 1.0f - guard;
+        t = vmin + (int)fl;
+    }
+    if (!sure) {
+        const double tmp = __dadd_rn((double)vmin,
+            __dmul_rn(__ddiv_rn(__dsub_rn(T, (double)wlo), (double)den), (double)range));
+        if (tmp < (double)alo)
+            return alo - 1;
+        if (tmp >= (double)ahi)
+            return ahi;
+        return (int)floor(tmp);
+    }
     // tmp < alo -> alo - 1;  tmp >= ahi -> ahi;  else floor(tmp)
-    if (tmp < (double)alo)
-        return alo - 1;
-    if (tmp >= (double)ahi)
-        return ahi;
-    return (int)floor(tmp);
+    return min(max(t, alo - 1), ahi);
 }
 
 // Integer boundary ceil(cut) of the weighted-median cut of bins [c0, c1] for a set of num_parts
@@ -586,9 +600,11 @@ __device__ __forceinline__ int guess_bin(int vmin, double num, double den, int r
 //
 // Zoltan keeps weightlo / weighthi / totallo / totalhi as doubles, but with unit weights they are
 // exact integers: here they are integers read off the prefix sums (dots in [c0, t] = weightlo +
-// totallo, dots in (t, c1] = weighthi + totalhi), converted to double exactly where Zoltan
-// compares them with the (non-integer) targets or forms the tie-rule differences.  One iteration
-// is then one guess, one prefix-sum load, one bit-map query and one more prefix-sum load.
+// totallo, dots in (t, c1] = weighthi + totalhi).  Comparing such an integer m with a target T is
+// done against ceil(T): m < T <=> m < ceil(T); and Zoltan's tolerance test fl(T - m) <= 1.0 (for
+// m < T, where the subtraction is exact because m is a multiple of ulp(T)) <=> m >= ceil(T) - 1.
+// FP64 is only touched for the tie rule that ends a search, for an ambiguous guess, and to form
+// the targets when the part counts are not split in half (fractionlo != 0.5).
 __device__ inline int median_boundary(const Hist& H, int c0, int c1, int nlo, int num_parts,
     int* iters)
 {
@@ -599,78 +615,71 @@ __device__ inline int median_boundary(const Hist& H, int c0, int c1, int nlo, in
         *iters += 1;
         return c0 + ((c1 + 1 - c0) >> 1);
     }
-    const double weight = (double)Wn;
-    const double fractionlo = __ddiv_rn((double)nlo, (double)num_parts);
+    // targetlo = fl(fl(nlo / num_parts) * W), targethi = fl(W - targetlo)
+    double T, Thi;
+    unsigned Ti, ceilT, ceilThi;
+    float Tfrac;
+    if (2 * nlo == num_parts) { // fractionlo = 0.5: both targets are W / 2 exactly
+        T = Thi = 0.5 * (double)Wn;
+        Ti = Wn >> 1;
+        Tfrac = (Wn & 1u) ? 0.5f : 0.0f;
+        ceilT = ceilThi = (Wn + 1u) >> 1;
+    } else {
+        T = __dmul_rn(__ddiv_rn((double)nlo, (double)num_parts), (double)Wn);
+        Thi = __dsub_rn((double)Wn, T);
+        const double fT = floor(T);
+        Ti = (unsigned)fT;
+        Tfrac = (float)(T - fT);
+        ceilT = (unsigned)ceil(T);
+        ceilThi = (unsigned)ceil(Thi);
+    }
     const int first = first_nonempty(H, c0, c1), last = last_nonempty(H, c0, c1);
     int vmin = first, vmax = last; // valuemin, valuemax (always bin indices)
     int alo = first, ahi = last; // the active bins
     int B;
     unsigned wlo = 0, whi = 0; // weightlo, weighthi
-    const double targetlo = __dmul_rn(fractionlo, weight);
-    const double targethi = __dsub_rn(weight, targetlo);
     int it = 0;
     for (;;) {
-        const int t = guess_bin(vmin, __dsub_rn(targetlo, (double)wlo), (double)(Wn - wlo - whi), vmax - vmin, alo, ahi);
+        const int t = guess_bin(vmin, vmax - vmin, Ti, Tfrac, T, wlo, Wn - wlo - whi, alo, ahi);
         it++;
         B = t;
-        const unsigned cum = pfx[t + 1] - base; // dots in [c0, t]
-        const double dcum = (double)cum;
-        if (dcum < targetlo) { // lower half TOO SMALL (weightlo + totallo < targetlo)
+        const unsigned cum = pfx[t + 1] - base; // dots in [c0, t] = weightlo + totallo
+        if (cum < ceilT) { // lower half TOO SMALL (weightlo + totallo < targetlo)
             const int vhi = first_nonempty(H, t + 1, ahi);
             if (vhi < 0)
                 break;
-            const unsigned moved_n = pfx[vhi + 1] - base; // weightlo + wthi
-            const double moved = (double)moved_n;
-            if (moved_n - cum == 1u) { // a single dot: move only if strictly better
-                if (moved < targetlo) {
+            const unsigned moved = pfx[vhi + 1] - base; // weightlo + wthi
+            if (moved >= ceilT) { // the bin that crosses the target: Zoltan's tie rules, in FP64
+                const double over = __dsub_rn((double)moved, T), under = __dsub_rn(T, (double)cum);
+                if (moved - cum == 1u ? over < under // a single dot moves only if strictly better
+                                      : !(over > under)) // a whole column moves unless strictly worse
                     B = vhi;
-                } else {
-                    if (__dsub_rn(moved, targetlo) < __dsub_rn(targetlo, dcum))
-                        B = vhi;
-                    break;
-                }
-            } else { // a whole column: move unless strictly worse
-                if (moved >= targetlo) {
-                    if (!(__dsub_rn(moved, targetlo) > __dsub_rn(targetlo, dcum)))
-                        B = vhi;
-                    break;
-                }
-                B = vhi;
+                break;
             }
-            wlo = moved_n;
-            if (__dsub_rn(targetlo, moved) <= 1.0) // tolerance = weight of one dot
+            B = vhi;
+            wlo = moved;
+            if (moved >= ceilT - 1u) // targetlo - weightlo <= tolerance (the weight of one dot)
                 break;
             vmin = vhi;
             alo = vhi + 1;
         } else {
             const unsigned above = Wn - cum; // dots in (t, c1] = weighthi + totalhi
-            const double dabove = (double)above;
-            if (!(dabove < targethi))
+            if (above >= ceilThi)
                 break; // both halves just right
             // upper half TOO SMALL
             const int vlo = last_nonempty(H, alo, t);
             if (vlo < 0)
                 break;
-            const unsigned moved_n = Wn - (pfx[vlo] - base); // weighthi + wtlo = dots in [vlo, c1]
-            const double moved = (double)moved_n;
-            if (moved_n - above == 1u) {
-                if (moved < targethi) {
+            const unsigned moved = Wn - (pfx[vlo] - base); // weighthi + wtlo = dots in [vlo, c1]
+            if (moved >= ceilThi) {
+                const double over = __dsub_rn((double)moved, Thi), under = __dsub_rn(Thi, (double)above);
+                if (moved - above == 1u ? over < under : !(over > under))
                     B = vlo - 1;
-                } else {
-                    if (__dsub_rn(moved, targethi) < __dsub_rn(targethi, dabove))
-                        B = vlo - 1;
-                    break;
-                }
-            } else {
-                if (moved >= targethi) {
-                    if (!(__dsub_rn(moved, targethi) > __dsub_rn(targethi, dabove)))
-                        B = vlo - 1;
-                    break;
-                }
-                B = vlo - 1;
+                break;
             }
-            whi = moved_n;
-            if (__dsub_rn(targethi, moved) <= 1.0)
+            B = vlo - 1;
+            whi = moved;
+            if (moved >= ceilThi - 1u)
                 break;
             vmax = vlo;
             ahi = vlo - 1;
@@ -704,9 +713,10 @@ __device__ __forceinline__ int leaves_below(int n, int levels)
     return levels >= 31 ? n : min(n, 1 << levels);
 }
 // threads that share one leaf's walk: the largest power of two <= 32 with lanes * leaves <= threads
+__device__ int g_walk_lanes = 32; // upper bound (tuning knob, set by the host)
 __device__ __forceinline__ int walk_lanes(int leaves, int threads)
 {
-    int lanes = 32;
+    int lanes = g_walk_lanes;
     while (lanes > 1 && (long long)lanes * leaves > threads)
         lanes >>= 1;
     return lanes;
@@ -793,6 +803,8 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     __shared__ int s_ix, s_iters;
     unsigned* pfx = SMEM ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
+    if (tid == 0)
+        plan->ts[0] = global_ns();
 
     // 0. exchange step 1: every rank's mask scan is done and its column counts can be read
     if (ps.enabled) {
@@ -808,9 +820,13 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     }
 
     // 1. pfx[i] = ocean cells in columns [0, i)
+    if (tid == 0)
+        plan->ts[1] = global_ns();
     unsigned* bitmap = SMEM ? smem_dyn + (((size_t)NX + 1 + 3) & ~(size_t)3) : nullptr;
     block_prefix_wide<PFX_E>([&](int i0, unsigned (&v)[PFX_E]) { load_counts_u32(pc, i0, NX, v); }, NX, pfx, wsum,
         bitmap);
+    if (tid == 0)
+        plan->ts[2] = global_ns();
     const Hist H = make_hist(pfx, bitmap, NX);
 
     // 2. the plan: bounding box of all dots -> preset direction of every level
@@ -839,10 +855,10 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         for (int i = 0; i < nlev; i++) {
             if (wx > wy) { // a tie cuts y (Q1)
                 ix++;
-                wx = __ddiv_rn(wx, 2.0);
+                wx = wx * 0.5; // exact, like the division by 2
             } else {
                 iy++;
-                wy = __ddiv_rn(wy, 2.0);
+                wy = wy * 0.5;
             }
         }
         plan->nlev = nlev;
@@ -856,6 +872,7 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         plan->mismatch = (ix != aix || iy != aiy) ? 1 : 0;
         s_ix = ix;
         s_iters = 0;
+        plan->ts[3] = global_ns();
     }
     __syncthreads();
 
@@ -894,6 +911,8 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         plan->S = nstrips;
     }
     __syncthreads(); // the strip table is complete (this block wrote it: visible after the barrier)
+    if (tid == 0)
+        plan->ts[4] = global_ns();
     // 5. strip of every column: the strips tile [0, NX) in order, so every warp paints the column
     //    ranges of its strips (a zero-width strip paints nothing: the strip that follows it owns
     //    the shared start column).
@@ -914,8 +933,11 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         }
     }
     __syncthreads();
-    if (tid == 0)
+    if (tid == 0) {
         plan->iters = s_iters;
+        plan->ts[5] = global_ns();
+        plan->ts[10] = 0ull;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -955,6 +977,109 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
         }
     }
     rowcount[(size_t)s * Rmax + row] = (CT)cnt;
+}
+
+// The same counts, coalesced: a block takes 32 consecutive rows and streams them ONCE -- a warp
+// reads a row 512 contiguous bytes at a time (lane = one 16-byte group of 128 columns), turns the
+// per-group popcounts into a running prefix with one warp scan, and the lanes whose group holds a
+// strip boundary record the prefix AT the boundary in shared memory.  The row count of strip s is the
+// difference of two neighbouring boundary prefixes; the block writes them out with lanes along the
+// rows (32 consecutive counts per strip).  Used when the boundary table fits shared memory.
+// dynamic smem (ints): gfirst[NG + 1] | xb[S + 1] | pb[32][PS], PS = (S + 1) | 1
+__host__ __device__ inline size_t strip_scan_smem_words(int NG, int S)
+{
+    return (size_t)(NG + 1) + (size_t)(S + 1) + 32 * (size_t)((S + 1) | 1);
+}
+__device__ __forceinline__ unsigned popc_below(const uint4& w, int k) // bits [0, k) of a 128-bit group
+{
+    const unsigned m0 = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+    const unsigned m1 = k >= 64 ? 0xffffffffu : (k <= 32 ? 0u : ((1u << (k - 32)) - 1u));
+    const unsigned m2 = k >= 96 ? 0xffffffffu : (k <= 64 ? 0u : ((1u << (k - 64)) - 1u));
+    const unsigned m3 = k >= 128 ? 0xffffffffu : (k <= 96 ? 0u : ((1u << (k - 96)) - 1u));
+    return __popc(w.x & m0) + __popc(w.y & m1) + __popc(w.z & m2) + __popc(w.w & m3);
+}
+template <typename CT>
+__global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restrict__ bits, int NB, int NX, int rows,
+    const int* __restrict__ st_x0, const int* __restrict__ st_p0, const Plan* __restrict__ plan, int Scap,
+    CT* __restrict__ rowcount, int Rmax)
+{
+    extern __shared__ int sm_scan[];
+    if (plan->mismatch)
+        return;
+    const int S = min(plan->S, Scap);
+    const int NG = NB >> 4;
+    const int PS = (S + 1) | 1;
+    int* gfirst = sm_scan; // first boundary at or after column g * 128
+    int* xb = sm_scan + NG + 1; // boundaries: xb[b] = first column of strip b, xb[S] = NX
+    unsigned* pb = reinterpret_cast<unsigned*>(xb + S + 1); // [32][PS] ocean cells of the row left of boundary b
+    const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    for (int b = tid; b <= S; b += blockDim.x)
+        xb[b] = b < S ? st_x0[b] : NX;
+    __syncthreads();
+    for (int g = tid; g <= NG; g += blockDim.x) {
+        const int x = g * 128;
+        int lo = 0, hi = S + 1; // first b in [0, S] with xb[b] >= x (S + 1 if none)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (xb[mid] >= x)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        gfirst[g] = lo;
+    }
+    __syncthreads();
+    // a warp owns rows warp, warp + 8, warp + 16, warp + 24 of the block and walks them in lockstep:
+    // four independent 512-byte loads in flight per warp
+    const int r_base = blockIdx.x * 32;
+    const uint4* rp[4];
+    bool live[4];
+    unsigned carry[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int row = r_base + warp + 8 * k;
+        live[k] = row < rows;
+        rp[k] = reinterpret_cast<const uint4*>(bits + (size_t)(live[k] ? row : 0) * NB);
+        carry[k] = 0u;
+    }
+    for (int g0 = 0; g0 < NG; g0 += 32) {
+        const int g = g0 + lane;
+        const bool in = g < NG;
+        uint4 w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            w[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (in && live[k])
+                w[k] = __ldg(rp[k] + g);
+        }
+        const int b0 = in ? gfirst[g] : 0, b1 = in ? gfirst[g + 1] : 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned pc = __popc(w[k].x) + __popc(w[k].y) + __popc(w[k].z) + __popc(w[k].w);
+            unsigned inc = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += t;
+            }
+            const unsigned excl = carry[k] + inc - pc;
+            unsigned* prow = pb + (warp + 8 * k) * PS;
+            for (int b = b0; b < b1; b++)
+                prow[b] = excl + popc_below(w[k], xb[b] - g * 128);
+            carry[k] += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) // boundaries at the very end of the padded row
+        for (int b = gfirst[NG] + lane; b <= S; b += 32)
+            pb[(warp + 8 * k) * PS + b] = carry[k];
+    __syncthreads();
+    for (int i = tid; i < S * 32; i += blockDim.x) {
+        const int s = i >> 5, rl = i & 31, row = r_base + rl;
+        if (row < rows && st_p0[s + 1] - st_p0[s] > 1) // leaf strips are never cut in y
+            rowcount[(size_t)s * Rmax + row] = (CT)(pb[rl * PS + s + 1] - pb[rl * PS + s]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1024,6 +1149,9 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t
     __shared__ unsigned wsum[33];
     if (plan->mismatch)
         return;
+    const unsigned long long t_start = global_ns();
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        plan->ts[6] = t_start;
     // exchange step 2: every rank's strip row counts are written (block 0 says so for this rank)
     if (ps.enabled) {
         bool ok = true;
@@ -1036,6 +1164,8 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t
             return;
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        plan->ts[7] = global_ns();
     unsigned* pfx = SMEM ? smem_dyn : pfx_g + (size_t)blockIdx.x * (((size_t)NY + 1 + 3) & ~(size_t)3);
     unsigned* bitmap = SMEM ? smem_dyn + (((size_t)NY + 1 + 3) & ~(size_t)3) : nullptr;
     const Hist H = make_hist(pfx, bitmap, NY);
@@ -1052,6 +1182,8 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t
         block_prefix_wide<PFX_E>(
             [&](int i0, unsigned (&v)[PFX_E]) { load_row_counts<CT>(pr, rank_stride, strip_off, Rmax, i0, NY, v); }, NY,
             pfx, wsum, bitmap);
+        if (blockIdx.x == 0 && tid == 0)
+            plan->ts[8] = global_ns();
         // a group of `lanes` threads walks to the j-th part of the strip (parts come out y-sorted)
         const int sx0 = st.x0[s], sx1 = st.x1[s];
         const int lanes = walk_lanes(n, blockDim.x);
@@ -1071,6 +1203,13 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t
     }
     if (my_iters)
         atomicAdd(&plan->iters, my_iters);
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long t_end = global_ns();
+        if (blockIdx.x == 0)
+            plan->ts[9] = t_end;
+        atomicMax(&plan->ts[10], t_end - t_start);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -687,6 +688,8 @@ static double find_median_hist(hist_t* H, int c0, int c1, double fractionlo)
     }
     if (H->iters - iters0 > g_max_single_iters)
         g_max_single_iters = H->iters - iters0;
+    if (getenv("ORC_TRACE_ITERS")) /* diagnostics: bins, dots, iterations of every median */
+        fprintf(stderr, "median bins %d dots %lld iters %ld\n", c1 - c0 + 1, (long long)Wn, H->iters - iters0);
     int L = last_nonempty(H, c0, B), U = first_nonempty(H, B + 1, c1);
     return average_cut(L >= 0, (double)L, U >= 0, (double)U, (double)c0, (double)(c1 + 1));
 }

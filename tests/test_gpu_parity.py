@@ -127,7 +127,9 @@ def test_arctic25km_64_parts(capi, handle, oracle, px, py):
 
 
 @pytest.mark.parametrize("nx,ny,P,land", [(1024, 768, 96, 0.45), (777, 1033, 37, 0.6), (2048, 2048, 256, 0.45),
-                                          (4096, 128, 64, 0.3), (100, 3000, 50, 0.5)])
+                                          (4096, 128, 64, 0.3), (100, 3000, 50, 0.5),
+                                          # 512 strips: the gather variant of the strip row counts
+                                          (16384, 64, 2048, 0.3)])
 def test_medium_masks(capi, handle, oracle, nx, ny, P, land):
     m = capi.generate_mask_host(nx, ny, seed=3, land_frac=land)
     assert_same(run_gpu(handle, m, P, True, False), oracle.partition(m, P, True, False, use_hist=True),
