@@ -795,8 +795,7 @@ __device__ __forceinline__ void load_counts_u32(const PeerCols& pc, int i0, int 
 // aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
-    int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads,
-    int* strip_of_col)
+    int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads)
 {
     extern __shared__ __align__(16) unsigned smem_dyn[];
     __shared__ unsigned wsum[33];
@@ -910,33 +909,30 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         *st.always = 0;
         plan->S = nstrips;
     }
-    __syncthreads(); // the strip table is complete (this block wrote it: visible after the barrier)
     if (tid == 0)
         plan->ts[4] = global_ns();
-    // 5. strip of every column: the strips tile [0, NX) in order, so every warp paints the column
-    //    ranges of its strips (a zero-width strip paints nothing: the strip that follows it owns
-    //    the shared start column).
-    {
-        const int lane = lane_id(), warp = tid >> 5, nwarp = blockDim.x >> 5;
-        if (nstrips < nwarp) { // few wide strips: the whole block paints each of them
-            for (int i = 0; i < nstrips; i++) {
-                const int x0 = st.x0[i], x1 = st.x1[i];
-                for (int x = x0 + tid; x < x1; x += blockDim.x)
-                    strip_of_col[x] = i;
-            }
-        } else {
-            for (int i = warp; i < nstrips; i += nwarp) {
-                const int x0 = st.x0[i], x1 = st.x1[i];
-                for (int x = x0 + lane; x < x1; x += 32)
-                    strip_of_col[x] = i;
-            }
-        }
-    }
     __syncthreads();
     if (tid == 0) {
         plan->iters = s_iters;
         plan->ts[5] = global_ns();
         plan->ts[10] = 0ull;
+    }
+}
+
+// strip of every column (read by the labelling kernel; runs beside K3 / K4 on the second stream).
+// The strips tile [0, NX) in order: one warp paints the column range of one strip; a zero-width
+// strip paints nothing, the strip that follows it owns the shared start column.
+__global__ void __launch_bounds__(256) k_paint_strips(StripTable st, const Plan* __restrict__ plan,
+    int* __restrict__ strip_of_col)
+{
+    if (plan->mismatch)
+        return;
+    const int S = *st.S;
+    const int lane = lane_id();
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < S; i += gridDim.x * 8) {
+        const int x0 = st.x0[i], x1 = st.x1[i];
+        for (int x = x0 + lane; x < x1; x += 32)
+            strip_of_col[x] = i;
     }
 }
 
@@ -990,14 +986,6 @@ __host__ __device__ inline size_t strip_scan_smem_words(int NG, int S)
 {
     return (size_t)(NG + 1) + (size_t)(S + 1) + 32 * (size_t)((S + 1) | 1);
 }
-__device__ __forceinline__ unsigned popc_below(const uint4& w, int k) // bits [0, k) of a 128-bit group
-{
-    const unsigned m0 = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
-    const unsigned m1 = k >= 64 ? 0xffffffffu : (k <= 32 ? 0u : ((1u << (k - 32)) - 1u));
-    const unsigned m2 = k >= 96 ? 0xffffffffu : (k <= 64 ? 0u : ((1u << (k - 64)) - 1u));
-    const unsigned m3 = k >= 128 ? 0xffffffffu : (k <= 96 ? 0u : ((1u << (k - 96)) - 1u));
-    return __popc(w.x & m0) + __popc(w.y & m1) + __popc(w.z & m2) + __popc(w.w & m3);
-}
 template <typename CT>
 __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restrict__ bits, int NB, int NX, int rows,
     const int* __restrict__ st_x0, const int* __restrict__ st_p0, const Plan* __restrict__ plan, int Scap,
@@ -1010,18 +998,18 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     const int NG = NB >> 4;
     const int PS = (S + 1) | 1;
     int* gfirst = sm_scan; // first boundary at or after column g * 128
-    int* xb = sm_scan + NG + 1; // boundaries: xb[b] = first column of strip b, xb[S] = NX
+    int* xb = sm_scan + NG + 1; // boundaries: xb[b] = first column of strip b (bit 31: leaf strip), xb[S] = NX
     unsigned* pb = reinterpret_cast<unsigned*>(xb + S + 1); // [32][PS] ocean cells of the row left of boundary b
     const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     for (int b = tid; b <= S; b += blockDim.x)
-        xb[b] = b < S ? st_x0[b] : NX;
+        xb[b] = b < S ? (st_x0[b] | (st_p0[b + 1] - st_p0[b] <= 1 ? (int)0x80000000 : 0)) : NX;
     __syncthreads();
     for (int g = tid; g <= NG; g += blockDim.x) {
         const int x = g * 128;
         int lo = 0, hi = S + 1; // first b in [0, S] with xb[b] >= x (S + 1 if none)
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (xb[mid] >= x)
+            if ((xb[mid] & 0x7fffffff) >= x)
                 hi = mid;
             else
                 lo = mid + 1;
@@ -1030,7 +1018,8 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     }
     __syncthreads();
     // a warp owns rows warp, warp + 8, warp + 16, warp + 24 of the block and walks them in lockstep:
-    // four independent 512-byte loads in flight per warp
+    // four independent 512-byte loads in flight per warp.  The four per-group popcounts (<= 128, their
+    // running sums over a chunk <= 4096) are scanned two to a register.
     const int r_base = blockIdx.x * 32;
     const uint4* rp[4];
     bool live[4];
@@ -1045,30 +1034,45 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     for (int g0 = 0; g0 < NG; g0 += 32) {
         const int g = g0 + lane;
         const bool in = g < NG;
-        uint4 w[4];
+        unsigned long long wl[4], wh[4]; // columns 0-63 and 64-127 of my group, per row
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            w[k] = make_uint4(0u, 0u, 0u, 0u);
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
             if (in && live[k])
-                w[k] = __ldg(rp[k] + g);
+                w = __ldg(rp[k] + g);
+            wl[k] = (unsigned long long)w.x | ((unsigned long long)w.y << 32);
+            wh[k] = (unsigned long long)w.z | ((unsigned long long)w.w << 32);
         }
-        const int b0 = in ? gfirst[g] : 0, b1 = in ? gfirst[g + 1] : 0;
+        unsigned pc[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const unsigned pc = __popc(w[k].x) + __popc(w[k].y) + __popc(w[k].z) + __popc(w[k].w);
-            unsigned inc = pc;
+        for (int k = 0; k < 4; k++)
+            pc[k] = __popcll(wl[k]) + __popcll(wh[k]);
+        unsigned i01 = pc[0] | (pc[1] << 16), i23 = pc[2] | (pc[3] << 16);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o)
-                    inc += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t01 = __shfl_up_sync(0xffffffffu, i01, o), t23 = __shfl_up_sync(0xffffffffu, i23, o);
+            if (lane >= o) {
+                i01 += t01;
+                i23 += t23;
             }
-            const unsigned excl = carry[k] + inc - pc;
-            unsigned* prow = pb + (warp + 8 * k) * PS;
-            for (int b = b0; b < b1; b++)
-                prow[b] = excl + popc_below(w[k], xb[b] - g * 128);
-            carry[k] += __shfl_sync(0xffffffffu, inc, 31);
         }
+        const unsigned inc[4] = { i01 & 0xffffu, i01 >> 16, i23 & 0xffffu, i23 >> 16 };
+        if (in) {
+            const int b1 = gfirst[g + 1];
+            for (int b = gfirst[g]; b < b1; b++) {
+                const int kk = (xb[b] & 0x7fffffff) - g * 128; // 0 .. 127: columns of my group left of the boundary
+                const unsigned long long ml = kk >= 64 ? ~0ull : ((1ull << kk) - 1ull);
+                const unsigned long long mh = kk > 64 ? ((1ull << (kk - 64)) - 1ull) : 0ull;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    pb[(warp + 8 * k) * PS + b] = carry[k] + inc[k] - pc[k] + __popcll(wl[k] & ml) + __popcll(wh[k] & mh);
+            }
+        }
+        const unsigned e01 = __shfl_sync(0xffffffffu, i01, 31), e23 = __shfl_sync(0xffffffffu, i23, 31);
+        carry[0] += e01 & 0xffffu;
+        carry[1] += e01 >> 16;
+        carry[2] += e23 & 0xffffu;
+        carry[3] += e23 >> 16;
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) // boundaries at the very end of the padded row
@@ -1077,7 +1081,7 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     __syncthreads();
     for (int i = tid; i < S * 32; i += blockDim.x) {
         const int s = i >> 5, rl = i & 31, row = r_base + rl;
-        if (row < rows && st_p0[s + 1] - st_p0[s] > 1) // leaf strips are never cut in y
+        if (row < rows && xb[s] >= 0) // leaf strips are never cut in y
             rowcount[(size_t)s * Rmax + row] = (CT)(pb[rl * PS + s + 1] - pb[rl * PS + s]);
     }
 }

@@ -90,6 +90,90 @@ __global__ void __launch_bounds__(256) write_rows(int32_t* __restrict__ pid, int
         __stcs(reinterpret_cast<int4*>(pid + (size_t)r * NX + x), make_int4(r, x, 2, 3));
 }
 
+
+// ---- TMA-style 1-D bulk copies (cp.async.bulk): does a bulk pipeline beat LDG / STG streams? ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem, const void* smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
+}
+// persistent CTAs, STAGES x CH bytes of shared memory, one elected thread issues the bulk loads
+template <int STAGES, int CH>
+__global__ void __launch_bounds__(256) read_bulk(const char* __restrict__ p, size_t nchunks, unsigned* out)
+{
+    extern __shared__ __align__(128) char sm[];
+    __shared__ uint64_t bar[STAGES];
+    if (threadIdx.x == 0)
+        for (int i = 0; i < STAGES; i++) mbar_init(&bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned acc = 0;
+    const size_t first = blockIdx.x, step = gridDim.x;
+    // prologue
+    if (threadIdx.x == 0)
+        for (int i = 0; i < STAGES; i++) {
+            const size_t c = first + (size_t)i * step;
+            if (c < nchunks) { mbar_expect_tx(&bar[i], CH); bulk_load(sm + i * CH, p + c * CH, CH, &bar[i]); }
+        }
+    int it = 0;
+    for (size_t c = first; c < nchunks; c += step, it++) {
+        const int st = it % STAGES;
+        const uint32_t par = (it / STAGES) & 1;
+        while (!mbar_try_wait(&bar[st], par)) { }
+        const int4* q = reinterpret_cast<const int4*>(sm + st * CH);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < CH / 16; i += 256) {
+            const int4 v = q[i];
+            acc += (v.x > 0) + (v.y > 0) + (v.z > 0) + (v.w > 0);
+        }
+        __syncthreads(); // everyone is done with the stage
+        const size_t nc = c + (size_t)STAGES * step;
+        if (threadIdx.x == 0 && nc < nchunks) { mbar_expect_tx(&bar[st], CH); bulk_load(sm + st * CH, p + nc * CH, CH, &bar[st]); }
+    }
+    if (acc == 0xffffffffu) *out = acc;
+}
+template <int STAGES, int CH>
+__global__ void __launch_bounds__(256) write_bulk(char* __restrict__ p, size_t nchunks)
+{
+    extern __shared__ __align__(128) char sm[];
+    const size_t first = blockIdx.x, step = gridDim.x;
+    int it = 0;
+    for (size_t c = first; c < nchunks; c += step, it++) {
+        const int st = it % STAGES;
+        if (it >= STAGES) { // the bulk store that last read this stage must have finished reading it
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(STAGES - 1) : "memory");
+            __syncthreads();
+        }
+        int4* q = reinterpret_cast<int4*>(sm + st * CH);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < CH / 16; i += 256) q[i] = make_int4((int)c, i, 2, 3);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) { bulk_store(p + c * CH, q, CH); asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename F>
 static void timeit(const char* name, double bytes, F f)
 {
@@ -145,6 +229,21 @@ int main()
         char nm[96];
         snprintf(nm, sizeof nm, "write rows (label pattern) grid=%dx%d", grid.x, grid.y);
         timeit(nm, bytes, [&] { write_rows<<<grid, 256>>>(b, NX, NY, NG, rpc); });
+    }
+
+    {
+        char nm[96];
+#define RB(ST, CHK, MULT)                                                                           \
+    {                                                                                              \
+        cudaFuncSetAttribute(read_bulk<ST, CHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST * CHK);   \
+        snprintf(nm, sizeof nm, "read bulk %d x %d KiB grid=148*%d", ST, CHK / 1024, MULT);        \
+        timeit(nm, bytes, [&] { read_bulk<ST, CHK><<<148 * MULT, 256, ST * CHK>>>((const char*)a, (n * 4) / CHK, out); }); \
+        cudaFuncSetAttribute(write_bulk<ST, CHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST * CHK);  \
+        snprintf(nm, sizeof nm, "write bulk %d x %d KiB grid=148*%d", ST, CHK / 1024, MULT);       \
+        timeit(nm, bytes, [&] { write_bulk<ST, CHK><<<148 * MULT, 256, ST * CHK>>>((char*)b, (n * 4) / CHK); }); \
+    }
+        RB(4, 16384, 1) RB(4, 16384, 2) RB(4, 16384, 3) RB(4, 32768, 1) RB(6, 32768, 1) RB(8, 8192, 3) RB(3, 16384, 4)
+        CK(cudaDeviceSynchronize());
     }
     return 0;
 }
