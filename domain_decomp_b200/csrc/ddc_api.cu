@@ -123,7 +123,7 @@ struct ddc_handle_s {
 
     // device buffers
     DevBuf<uint8_t> bits;
-    DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx;
+    DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx, done;
     DevBuf<DevScalars> sc;
     DevBuf<Plan> plan;
     DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
@@ -136,15 +136,16 @@ struct ddc_handle_s {
     // the plan the launches were sized for, and what it was assumed for (see enqueue_partition)
     int plan_nx = 0, plan_ny = 0, plan_P = 0, aix = 0, aiy = 0;
     bool pending = false, profiled = false; // a step is enqueued but not yet validated
-    int last_flags = 0;
+    int last_flags = 0, strip_k = 0;
     size_t xcuts_smem = 0, ycuts16_smem = 0, ycuts32_smem = 0; // dynamic smem opt-ins already made
     cudaStream_t side_stream = nullptr; // speculative neighbour tables run beside the labelling
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k2 = nullptr, ev_paint = nullptr;
     // peer exchange (CUDA IPC): one buffer per rank, mapped by all ranks
-    //   [flags: PEER_STAGES * MAX_PEERS u32, padded to 256 B][col 0][col 1][row 0][row 1]
+    //   [flags: PEER_STAGES * MAX_PEERS u32, padded to 256 B][col: 2 parities x G slots][row: 2 parities x G slots]
+    //   slot g of a rank's buffer is WRITTEN by rank g (pushed by its producing kernel) and read locally
     unsigned* xbuf = nullptr; // this rank's buffer
     unsigned* xpeer[MAX_PEERS] = {}; // every rank's buffer as mapped here (xpeer[rank] == xbuf)
-    size_t x_colcap = 0, x_rowcap = 0; // capacity of one col / row copy, in 32-bit words
+    size_t x_colcap = 0, x_rowcap = 0; // capacity of one col / row slot, in 32-bit words
     bool p2p = false;
     unsigned step = 0; // decompositions enqueued so far (the flag value of the exchange barriers)
     int h_totals[8] = { 0 };
@@ -377,6 +378,10 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     for (auto& ev : h->ev)
         CREATE_TRY(cudaEventCreate(&ev));
     h->ev_ok = true;
+    if (const char* e = getenv("DDC_STRIP_K")) { // tuning knob of the strip row-count kernel
+        const int v = atoi(e);
+        h->strip_k = (v == 1 || v == 2 || v == 4) ? v : 0;
+    }
     if (const char* e = getenv("DDC_WALK_LANES")) { // tuning knob of the cut kernels
         const int v = std::max(1, std::min(32, atoi(e)));
         CREATE_TRY(cudaMemcpyToSymbol(g_walk_lanes, &v, sizeof v));
@@ -427,6 +432,7 @@ int ddc_destroy(ddc_handle_t h)
     h->rowcount.release();
     h->rowcount_all.release();
     h->ypfx.release();
+    h->done.release();
     h->sc.release();
     h->plan.release();
     h->strips.release();
@@ -484,7 +490,7 @@ int ddc_peer_export(ddc_handle_t h, int nx, int ny, int nparts, void* ipc_handle
         return fail(h, DDC_ERR_STATE, "ddc_peer_export: already exported");
     CUDA_TRY(h, cudaSetDevice(h->device));
     peer_capacity(nx, ny, nparts, h->nranks, &h->x_colcap, &h->x_rowcap);
-    const size_t words = 64 + 2 * h->x_colcap + 2 * h->x_rowcap;
+    const size_t words = 64 + 2 * (size_t)h->nranks * (h->x_colcap + h->x_rowcap);
     CUDA_TRY(h, cudaMalloc((void**)&h->xbuf, words * sizeof(unsigned)));
     CUDA_TRY(h, cudaMemset(h->xbuf, 0, words * sizeof(unsigned)));
     cudaIpcMemHandle_t ipc;
@@ -731,10 +737,13 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const bool p2p = G > 1 && h->p2p && (size_t)ncol <= h->x_colcap && (!ycuts || rc_words + 4 <= h->x_rowcap);
     const int par = (int)(h->step & 1u);
     constexpr size_t XFLAGS = 64; // words reserved for the flags at the head of an exchange buffer
-    auto xcol = [&](int q) { return h->xpeer[q] + XFLAGS + (size_t)par * h->x_colcap; };
-    auto xrow = [&](int q) { return h->xpeer[q] + XFLAGS + 2 * h->x_colcap + (size_t)par * h->x_rowcap; };
-    unsigned* colcount = p2p ? xcol(h->rank) : h->colcount.p;
-    unsigned* rowcount = p2p ? xrow(h->rank) : h->rowcount.p;
+    // slot `slot` (written by rank `slot`) of the buffer of rank q, for this step's parity
+    auto xcol = [&](int q, int slot) { return h->xpeer[q] + XFLAGS + ((size_t)par * G + slot) * h->x_colcap; };
+    auto xrow = [&](int q, int slot) {
+        return h->xpeer[q] + XFLAGS + 2 * (size_t)G * h->x_colcap + ((size_t)par * G + slot) * h->x_rowcap;
+    };
+    unsigned* colcount = p2p ? xcol(h->rank, h->rank) : h->colcount.p;
+    unsigned* rowcount = p2p ? xrow(h->rank, h->rank) : h->rowcount.p;
     PeerSync ps {};
     ps.rank = h->rank;
     ps.G = G;
@@ -742,35 +751,44 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     ps.step = h->step;
     PeerCols pc {};
     PeerRows pr {};
+    PeerPush push_col {}, push_row {};
+    push_col.rank = push_row.rank = h->rank;
     if (p2p) {
         for (int q = 0; q < G; q++) {
             ps.flags[q] = h->xpeer[q];
-            pc.col[q] = xcol(q);
-            pr.row[q] = xrow(q);
+            pc.col[q] = xcol(h->rank, q); // what rank q pushed into my buffer
+            pr.row[q] = xrow(h->rank, q);
+            push_col.dst[q] = xcol(q, h->rank); // my slot in rank q's buffer
+            push_row.dst[q] = xrow(q, h->rank);
         }
-        pc.n = pr.n = G;
+        pc.n = pr.n = push_col.n = push_row.n = G;
     } else {
         pc.col[0] = colcount;
         pc.n = pr.n = 1;
+        push_col.dst[0] = colcount;
+        push_row.dst[0] = rowcount;
+        push_col.n = push_row.n = 1;
     }
 
     mark(0);
     // ---- K1: mask scan -----------------------------------------------------------------------
-    k_init<<<(ncol + 255) / 256, 256, 0, s>>>(colcount, ncol, yr_off, h->rank, h->sc.p, h->loadmm.p);
-    launches++;
     const int gridx = (NG + 7) / 8;
+    CUDA_TRY(h, h->done.ensure((size_t)gridx + 1));
+    k_init<<<(ncol + 255) / 256, 256, 0, s>>>(colcount, ncol, yr_off, h->rank, h->sc.p, h->loadmm.p, h->done.p,
+        gridx + 1);
+    launches++;
     const bool vec = (NX % 4 == 0) && (((uintptr_t)h->d_mask) % 16 == 0);
     int* yr = reinterpret_cast<int*>(colcount + yr_off + 2 * h->rank);
-    if (rows > 0) {
-        const int rpc = vec ? pick_rows_per_cta(k_scan_mask<true>, rows, gridx)
-                            : pick_rows_per_cta(k_scan_mask<false>, rows, gridx);
-        dim3 grid(gridx, (rows + rpc - 1) / rpc);
+    if (rows > 0 || p2p) { // an empty shard still has to push its (empty) counts and raise its flag
+        const int rpc = vec ? pick_rows_per_cta(k_scan_mask<true>, std::max(rows, 1), gridx)
+                            : pick_rows_per_cta(k_scan_mask<false>, std::max(rows, 1), gridx);
+        dim3 grid(gridx, std::max(1, (rows + rpc - 1) / rpc));
         if (vec)
             k_scan_mask<true><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
-                colcount, yr);
+                colcount, yr, push_col, ps, h->done.p, yr_off);
         else
             k_scan_mask<false><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
-                colcount, yr);
+                colcount, yr, push_col, ps, h->done.p, yr_off);
         launches++;
     }
     if (G > 1 && !p2p) // the first exchange step: column histogram and every rank's dot y-range in one sum
@@ -798,26 +816,45 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     mark(2);
     // ---- K3 + K4: strip row counts, y cuts -----------------------------------------------------
     if (ycuts) {
-        if (rows < Rmax) // short last shard: its padding rows must read as empty
-            CUDA_TRY(h, cudaMemsetAsync(rowcount, 0, sizeof(unsigned) * rc_words, s));
-        if (rows > 0) {
-            const size_t scan_smem = sizeof(int) * strip_scan_smem_words(NG, Scap);
+        {
+            // the grid covers the Rmax rows of the largest shard: a short (or empty) shard writes its
+            // missing rows as empty, and with the peer exchange every count goes to all ranks
+            // rows per warp of the streaming kernel: fewer for small shards, so that the grid fills the SMs
+            int K = Rmax >= 32 * 4 * 148 ? 4 : (Rmax >= 16 * 4 * 148 ? 2 : 1);
+            if (h->strip_k) // DDC_STRIP_K: tuning knob
+                K = h->strip_k;
+            while (K > 1 && sizeof(int) * strip_scan_smem_words(NG, Scap, K) > 48 * 1024)
+                K >>= 1;
+            const size_t scan_smem = sizeof(int) * strip_scan_smem_words(NG, Scap, K);
             if (scan_smem <= 48 * 1024) { // the streaming kernel: boundary table in shared memory
-                const int grid = (rows + 31) / 32;
-                if (narrow)
-                    k_strip_rows_scan<uint16_t><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0,
-                        h->plan.p, Scap, reinterpret_cast<uint16_t*>(rowcount), Rmax);
-                else
-                    k_strip_rows_scan<unsigned><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0,
-                        h->plan.p, Scap, rowcount, Rmax);
+                const int grid = (Rmax + 8 * K - 1) / (8 * K);
+#define LAUNCH_SCAN(CT, KK)                                                                        \
+    k_strip_rows_scan<CT, KK><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0, h->plan.p, Scap, \
+        push_row, Rmax)
+                if (narrow) {
+                    if (K == 4)
+                        LAUNCH_SCAN(uint16_t, 4);
+                    else if (K == 2)
+                        LAUNCH_SCAN(uint16_t, 2);
+                    else
+                        LAUNCH_SCAN(uint16_t, 1);
+                } else {
+                    if (K == 4)
+                        LAUNCH_SCAN(unsigned, 4);
+                    else if (K == 2)
+                        LAUNCH_SCAN(unsigned, 2);
+                    else
+                        LAUNCH_SCAN(unsigned, 1);
+                }
+#undef LAUNCH_SCAN
             } else {
-                dim3 grid((rows + 31) / 32, (Scap + 7) / 8);
+                dim3 grid((Rmax + 31) / 32, (Scap + 7) / 8);
                 if (narrow)
                     k_strip_rows<uint16_t><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
-                        h->plan.p, Scap, reinterpret_cast<uint16_t*>(rowcount), Rmax);
+                        h->plan.p, Scap, push_row, Rmax);
                 else
                     k_strip_rows<unsigned><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
-                        h->plan.p, Scap, rowcount, Rmax);
+                        h->plan.p, Scap, push_row, Rmax);
             }
             launches++;
         }

@@ -55,12 +55,15 @@ struct NaiveParams { // Grid.cpp:150-166
 // multi-GPU exchange over peer memory (NVLink / NVSwitch)
 // ------------------------------------------------------------------------------------------------
 // With several GPUs the three exchange steps of a decomposition (column counts, strip row counts,
-// the `changes` flag) are not separate collectives: the kernel that consumes the data reads it
-// straight out of the peers' buffers (mapped with CUDA IPC), after a flag barrier in its prologue.
-//   signal  every rank stores 2 * step + bit into slot [stage][own rank] of EVERY rank's flag array
-//           (st.release.sys over NVLink) once the producing kernel before it on the stream is done;
-//   wait    it then polls its OWN flag array (local memory) until all G slots of the stage have
-//           reached 2 * step.  Steps only grow, so flags are never reset, and the data buffers
+// the `changes` flag) are not separate collectives.  The PRODUCING kernel pushes its histogram into
+// a slot of every peer's exchange buffer (mapped with CUDA IPC; posted stores over NVLink, spread
+// over all its CTAs), and the CONSUMING kernel waits for a flag in its prologue and then reads
+// local memory only -- a remote LOAD costs a full NVLink round trip per dependent access, which a
+// single cut CTA cannot hide (measured: 160 us to pull 8 x 128 KiB with one CTA).
+//   signal  rank r stores 2 * step + bit into slot [stage][r] of EVERY rank's flag array
+//           (st.release.sys over NVLink) once everything it pushed for the stage is performed;
+//   wait    a rank polls its OWN flag array (local memory) until all G slots of the stage have
+//           reached 2 * step.  Steps only grow, so flags are never reset, and the data slots
 //           alternate between two copies by step parity, so a rank may run ahead into the next
 //           step without overwriting what a slower peer is still reading.
 // Each rank runs on its own GPU; a rank that does not show up within PEER_TIMEOUT_NS makes the
@@ -73,13 +76,20 @@ struct PeerSync {
     int rank, G, enabled;
     unsigned step;
 };
-struct PeerCols { // the column-count buffer of every rank; n == 1: col[0] already holds global counts
+struct PeerCols { // column counts of every rank: slot g of MY exchange buffer (pushed there by rank g);
+                  // n == 1: col[0] already holds global counts (single GPU, or after an all-reduce)
     const unsigned* col[MAX_PEERS];
     int n;
 };
-struct PeerRows { // the strip-row-count block of every rank; n == 1: row[0] is the gathered [G][rank_stride]
+struct PeerRows { // strip row counts of every rank: slot g of MY exchange buffer; n == 1: row[0] is
+                  // the gathered [G][rank_stride] (or the only rank's block)
     const void* row[MAX_PEERS];
     int n;
+};
+struct PeerPush { // where a producing kernel stores its histogram: dst[q] = MY slot in rank q's exchange
+                  // buffer (dst[rank] is local memory); n <= 1: nothing to push, dst[0] is the local buffer
+    void* dst[MAX_PEERS];
+    int n, rank;
 };
 __device__ __forceinline__ unsigned long long global_ns()
 {
@@ -87,18 +97,20 @@ __device__ __forceinline__ unsigned long long global_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Called by the first G threads of a block (thread q talks to rank q).  do_signal: exactly one
-// block per rank sends.  Returns false on timeout; *seen = the flag value read from rank q.
-__device__ __forceinline__ bool peer_barrier(const PeerSync& ps, int stage, unsigned bit, bool do_signal,
-    unsigned* seen)
+// thread q of a block tells rank q that this rank has reached `stage` of the current step.  The
+// caller makes sure (fences + barriers) that everything pushed for the stage is ordered before.
+__device__ __forceinline__ void peer_signal(const PeerSync& ps, int stage, unsigned bit)
+{
+    const int q = threadIdx.x;
+    __threadfence_system();
+    unsigned* dst = ps.flags[q] + stage * MAX_PEERS + ps.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(2u * ps.step + bit) : "memory");
+}
+// thread q waits until rank q has reached `stage`.  Returns false on timeout; *seen = its flag value.
+__device__ __forceinline__ bool peer_wait(const PeerSync& ps, int stage, unsigned* seen)
 {
     const int q = threadIdx.x;
     const unsigned want = 2u * ps.step;
-    if (do_signal) {
-        __threadfence_system();
-        unsigned* dst = ps.flags[q] + stage * MAX_PEERS + ps.rank;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(want + bit) : "memory");
-    }
     const unsigned* src = ps.flags[ps.rank] + stage * MAX_PEERS + q;
     const unsigned long long t0 = global_ns();
     unsigned v;
@@ -111,6 +123,15 @@ __device__ __forceinline__ bool peer_barrier(const PeerSync& ps, int stage, unsi
     }
     *seen = v;
     return true;
+}
+// Called by the first G threads of a block (thread q talks to rank q).  do_signal: exactly one
+// block per rank sends.
+__device__ __forceinline__ bool peer_barrier(const PeerSync& ps, int stage, unsigned bit, bool do_signal,
+    unsigned* seen)
+{
+    if (do_signal)
+        peer_signal(ps, stage, bit);
+    return peer_wait(ps, stage, seen);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -224,7 +245,7 @@ __device__ __forceinline__ Hist make_hist(const unsigned* pfx, const unsigned* b
     H.nl2 = tiles;
     return H;
 }
-constexpr int HIST_TILE = 32768; // bins per tile of block_prefix_wide<32> with 1024 threads
+constexpr int HIST_TILE = 32768; // bins per tile of block_prefix_tiles (1024 threads)
 __host__ __device__ inline size_t hist_bitmap_words(int n) // words behind pfx for n bins
 {
     const size_t tiles = ((size_t)n + HIST_TILE - 1) / HIST_TILE;
@@ -286,76 +307,122 @@ __device__ __forceinline__ int bitmap_next(const Hist& H, int t, int b)
 }
 
 // Same result as block_prefix<false> (dst[i] = sum of the first i elements, n + 1 outputs, 32-bit
-// sums), but every thread owns E CONSECUTIVE elements: a 1024-thread block covers 1024 * E elements
-// with ONE block scan instead of one per 4096, which is what the latency of the cut kernels is made
-// of.  load(i0, v) fills v[k] = element i0 + k (0 beyond n); dst may be shared or global memory.
-// bitmap != nullptr (needs E == 32 and 1024 threads): also writes the three-level bit map of the
-// non-empty elements, l0 / l1 / l2 = bitmap + 0 / tiles * 1024 / tiles * (1024 + 32).
-template <int E, typename F>
-__device__ inline unsigned block_prefix_wide(F load, int n, unsigned* dst, unsigned* wsum /* >= 33 */,
-    unsigned* bitmap = nullptr)
+// sums) for a 1024-thread block, built for the latency of the cut kernels: a tile of 32768 elements
+// is ONE pass with two block barriers.  The tile is cut into 8 sub-tiles of 4096; thread t owns the 4
+// consecutive elements [4 t, 4 t + 4) of every sub-tile, so that every load and every store of a warp
+// is one contiguous 512-byte run (a single SM pulls the whole histogram out of L2: with 32
+// consecutive elements per thread every load instruction touched 32 different lines and, because
+// data written by other GPUs has to bypass L1, each line crossed the L2 interface 8 times).  The 8
+// sub-tile scans run side by side: 8 independent shuffle chains per thread, then warp q scans the
+// 32 warp totals of sub-tile q.
+// load4(i) returns elements i .. i + 3 (0 beyond n), i a multiple of 4; dst may be shared or global
+// memory.  bitmap != nullptr: also writes the three-level bit map of the non-empty elements,
+// l0 / l1 / l2 = bitmap + 0 / tiles * 1024 / tiles * (1024 + 32).   ws: >= 8 * 32 + 8 words.
+constexpr int PFX_Q = 8; // sub-tiles of a tile
+constexpr int PFX_WS = PFX_Q * 32 + PFX_Q;
+template <typename F>
+__device__ inline unsigned block_prefix_tiles(F load4, int n, unsigned* dst, unsigned* ws, unsigned* bitmap = nullptr)
 {
-    static_assert(E % 4 == 0, "E must be a multiple of 4");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles = (n + HIST_TILE - 1) / HIST_TILE;
     unsigned carry = 0;
-    const int tile = blockDim.x * E;
-    const int tiles = (n + tile - 1) / tile;
-    for (int base = 0; base < n; base += tile) {
-        const int i0 = base + threadIdx.x * E;
-        unsigned v[E];
-        if (i0 < n)
-            load(i0, v);
-        else {
+    for (int t = 0; t < tiles; t++) {
+        const int base = t * HIST_TILE + tid * 4;
+        uint4 v[PFX_Q];
+        unsigned s[PFX_Q], inc[PFX_Q];
 #pragma unroll
-            for (int k = 0; k < E; k++)
-                v[k] = 0u;
+        for (int q = 0; q < PFX_Q; q++) {
+            const int i = base + q * 4096;
+            v[q] = i < n ? load4(i) : make_uint4(0u, 0u, 0u, 0u);
         }
-        if (E == 32 && bitmap) {
-            unsigned word = 0;
 #pragma unroll
-            for (int k = 0; k < E; k++)
-                word |= (unsigned)(v[k] != 0u) << (k & 31);
-            const int t = base / tile;
-            bitmap[t * 1024 + threadIdx.x] = word; // l0
-            const unsigned b1 = __ballot_sync(0xffffffffu, word != 0u);
-            if (lane_id() == 0)
-                bitmap[tiles * 1024 + t * 32 + (threadIdx.x >> 5)] = b1; // l1
-            // l2 word t = the non-zero l1 words of this tile
-            __syncthreads(); // the l1 words of the tile are written
-            if (threadIdx.x < 32) {
-                const unsigned b2 = __ballot_sync(0xffffffffu, bitmap[tiles * 1024 + t * 32 + threadIdx.x] != 0u);
-                if (threadIdx.x == 0)
-                    bitmap[tiles * (1024 + 32) + t] = b2; // l2
+        for (int q = 0; q < PFX_Q; q++)
+            inc[q] = s[q] = v[q].x + v[q].y + v[q].z + v[q].w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int q = 0; q < PFX_Q; q++) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, inc[q], o);
+                if (lane >= o)
+                    inc[q] += u;
             }
         }
-        unsigned sum = 0;
+        if (bitmap) { // l0: one bit per element; 8 neighbouring lanes make one 32-bit word
 #pragma unroll
-        for (int k = 0; k < E; k++)
-            sum += v[k];
-        unsigned total;
-        unsigned run = carry + block_exclusive_scan<unsigned>(sum, &total, wsum);
-        if (i0 + E <= n && ((uintptr_t)(dst + i0) & 15) == 0) {
-#pragma unroll
-            for (int q = 0; q < E / 4; q++) {
-                uint4 o;
-                o.x = run;
-                o.y = o.x + v[4 * q];
-                o.z = o.y + v[4 * q + 1];
-                o.w = o.z + v[4 * q + 2];
-                run = o.w + v[4 * q + 3];
-                *reinterpret_cast<uint4*>(dst + i0 + 4 * q) = o;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < E; k++) {
-                if (i0 + k < n)
-                    dst[i0 + k] = run;
-                run += v[k];
+            for (int q = 0; q < PFX_Q; q++) {
+                unsigned w = ((unsigned)(v[q].x != 0u) | ((unsigned)(v[q].y != 0u) << 1) | ((unsigned)(v[q].z != 0u) << 2)
+                                 | ((unsigned)(v[q].w != 0u) << 3))
+                    << (4 * (lane & 7));
+                w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                if ((lane & 7) == 0)
+                    bitmap[(base + q * 4096) >> 5] = w;
             }
         }
-        carry += total;
+        if (lane == 31) {
+#pragma unroll
+            for (int q = 0; q < PFX_Q; q++)
+                ws[q * 32 + warp] = inc[q];
+        }
+        __syncthreads();
+        if (warp < PFX_Q) { // warp q: exclusive scan of the 32 warp totals of sub-tile q
+            const unsigned w = ws[warp * 32 + lane];
+            unsigned winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o)
+                    winc += u;
+            }
+            ws[warp * 32 + lane] = winc - w;
+            if (lane == 31)
+                ws[PFX_Q * 32 + warp] = winc;
+        }
+        __syncthreads();
+        unsigned run = carry;
+#pragma unroll
+        for (int q = 0; q < PFX_Q; q++) {
+            const int i = base + q * 4096;
+            uint4 o;
+            o.x = run + ws[q * 32 + warp] + inc[q] - s[q];
+            o.y = o.x + v[q].x;
+            o.z = o.y + v[q].y;
+            o.w = o.z + v[q].z;
+            run += ws[PFX_Q * 32 + q];
+            if (i + 4 <= n && ((uintptr_t)(dst + i) & 15) == 0)
+                *reinterpret_cast<uint4*>(dst + i) = o;
+            else {
+                if (i < n)
+                    dst[i] = o.x;
+                if (i + 1 < n)
+                    dst[i + 1] = o.y;
+                if (i + 2 < n)
+                    dst[i + 2] = o.z;
+                if (i + 3 < n)
+                    dst[i + 3] = o.w;
+            }
+        }
+        carry = run;
+        __syncthreads(); // ws is reused by the next tile
     }
-    if (threadIdx.x == 0)
+    if (tid == 0)
         dst[n] = carry;
+    if (bitmap) { // l1: one bit per l0 word, l2: one bit per l1 word
+        unsigned* l1 = bitmap + tiles * 1024;
+        unsigned* l2 = bitmap + tiles * (1024 + 32);
+        for (int i = tid; i < tiles * 1024; i += 1024) {
+            const unsigned b1 = __ballot_sync(0xffffffffu, bitmap[i] != 0u);
+            if (lane == 0)
+                l1[i >> 5] = b1;
+        }
+        __syncthreads();
+        for (int i = tid; i < tiles * 32; i += 1024) { // whole warps: tiles * 32 is a multiple of 32
+            const unsigned b2 = __ballot_sync(0xffffffffu, l1[i] != 0u);
+            if (lane == 0)
+                l2[i >> 5] = b2;
+        }
+    }
     __syncthreads();
     return carry;
 }
@@ -380,9 +447,11 @@ constexpr int SCAN_STAGE_ROWS = 64; // bit-map rows staged in shared memory betw
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ mask, int NX, int rows,
     int y_begin, int NB, int rows_per_cta, uint8_t* __restrict__ bits, unsigned* __restrict__ colcount,
-    int* __restrict__ yr /* this rank's {-(first ocean row), last ocean row}, max-reduced */)
+    int* __restrict__ yr /* this rank's {-(first ocean row), last ocean row}, max-reduced */,
+    PeerPush push, PeerSync ps, unsigned* __restrict__ done /* [gridDim.x + 1], zeroed by k_init */, int yr_off)
 {
     __shared__ __align__(16) uint8_t sbits[SCAN_STAGE_ROWS][128];
+    __shared__ int s_last;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     // warps beyond the last 128-column group (last column block only) have no columns: they
     // load nothing (clamped, masked addresses below) but take part in the CTA barriers
@@ -503,6 +572,45 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
             atomicMax(&yr[0], ny0);
         if (y1 > yr[1])
             atomicMax(&yr[1], y1);
+    }
+    if (push.n <= 1)
+        return;
+    // Exchange step 1 (several GPUs): the LAST CTA of a column block to finish pushes the block's
+    // final counts into this rank's slot of every peer's exchange buffer, and the last column
+    // block to have done so pushes the dot y-range and raises this rank's flag at every peer --
+    // so the counts travel while the rest of the scan is still running and the x-cut kernel of
+    // every rank finds all of them in its own memory.
+    __threadfence(); // my atomics are performed before this CTA is counted as done
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&done[blockIdx.x], 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    const int c = blockIdx.x * 1024 + threadIdx.x * 4;
+    if (c < yr_off) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(colcount + c));
+        for (int q = 0; q < push.n; q++)
+            if (q != push.rank)
+                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned*>(push.dst[q]) + c) = v;
+    }
+    __threadfence_system(); // my stores are performed at the peers before this block is counted
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&done[gridDim.x], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    if (threadIdx.x < push.n) {
+        const int q = threadIdx.x;
+        if (q != push.rank) {
+            unsigned* d = reinterpret_cast<unsigned*>(push.dst[q]) + yr_off + 2 * push.rank;
+            d[0] = (unsigned)__ldcg(yr);
+            d[1] = (unsigned)__ldcg(yr + 1);
+        }
+        peer_signal(ps, 0, 0u); // fence.sys, then the flag: the pushes of all blocks come first
     }
 }
 
@@ -762,33 +870,28 @@ struct BoxTable { // final boxes, SoA
     int* ey;
 };
 
-constexpr int PFX_E = 32; // elements per thread of the wide prefix scans (1024 threads: 32768 per tile)
-
-// 32 consecutive column counts summed over the ranks' buffers (one buffer when the counts are
-// already global); vector loads when the chunk is whole and 16-byte aligned.  ld.global.cg: the
-// buffers of the peers are written by other GPUs.
-__device__ __forceinline__ void load_counts_u32(const PeerCols& pc, int i0, int n, unsigned (&v)[PFX_E])
+// 4 consecutive column counts summed over the ranks' slots (one buffer when the counts are already
+// global); one 16-byte load per slot when the chunk is whole and aligned.  ld.global.cg: the slots of
+// the other ranks are written by other GPUs.
+__device__ __forceinline__ uint4 load_counts4(const PeerCols& pc, int i, int n)
 {
-#pragma unroll
-    for (int k = 0; k < PFX_E; k++)
-        v[k] = 0u;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
     for (int g = 0; g < pc.n; g++) {
-        const unsigned* src = pc.col[g];
-        if (i0 + PFX_E <= n && ((uintptr_t)(src + i0) & 15) == 0) {
-#pragma unroll
-            for (int q = 0; q < PFX_E / 4; q++) {
-                const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src + i0) + q);
-                v[4 * q] += t.x;
-                v[4 * q + 1] += t.y;
-                v[4 * q + 2] += t.z;
-                v[4 * q + 3] += t.w;
-            }
+        const unsigned* src = pc.col[g] + i;
+        if (i + 4 <= n && ((uintptr_t)src & 15) == 0) {
+            const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src));
+            v.x += t.x;
+            v.y += t.y;
+            v.z += t.z;
+            v.w += t.w;
         } else {
-#pragma unroll
-            for (int k = 0; k < PFX_E; k++)
-                v[k] += i0 + k < n ? __ldcg(src + i0 + k) : 0u;
+            v.x += i < n ? __ldcg(src) : 0u;
+            v.y += i + 1 < n ? __ldcg(src + 1) : 0u;
+            v.z += i + 2 < n ? __ldcg(src + 2) : 0u;
+            v.w += i + 3 < n ? __ldcg(src + 3) : 0u;
         }
     }
+    return v;
 }
 
 // dynamic shared memory when SMEM: (NX + 1) unsigned, rounded up to 4, + hist_bitmap_words(NX).
@@ -798,19 +901,19 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads)
 {
     extern __shared__ __align__(16) unsigned smem_dyn[];
-    __shared__ unsigned wsum[33];
+    __shared__ unsigned wsum[PFX_WS];
     __shared__ int s_ix, s_iters;
     unsigned* pfx = SMEM ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
     if (tid == 0)
         plan->ts[0] = global_ns();
 
-    // 0. exchange step 1: every rank's mask scan is done and its column counts can be read
+    // 0. exchange step 1: every rank's mask scan has pushed its column counts into my buffer
     if (ps.enabled) {
         bool ok = true;
         unsigned seen;
         if (tid < ps.G)
-            ok = peer_barrier(ps, 0, 0u, true, &seen);
+            ok = peer_wait(ps, 0, &seen);
         if (__syncthreads_or(!ok)) {
             if (tid == 0)
                 plan->mismatch = 3;
@@ -822,8 +925,7 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     if (tid == 0)
         plan->ts[1] = global_ns();
     unsigned* bitmap = SMEM ? smem_dyn + (((size_t)NX + 1 + 3) & ~(size_t)3) : nullptr;
-    block_prefix_wide<PFX_E>([&](int i0, unsigned (&v)[PFX_E]) { load_counts_u32(pc, i0, NX, v); }, NX, pfx, wsum,
-        bitmap);
+    block_prefix_tiles([&](int i) { return load_counts4(pc, i, NX); }, NX, pfx, wsum, bitmap);
     if (tid == 0)
         plan->ts[2] = global_ns();
     const Hist H = make_hist(pfx, bitmap, NX);
@@ -943,10 +1045,24 @@ __global__ void __launch_bounds__(256) k_paint_strips(StripTable st, const Plan*
 // strip overlaps straight from global memory (neighbouring strips share the boundary group, which
 // L1 / L2 serve) and the warp writes 32 consecutive counts.  rowcount layout [S][Rmax], rows local
 // to this rank.  Leaf strips (one part, never cut in y) are skipped.
+// store one count into this rank's block of the row counts -- of every rank when they are exchanged
+// through peer memory (exchange step 2: pushed by the producer, read locally by the y-cut kernels)
+template <typename CT>
+__device__ __forceinline__ void store_row_count(const PeerPush& out, size_t idx, CT v)
+{
+    if (out.n <= 1)
+        reinterpret_cast<CT*>(out.dst[0])[idx] = v;
+    else
+        for (int q = 0; q < out.n; q++)
+            reinterpret_cast<CT*>(out.dst[q])[idx] = v;
+}
+
+// The grid covers Rmax rows (the rows of the largest shard): rows beyond this rank's `rows` are
+// written as empty, so that a short last shard needs no separate clearing pass.
 template <typename CT /* uint16_t when NX < 65536, else unsigned */>
 __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ bits, int NB, int rows,
     const int* __restrict__ st_x0, const int* __restrict__ st_x1, const int* __restrict__ st_p0,
-    const Plan* __restrict__ plan, int Scap, CT* __restrict__ rowcount, int Rmax)
+    const Plan* __restrict__ plan, int Scap, PeerPush out, int Rmax)
 {
     if (plan->mismatch)
         return;
@@ -955,11 +1071,11 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
     if (s >= S || s >= Scap || st_p0[s + 1] - st_p0[s] <= 1)
         return;
     const int row = blockIdx.x * 32 + lane_id();
-    if (row >= rows)
+    if (row >= Rmax)
         return;
     const int x0 = st_x0[s], x1 = st_x1[s];
     unsigned cnt = 0;
-    if (x1 > x0) {
+    if (x1 > x0 && row < rows) {
         const int g0 = x0 >> 7, g1 = (x1 - 1) >> 7;
         const uint4* rp = reinterpret_cast<const uint4*>(bits + (size_t)row * NB);
         for (int g = g0; g <= g1; g++) {
@@ -972,7 +1088,7 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
                     + __popc(w.z & word_range_mask(a - 64, b - 64)) + __popc(w.w & word_range_mask(a - 96, b - 96));
         }
     }
-    rowcount[(size_t)s * Rmax + row] = (CT)cnt;
+    store_row_count<CT>(out, (size_t)s * Rmax + row, (CT)cnt);
 }
 
 // The same counts, coalesced: a block takes 32 consecutive rows and streams them ONCE -- a warp
@@ -981,26 +1097,48 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
 // strip boundary record the prefix AT the boundary in shared memory.  The row count of strip s is the
 // difference of two neighbouring boundary prefixes; the block writes them out with lanes along the
 // rows (32 consecutive counts per strip).  Used when the boundary table fits shared memory.
-// dynamic smem (ints): gfirst[NG + 1] | xb[S + 1] | pb[32][PS], PS = (S + 1) | 1
-__host__ __device__ inline size_t strip_scan_smem_words(int NG, int S)
+// K = rows per warp (a block takes 8 K consecutive rows): small shards take fewer rows per block so
+// that the grid still fills the SMs; every lane always has 2 K independent 16-byte loads in flight
+// (the chunk being counted and the next one).
+// dynamic smem (ints): gfirst[NG + 1] | xb[S + 1] | pb[8 K][PS], PS = (S + 1) | 1
+__host__ __device__ inline size_t strip_scan_smem_words(int NG, int S, int K)
 {
-    return (size_t)(NG + 1) + (size_t)(S + 1) + 32 * (size_t)((S + 1) | 1);
+    return (size_t)(NG + 1) + (size_t)(S + 1) + 8 * (size_t)K * (size_t)((S + 1) | 1);
 }
-template <typename CT>
+template <typename CT, int K>
 __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restrict__ bits, int NB, int NX, int rows,
     const int* __restrict__ st_x0, const int* __restrict__ st_p0, const Plan* __restrict__ plan, int Scap,
-    CT* __restrict__ rowcount, int Rmax)
+    PeerPush out, int Rmax)
 {
     extern __shared__ int sm_scan[];
     if (plan->mismatch)
         return;
+    constexpr int RB = 8 * K; // rows per block
+    constexpr int KP = (K + 1) / 2; // packed scan registers (two 16-bit running sums each)
     const int S = min(plan->S, Scap);
     const int NG = NB >> 4;
     const int PS = (S + 1) | 1;
     int* gfirst = sm_scan; // first boundary at or after column g * 128
     int* xb = sm_scan + NG + 1; // boundaries: xb[b] = first column of strip b (bit 31: leaf strip), xb[S] = NX
-    unsigned* pb = reinterpret_cast<unsigned*>(xb + S + 1); // [32][PS] ocean cells of the row left of boundary b
+    unsigned* pb = reinterpret_cast<unsigned*>(xb + S + 1); // [RB][PS] ocean cells of the row left of boundary b
     const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    // a warp owns rows warp, warp + 8, ... of the block and walks them in lockstep; their first
+    // chunks are requested before the boundary table is built
+    const int r_base = blockIdx.x * RB;
+    const uint4* rp[K];
+    bool live[K];
+    unsigned carry[K];
+    uint4 nxt[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int row = r_base + warp + 8 * k;
+        live[k] = row < rows;
+        rp[k] = reinterpret_cast<const uint4*>(bits + (size_t)(live[k] ? row : 0) * NB);
+        carry[k] = 0u;
+        nxt[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (live[k] && lane < NG)
+            nxt[k] = __ldg(rp[k] + lane);
+    }
     for (int b = tid; b <= S; b += blockDim.x)
         xb[b] = b < S ? (st_x0[b] | (st_p0[b + 1] - st_p0[b] <= 1 ? (int)0x80000000 : 0)) : NX;
     __syncthreads();
@@ -1017,46 +1155,39 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
         gfirst[g] = lo;
     }
     __syncthreads();
-    // a warp owns rows warp, warp + 8, warp + 16, warp + 24 of the block and walks them in lockstep:
-    // four independent 512-byte loads in flight per warp.  The four per-group popcounts (<= 128, their
-    // running sums over a chunk <= 4096) are scanned two to a register.
-    const int r_base = blockIdx.x * 32;
-    const uint4* rp[4];
-    bool live[4];
-    unsigned carry[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int row = r_base + warp + 8 * k;
-        live[k] = row < rows;
-        rp[k] = reinterpret_cast<const uint4*>(bits + (size_t)(live[k] ? row : 0) * NB);
-        carry[k] = 0u;
-    }
+    // The per-group popcounts (<= 128, their running sums over a chunk <= 4096) are scanned two to a register.
     for (int g0 = 0; g0 < NG; g0 += 32) {
         const int g = g0 + lane;
         const bool in = g < NG;
-        unsigned long long wl[4], wh[4]; // columns 0-63 and 64-127 of my group, per row
+        unsigned long long wl[K], wh[K]; // columns 0-63 and 64-127 of my group, per row
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (in && live[k])
-                w = __ldg(rp[k] + g);
-            wl[k] = (unsigned long long)w.x | ((unsigned long long)w.y << 32);
-            wh[k] = (unsigned long long)w.z | ((unsigned long long)w.w << 32);
+        for (int k = 0; k < K; k++) {
+            wl[k] = (unsigned long long)nxt[k].x | ((unsigned long long)nxt[k].y << 32);
+            wh[k] = (unsigned long long)nxt[k].z | ((unsigned long long)nxt[k].w << 32);
+            nxt[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (live[k] && g + 32 < NG)
+                nxt[k] = __ldg(rp[k] + g + 32);
         }
-        unsigned pc[4];
+        unsigned pc[K], ip[KP];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < K; k++)
             pc[k] = __popcll(wl[k]) + __popcll(wh[k]);
-        unsigned i01 = pc[0] | (pc[1] << 16), i23 = pc[2] | (pc[3] << 16);
+#pragma unroll
+        for (int j = 0; j < KP; j++)
+            ip[j] = pc[2 * j] | (2 * j + 1 < K ? pc[(2 * j + 1) % K] << 16 : 0u);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t01 = __shfl_up_sync(0xffffffffu, i01, o), t23 = __shfl_up_sync(0xffffffffu, i23, o);
-            if (lane >= o) {
-                i01 += t01;
-                i23 += t23;
+#pragma unroll
+            for (int j = 0; j < KP; j++) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, ip[j], o);
+                if (lane >= o)
+                    ip[j] += u;
             }
         }
-        const unsigned inc[4] = { i01 & 0xffffu, i01 >> 16, i23 & 0xffffu, i23 >> 16 };
+        unsigned inc[K];
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            inc[k] = (k & 1) ? ip[k / 2] >> 16 : ip[k / 2] & 0xffffu;
         if (in) {
             const int b1 = gfirst[g + 1];
             for (int b = gfirst[g]; b < b1; b++) {
@@ -1064,25 +1195,27 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
                 const unsigned long long ml = kk >= 64 ? ~0ull : ((1ull << kk) - 1ull);
                 const unsigned long long mh = kk > 64 ? ((1ull << (kk - 64)) - 1ull) : 0ull;
 #pragma unroll
-                for (int k = 0; k < 4; k++)
+                for (int k = 0; k < K; k++)
                     pb[(warp + 8 * k) * PS + b] = carry[k] + inc[k] - pc[k] + __popcll(wl[k] & ml) + __popcll(wh[k] & mh);
             }
         }
-        const unsigned e01 = __shfl_sync(0xffffffffu, i01, 31), e23 = __shfl_sync(0xffffffffu, i23, 31);
-        carry[0] += e01 & 0xffffu;
-        carry[1] += e01 >> 16;
-        carry[2] += e23 & 0xffffu;
-        carry[3] += e23 >> 16;
+#pragma unroll
+        for (int j = 0; j < KP; j++) {
+            const unsigned e = __shfl_sync(0xffffffffu, ip[j], 31);
+            carry[2 * j] += e & 0xffffu;
+            if (2 * j + 1 < K)
+                carry[(2 * j + 1) % K] += e >> 16;
+        }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) // boundaries at the very end of the padded row
+    for (int k = 0; k < K; k++) // boundaries at the very end of the padded row
         for (int b = gfirst[NG] + lane; b <= S; b += 32)
             pb[(warp + 8 * k) * PS + b] = carry[k];
     __syncthreads();
-    for (int i = tid; i < S * 32; i += blockDim.x) {
-        const int s = i >> 5, rl = i & 31, row = r_base + rl;
-        if (row < rows && xb[s] >= 0) // leaf strips are never cut in y
-            rowcount[(size_t)s * Rmax + row] = (CT)(pb[rl * PS + s + 1] - pb[rl * PS + s]);
+    for (int i = tid; i < S * RB; i += blockDim.x) {
+        const int s = i / RB, rl = i % RB, row = r_base + rl;
+        if (row < Rmax && xb[s] >= 0) // leaf strips are never cut in y; rows beyond `rows` count 0
+            store_row_count<CT>(out, (size_t)s * Rmax + row, (CT)(pb[rl * PS + s + 1] - pb[rl * PS + s]));
     }
 }
 
@@ -1099,50 +1232,31 @@ __device__ __forceinline__ const CT* row_segment(const PeerRows& pr, size_t rank
     return pr.n == 1 ? reinterpret_cast<const CT*>(pr.row[0]) + (size_t)g * rank_stride
                      : reinterpret_cast<const CT*>(pr.row[g]);
 }
-// 32 consecutive row counts of strip s starting at global row i0 (rank g = y / Rmax holds row y)
+// 4 consecutive row counts of strip s starting at global row i (rank g = y / Rmax holds row y)
 template <typename CT>
-__device__ __forceinline__ void load_row_counts(const PeerRows& pr, size_t rank_stride, size_t strip_off, int Rmax,
-    int i0, int NY, unsigned (&v)[PFX_E])
+__device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, size_t rank_stride, size_t strip_off, int Rmax,
+    int i, int NY)
 {
-    const int g = i0 / Rmax, yl = i0 - g * Rmax;
+    const int g = i / Rmax, yl = i - g * Rmax;
     const CT* src = row_segment<CT>(pr, rank_stride, g) + strip_off + yl;
-    if (i0 + PFX_E <= NY && yl + PFX_E <= Rmax && ((uintptr_t)src & 15) == 0) {
-        // the chunk lies inside one rank's rows: vector loads
-        if (sizeof(CT) == 4) {
+    if (i + 4 <= NY && yl + 4 <= Rmax && ((uintptr_t)src & (4 * sizeof(CT) - 1)) == 0) {
+        // the chunk lies inside one rank's rows: one vector load
+        if (sizeof(CT) == 4)
+            return __ldcg(reinterpret_cast<const uint4*>(src));
+        const uint2 t = __ldcg(reinterpret_cast<const uint2*>(src));
+        return make_uint4(t.x & 0xffffu, t.x >> 16, t.y & 0xffffu, t.y >> 16);
+    }
+    unsigned c[4];
 #pragma unroll
-            for (int q = 0; q < PFX_E / 4; q++) {
-                const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src) + q);
-                v[4 * q] = t.x;
-                v[4 * q + 1] = t.y;
-                v[4 * q + 2] = t.z;
-                v[4 * q + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < PFX_E / 8; q++) {
-                const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src) + q);
-                v[8 * q] = t.x & 0xffffu;
-                v[8 * q + 1] = t.x >> 16;
-                v[8 * q + 2] = t.y & 0xffffu;
-                v[8 * q + 3] = t.y >> 16;
-                v[8 * q + 4] = t.z & 0xffffu;
-                v[8 * q + 5] = t.z >> 16;
-                v[8 * q + 6] = t.w & 0xffffu;
-                v[8 * q + 7] = t.w >> 16;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < PFX_E; k++) {
-            const int y = i0 + k;
-            unsigned c = 0u;
-            if (y < NY) {
-                const int gg = y / Rmax;
-                c = (unsigned)__ldcg(row_segment<CT>(pr, rank_stride, gg) + strip_off + (y - gg * Rmax));
-            }
-            v[k] = c;
+    for (int k = 0; k < 4; k++) {
+        const int y = i + k;
+        c[k] = 0u;
+        if (y < NY) {
+            const int gg = y / Rmax;
+            c[k] = (unsigned)__ldcg(row_segment<CT>(pr, rank_stride, gg) + strip_off + (y - gg * Rmax));
         }
     }
+    return make_uint4(c[0], c[1], c[2], c[3]);
 }
 
 template <typename CT, bool SMEM>
@@ -1150,7 +1264,7 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t
     int Rmax, int NY, StripTable st, unsigned* pfx_g, BoxTable bx, long long* loads, Plan* plan)
 {
     extern __shared__ __align__(16) unsigned smem_dyn[];
-    __shared__ unsigned wsum[33];
+    __shared__ unsigned wsum[PFX_WS];
     if (plan->mismatch)
         return;
     const unsigned long long t_start = global_ns();
@@ -1183,9 +1297,8 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t
             continue; // K2 already wrote the box of a leaf strip
         __syncthreads(); // previous strip done with pfx
         const size_t strip_off = (size_t)s * Rmax;
-        block_prefix_wide<PFX_E>(
-            [&](int i0, unsigned (&v)[PFX_E]) { load_row_counts<CT>(pr, rank_stride, strip_off, Rmax, i0, NY, v); }, NY,
-            pfx, wsum, bitmap);
+        block_prefix_tiles(
+            [&](int i) { return load_row_counts4<CT>(pr, rank_stride, strip_off, Rmax, i, NY); }, NY, pfx, wsum, bitmap);
         if (blockIdx.x == 0 && tid == 0)
             plan->ts[8] = global_ns();
         // a group of `lanes` threads walks to the j-th part of the strip (parts come out y-sorted)
@@ -1815,9 +1928,11 @@ __global__ void __launch_bounds__(1024) k_neighbours_redo(BoxTable bx, int P, in
 // (this rank's slot to "no dot yet", the others to 0 so that the SUM all-reduce of the whole
 // buffer delivers every rank's pair), scalars, load min / max
 __global__ void __launch_bounds__(256) k_init(unsigned* __restrict__ colcount, int n, int yr_off, int rank,
-    DevScalars* __restrict__ sc, long long* __restrict__ loadmm)
+    DevScalars* __restrict__ sc, long long* __restrict__ loadmm, unsigned* __restrict__ done, int ndone)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ndone)
+        done[i] = 0u;
     if (i < n) {
         unsigned v = 0u;
         if (i == yr_off + 2 * rank)
