@@ -475,7 +475,7 @@ static void peer_capacity(int nx, int ny, int nparts, int G, size_t* colcap, siz
     guess_plan_public(nparts, nx, ny, &ix, &iy);
     const size_t Scap = (size_t)std::min<long long>(nparts, 1LL << std::min(ix, 30));
     const size_t Rmax = ((size_t)ny + G - 1) / G;
-    const size_t elems = iy > 0 ? Scap * Rmax : 0;
+    const size_t elems = iy > 0 ? Scap * ((Rmax + 31) & ~(size_t)31) : 0; // whole row blocks (row_count_index)
     *colcap = ((((size_t)nx + 3) & ~(size_t)3) + 2 * (size_t)G + 4 + 3) & ~(size_t)3;
     *rowcap = ((nx < 65536 ? (elems + 1) / 2 : elems) + 4 + 3) & ~(size_t)3;
 }
@@ -699,7 +699,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     CUDA_TRY(h, h->loadmm.ensure(2));
     if (want_pid)
         CUDA_TRY(h, h->pid.ensure((size_t)std::max(rows, 1) * NX));
-    const size_t rc_elems = (size_t)Scap * Rmax; // per rank
+    const size_t rc_elems = (size_t)Scap * (((size_t)Rmax + 31) & ~(size_t)31); // per rank, whole row blocks
     const size_t rc_words = narrow ? (rc_elems + 1) / 2 : rc_elems; // 32-bit words per rank
     const size_t rank_stride = narrow ? rc_words * 2 : rc_words; // elements between two ranks' blocks
     if (ycuts) {
@@ -762,6 +762,8 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             push_row.dst[q] = xrow(q, h->rank);
         }
         pc.n = pr.n = push_col.n = push_row.n = G;
+        pc.own = h->rank;
+        pc.packed = push_col.packed = Rmax < 65536 ? 1 : 0; // a rank's column counts fit 16 bits
     } else {
         pc.col[0] = colcount;
         pc.n = pr.n = 1;
@@ -816,6 +818,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     mark(2);
     // ---- K3 + K4: strip row counts, y cuts -----------------------------------------------------
     if (ycuts) {
+        int rb_shift = 5; // log2(rows per block) of the kernel that writes the row counts
         {
             // the grid covers the Rmax rows of the largest shard: a short (or empty) shard writes its
             // missing rows as empty, and with the peer exchange every count goes to all ranks
@@ -828,6 +831,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             const size_t scan_smem = sizeof(int) * strip_scan_smem_words(NG, Scap, K);
             if (scan_smem <= 48 * 1024) { // the streaming kernel: boundary table in shared memory
                 const int grid = (Rmax + 8 * K - 1) / (8 * K);
+                rb_shift = K == 4 ? 5 : (K == 2 ? 4 : 3);
 #define LAUNCH_SCAN(CT, KK)                                                                        \
     k_strip_rows_scan<CT, KK><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0, h->plan.p, Scap, \
         push_row, Rmax)
@@ -866,14 +870,15 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             }
         }
         mark(3);
+        const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
 #define LAUNCH_YCUTS(CT, SM, opted)                                                                \
     do {                                                                                           \
         if (SM && opted < yneed) {                                                                 \
             CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<CT, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed)); \
             opted = yneed;                                                                         \
         }                                                                                          \
-        k_ycuts<CT, SM><<<ygrid, 1024, SM ? yneed : 0, s>>>(pr, ps, rank_stride, Rmax, NY, t.st, h->ypfx.p, t.bx, \
-            h->loads.p, h->plan.p);                                                                \
+        k_ycuts<CT, SM><<<ygrid, 1024, SM ? yneed : 0, s>>>(pr, ps, rl, NY, t.st, h->ypfx.p, t.bx, h->loads.p, \
+            h->plan.p);                                                                \
     } while (0)
         if (narrow) {
             if (y_smem)

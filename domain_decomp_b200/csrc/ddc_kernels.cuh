@@ -80,6 +80,7 @@ struct PeerCols { // column counts of every rank: slot g of MY exchange buffer (
                   // n == 1: col[0] already holds global counts (single GPU, or after an all-reduce)
     const unsigned* col[MAX_PEERS];
     int n;
+    int own, packed; // packed: every slot but col[own] holds 16-bit counts (see PeerPush)
 };
 struct PeerRows { // strip row counts of every rank: slot g of MY exchange buffer; n == 1: row[0] is
                   // the gathered [G][rank_stride] (or the only rank's block)
@@ -90,6 +91,7 @@ struct PeerPush { // where a producing kernel stores its histogram: dst[q] = MY 
                   // buffer (dst[rank] is local memory); n <= 1: nothing to push, dst[0] is the local buffer
     void* dst[MAX_PEERS];
     int n, rank;
+    int packed; // column counts only: pushed as 16-bit values (every rank holds < 65536 rows)
 };
 __device__ __forceinline__ unsigned long long global_ns()
 {
@@ -580,29 +582,40 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
     // block to have done so pushes the dot y-range and raises this rank's flag at every peer --
     // so the counts travel while the rest of the scan is still running and the x-cut kernel of
     // every rank finds all of them in its own memory.
-    __threadfence(); // my atomics are performed before this CTA is counted as done
-    __syncthreads();
-    if (threadIdx.x == 0)
+    __syncthreads(); // every thread's atomics are issued ...
+    if (threadIdx.x == 0) {
+        __threadfence(); // ... and performed (cumulative over the barrier) before this CTA is counted as done
         s_last = atomicAdd(&done[blockIdx.x], 1u) == gridDim.y - 1;
+        if (s_last)
+            __threadfence();
+    }
     __syncthreads();
     if (!s_last)
         return;
-    __threadfence();
     const int c = blockIdx.x * 1024 + threadIdx.x * 4;
     if (c < yr_off) {
         const uint4 v = __ldcg(reinterpret_cast<const uint4*>(colcount + c));
-        for (int q = 0; q < push.n; q++)
-            if (q != push.rank)
-                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned*>(push.dst[q]) + c) = v;
+        if (push.packed) { // a rank holds < 65536 rows: its counts travel (and are read) as 16-bit values
+            const uint2 w = make_uint2(v.x | (v.y << 16), v.z | (v.w << 16));
+            for (int q = 0; q < push.n; q++)
+                if (q != push.rank)
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(push.dst[q]) + c) = w;
+        } else {
+            for (int q = 0; q < push.n; q++)
+                if (q != push.rank)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned*>(push.dst[q]) + c) = v;
+        }
     }
-    __threadfence_system(); // my stores are performed at the peers before this block is counted
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
+        __threadfence_system(); // the block's stores are performed at the peers before it is counted
         s_last = atomicAdd(&done[gridDim.x], 1u) == gridDim.x - 1;
+        if (s_last)
+            __threadfence();
+    }
     __syncthreads();
     if (!s_last)
         return;
-    __threadfence();
     if (threadIdx.x < push.n) {
         const int q = threadIdx.x;
         if (q != push.rank) {
@@ -877,6 +890,22 @@ __device__ __forceinline__ uint4 load_counts4(const PeerCols& pc, int i, int n)
 {
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     for (int g = 0; g < pc.n; g++) {
+        if (pc.packed && g != pc.own) {
+            const uint16_t* src = reinterpret_cast<const uint16_t*>(pc.col[g]) + i;
+            if (i + 4 <= n && ((uintptr_t)src & 7) == 0) {
+                const uint2 t = __ldcg(reinterpret_cast<const uint2*>(src));
+                v.x += t.x & 0xffffu;
+                v.y += t.x >> 16;
+                v.z += t.y & 0xffffu;
+                v.w += t.y >> 16;
+            } else {
+                v.x += i < n ? (unsigned)__ldcg(src) : 0u;
+                v.y += i + 1 < n ? (unsigned)__ldcg(src + 1) : 0u;
+                v.z += i + 2 < n ? (unsigned)__ldcg(src + 2) : 0u;
+                v.w += i + 3 < n ? (unsigned)__ldcg(src + 3) : 0u;
+            }
+            continue;
+        }
         const unsigned* src = pc.col[g] + i;
         if (i + 4 <= n && ((uintptr_t)src & 15) == 0) {
             const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src));
@@ -1043,10 +1072,28 @@ __global__ void __launch_bounds__(256) k_paint_strips(StripTable st, const Plan*
 // ------------------------------------------------------------------------------------------------
 // One warp = 32 consecutive rows of one strip; lane = row.  A lane reads the few 16-byte groups its
 // strip overlaps straight from global memory (neighbouring strips share the boundary group, which
-// L1 / L2 serve) and the warp writes 32 consecutive counts.  rowcount layout [S][Rmax], rows local
+// L1 / L2 serve) and the warp writes 32 consecutive counts (layout: row_count_index), rows local
 // to this rank.  Leaf strips (one part, never cut in y) are skipped.
-// store one count into this rank's block of the row counts -- of every rank when they are exchanged
-// through peer memory (exchange step 2: pushed by the producer, read locally by the y-cut kernels)
+// Layout of one rank's strip row counts: [row block][strip][RB rows], RB = 1 << rb_shift rows per
+// block of the kernel that wrote them.  A block of the row-count kernels therefore writes ONE
+// contiguous chunk of Scap * RB counts -- which is what makes pushing it to the other ranks cheap:
+// whole 16-byte stores, 512 contiguous bytes per warp (exchange step 2; the y-cut kernels read
+// their own copy).  With rows contiguous per strip every block scattered 16-byte fragments over all
+// strips and all peers, and the push took 4 x longer than the counting.
+__host__ __device__ __forceinline__ size_t row_count_index(int s, int yl, int Scap, int rb_shift)
+{
+    return ((((size_t)(yl >> rb_shift) * Scap + s) << rb_shift) + (yl & ((1 << rb_shift) - 1)));
+}
+// store 16 bytes of counts at element index idx of this rank's block -- in the buffer of every rank
+// when the counts are exchanged through peer memory
+__device__ __forceinline__ void store_row_counts16(const PeerPush& out, size_t byte_off, const uint4& v)
+{
+    if (out.n <= 1)
+        *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out.dst[0]) + byte_off) = v;
+    else
+        for (int q = 0; q < out.n; q++)
+            *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out.dst[q]) + byte_off) = v;
+}
 template <typename CT>
 __device__ __forceinline__ void store_row_count(const PeerPush& out, size_t idx, CT v)
 {
@@ -1088,7 +1135,7 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
                     + __popc(w.z & word_range_mask(a - 64, b - 64)) + __popc(w.w & word_range_mask(a - 96, b - 96));
         }
     }
-    store_row_count<CT>(out, (size_t)s * Rmax + row, (CT)cnt);
+    store_row_count<CT>(out, row_count_index(s, row, Scap, 5), (CT)cnt); // 32 consecutive counts per warp
 }
 
 // The same counts, coalesced: a block takes 32 consecutive rows and streams them ONCE -- a warp
@@ -1212,35 +1259,56 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
         for (int b = gfirst[NG] + lane; b <= S; b += 32)
             pb[(warp + 8 * k) * PS + b] = carry[k];
     __syncthreads();
-    for (int i = tid; i < S * RB; i += blockDim.x) {
-        const int s = i / RB, rl = i % RB, row = r_base + rl;
-        if (row < Rmax && xb[s] >= 0) // leaf strips are never cut in y; rows beyond `rows` count 0
-            store_row_count<CT>(out, (size_t)s * Rmax + row, (CT)(pb[rl * PS + s + 1] - pb[rl * PS + s]));
+    // this block's chunk of the [row block][strip][RB] layout, written 16 bytes at a time
+    constexpr int V = 16 / (int)sizeof(CT); // counts per store
+    static_assert(RB % V == 0, "a 16-byte store must not straddle two strips");
+    const size_t chunk = (size_t)blockIdx.x * Scap * RB;
+    for (int i = tid; i < S * RB / V; i += blockDim.x) {
+        const int e = i * V, s = e / RB, rl = e % RB;
+        if (xb[s] < 0)
+            continue; // leaf strips are never cut in y
+        unsigned c[V];
+#pragma unroll
+        for (int v = 0; v < V; v++)
+            c[v] = pb[(rl + v) * PS + s + 1] - pb[(rl + v) * PS + s]; // rows beyond `rows` count 0
+        uint4 o;
+        if (sizeof(CT) == 2) {
+            o.x = c[0] | (c[1 % V] << 16);
+            o.y = c[2 % V] | (c[3 % V] << 16);
+            o.z = c[4 % V] | (c[5 % V] << 16);
+            o.w = c[6 % V] | (c[7 % V] << 16);
+        } else
+            o = make_uint4(c[0], c[1 % V], c[2 % V], c[3 % V]);
+        store_row_counts16(out, (chunk + e) * sizeof(CT), o);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4: y levels, one CTA per strip (grid-stride), boxes out
 // ------------------------------------------------------------------------------------------------
-// rowcount_all layout [G][rank_stride >= Scap * Rmax] (the NCCL all-gather of every rank's [Scap][Rmax]); global row y
-// lives at rank y / Rmax, local row y % Rmax.  dynamic smem: (NY + 1) unsigned when use_smem,
-// otherwise pfx_g holds gridDim.x slices of NY + 1.  The set lists of strip s live in
-// listA/listB[p0[s] .. p0[s+1]) (strips own disjoint part ranges).
+// Row counts of rank g: the block [row block][Scap][RB] described above (row_count_index); the blocks
+// of all ranks are either the G slots of this rank's exchange buffer or, after an NCCL all-gather,
+// one buffer [G][rank_stride].  Global row y lives at rank y / Rmax, local row y % Rmax.
+// dynamic smem of k_ycuts: (NY + 1) unsigned + the bit map when use_smem, otherwise pfx_g holds
+// gridDim.x slices of NY + 1.
 template <typename CT>
 __device__ __forceinline__ const CT* row_segment(const PeerRows& pr, size_t rank_stride, int g)
 {
     return pr.n == 1 ? reinterpret_cast<const CT*>(pr.row[0]) + (size_t)g * rank_stride
                      : reinterpret_cast<const CT*>(pr.row[g]);
 }
-// 4 consecutive row counts of strip s starting at global row i (rank g = y / Rmax holds row y)
+struct RowLayout {
+    size_t rank_stride;
+    int Rmax, Scap, rb_shift;
+};
+// 4 consecutive row counts of strip s starting at global row i (a multiple of 4)
 template <typename CT>
-__device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, size_t rank_stride, size_t strip_off, int Rmax,
-    int i, int NY)
+__device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowLayout& rl, int s, int i, int NY)
 {
-    const int g = i / Rmax, yl = i - g * Rmax;
-    const CT* src = row_segment<CT>(pr, rank_stride, g) + strip_off + yl;
-    if (i + 4 <= NY && yl + 4 <= Rmax && ((uintptr_t)src & (4 * sizeof(CT) - 1)) == 0) {
-        // the chunk lies inside one rank's rows: one vector load
+    const int g = i / rl.Rmax, yl = i - g * rl.Rmax;
+    const CT* src = row_segment<CT>(pr, rl.rank_stride, g) + row_count_index(s, yl, rl.Scap, rl.rb_shift);
+    if (i + 4 <= NY && yl + 4 <= rl.Rmax && (yl & 3) == 0 && ((uintptr_t)src & (4 * sizeof(CT) - 1)) == 0) {
+        // the chunk lies inside one rank's rows and inside one row block (RB is a multiple of 4)
         if (sizeof(CT) == 4)
             return __ldcg(reinterpret_cast<const uint4*>(src));
         const uint2 t = __ldcg(reinterpret_cast<const uint2*>(src));
@@ -1252,16 +1320,16 @@ __device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, size_t ran
         const int y = i + k;
         c[k] = 0u;
         if (y < NY) {
-            const int gg = y / Rmax;
-            c[k] = (unsigned)__ldcg(row_segment<CT>(pr, rank_stride, gg) + strip_off + (y - gg * Rmax));
+            const int gg = y / rl.Rmax;
+            c[k] = (unsigned)__ldcg(row_segment<CT>(pr, rl.rank_stride, gg)
+                + row_count_index(s, y - gg * rl.Rmax, rl.Scap, rl.rb_shift));
         }
     }
     return make_uint4(c[0], c[1], c[2], c[3]);
 }
 
 template <typename CT, bool SMEM>
-__global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t rank_stride,
-    int Rmax, int NY, StripTable st, unsigned* pfx_g, BoxTable bx, long long* loads, Plan* plan)
+__global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st, unsigned* pfx_g, BoxTable bx, long long* loads, Plan* plan)
 {
     extern __shared__ __align__(16) unsigned smem_dyn[];
     __shared__ unsigned wsum[PFX_WS];
@@ -1296,9 +1364,8 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, size_t
         if (n <= 1)
             continue; // K2 already wrote the box of a leaf strip
         __syncthreads(); // previous strip done with pfx
-        const size_t strip_off = (size_t)s * Rmax;
         block_prefix_tiles(
-            [&](int i) { return load_row_counts4<CT>(pr, rank_stride, strip_off, Rmax, i, NY); }, NY, pfx, wsum, bitmap);
+            [&](int i) { return load_row_counts4<CT>(pr, rl, s, i, NY); }, NY, pfx, wsum, bitmap);
         if (blockIdx.x == 0 && tid == 0)
             plan->ts[8] = global_ns();
         // a group of `lanes` threads walks to the j-th part of the strip (parts come out y-sorted)
