@@ -150,7 +150,8 @@ struct ddc_handle_s {
     unsigned step = 0; // decompositions enqueued so far (the flag value of the exchange barriers)
     int h_totals[8] = { 0 };
     bool totals_valid = false;
-    Plan* pin_plan = nullptr; // pinned staging for the plan read-back
+    Plan* pin_plan = nullptr; // pinned, device-mapped: the last kernel of a step writes the plan here
+    Plan* pin_plan_dev = nullptr; // the same memory as the device addresses it
     cudaEvent_t ev[DDC_N_STAGES + 2] = {};
     bool ev_ok = false;
 };
@@ -374,13 +375,15 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_k2, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_paint, cudaEventDisableTiming));
-    CREATE_TRY(cudaMallocHost((void**)&h->pin_plan, sizeof(Plan)));
+    CREATE_TRY(cudaHostAlloc((void**)&h->pin_plan, sizeof(Plan), cudaHostAllocMapped));
+    CREATE_TRY(cudaHostGetDevicePointer((void**)&h->pin_plan_dev, h->pin_plan, 0));
+    memset(h->pin_plan, 0, sizeof(Plan));
     for (auto& ev : h->ev)
         CREATE_TRY(cudaEventCreate(&ev));
     h->ev_ok = true;
     if (const char* e = getenv("DDC_STRIP_K")) { // tuning knob of the strip row-count kernel
         const int v = atoi(e);
-        h->strip_k = (v == 1 || v == 2 || v == 4) ? v : 0;
+        h->strip_k = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
     }
     if (const char* e = getenv("DDC_WALK_LANES")) { // tuning knob of the cut kernels
         const int v = std::max(1, std::min(32, atoi(e)));
@@ -803,10 +806,10 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             h->xcuts_smem = xneed;
         }
         k_xcuts<true><<<1, 1024, xneed, s>>>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, h->plan.p, t.st, t.bx,
-            h->loads.p);
+            h->loads.p, h->loadmm.p);
     } else
         k_xcuts<false><<<1, 1024, 0, s>>>(pc, ps, NX, NY, P, h->colpfx.p, yr_off, G, aix, aiy, h->plan.p, t.st,
-            t.bx, h->loads.p);
+            t.bx, h->loads.p, h->loadmm.p);
     // the column -> strip table is only needed by K6: painted on the second stream, beside K3 / K4
     CUDA_TRY(h, cudaEventRecord(h->ev_k2, s));
     CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_k2, 0));
@@ -824,31 +827,37 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             // missing rows as empty, and with the peer exchange every count goes to all ranks
             // rows per warp of the streaming kernel: fewer for small shards, so that the grid fills the SMs
             int K = Rmax >= 32 * 4 * 148 ? 4 : (Rmax >= 16 * 4 * 148 ? 2 : 1);
-            if (h->strip_k) // DDC_STRIP_K: tuning knob
-                K = h->strip_k;
+            if (h->strip_k) // DDC_STRIP_K: tuning knob (1, 2, 4: rows per warp; 8: one row per warp, whole row at once)
+                K = h->strip_k == 8 ? 1 : h->strip_k;
             while (K > 1 && sizeof(int) * strip_scan_smem_words(NG, Scap, K) > 48 * 1024)
                 K >>= 1;
             const size_t scan_smem = sizeof(int) * strip_scan_smem_words(NG, Scap, K);
             if (scan_smem <= 48 * 1024) { // the streaming kernel: boundary table in shared memory
                 const int grid = (Rmax + 8 * K - 1) / (8 * K);
                 rb_shift = K == 4 ? 5 : (K == 2 ? 4 : 3);
-#define LAUNCH_SCAN(CT, KK)                                                                        \
-    k_strip_rows_scan<CT, KK><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0, h->plan.p, Scap, \
-        push_row, Rmax)
+#define LAUNCH_SCAN(CT, KK, FF)                                                                    \
+    k_strip_rows_scan<CT, KK, FF><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0, h->plan.p, \
+        Scap, push_row, Rmax)
+                // small shards: one row per warp, the whole row requested at once (rows of <= 8 chunks)
+                const bool full = K == 1 && NG <= 256 && h->strip_k != 1;
                 if (narrow) {
                     if (K == 4)
-                        LAUNCH_SCAN(uint16_t, 4);
+                        LAUNCH_SCAN(uint16_t, 4, false);
                     else if (K == 2)
-                        LAUNCH_SCAN(uint16_t, 2);
+                        LAUNCH_SCAN(uint16_t, 2, false);
+                    else if (full)
+                        LAUNCH_SCAN(uint16_t, 1, true);
                     else
-                        LAUNCH_SCAN(uint16_t, 1);
+                        LAUNCH_SCAN(uint16_t, 1, false);
                 } else {
                     if (K == 4)
-                        LAUNCH_SCAN(unsigned, 4);
+                        LAUNCH_SCAN(unsigned, 4, false);
                     else if (K == 2)
-                        LAUNCH_SCAN(unsigned, 2);
+                        LAUNCH_SCAN(unsigned, 2, false);
+                    else if (full)
+                        LAUNCH_SCAN(unsigned, 1, true);
                     else
-                        LAUNCH_SCAN(unsigned, 1);
+                        LAUNCH_SCAN(unsigned, 1, false);
                 }
 #undef LAUNCH_SCAN
             } else {
@@ -878,7 +887,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             opted = yneed;                                                                         \
         }                                                                                          \
         k_ycuts<CT, SM><<<ygrid, 1024, SM ? yneed : 0, s>>>(pr, ps, rl, NY, t.st, h->ypfx.p, t.bx, h->loads.p, \
-            h->plan.p);                                                                \
+            h->loadmm.p, h->plan.p);                                                                \
     } while (0)
         if (narrow) {
             if (y_smem)
@@ -944,19 +953,17 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     // ---- K5: naive blocks when nothing moved; load statistics -----------------------------------
     if (want_nbr)
         CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0)); // K5 rewrites the boxes K7 is reading
-    k_finalize<<<std::min((P + 255) / 256, 148), 256, 0, s>>>(ps, P, NX, NY, nv, h->sc.p, h->plan.p, t.st, t.bx,
-        h->loads.p, h->loadmm.p);
+    // (one block; when nothing moved it also rebuilds the neighbour tables from the naive blocks, and it
+    //  writes the plan into the host's pinned copy: no separate read-back at the end of the step)
+    const NbrTables nb = { h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p,
+        h->nbr_starts.p };
+    k_finalize<<<1, 1024, 0, s>>>(ps, P, NX, NY, px, py, nv, h->sc.p, h->plan.p, t.st, t.bx, want_nbr ? 1 : 0, nb,
+        h->pin_plan_dev);
     launches++;
     mark(6);
-    // ---- K7 again, only if the naive blocks replaced the RCB boxes (the kernels return at once otherwise)
-    if (want_nbr) {
-        k_neighbours_redo<<<1, 1024, 0, s>>>(t.bx, P, NX, NY, px, py, t.st, h->nbr_counts.p, h->nbr_offsets.p,
-            h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p, h->sc.p, h->plan.p);
-        launches++;
+    if (want_nbr)
         h->have_nbr = true;
-    }
     mark(7);
-    CUDA_TRY(h, cudaMemcpyAsync(h->pin_plan, h->plan.p, sizeof(Plan), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaGetLastError());
 
     h->stats.gpu_launches = launches;

@@ -141,6 +141,22 @@ __device__ __forceinline__ bool peer_barrier(const PeerSync& ps, int stage, unsi
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
+// part loads -> global min / max (loadmm = {min, max}, pre-set to {LLONG_MAX, -1} by k_init); called by
+// all threads of a block with the extremes of the parts each of them wrote (or the neutral values)
+__device__ __forceinline__ void reduce_load_extremes(long long mn, long long mx, long long* loadmm)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if (lane_id() == 0 && mx >= 0) {
+        atomicMin(loadmm, mn);
+        atomicMax(loadmm + 1, mx);
+    }
+}
+
 // bits of a 32-column word that belong to word-relative columns [a, b), clipped to [0, 32]
 __device__ __forceinline__ unsigned word_range_mask(int a, int b)
 {
@@ -927,7 +943,7 @@ __device__ __forceinline__ uint4 load_counts4(const PeerCols& pc, int i, int n)
 // aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
-    int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads)
+    int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm)
 {
     extern __shared__ __align__(16) unsigned smem_dyn[];
     __shared__ unsigned wsum[PFX_WS];
@@ -1013,6 +1029,7 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     const int nstrips = leaves_below(P, ix);
     const int lanes = walk_lanes(nstrips, blockDim.x);
     int my_iters = 0;
+    long long lmn = 0x7fffffffffffffffLL, lmx = -1;
     for (int i = tid / lanes; i < nstrips; i += blockDim.x / lanes) {
         const RcbSet root = { 0, NX, 0, P };
         int it = 0;
@@ -1029,9 +1046,13 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
             bx.ex[r.plo] = r.hi - r.lo;
             bx.y0[r.plo] = 0;
             bx.ey[r.plo] = NY;
-            loads[r.plo] = (long long)hcnt(pfx, r.lo, r.hi - 1);
+            const long long w = (long long)hcnt(pfx, r.lo, r.hi - 1);
+            loads[r.plo] = w;
+            lmn = w < lmn ? w : lmn;
+            lmx = w > lmx ? w : lmx;
         }
     }
+    reduce_load_extremes(lmn, lmx, loadmm);
     if (my_iters)
         atomicAdd(&s_iters, my_iters);
     if (tid == 0) {
@@ -1152,7 +1173,9 @@ __host__ __device__ inline size_t strip_scan_smem_words(int NG, int S, int K)
 {
     return (size_t)(NG + 1) + (size_t)(S + 1) + 8 * (size_t)K * (size_t)((S + 1) | 1);
 }
-template <typename CT, int K>
+// FULL (K == 1, rows of at most 8 chunks = 32768 columns): a lane requests ALL chunks of its row before
+// the boundary table is built, so that a block pays the memory latency once.
+template <typename CT, int K, bool FULL>
 __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restrict__ bits, int NB, int NX, int rows,
     const int* __restrict__ st_x0, const int* __restrict__ st_p0, const Plan* __restrict__ plan, int Scap,
     PeerPush out, int Rmax)
@@ -1160,8 +1183,10 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     extern __shared__ int sm_scan[];
     if (plan->mismatch)
         return;
+    static_assert(!FULL || K == 1, "FULL holds one row per warp in registers");
     constexpr int RB = 8 * K; // rows per block
     constexpr int KP = (K + 1) / 2; // packed scan registers (two 16-bit running sums each)
+    constexpr int NCH = FULL ? 8 : 1; // chunks held in registers
     const int S = min(plan->S, Scap);
     const int NG = NB >> 4;
     const int PS = (S + 1) | 1;
@@ -1175,7 +1200,7 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     const uint4* rp[K];
     bool live[K];
     unsigned carry[K];
-    uint4 nxt[K];
+    uint4 nxt[K], all[NCH];
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const int row = r_base + warp + 8 * k;
@@ -1183,8 +1208,16 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
         rp[k] = reinterpret_cast<const uint4*>(bits + (size_t)(live[k] ? row : 0) * NB);
         carry[k] = 0u;
         nxt[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (live[k] && lane < NG)
+        if (!FULL && live[k] && lane < NG)
             nxt[k] = __ldg(rp[k] + lane);
+    }
+    if (FULL) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            all[c] = make_uint4(0u, 0u, 0u, 0u);
+            if (live[0] && c * 32 + lane < NG)
+                all[c] = __ldg(rp[0] + c * 32 + lane);
+        }
     }
     for (int b = tid; b <= S; b += blockDim.x)
         xb[b] = b < S ? (st_x0[b] | (st_p0[b + 1] - st_p0[b] <= 1 ? (int)0x80000000 : 0)) : NX;
@@ -1203,17 +1236,26 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     }
     __syncthreads();
     // The per-group popcounts (<= 128, their running sums over a chunk <= 4096) are scanned two to a register.
-    for (int g0 = 0; g0 < NG; g0 += 32) {
+    const int nchunks = (NG + 31) >> 5;
+#pragma unroll(FULL ? NCH : 1)
+    for (int ch = 0; ch < (FULL ? NCH : nchunks); ch++) {
+        const int g0 = ch * 32;
+        if (FULL && g0 >= NG)
+            break;
         const int g = g0 + lane;
         const bool in = g < NG;
         unsigned long long wl[K], wh[K]; // columns 0-63 and 64-127 of my group, per row
 #pragma unroll
         for (int k = 0; k < K; k++) {
+            if (FULL)
+                nxt[k] = all[ch % NCH];
             wl[k] = (unsigned long long)nxt[k].x | ((unsigned long long)nxt[k].y << 32);
             wh[k] = (unsigned long long)nxt[k].z | ((unsigned long long)nxt[k].w << 32);
-            nxt[k] = make_uint4(0u, 0u, 0u, 0u);
-            if (live[k] && g + 32 < NG)
-                nxt[k] = __ldg(rp[k] + g + 32);
+            if (!FULL) {
+                nxt[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (live[k] && g + 32 < NG)
+                    nxt[k] = __ldg(rp[k] + g + 32);
+            }
         }
         unsigned pc[K], ip[KP];
 #pragma unroll
@@ -1329,7 +1371,8 @@ __device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowL
 }
 
 template <typename CT, bool SMEM>
-__global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st, unsigned* pfx_g, BoxTable bx, long long* loads, Plan* plan)
+__global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st,
+    unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan)
 {
     extern __shared__ __align__(16) unsigned smem_dyn[];
     __shared__ unsigned wsum[PFX_WS];
@@ -1359,6 +1402,7 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     const int S = *st.S;
     const int ylevels = plan->iy;
     int my_iters = 0;
+    long long lmn = 0x7fffffffffffffffLL, lmx = -1;
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
         const int plo = st.p0[s], n = st.p0[s + 1] - plo;
         if (n <= 1)
@@ -1382,9 +1426,13 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
             bx.ex[r.plo] = sx1 - sx0;
             bx.y0[r.plo] = r.lo;
             bx.ey[r.plo] = r.hi - r.lo;
-            loads[r.plo] = (long long)hcnt(pfx, r.lo, r.hi - 1);
+            const long long w = (long long)hcnt(pfx, r.lo, r.hi - 1);
+            loads[r.plo] = w;
+            lmn = w < lmn ? w : lmn;
+            lmx = w > lmx ? w : lmx;
         }
     }
+    reduce_load_extremes(lmn, lmx, loadmm);
     if (my_iters)
         atomicAdd(&plan->iters, my_iters);
     __syncthreads();
@@ -1586,79 +1634,6 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
         }
         if (check && (r & 63) == 0)
             check = *reinterpret_cast<volatile int*>(&sc->changes) == 0;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K5: `changes == 0`  =>  report the naive blocks (ZoltanPartitioner.cpp:182-187)
-// ------------------------------------------------------------------------------------------------
-// Also reduces the part loads to their min / max (loadmm pre-set to LLONG_MAX, -1 by k_init).
-__global__ void __launch_bounds__(256) k_finalize(PeerSync ps, int P, int NX, int NY, NaiveParams nv,
-    DevScalars* __restrict__ sc, Plan* __restrict__ plan, StripTable st, BoxTable bx,
-    const long long* __restrict__ loads, long long* __restrict__ loadmm)
-{
-    if (plan->mismatch)
-        return;
-    // exchange step 3: `changes` of every rank rides in the low bit of its flag
-    int changes = sc->changes;
-    if (ps.enabled) {
-        bool ok = true;
-        unsigned seen = 0u;
-        if (threadIdx.x < ps.G)
-            ok = peer_barrier(ps, 2, changes ? 1u : 0u, blockIdx.x == 0, &seen);
-        if (__syncthreads_or(!ok)) {
-            if (threadIdx.x == 0)
-                plan->mismatch = 3;
-            return;
-        }
-        changes = __syncthreads_or(threadIdx.x < ps.G && (seen & 1u));
-    }
-    long long mn = 0x7fffffffffffffffLL, mx = -1;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-        const long long v = loads[p];
-        mn = v < mn ? v : mn;
-        mx = v > mx ? v : mx;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
-        mn = a < mn ? a : mn;
-        mx = b > mx ? b : mx;
-    }
-    if (lane_id() == 0) {
-        atomicMin(loadmm, mn);
-        atomicMax(loadmm + 1, mx);
-    }
-    if (ps.enabled && blockIdx.x == 0 && threadIdx.x == 0)
-        sc->changes_all = changes; // only this block reads sc->changes (above); later kernels read changes_all
-    if (!ps.enabled && blockIdx.x == 0 && threadIdx.x == 0)
-        sc->changes_all = changes;
-    if (P == 1 || changes != 0)
-        return;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-        const int bxi = p / nv.np1, byi = p % nv.np1; // Grid.cpp:158-159
-        int ex = nv.lx, ey = nv.ly;
-        if (bxi == nv.np0 - 1)
-            ex = NX - bxi * nv.lx;
-        if (byi == nv.np1 - 1)
-            ey = NY - byi * nv.ly;
-        bx.x0[p] = bxi * nv.lx;
-        bx.y0[p] = byi * nv.ly;
-        bx.ex[p] = ex;
-        bx.ey[p] = ey;
-        if (byi == 0) {
-            st.x0[bxi] = bxi * nv.lx;
-            st.x1[bxi] = bxi * nv.lx + ex;
-            st.p0[bxi] = p;
-        }
-        if (p == 0) {
-            st.p0[nv.np0] = P;
-            *st.S = nv.np0;
-            // ceil() over-covering makes trailing blocks start beyond the extent (non-positive
-            // extents, y no longer sorted): let the neighbour kernel test all pairs then
-            if ((nv.np0 - 1) * nv.lx >= NX || (nv.np1 - 1) * nv.ly >= NY)
-                *st.always = 1;
-        }
     }
 }
 
@@ -1934,44 +1909,113 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
         totals[l] = (int)total;
 }
 
-// The tables above are built speculatively from the RCB boxes, beside the labelling kernel that is
-// still looking for `changes`.  In the rare case that nothing moved (`changes == 0`) K5 replaced the
-// boxes by the naive blocks and the tables are built again here: count, scan and fill in ONE block,
-// so that the common case costs a single launch that returns at once.
-__global__ void __launch_bounds__(1024) k_neighbours_redo(BoxTable bx, int P, int NX, int NY, int px, int py,
-    StripTable st, int* __restrict__ counts, int* __restrict__ offsets, int* __restrict__ totals, int cap,
-    int* __restrict__ ids, int* __restrict__ halos, int* __restrict__ starts, DevScalars* sc,
-    const Plan* __restrict__ plan)
+// ------------------------------------------------------------------------------------------------
+// K5: the end of a step, ONE block
+// ------------------------------------------------------------------------------------------------
+//  * exchange step 3: `changes` of every rank (it rides in the low bit of the flag);
+//  * `changes == 0`  =>  the naive blocks are reported (ZoltanPartitioner.cpp:182-187).  The neighbour
+//    tables were built speculatively from the RCB boxes, beside the labelling kernel that was still
+//    looking for `changes`; in this rare case they are built again here from the naive blocks
+//    (count, scan and fill in this one block);
+//  * the plan (levels, mismatch flag, iteration count) is written straight into the host's pinned
+//    copy, so that the step ends without a separate device -> host copy.
+struct NbrTables {
+    int* counts;
+    int* offsets;
+    int* totals;
+    int cap;
+    int* ids;
+    int* halos;
+    int* starts;
+};
+__device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
+{
+    static_assert(sizeof(Plan) % 4 == 0, "Plan is copied word by word");
+    if (threadIdx.x < sizeof(Plan) / 4)
+        reinterpret_cast<volatile unsigned*>(host_plan)[threadIdx.x]
+            = reinterpret_cast<const volatile unsigned*>(plan)[threadIdx.x];
+}
+__global__ void __launch_bounds__(1024) k_finalize(PeerSync ps, int P, int NX, int NY, int px, int py, NaiveParams nv,
+    DevScalars* __restrict__ sc, Plan* __restrict__ plan, StripTable st, BoxTable bx,
+    int want_nbr, NbrTables nb, Plan* __restrict__ host_plan)
 {
     __shared__ unsigned long long wsum64[33];
     __shared__ int s_over;
-    if (plan->mismatch || sc->changes_all != 0)
-        return;
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        sc->edge_cut = 0ull;
-        sc->overflow = 0;
-        s_over = 0;
+    if (plan->mismatch) {
+        publish_plan(plan, host_plan);
+        return;
     }
-    __syncthreads();
+    int changes = sc->changes;
+    if (ps.enabled) {
+        bool ok = true;
+        unsigned seen = 0u;
+        if (tid < ps.G)
+            ok = peer_barrier(ps, 2, changes ? 1u : 0u, true, &seen);
+        if (__syncthreads_or(!ok)) {
+            if (tid == 0)
+                plan->mismatch = 3;
+            __syncthreads();
+            publish_plan(plan, host_plan);
+            return;
+        }
+        changes = __syncthreads_or(tid < ps.G && (seen & 1u));
+    }
+    if (tid == 0)
+        sc->changes_all = changes;
+    publish_plan(plan, host_plan); // K4 is done: the iteration count is final
+    if (P == 1 || changes != 0)
+        return;
+    // ---- nothing moved: the naive blocks (Grid.cpp:150-166) replace the RCB boxes ----
+    for (int p = tid; p < P; p += blockDim.x) {
+        const int bxi = p / nv.np1, byi = p % nv.np1; // Grid.cpp:158-159
+        int ex = nv.lx, ey = nv.ly;
+        if (bxi == nv.np0 - 1)
+            ex = NX - bxi * nv.lx;
+        if (byi == nv.np1 - 1)
+            ey = NY - byi * nv.ly;
+        bx.x0[p] = bxi * nv.lx;
+        bx.y0[p] = byi * nv.ly;
+        bx.ex[p] = ex;
+        bx.ey[p] = ey;
+        if (byi == 0) {
+            st.x0[bxi] = bxi * nv.lx;
+            st.x1[bxi] = bxi * nv.lx + ex;
+            st.p0[bxi] = p;
+        }
+        if (p == 0) {
+            st.p0[nv.np0] = P;
+            *st.S = nv.np0;
+            // ceil() over-covering makes trailing blocks start beyond the extent (non-positive
+            // extents, y no longer sorted): let the neighbour search test all pairs then
+            *st.always = ((nv.np0 - 1) * nv.lx >= NX || (nv.np1 - 1) * nv.ly >= NY) ? 1 : 0;
+            sc->edge_cut = 0ull;
+            sc->overflow = 0;
+            s_over = 0;
+        }
+    }
+    __syncthreads(); // the boxes and the strip table are in place (same block: visible after the barrier)
+    if (!want_nbr)
+        return;
     const bool all = *st.always != 0;
     const int Ppad = (P + 31) & ~31;
     if (all) {
         for (int me = tid >> 5; me < P; me += blockDim.x >> 5)
-            neighbours_all_pairs<false>(bx, P, NX, NY, px, py, me, counts, offsets, cap, ids, halos, starts, sc);
+            neighbours_all_pairs<false>(bx, P, NX, NY, px, py, me, nb.counts, nb.offsets, nb.cap, nb.ids, nb.halos,
+                nb.starts, sc);
     } else {
         for (int t = tid; t < 8 * Ppad; t += blockDim.x)
-            neighbours_structured<false>(bx, P, NX, NY, px, py, st, t / Ppad, t % Ppad, counts, offsets, cap, ids,
-                halos, starts, sc);
+            neighbours_structured<false>(bx, P, NX, NY, px, py, st, t / Ppad, t % Ppad, nb.counts, nb.offsets, nb.cap,
+                nb.ids, nb.halos, nb.starts, sc);
     }
     __syncthreads();
     for (int l = 0; l < 8; l++) {
-        const int* c = counts + (size_t)l * P;
+        const int* c = nb.counts + (size_t)l * P;
         const unsigned long long total = block_prefix<false>([&](int i) { return (unsigned)c[i]; }, P,
-            reinterpret_cast<unsigned*>(offsets) + (size_t)l * (P + 1), 0, wsum64);
+            reinterpret_cast<unsigned*>(nb.offsets) + (size_t)l * (P + 1), 0, wsum64);
         if (tid == 0) {
-            totals[l] = (int)total;
-            if ((long long)total > cap)
+            nb.totals[l] = (int)total;
+            if ((long long)total > nb.cap)
                 s_over = 1;
         }
     }
@@ -1983,11 +2027,12 @@ __global__ void __launch_bounds__(1024) k_neighbours_redo(BoxTable bx, int P, in
     }
     if (all) {
         for (int me = tid >> 5; me < P; me += blockDim.x >> 5)
-            neighbours_all_pairs<true>(bx, P, NX, NY, px, py, me, counts, offsets, cap, ids, halos, starts, sc);
+            neighbours_all_pairs<true>(bx, P, NX, NY, px, py, me, nb.counts, nb.offsets, nb.cap, nb.ids, nb.halos,
+                nb.starts, sc);
     } else {
         for (int t = tid; t < 8 * Ppad; t += blockDim.x)
-            neighbours_structured<true>(bx, P, NX, NY, px, py, st, t / Ppad, t % Ppad, counts, offsets, cap, ids,
-                halos, starts, sc);
+            neighbours_structured<true>(bx, P, NX, NY, px, py, st, t / Ppad, t % Ppad, nb.counts, nb.offsets, nb.cap,
+                nb.ids, nb.halos, nb.starts, sc);
     }
 }
 

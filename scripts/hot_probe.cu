@@ -181,7 +181,7 @@ int main(int argc, char** argv)
     // reference outputs from the product kernel
     {
         dim3 grid(gridx, NY / 128);
-        k_scan_mask<true><<<grid, 256>>>(mask, NX, NY, 0, NB, 128, bits, col, yr);
+        k_scan_mask<true><<<grid, 256>>>(mask, NX, NY, 0, NB, 128, bits, col, yr, PeerPush{}, PeerSync{}, nullptr, 0);
         CK(cudaDeviceSynchronize());
     }
     auto check = [&](const char* what) {
@@ -193,7 +193,7 @@ int main(int argc, char** argv)
     };
     for (int rpc : { 32, 64, 128 }) {
         dim3 grid(gridx, NY / rpc);
-        float ms = timeit([&] { k_scan_mask<true><<<grid, 256>>>(mask, NX, NY, 0, NB, rpc, bits2, col2, yr); });
+        float ms = timeit([&] { k_scan_mask<true><<<grid, 256>>>(mask, NX, NY, 0, NB, rpc, bits2, col2, yr, PeerPush{}, PeerSync{}, nullptr, 0); });
         printf("scan product            rpc %-4d %8.3f ms %8.1f GB/s\n", rpc, ms, bytes / ms / 1e6);
 #define SV(ST, B, A, U)                                                                              \
     {                                                                                              \

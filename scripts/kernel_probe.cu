@@ -40,7 +40,7 @@ int main(int argc, char** argv)
     for (int gy : { 148 * occ / gridx, 2 * 148 * occ / gridx, 64, 128, 256, 512, 1024, 2048, 4096 }) {
         int rpc = ((NY + gy - 1) / gy + 7) / 8 * 8;
         dim3 grid(gridx, (NY + rpc - 1) / rpc);
-        float ms = timeit([&] { k_scan_mask<true><<<grid, 256>>>(mask, NX, NY, 0, NB, rpc, bits, col, sc); });
+        float ms = timeit([&] { k_scan_mask<true><<<grid, 256>>>(mask, NX, NY, 0, NB, rpc, bits, col, reinterpret_cast<int*>(col) + NX, PeerPush{}, PeerSync{}, nullptr, 0); });
         printf("  scan  grid %dx%-5d rpc %-5d %8.3f ms %8.1f GB/s\n", grid.x, grid.y, rpc, ms, bytes / ms / 1e6);
     }
     // a plausible strip / part layout for the label kernel: 128 strips x 128 parts
@@ -54,12 +54,14 @@ int main(int argc, char** argv)
     CK(cudaMemcpy(ds, hs.data(), NX * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dp0, hp0.data(), (S + 1) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dy0, hy0.data(), P * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dey, hey.data(), P * 4, cudaMemcpyHostToDevice));
     NaiveParams nv { 128, 128, NX / 128, NY / 128 };
+    Plan* dplan;
+    CK(cudaMalloc(&dplan, sizeof(Plan))); CK(cudaMemset(dplan, 0, sizeof(Plan)));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_label<true, true>, 256, 0);
     printf("k_label<true,true>: %d CTAs/SM\n", occ);
     for (int rpc : { 32, 64, 128, 256, 512, 1024, 2048 }) {
         dim3 grid(gridx, (NY + rpc - 1) / rpc);
         CK(cudaMemset(sc, 0, sizeof(DevScalars)));
-        float ms = timeit([&] { k_label<true, true><<<grid, 256>>>(bits, NX, NY, 0, NB, rpc, ds, dp0, dy0, dey, nv, pid, sc); });
+        float ms = timeit([&] { k_label<true, true><<<grid, 256>>>(bits, NX, NY, 0, NB, rpc, ds, dp0, dy0, dey, nv, pid, sc, dplan); });
         printf("  label grid %dx%-5d rpc %-5d %8.3f ms %8.1f GB/s\n", grid.x, grid.y, rpc, ms, bytes / ms / 1e6);
     }
     return 0;

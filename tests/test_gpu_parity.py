@@ -237,3 +237,18 @@ def test_nothing_moved_reports_naive_blocks(handle, oracle, n, P):
     for px, py in ((False, False), (True, True)):
         o = oracle.partition(m, P, px, py)
         assert_same(run_gpu(handle, m, P, px, py), o, "all ocean n=%d P=%d" % (n, P))
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+def test_strip_row_kernel_variants(capi, oracle, k, monkeypatch):
+    """every variant of the strip row-count kernel (rows per warp 1 / 2 / 4, whole row in registers),
+    forced through the DDC_STRIP_K knob that ddc_create() reads"""
+    monkeypatch.setenv("DDC_STRIP_K", str(k))
+    h = capi.Handle(0)
+    try:
+        for (nx, ny, P, land, seed) in [(1024, 768, 96, 0.45, 4), (777, 1033, 37, 0.6, 9), (4096, 515, 64, 0.5, 2)]:
+            m = capi.generate_mask_host(nx, ny, seed, land)
+            assert_same(run_gpu(h, m, P, True, False), oracle.partition(m, P, True, False, use_hist=True),
+                        "k=%d %dx%d" % (k, nx, ny))
+    finally:
+        h.close()
