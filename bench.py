@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="multi-GPU exchange: loads from peer memory inside the kernels (default) or NCCL collectives")
+                    help="multi-GPU exchange: stores into the peers' memory from inside the kernels (default) or NCCL collectives")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -367,7 +367,7 @@ def main():
             "config": {"workload": args.workload, "nx": nx, "ny": ny, "parts": P, "land_frac_target": land,
                        "ocean_frac_measured": st["n_ocean"] / cells, "seed": seed, "periodic_x": px,
                        "periodic_y": py, "sharding": "rows over %d GPU(s)%s" % (world, "" if world == 1 else (
-                           ", histograms read from peer memory over NVLink inside the cut kernels" if st["exchange"] == 2
+                           ", histograms pushed into the peers' memory over NVLink by the producing kernels, flag barriers in the cut kernels" if st["exchange"] == 2
                            else ", NCCL allreduce + allgather")),
                        "outputs": "boxes + pid + neighbour/halo tables",
                        "l2": ("L2 flushed between timed iterations (256 MiB write)" if need_flush else
