@@ -11,8 +11,9 @@ from . import build as b
 HOST_LIB = os.path.join(b.PKG, "libdomain_decomp.so")
 DECOMP = os.path.join(b.PKG, "decomp")
 HOST_TESTS = os.path.join(b.PKG, "host_tests")
+NC_TOOL = os.path.join(b.PKG, "nc_tool")
 
-LIB_SRCS = ["CdlIO.cpp", "DomainUtils.cpp", "Grid.cpp", "Partitioner.cpp", "CudaRcbPartitioner.cpp"]
+LIB_SRCS = ["CdlIO.cpp", "NcClassic.cpp", "DomainUtils.cpp", "Grid.cpp", "Partitioner.cpp", "CudaRcbPartitioner.cpp"]
 
 
 def _cxx() -> str:
@@ -27,7 +28,7 @@ def build_host(force: bool = False, verbose: bool = False) -> None:
     flags = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra", "-pedantic"]
     srcs = [os.path.join(b.HOST, s) for s in LIB_SRCS]
     hdrs = [os.path.join(b.INCLUDE, "domain_decomp", h) for h in os.listdir(os.path.join(b.INCLUDE, "domain_decomp")) if h.endswith(".hpp")]
-    hdrs += [os.path.join(b.HOST, "CdlIO.hpp"), os.path.join(b.INCLUDE, "ddc.h"), __file__]
+    hdrs += [os.path.join(b.HOST, "CdlIO.hpp"), os.path.join(b.HOST, "NcClassic.hpp"), os.path.join(b.INCLUDE, "ddc.h"), __file__]
     rpath = "-Wl,-rpath,$ORIGIN"
 
     def run(cmd):
@@ -37,7 +38,9 @@ def build_host(force: bool = False, verbose: bool = False) -> None:
 
     if force or b._stale(HOST_LIB, srcs + hdrs + [b.CUDA_LIB]):
         run([_cxx()] + flags + inc + ["-shared", "-o", HOST_LIB] + srcs + ["-L", b.PKG, "-lddc_cuda", rpath])
-    for exe, src in ((DECOMP, "main.cpp"), (HOST_TESTS, "host_tests.cpp")):
+    for exe, src in ((DECOMP, "main.cpp"), (HOST_TESTS, "host_tests.cpp"), (NC_TOOL, "nc_tool.cpp")):
         s = os.path.join(b.HOST, src)
-        if force or b._stale(exe, [s, HOST_LIB] + hdrs):
-            run([_cxx()] + flags + inc + ["-o", exe, s, "-L", b.PKG, "-ldomain_decomp", "-lddc_cuda", rpath])
+        # nc_tool also reaches the (non-exported) file readers / writers: it compiles them in
+        extra = [os.path.join(b.HOST, x) for x in ("NcClassic.cpp", "CdlIO.cpp")] if exe == NC_TOOL else []
+        if force or b._stale(exe, [s, HOST_LIB] + hdrs + extra):
+            run([_cxx()] + flags + inc + ["-o", exe, s] + extra + ["-L", b.PKG, "-ldomain_decomp", "-lddc_cuda", rpath])

@@ -8,6 +8,7 @@
 #include "Grid.hpp"
 
 #include "CdlIO.hpp"
+#include "NcClassic.hpp"
 
 #include <cmath>
 #include <stdexcept>
@@ -72,7 +73,16 @@ void Grid::load_file(const std::string& filename, const std::string& xdim, const
 {
     if (order.size() != 2 || !((order[0] == 1 && order[1] == 0) || (order[0] == 0 && order[1] == 1)))
         throw std::runtime_error("ERROR: dim_order must be {1, 0} (yx) or {0, 1} (xy)");
-    const ddc_host::CdlFile file = ddc_host::read_cdl(filename);
+    // netCDF classic files (CDF-1 / CDF-2 / CDF-5: what `ncgen -b` makes of the reference's test
+    // inputs) are read directly; netCDF-4 needs HDF5, which this build does not have; anything else
+    // is taken as CDL text (`ncdump grid.nc > grid.cdl`)
+    const ddc_host::FileKind kind = ddc_host::sniff_file_kind(filename);
+    if (kind == ddc_host::FileKind::Hdf5)
+        throw std::runtime_error("ERROR: NetCDF: '" + filename + "' is a netCDF-4 / HDF5 file; this build reads "
+            "netCDF classic files and CDL text (convert with `nccopy -k classic` or `ncdump`)");
+    const ddc_host::CdlFile file = kind == ddc_host::FileKind::NetcdfClassic
+        ? ddc_host::read_netcdf_classic(filename, ignore_mask ? std::string("\x01none") : mask_name)
+        : ddc_host::read_cdl(filename);
     // enhanced data model: nextSIM restart files keep everything in group "data" (Grid.cpp:58-62)
     const ddc_host::CdlGroup* grp = &file.root;
     auto it = file.root.groups.find("data");

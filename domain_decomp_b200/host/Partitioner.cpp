@@ -7,6 +7,7 @@
 #include "Partitioner.hpp"
 
 #include "CdlIO.hpp"
+#include "NcClassic.hpp"
 #include "CudaRcbPartitioner.hpp"
 
 #include <fstream>
@@ -275,6 +276,14 @@ void Partitioner::save_mask(const std::string& filename) const
     if (_rank != 0)
         return;
     write_text(ddc_host::cdl_path_of(filename), mask_cdl(ddc_host::netcdf_name_of(filename)));
+    // a real netCDF file as well when a ".nc" name was asked for: classic format (the reference
+    // writes netCDF-4; dimensions, variable, attribute and values are the same, so `ncdump` prints
+    // the CDL above and every netCDF reader opens it) -- Partitioner.cpp:128-166
+    if (filename.size() > 3 && filename.compare(filename.size() - 3, 3, ".nc") == 0) {
+        const int NX = _global_ext[0], NY = _global_ext[1];
+        ddc_host::write_netcdf_classic(filename, { { "y", (uint64_t)NY }, { "x", (uint64_t)NX } },
+            { { "num_processes", _num_parts } }, { { "pid", { 0, 1 }, _pid_global.data() } });
+    }
 }
 
 void Partitioner::save_metadata(const std::string& filename) const

@@ -89,3 +89,31 @@ def test_decomp_cli_errors(fixture_dir, tmp_path):
     assert r.returncode == 1  # default names x / y / mask do not exist in test_2
     r = subprocess.run([exe, "-h"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0 and "--grid" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("version", [1, 2])
+def test_decomp_cli_on_binary_netcdf(goldens, tmp_path, version):
+    """the same integration case with the grid in a real (classic-format) netCDF file -- what the
+    reference's build makes of test/test_1.cdl with `ncgen -b` -- and the mask read back from the
+    partition_mask_3.nc the CLI wrote"""
+    scipy_io = pytest.importorskip("scipy.io")
+    inp = goldens["inputs"]["test_1"]
+    grid = str(tmp_path / "test_1.nc")
+    f = scipy_io.netcdf_file(grid, "w", version=version)
+    f.createDimension(inp["xdim"], inp["nx"])
+    f.createDimension(inp["ydim"], inp["ny"])
+    f.createVariable(inp["mask_name"], "i4", (inp["ydim"], inp["xdim"]))[:] = np.asarray(
+        inp["mask"], dtype=np.int32).reshape(inp["ny"], inp["nx"])
+    f.close()
+    exe = os.path.join(PKG, "decomp")
+    out = subprocess.run([exe, "-g", grid, "--parts", "3", "--px"], capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stdout + out.stderr
+    G = goldens["integration"]["test_1_px"]
+    for fname, key in (("partition_mask_3.cdl", "mask_cdl_sha256"), ("partition_metadata_3.cdl", "metadata_cdl_sha256")):
+        text = open(os.path.join(tmp_path, fname)).read()
+        assert hashlib.sha256(text.encode()).hexdigest() == G[key], "%s differs from the golden:\n%s" % (fname, text)
+    m = scipy_io.netcdf_file(str(tmp_path / "partition_mask_3.nc"), "r", mmap=False)
+    assert m.num_processes == 3 and list(m.dimensions.items()) == [("y", inp["ny"]), ("x", inp["nx"])]
+    assert m.variables["pid"].data.ravel().tolist() == list(G["pid"])
+    m.close()
