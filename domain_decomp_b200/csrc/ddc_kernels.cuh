@@ -1,22 +1,25 @@
 // ddc_kernels.cuh -- hand-written sm_100a kernels of the domain-decomposition hot path.
 //
-// Pipeline (one GPU; with several GPUs every rank runs it on its own block of mask rows and the
-// two histograms are combined with NCCL between the kernels, see ddc_api.cu):
+// Pipeline (one GPU; with several GPUs every rank runs it on its own block of mask rows, K1 and K3
+// push their histograms into the other ranks' memory over NVLink and K2 / K4 / K5 wait for flags,
+// see "multi-GPU exchange" below; NCCL collectives between the kernels are the fallback, ddc_api.cu):
 //
 //   K1 k_scan_mask     int32 mask -> 1-bit ocean map + per-column ocean counts + dot y-range
 //                      (replaces Grid.cpp:176-188 and the Zoltan geometry callbacks
 //                       ZoltanPartitioner.cpp:19-67; HBM-bound, 4 B/cell read)
 //   K2 k_xcuts         prefix sums of the column counts, preset cut directions, all x levels of
-//                      the RCB: one batched weighted-median step per level over every active set
+//                      the RCB: every strip's path root -> strip walked at once, no level barriers
 //   K3 k_strip_rows    per-strip per-row ocean counts from the bit map (1/32 of the mask bytes)
 //   K4 k_ycuts         all y levels, one CTA per vertical strip -> integer part boxes
 //                      (K2+K4 replace Zoltan::LB_Partition + RCB_Box + the ceil/clamp of
 //                       ZoltanPartitioner.cpp:161-195)
 //   K6 k_label         pid[y][x] = ocean ? part : -1 and Zoltan's `changes` flag
 //                      (ZoltanPartitioner.cpp:201-219; HBM-bound, 4 B/cell written)
-//   K5 k_finalize      `changes == 0` => report the naive blocks (ZoltanPartitioner.cpp:182-187)
 //   K7 k_neighbours    interval-intersection kernel: neighbour ids, halo sizes, halo starts,
-//                      interior and periodic (Partitioner.cpp:20-80,329-435, DomainUtils.cpp:15-35)
+//                      interior and periodic (Partitioner.cpp:20-80,329-435, DomainUtils.cpp:15-35);
+//                      runs beside K6 on a second stream
+//   K5 k_finalize      one block ends the step: `changes` of all ranks; `changes == 0` => report the
+//                      naive blocks (ZoltanPartitioner.cpp:182-187) and rebuild K7's tables from them
 //
 // Bit map layout: plain row-major little-endian bit map, bit (x & 7) of byte x >> 3 of a row is
 // column x; rows are padded to NB = 16 * ceil(NX / 128) bytes so that every row is 16-byte aligned.
@@ -34,7 +37,7 @@ struct DevScalars {
     unsigned long long edge_cut; // sum of interior halo lengths
 };
 
-struct Plan { // written by K2, read back by the host
+struct Plan { // written by K2 (K4 adds iterations), copied into the host's pinned memory by K5
     int nlev, ix, iy, S;
     int xmin, xmax, ymin, ymax;
     long long W;

@@ -19,7 +19,8 @@
  *     (Partitioner.hpp:166-170).  The number of parts is a parameter here, not the world size.
  *   - edges are numbered as DomainUtils.hpp:15: LEFT=0, RIGHT=1, BOTTOM=2, TOP=3.
  *   - one handle drives one GPU.  With nranks > 1 every rank owns a contiguous block of mask
- *     rows; the per-column and per-strip-row histograms are combined with NCCL.  All ranks
+ *     rows; the per-column and per-strip-row histograms are exchanged through peer memory over
+ *     NVLink (ddc_peer_export / ddc_peer_import) or, without that, with NCCL.  All ranks
  *     hold identical boxes / neighbour tables afterwards; pid stays row-sharded.
  *   - a handle is not thread-safe; distinct handles are independent.
  */
@@ -97,9 +98,10 @@ DDC_API const char* ddc_last_error(ddc_handle_t h);
 
 /* Peer-memory exchange (nranks > 1, all GPUs of one NVLink / NVSwitch box, one process per GPU).
    The reference exchanges through MPI inside Zoltan and with four MPI_Allgather calls in
-   discover_neighbours (Partitioner.cpp:378-388).  Here the kernels that consume the exchanged
-   histograms read them straight out of the other ranks' buffers: ddc_peer_export() allocates this
-   rank's exchange buffer for masks up to nx * ny into nparts parts and returns its CUDA IPC
+   discover_neighbours (Partitioner.cpp:378-388).  Here the kernels that produce a histogram store it
+   straight into the other ranks' exchange buffers, and the kernels that consume it wait for a flag
+   and read their own memory: ddc_peer_export() allocates this rank's exchange buffer for masks up
+   to nx * ny into nparts parts (one slot per rank and histogram) and returns its CUDA IPC
    handle; the host gathers the handles of all ranks (MPI_Allgather / torch.distributed) and hands
    them, in rank order, to ddc_peer_import().  Without these two calls -- or for a decomposition
    that does not fit the exported capacity -- the exchange steps are NCCL collectives. */
