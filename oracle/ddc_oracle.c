@@ -31,7 +31,11 @@
  * parameters the reference sets.  Parity is PINNED by the reference's own
  * goldens (tests/golden/reference_goldens.json: 8 bounding-box known-answer
  * tests + 5 integration pid maps + 5 metadata files); see DESIGN.md for what
- * those goldens do not pin (the Q-items).
+ * those goldens do not pin (the Q-items).  Everything here that is NOT Zoltan
+ * (naive blocks, ocean ids, box clamp, labelling, neighbour discovery, halo
+ * starts, flattening) is additionally validated against the reference's own
+ * Grid.cpp / Partitioner.cpp / DomainUtils.cpp, compiled where they lie into
+ * oracle/_ref/ (Makefile target `ref`, tests/test_reference_hostpath.py).
  *
  * Floating point: every expression that Zoltan evaluates in double is
  * evaluated here in the same order, in IEEE double, compiled with

@@ -16,6 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libddc_oracle.so")
 _REF_LIB = os.path.join(_HERE, "_ref", "libref_domainutils.so")
+_REF_HOST_LIB = os.path.join(_HERE, "_ref", "libref_hostpath.so")
 
 EDGES = ("left", "right", "bottom", "top")  # DomainUtils.hpp:15 enum order L,R,B,T
 
@@ -25,8 +26,8 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "ddc_oracle.c")
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_oracle.so"])
-    if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF_LIB)):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    if os.path.isdir("/root/reference"):  # make decides what is stale
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"] + (["-B"] if force else []))
     return _LIB
 
 
@@ -64,6 +65,74 @@ def ref_lib():
     L.ref_domain_overlap.argtypes = [C.c_int] * 9
     L.ref_domain_overlap.restype = C.c_int
     return L
+
+
+_ref_host = None
+
+
+def ref_host_lib():
+    """The reference's own Grid.cpp + Partitioner.cpp + DomainUtils.cpp compiled in oracle/_ref against
+    the stand-in MPI / netCDF headers of oracle/ref_shim (None if not built)."""
+    global _ref_host
+    if _ref_host is None:
+        if not os.path.exists(_REF_HOST_LIB):
+            return None
+        L = C.CDLL(_REF_HOST_LIB)
+        i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+        L.ref_host_run.argtypes = [C.c_int, C.c_int, C.c_int, i32p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_host_run.restype = C.c_char_p
+        L.ref_host_error.restype = C.c_char_p
+        _ref_host = L
+    return _ref_host
+
+
+def ref_host_run(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, boxes=None, pid=None,
+                 changes: int = 1, xdim: str = "x", ydim: str = "y", maskname: str = "mask", order_xy: bool = False,
+                 file_order_xy=None, data_group: bool = False, ignore_mask: bool = False) -> dict:
+    """Run the REFERENCE's host path (Grid::create, the code around the Zoltan call, discover_neighbours,
+    the getters, save_mask, save_metadata) on P thread-ranks; boxes [P,4] / pid [NY,NX] stand in for
+    Zoltan's answers (None: only Grid is exercised).  Returns the parsed report:
+      ranks[r] = {block, objects, nonzero, mask, ids, box, nbr[periodic][edge] = [(id, halo, start), ...]}
+      files[name] = {dims: [(name, len)], atts: {..}, vars: {(group, name): (dims, values)}, unwritten: {..}}"""
+    L = ref_host_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_hostpath.so is not built (needs /root/reference)")
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    ny, nx = mask.shape
+    b = None if boxes is None else np.ascontiguousarray(boxes, dtype=np.int32)
+    q = None if pid is None else np.ascontiguousarray(pid, dtype=np.int32)
+    out = L.ref_host_run(P, nx, ny, mask, xdim.encode(), ydim.encode(), maskname.encode(), int(order_xy),
+                         int(order_xy if file_order_xy is None else file_order_xy), int(data_group), int(ignore_mask), int(px), int(py), int(changes),
+                         None if b is None else b.ctypes.data, None if q is None else q.ctypes.data)
+    if out is None:
+        raise RuntimeError(L.ref_host_error().decode())
+    ranks = [dict(nbr=[[None] * 4 for _ in range(2)]) for _ in range(P)]
+    files, cur = {}, None
+    for line in out.decode().splitlines():
+        t = line.split()
+        if t[0] == "rank":
+            r, what = ranks[int(t[1])], t[2]
+            if what == "block":
+                r["block"] = list(map(int, t[3:7]))
+                r["objects"], r["nonzero"] = int(t[8]), int(t[10])
+            elif what in ("mask", "ids"):
+                r[what] = list(map(int, t[3:]))
+            elif what == "box":
+                r["box"] = list(map(int, t[3:7]))
+            elif what == "nbr":
+                r["nbr"][int(t[4])][int(t[3])] = [tuple(map(int, x.split(":"))) for x in t[5:]]
+        elif t[0] == "file":
+            cur = files.setdefault(t[1], dict(dims=[], atts={}, vars={}, unwritten={}))
+        elif t[0] == "dim":
+            cur["dims"].append((t[1], int(t[2])))
+        elif t[0] == "att":
+            cur["atts"][t[1]] = int(t[2])
+        elif t[0] == "var":
+            cur["vars"][(t[1], t[2])] = (t[3], list(map(int, t[4:])))
+        elif t[0] == "unwritten":
+            cur["unwritten"][t[1]] = int(t[2])
+    return dict(ranks=ranks, files=files)
 
 
 def set_threads(t: int) -> None:

@@ -1,0 +1,622 @@
+// ref_hostpath_shim.cpp -- TEST INFRASTRUCTURE (never linked into the product).
+//
+// Runs the REFERENCE's own host path -- Grid.cpp, Partitioner.cpp and DomainUtils.cpp, compiled from
+// the reference checkout where they lie (oracle/Makefile target `ref`, output oracle/_ref/) -- on P
+// "MPI ranks" that are P threads of this process, with
+//   * a miniature MPI (ref_shim/mpi.h): the collectives of Grid.cpp:142-146 and
+//     Partitioner.cpp:85-86,190-205,378-388 over a generation barrier;
+//   * an in-memory netCDF (ref_shim/netcdf.h): the files the reference reads and writes are tables
+//     in this process (Grid.cpp:51-130, Partitioner.cpp:128-318);
+//   * a Partitioner subclass that receives the part boxes and the pid map instead of computing them
+//     with Zoltan (which is not available) and then does exactly what ZoltanPartitioner::partition
+//     does around the Zoltan call (ZoltanPartitioner.cpp:96-121,172-219): P == 1 shortcut, box
+//     clamp, discover_neighbours(), labelling of the rank's naive block.
+// What this validates against REAL reference code: the naive block decomposition and ocean lists
+// (SURVEY 8a a1, a2), neighbour discovery / halo sizes / halo starts incl. the periodic variants
+// (a7-a10), the flattening and the layout of both output files (a11).  The RCB itself (a4) stays a
+// restatement of Zoltan.
+#include <algorithm>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <mpi.h>
+#include <netcdf.h>
+#include <netcdf_par.h>
+
+#include "Grid.hpp"
+#include "Partitioner.hpp"
+#include "ZoltanPartitioner.hpp"
+
+// ------------------------------------------------------------------------------------------------
+// miniature MPI: ranks are threads
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct World {
+    int size = 1;
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0;
+    long generation = 0;
+    std::vector<int> slots; // one contribution per rank (every collective here moves ints)
+    void barrier()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const long gen = generation;
+        if (++arrived == size) {
+            arrived = 0;
+            generation++;
+            cv.notify_all();
+        } else
+            cv.wait(lk, [&] { return generation != gen; });
+    }
+};
+} // namespace
+struct ref_shim_comm {
+    World* world;
+    int rank;
+};
+
+extern "C" {
+int MPI_Comm_rank(MPI_Comm c, int* rank)
+{
+    *rank = c->rank;
+    return MPI_SUCCESS;
+}
+int MPI_Comm_size(MPI_Comm c, int* size)
+{
+    *size = c->world->size;
+    return MPI_SUCCESS;
+}
+// every rank deposits `count` ints, waits for the others, and `use` reads the table
+static void exchange(MPI_Comm c, const int* send, int count, const std::function<void(const std::vector<int>&)>& use)
+{
+    World& w = *c->world;
+    {
+        std::lock_guard<std::mutex> lk(w.m);
+        if ((int)w.slots.size() != w.size * count)
+            w.slots.assign((size_t)w.size * count, 0);
+    }
+    w.barrier(); // the table has its size before anyone writes
+    std::copy(send, send + count, w.slots.begin() + (size_t)c->rank * count);
+    w.barrier();
+    use(w.slots);
+    w.barrier(); // nobody overwrites the table while another rank still reads it
+}
+int MPI_Allgather(const void* sendbuf, int sendcount, MPI_Datatype, void* recvbuf, int, MPI_Datatype, MPI_Comm c)
+{
+    exchange(c, static_cast<const int*>(sendbuf), sendcount,
+        [&](const std::vector<int>& t) { std::copy(t.begin(), t.end(), static_cast<int*>(recvbuf)); });
+    return MPI_SUCCESS;
+}
+int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype, MPI_Op, MPI_Comm c)
+{
+    exchange(c, static_cast<const int*>(sendbuf), count, [&](const std::vector<int>& t) {
+        for (int k = 0; k < count; k++) {
+            int s = 0;
+            for (int r = 0; r < c->world->size; r++)
+                s += t[(size_t)r * count + k];
+            static_cast<int*>(recvbuf)[k] = s;
+        }
+    });
+    return MPI_SUCCESS;
+}
+int MPI_Exscan(const void* sendbuf, void* recvbuf, int count, MPI_Datatype, MPI_Op, MPI_Comm c)
+{
+    exchange(c, static_cast<const int*>(sendbuf), count, [&](const std::vector<int>& t) {
+        if (c->rank == 0)
+            return; // MPI leaves rank 0's receive buffer untouched
+        for (int k = 0; k < count; k++) {
+            int s = 0;
+            for (int r = 0; r < c->rank; r++)
+                s += t[(size_t)r * count + k];
+            static_cast<int*>(recvbuf)[k] = s;
+        }
+    });
+    return MPI_SUCCESS;
+}
+int MPI_Error_string(int code, char* s, int* len)
+{
+    *len = std::snprintf(s, MPI_MAX_ERROR_STRING, "shim MPI error %d", code);
+    return MPI_SUCCESS;
+}
+int MPI_Finalize(void) { return MPI_SUCCESS; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// in-memory netCDF
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct MemDim {
+    std::string name;
+    size_t len;
+};
+struct MemVar {
+    std::string name;
+    int group;
+    std::vector<int> dimids;
+    std::vector<int> data;
+    std::vector<char> written;
+};
+struct MemFile {
+    std::string path;
+    std::vector<MemDim> dims; // file-wide (the reference defines all dimensions in the root group)
+    std::vector<std::string> groups { "" }; // 0 = root
+    std::vector<MemVar> vars;
+    std::vector<std::pair<std::string, int>> atts; // global int attributes
+};
+std::mutex g_fs_mutex;
+std::vector<MemFile> g_files;
+
+// ncid = file index * 256 + group index
+MemFile* file_of(int ncid)
+{
+    const int f = ncid >> 8;
+    return f >= 0 && f < (int)g_files.size() ? &g_files[f] : nullptr;
+}
+int group_of(int ncid) { return ncid & 255; }
+int find_file(const std::string& path)
+{
+    for (size_t i = 0; i < g_files.size(); i++)
+        if (g_files[i].path == path)
+            return (int)i;
+    return -1;
+}
+size_t var_size(const MemFile& f, const MemVar& v)
+{
+    size_t n = 1;
+    for (int d : v.dimids)
+        n *= f.dims[d].len;
+    return n;
+}
+void ensure_storage(const MemFile& f, MemVar& v)
+{
+    const size_t n = var_size(f, v);
+    if (v.data.size() != n) {
+        v.data.assign(n, 0);
+        v.written.assign(n, 0);
+    }
+}
+} // namespace
+
+extern "C" {
+const char* nc_strerror(int err)
+{
+    switch (err) {
+    case NC_NOERR:
+        return "No error";
+    case NC_EBADID:
+        return "NetCDF: Not a valid ID";
+    case NC_EBADDIM:
+        return "NetCDF: Invalid dimension ID or name";
+    case NC_ENOTVAR:
+        return "NetCDF: Variable not found";
+    case NC_EEDGE:
+        return "NetCDF: Start+count exceeds dimension bound";
+    case NC_ENOGRP:
+        return "NetCDF: Bad group ID";
+    case NC_ENOENT:
+        return "No such file or directory";
+    }
+    return "NetCDF: unknown error";
+}
+int nc_open_par(const char* path, int, MPI_Comm, MPI_Info, int* ncidp)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    const int f = find_file(path);
+    if (f < 0)
+        return NC_ENOENT;
+    *ncidp = f << 8;
+    return NC_NOERR;
+}
+int nc_create_par(const char* path, int, MPI_Comm, MPI_Info, int* ncidp)
+{
+    // collective in the reference: the first rank to arrive creates the file, the others join it
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    int f = find_file(path);
+    if (f < 0) {
+        MemFile nf;
+        nf.path = path;
+        g_files.push_back(nf);
+        f = (int)g_files.size() - 1;
+    }
+    *ncidp = f << 8;
+    return NC_NOERR;
+}
+int nc_close(int) { return NC_NOERR; }
+int nc_enddef(int) { return NC_NOERR; }
+int nc_var_par_access(int, int, int) { return NC_NOERR; }
+int nc_inq_ncid(int ncid, const char* name, int* grp)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f)
+        return NC_EBADID;
+    for (size_t g = 1; g < f->groups.size(); g++)
+        if (f->groups[g] == name) {
+            *grp = (ncid & ~255) | (int)g;
+            return NC_NOERR;
+        }
+    return NC_ENOGRP;
+}
+int nc_inq_dimid(int ncid, const char* name, int* idp)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f)
+        return NC_EBADID;
+    for (size_t d = 0; d < f->dims.size(); d++)
+        if (f->dims[d].name == name) {
+            *idp = (int)d;
+            return NC_NOERR;
+        }
+    return NC_EBADDIM;
+}
+int nc_inq_dimlen(int ncid, int dimid, size_t* lenp)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f || dimid < 0 || dimid >= (int)f->dims.size())
+        return NC_EBADDIM;
+    *lenp = f->dims[dimid].len;
+    return NC_NOERR;
+}
+int nc_inq_dimname(int ncid, int dimid, char* name)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f || dimid < 0 || dimid >= (int)f->dims.size())
+        return NC_EBADDIM;
+    std::strcpy(name, f->dims[dimid].name.c_str());
+    return NC_NOERR;
+}
+int nc_inq_varid(int ncid, const char* name, int* varidp)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f)
+        return NC_EBADID;
+    for (size_t v = 0; v < f->vars.size(); v++)
+        if (f->vars[v].group == group_of(ncid) && f->vars[v].name == name) {
+            *varidp = (int)v;
+            return NC_NOERR;
+        }
+    return NC_ENOTVAR;
+}
+int nc_inq_vardimid(int ncid, int varid, int* dimidsp)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f || varid < 0 || varid >= (int)f->vars.size())
+        return NC_ENOTVAR;
+    std::copy(f->vars[varid].dimids.begin(), f->vars[varid].dimids.end(), dimidsp);
+    return NC_NOERR;
+}
+// row-major hyperslab walk shared by get / put
+static int slab(MemFile* f, MemVar& v, const size_t* start, const size_t* count, int* out, const int* in)
+{
+    const size_t nd = v.dimids.size();
+    size_t total = 1;
+    for (size_t d = 0; d < nd; d++) {
+        if (count[d] && start[d] + count[d] > f->dims[v.dimids[d]].len)
+            return NC_EEDGE;
+        total *= count[d];
+    }
+    std::vector<size_t> idx(nd, 0);
+    for (size_t k = 0; k < total; k++) {
+        size_t off = 0;
+        for (size_t d = 0; d < nd; d++)
+            off = off * f->dims[v.dimids[d]].len + start[d] + idx[d];
+        if (out)
+            out[k] = v.data[off];
+        else {
+            v.data[off] = in[k];
+            v.written[off] = 1;
+        }
+        for (size_t d = nd; d-- > 0;) {
+            if (++idx[d] < count[d])
+                break;
+            idx[d] = 0;
+        }
+    }
+    return NC_NOERR;
+}
+int nc_get_vara_int(int ncid, int varid, const size_t* startp, const size_t* countp, int* ip)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f || varid < 0 || varid >= (int)f->vars.size())
+        return NC_ENOTVAR;
+    return slab(f, f->vars[varid], startp, countp, ip, nullptr);
+}
+int nc_def_dim(int ncid, const char* name, size_t len, int* idp)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f)
+        return NC_EBADID;
+    for (size_t d = 0; d < f->dims.size(); d++)
+        if (f->dims[d].name == name) { // another rank defined it already (collective call)
+            *idp = (int)d;
+            return f->dims[d].len == len ? NC_NOERR : NC_EBADDIM;
+        }
+    f->dims.push_back({ name, len });
+    *idp = (int)f->dims.size() - 1;
+    return NC_NOERR;
+}
+int nc_def_grp(int parent, const char* name, int* new_ncid)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(parent);
+    if (!f)
+        return NC_EBADID;
+    size_t g = 1;
+    for (; g < f->groups.size(); g++)
+        if (f->groups[g] == name)
+            break;
+    if (g == f->groups.size())
+        f->groups.push_back(name);
+    *new_ncid = (parent & ~255) | (int)g;
+    return NC_NOERR;
+}
+int nc_def_var(int ncid, const char* name, int, int ndims, const int* dimidsp, int* varidp)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f)
+        return NC_EBADID;
+    for (size_t v = 0; v < f->vars.size(); v++)
+        if (f->vars[v].group == group_of(ncid) && f->vars[v].name == name) {
+            *varidp = (int)v;
+            return NC_NOERR;
+        }
+    MemVar nv;
+    nv.name = name;
+    nv.group = group_of(ncid);
+    nv.dimids.assign(dimidsp, dimidsp + ndims);
+    f->vars.push_back(nv);
+    *varidp = (int)f->vars.size() - 1;
+    return NC_NOERR;
+}
+int nc_put_att_int(int ncid, int, const char* name, int, size_t, const int* op)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f)
+        return NC_EBADID;
+    for (auto& a : f->atts)
+        if (a.first == name) {
+            a.second = *op;
+            return NC_NOERR;
+        }
+    f->atts.push_back({ name, *op });
+    return NC_NOERR;
+}
+int nc_put_vara_int(int ncid, int varid, const size_t* startp, const size_t* countp, const int* op)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f || varid < 0 || varid >= (int)f->vars.size())
+        return NC_ENOTVAR;
+    ensure_storage(*f, f->vars[varid]);
+    return slab(f, f->vars[varid], startp, countp, nullptr, op);
+}
+int nc_put_var1_int(int ncid, int varid, const size_t* indexp, const int* op)
+{
+    std::lock_guard<std::mutex> lk(g_fs_mutex);
+    MemFile* f = file_of(ncid);
+    if (!f || varid < 0 || varid >= (int)f->vars.size())
+        return NC_ENOTVAR;
+    MemVar& v = f->vars[varid];
+    ensure_storage(*f, v);
+    std::vector<size_t> one(v.dimids.size(), 1);
+    return slab(f, v, indexp, one.data(), nullptr, op);
+}
+}
+
+// ------------------------------------------------------------------------------------------------
+// the Zoltan-free partitioner and the driver
+// ------------------------------------------------------------------------------------------------
+// never called: Partitioner::Factory::create (Partitioner.cpp:320-327) refers to it
+ZoltanPartitioner* ZoltanPartitioner::create(MPI_Comm, int, char**) { return nullptr; }
+
+namespace {
+struct Given {
+    int changes; // what Zoltan's LB_Partition would have reported
+    const int* boxes; // [P][4] x0, y0, ext_x, ext_y of every part (what RCB_Box + ceil would give)
+    const int* pid; // [NY][NX] owner of every cell, -1 on land
+};
+
+class GivenBoxesPartitioner final : public Partitioner {
+public:
+    GivenBoxesPartitioner(MPI_Comm comm, const Given& g)
+        : Partitioner(comm)
+        , _g(g)
+    {
+    }
+    // the code around the Zoltan call of ZoltanPartitioner::partition, with Zoltan's answers handed in
+    void partition(Grid& grid) override
+    {
+        _num_procs = grid.get_num_procs();
+        _global_ext = grid.get_global_ext();
+        grid.get_bounding_box(_global[0], _global[1], _local_ext[0], _local_ext[1]);
+        _px = grid.get_px();
+        _py = grid.get_py();
+        const bool single = _total_num_procs == 1;
+        for (int d = 0; d < 2; d++) {
+            const bool from_rcb = !single && _g.changes == 1;
+            _global_new[d] = from_rcb ? _g.boxes[4 * _rank + d] : _global[d];
+            _local_ext_new[d] = from_rcb ? _g.boxes[4 * _rank + 2 + d] : _local_ext[d];
+        }
+        if (!single) {
+            for (int d = 0; d < 2; d++) // "adapt to blocking"
+                if (_global_new[d] + _local_ext_new[d] > _global_ext[d])
+                    _local_ext_new[d] = _global_ext[d] - _global_new[d];
+            discover_neighbours();
+        }
+        // owner of every cell of this rank's ORIGINAL block: own rank on ocean, then the exports
+        const int n = grid.get_num_objects();
+        const int* land = grid.get_land_mask();
+        const bool masked = n != grid.get_num_nonzero_objects();
+        _proc_id.assign(n, masked ? -1 : _rank);
+        for (int i = 0; i < n; i++) {
+            if (masked && !(land[i] > 0))
+                continue;
+            const int x = _global[0] + i % _local_ext[0], y = _global[1] + i / _local_ext[0];
+            _proc_id[i] = single ? _rank : _g.pid[(size_t)y * _global_ext[0] + x];
+        }
+    }
+
+private:
+    Given _g;
+};
+
+std::string g_report;
+std::string g_error;
+
+void dump_file(std::ostringstream& os, const char* label, const std::string& path)
+{
+    const int fi = find_file(path);
+    if (fi < 0)
+        return;
+    const MemFile& f = g_files[fi];
+    os << "file " << label << "\n";
+    for (const MemDim& d : f.dims)
+        os << "dim " << d.name << " " << d.len << "\n";
+    for (const auto& a : f.atts)
+        os << "att " << a.first << " " << a.second << "\n";
+    for (const MemVar& v : f.vars) {
+        os << "var " << (f.groups[v.group].empty() ? "/" : f.groups[v.group]) << " " << v.name << " (";
+        for (size_t k = 0; k < v.dimids.size(); k++)
+            os << (k ? "," : "") << f.dims[v.dimids[k]].name;
+        os << ")";
+        size_t unwritten = 0;
+        for (size_t k = 0; k < v.data.size(); k++) {
+            os << " " << v.data[k];
+            unwritten += v.written[k] ? 0 : 1;
+        }
+        os << "\n";
+        if (unwritten || v.data.size() != var_size(f, v))
+            os << "unwritten " << v.name << " " << unwritten + (var_size(f, v) - v.data.size()) << "\n";
+    }
+}
+} // namespace
+
+extern "C" {
+// Runs Grid::create + GivenBoxesPartitioner::partition + the getters + save_mask + save_metadata on P
+// thread-ranks and returns a text report (owned by the library, valid until the next call):
+//   rank r block x0 y0 ex ey objects N nonzero M
+//   rank r mask v v v ...            the rank's land-mask slab as Grid read it
+//   rank r ids g g g ...             Grid's global ids of the ocean cells
+//   rank r box x0 y0 ex ey           Partitioner::get_bounding_box
+//   rank r nbr <edge> <periodic> id:halo:start ...
+//   file mask|metadata / dim / att / var lines: the two output files as written
+// order_xy: the caller's `-o xy`; file_order_xy: the mask variable is DECLARED (xdim, ydim) in the file;
+// data_group: dims + variable live in group "data".
+// Returns NULL on failure (ref_host_error() has the message).
+__attribute__((visibility("default"))) const char* ref_host_run(int P, int nx, int ny, const int* mask, const char* xdim,
+    const char* ydim, const char* maskname, int order_xy, int file_order_xy, int data_group, int ignore_mask, int px,
+    int py, int changes, const int* boxes, const int* pid)
+{
+    g_error.clear();
+    g_report.clear();
+    {
+        std::lock_guard<std::mutex> lk(g_fs_mutex);
+        g_files.clear();
+        MemFile in;
+        in.path = "grid.nc";
+        in.dims = { { xdim, (size_t)nx }, { ydim, (size_t)ny } };
+        if (data_group)
+            in.groups.push_back("data");
+        MemVar v;
+        v.name = maskname;
+        v.group = data_group ? 1 : 0;
+        v.dimids = file_order_xy ? std::vector<int> { 0, 1 } : std::vector<int> { 1, 0 };
+        v.data.assign(mask, mask + (size_t)nx * ny);
+        v.written.assign(v.data.size(), 1);
+        in.vars.push_back(v);
+        g_files.push_back(in);
+    }
+    World world;
+    world.size = P;
+    std::vector<ref_shim_comm> comms(P);
+    std::vector<std::string> part(P), err(P);
+    const Given given { changes, boxes, pid };
+    auto body = [&](int r) {
+        comms[r] = { &world, r };
+        std::ostringstream os;
+        try {
+            const std::vector<int> order = order_xy ? std::vector<int> { 0, 1 } : std::vector<int> { 1, 0 };
+            Grid* grid = Grid::create(&comms[r], "grid.nc", xdim, ydim, order, maskname, ignore_mask != 0, px != 0, py != 0);
+            int b[4];
+            grid->get_bounding_box(b[0], b[1], b[2], b[3]);
+            os << "rank " << r << " block " << b[0] << " " << b[1] << " " << b[2] << " " << b[3] << " objects "
+               << grid->get_num_objects() << " nonzero " << grid->get_num_nonzero_objects() << "\n";
+            os << "rank " << r << " mask";
+            if (!ignore_mask)
+                for (int i = 0; i < grid->get_num_objects(); i++)
+                    os << " " << grid->get_land_mask()[i];
+            os << "\nrank " << r << " ids";
+            for (int i = 0; i < grid->get_num_nonzero_objects(); i++)
+                os << " " << grid->get_nonzero_object_ids()[i];
+            os << "\n";
+            if (boxes) {
+                GivenBoxesPartitioner p(&comms[r], given);
+                p.partition(*grid);
+                p.get_bounding_box(b[0], b[1], b[2], b[3]);
+                os << "rank " << r << " box " << b[0] << " " << b[1] << " " << b[2] << " " << b[3] << "\n";
+                for (int per = 0; per < 2; per++) {
+                    std::vector<std::vector<int>> ids(4), halos(4), starts(4);
+                    if (per)
+                        p.get_neighbour_info_periodic(ids, halos, starts);
+                    else
+                        p.get_neighbour_info(ids, halos, starts);
+                    for (int e = 0; e < 4; e++) {
+                        os << "rank " << r << " nbr " << e << " " << per;
+                        for (size_t k = 0; k < ids[e].size(); k++)
+                            os << " " << ids[e][k] << ":" << halos[e][k] << ":" << starts[e][k];
+                        os << "\n";
+                    }
+                }
+                p.save_mask("partition_mask.nc");
+                p.save_metadata("partition_metadata.nc");
+            }
+            delete grid;
+        } catch (const std::exception& e) {
+            err[r] = e.what();
+        }
+        part[r] = os.str();
+    };
+    // a rank that throws would leave the others waiting in a collective: Grid::create and the
+    // writers throw on the same condition on every rank, so either all ranks throw or none does
+    std::vector<std::thread> threads;
+    for (int r = 0; r < P; r++)
+        threads.emplace_back(body, r);
+    for (auto& t : threads)
+        t.join();
+    for (int r = 0; r < P; r++)
+        if (!err[r].empty()) {
+            g_error = "rank " + std::to_string(r) + ": " + err[r];
+            return nullptr;
+        }
+    std::ostringstream os;
+    for (int r = 0; r < P; r++)
+        os << part[r];
+    {
+        std::lock_guard<std::mutex> lk(g_fs_mutex);
+        dump_file(os, "mask", "partition_mask.nc");
+        dump_file(os, "metadata", "partition_metadata.nc");
+    }
+    g_report = os.str();
+    return g_report.c_str();
+}
+__attribute__((visibility("default"))) const char* ref_host_error(void) { return g_error.c_str(); }
+}
