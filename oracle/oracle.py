@@ -87,26 +87,7 @@ def ref_host_lib():
     return _ref_host
 
 
-def ref_host_run(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, boxes=None, pid=None,
-                 changes: int = 1, xdim: str = "x", ydim: str = "y", maskname: str = "mask", order_xy: bool = False,
-                 file_order_xy=None, data_group: bool = False, ignore_mask: bool = False) -> dict:
-    """Run the REFERENCE's host path (Grid::create, the code around the Zoltan call, discover_neighbours,
-    the getters, save_mask, save_metadata) on P thread-ranks; boxes [P,4] / pid [NY,NX] stand in for
-    Zoltan's answers (None: only Grid is exercised).  Returns the parsed report:
-      ranks[r] = {block, objects, nonzero, mask, ids, box, nbr[periodic][edge] = [(id, halo, start), ...]}
-      files[name] = {dims: [(name, len)], atts: {..}, vars: {(group, name): (dims, values)}, unwritten: {..}}"""
-    L = ref_host_lib()
-    if L is None:
-        raise RuntimeError("oracle/_ref/libref_hostpath.so is not built (needs /root/reference)")
-    mask = np.ascontiguousarray(mask, dtype=np.int32)
-    ny, nx = mask.shape
-    b = None if boxes is None else np.ascontiguousarray(boxes, dtype=np.int32)
-    q = None if pid is None else np.ascontiguousarray(pid, dtype=np.int32)
-    out = L.ref_host_run(P, nx, ny, mask, xdim.encode(), ydim.encode(), maskname.encode(), int(order_xy),
-                         int(order_xy if file_order_xy is None else file_order_xy), int(data_group), int(ignore_mask), int(px), int(py), int(changes),
-                         None if b is None else b.ctypes.data, None if q is None else q.ctypes.data)
-    if out is None:
-        raise RuntimeError(L.ref_host_error().decode())
+def _parse_report(out: bytes, P: int) -> dict:
     ranks = [dict(nbr=[[None] * 4 for _ in range(2)]) for _ in range(P)]
     files, cur = {}, None
     for line in out.decode().splitlines():
@@ -133,6 +114,67 @@ def ref_host_run(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *
         elif t[0] == "unwritten":
             cur["unwritten"][t[1]] = int(t[2])
     return dict(ranks=ranks, files=files)
+
+
+_ref_binding = {}
+
+
+def ref_binding_lib(cpu: bool):
+    """The reference's host sources + integration/reference_binding (the CudaRcbPartitioner a maintainer adds
+    to the reference tree) -- linked with the CUDA library (cpu=False) or, to test the binding's own logic
+    without a GPU, with the oracle answering its ddc_* calls (cpu=True).  None if not built."""
+    if cpu not in _ref_binding:
+        path = os.path.join(_HERE, "_ref", "libref_binding_cpu.so" if cpu else "libref_binding.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+        L.ref_binding_run.argtypes = [C.c_int, C.c_int, C.c_int, i32p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int,
+                                      C.c_int, C.c_int, C.c_int]
+        L.ref_binding_run.restype = C.c_char_p
+        L.ref_host_error.restype = C.c_char_p
+        _ref_binding[cpu] = L
+    return _ref_binding[cpu]
+
+
+def ref_binding_run(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, cpu: bool, xdim: str = "x",
+                    ydim: str = "y", maskname: str = "mask", ignore_mask: bool = False, device: int = 0) -> dict:
+    """Grid::create (reference) -> CudaRcbPartitioner::partition (the binding over the C ABI) -> the
+    reference's discover_neighbours, getters, save_mask, save_metadata, on P thread-ranks.  Same report as
+    ref_host_run."""
+    L = ref_binding_lib(cpu)
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_binding%s.so is not built" % ("_cpu" if cpu else ""))
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    ny, nx = mask.shape
+    out = L.ref_binding_run(P, nx, ny, mask, xdim.encode(), ydim.encode(), maskname.encode(), int(ignore_mask),
+                            int(px), int(py), device)
+    if out is None:
+        raise RuntimeError(L.ref_host_error().decode())
+    return _parse_report(out, P)
+
+
+def ref_host_run(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, boxes=None, pid=None,
+                 changes: int = 1, xdim: str = "x", ydim: str = "y", maskname: str = "mask", order_xy: bool = False,
+                 file_order_xy=None, data_group: bool = False, ignore_mask: bool = False) -> dict:
+    """Run the REFERENCE's host path (Grid::create, the code around the Zoltan call, discover_neighbours,
+    the getters, save_mask, save_metadata) on P thread-ranks; boxes [P,4] / pid [NY,NX] stand in for
+    Zoltan's answers (None: only Grid is exercised).  Returns the parsed report:
+      ranks[r] = {block, objects, nonzero, mask, ids, box, nbr[periodic][edge] = [(id, halo, start), ...]}
+      files[name] = {dims: [(name, len)], atts: {..}, vars: {(group, name): (dims, values)}, unwritten: {..}}"""
+    L = ref_host_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_hostpath.so is not built (needs /root/reference)")
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    ny, nx = mask.shape
+    b = None if boxes is None else np.ascontiguousarray(boxes, dtype=np.int32)
+    q = None if pid is None else np.ascontiguousarray(pid, dtype=np.int32)
+    out = L.ref_host_run(P, nx, ny, mask, xdim.encode(), ydim.encode(), maskname.encode(), int(order_xy),
+                         int(order_xy if file_order_xy is None else file_order_xy), int(data_group), int(ignore_mask), int(px), int(py), int(changes),
+                         None if b is None else b.ctypes.data, None if q is None else q.ctypes.data)
+    if out is None:
+        raise RuntimeError(L.ref_host_error().decode())
+    return _parse_report(out, P)
 
 
 def set_threads(t: int) -> None:

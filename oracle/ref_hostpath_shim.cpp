@@ -47,6 +47,7 @@ struct World {
     int arrived = 0;
     long generation = 0;
     std::vector<int> slots; // one contribution per rank (every collective here moves ints)
+    std::vector<const int*> sendptr; // MPI_Allgatherv: every rank's send buffer
     void barrier()
     {
         std::unique_lock<std::mutex> lk(m);
@@ -95,6 +96,22 @@ int MPI_Allgather(const void* sendbuf, int sendcount, MPI_Datatype, void* recvbu
 {
     exchange(c, static_cast<const int*>(sendbuf), sendcount,
         [&](const std::vector<int>& t) { std::copy(t.begin(), t.end(), static_cast<int*>(recvbuf)); });
+    return MPI_SUCCESS;
+}
+int MPI_Allgatherv(const void* sendbuf, int, MPI_Datatype, void* recvbuf, const int* recvcounts, const int* displs,
+    MPI_Datatype, MPI_Comm c)
+{
+    World& w = *c->world;
+    {
+        std::lock_guard<std::mutex> lk(w.m);
+        w.sendptr.resize(w.size);
+    }
+    w.barrier();
+    w.sendptr[c->rank] = static_cast<const int*>(sendbuf);
+    w.barrier();
+    for (int r = 0; r < w.size; r++)
+        std::copy(w.sendptr[r], w.sendptr[r] + recvcounts[r], static_cast<int*>(recvbuf) + displs[r]);
+    w.barrier(); // every rank has copied before any send buffer goes away
     return MPI_SUCCESS;
 }
 int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype, MPI_Op, MPI_Comm c)
@@ -510,37 +527,39 @@ void dump_file(std::ostringstream& os, const char* label, const std::string& pat
 }
 } // namespace
 
-extern "C" {
-// Runs Grid::create + GivenBoxesPartitioner::partition + the getters + save_mask + save_metadata on P
-// thread-ranks and returns a text report (owned by the library, valid until the next call):
+namespace {
+struct RunArgs {
+    int P, nx, ny;
+    const int* mask;
+    const char *xdim, *ydim, *maskname;
+    int order_xy, file_order_xy, data_group, ignore_mask, px, py;
+};
+// Grid::create + <partitioner>::partition + the getters + save_mask + save_metadata on P thread-ranks;
+// make(comm) returns the partitioner of a rank (nullptr: only Grid is exercised).  The text report:
 //   rank r block x0 y0 ex ey objects N nonzero M
 //   rank r mask v v v ...            the rank's land-mask slab as Grid read it
 //   rank r ids g g g ...             Grid's global ids of the ocean cells
 //   rank r box x0 y0 ex ey           Partitioner::get_bounding_box
 //   rank r nbr <edge> <periodic> id:halo:start ...
 //   file mask|metadata / dim / att / var lines: the two output files as written
-// order_xy: the caller's `-o xy`; file_order_xy: the mask variable is DECLARED (xdim, ydim) in the file;
-// data_group: dims + variable live in group "data".
-// Returns NULL on failure (ref_host_error() has the message).
-__attribute__((visibility("default"))) const char* ref_host_run(int P, int nx, int ny, const int* mask, const char* xdim,
-    const char* ydim, const char* maskname, int order_xy, int file_order_xy, int data_group, int ignore_mask, int px,
-    int py, int changes, const int* boxes, const int* pid)
+const char* run_ranks(const RunArgs& a, const std::function<Partitioner*(MPI_Comm)>& make)
 {
     g_error.clear();
     g_report.clear();
+    const int P = a.P;
     {
         std::lock_guard<std::mutex> lk(g_fs_mutex);
         g_files.clear();
         MemFile in;
         in.path = "grid.nc";
-        in.dims = { { xdim, (size_t)nx }, { ydim, (size_t)ny } };
-        if (data_group)
+        in.dims = { { a.xdim, (size_t)a.nx }, { a.ydim, (size_t)a.ny } };
+        if (a.data_group)
             in.groups.push_back("data");
         MemVar v;
-        v.name = maskname;
-        v.group = data_group ? 1 : 0;
-        v.dimids = file_order_xy ? std::vector<int> { 0, 1 } : std::vector<int> { 1, 0 };
-        v.data.assign(mask, mask + (size_t)nx * ny);
+        v.name = a.maskname;
+        v.group = a.data_group ? 1 : 0;
+        v.dimids = a.file_order_xy ? std::vector<int> { 0, 1 } : std::vector<int> { 1, 0 };
+        v.data.assign(a.mask, a.mask + (size_t)a.nx * a.ny);
         v.written.assign(v.data.size(), 1);
         in.vars.push_back(v);
         g_files.push_back(in);
@@ -549,36 +568,35 @@ __attribute__((visibility("default"))) const char* ref_host_run(int P, int nx, i
     world.size = P;
     std::vector<ref_shim_comm> comms(P);
     std::vector<std::string> part(P), err(P);
-    const Given given { changes, boxes, pid };
     auto body = [&](int r) {
         comms[r] = { &world, r };
         std::ostringstream os;
         try {
-            const std::vector<int> order = order_xy ? std::vector<int> { 0, 1 } : std::vector<int> { 1, 0 };
-            Grid* grid = Grid::create(&comms[r], "grid.nc", xdim, ydim, order, maskname, ignore_mask != 0, px != 0, py != 0);
+            const std::vector<int> order = a.order_xy ? std::vector<int> { 0, 1 } : std::vector<int> { 1, 0 };
+            Grid* grid = Grid::create(&comms[r], "grid.nc", a.xdim, a.ydim, order, a.maskname, a.ignore_mask != 0,
+                a.px != 0, a.py != 0);
             int b[4];
             grid->get_bounding_box(b[0], b[1], b[2], b[3]);
             os << "rank " << r << " block " << b[0] << " " << b[1] << " " << b[2] << " " << b[3] << " objects "
                << grid->get_num_objects() << " nonzero " << grid->get_num_nonzero_objects() << "\n";
             os << "rank " << r << " mask";
-            if (!ignore_mask)
+            if (!a.ignore_mask)
                 for (int i = 0; i < grid->get_num_objects(); i++)
                     os << " " << grid->get_land_mask()[i];
             os << "\nrank " << r << " ids";
             for (int i = 0; i < grid->get_num_nonzero_objects(); i++)
                 os << " " << grid->get_nonzero_object_ids()[i];
             os << "\n";
-            if (boxes) {
-                GivenBoxesPartitioner p(&comms[r], given);
-                p.partition(*grid);
-                p.get_bounding_box(b[0], b[1], b[2], b[3]);
+            if (Partitioner* p = make(&comms[r])) {
+                p->partition(*grid);
+                p->get_bounding_box(b[0], b[1], b[2], b[3]);
                 os << "rank " << r << " box " << b[0] << " " << b[1] << " " << b[2] << " " << b[3] << "\n";
                 for (int per = 0; per < 2; per++) {
                     std::vector<std::vector<int>> ids(4), halos(4), starts(4);
                     if (per)
-                        p.get_neighbour_info_periodic(ids, halos, starts);
+                        p->get_neighbour_info_periodic(ids, halos, starts);
                     else
-                        p.get_neighbour_info(ids, halos, starts);
+                        p->get_neighbour_info(ids, halos, starts);
                     for (int e = 0; e < 4; e++) {
                         os << "rank " << r << " nbr " << e << " " << per;
                         for (size_t k = 0; k < ids[e].size(); k++)
@@ -586,8 +604,9 @@ __attribute__((visibility("default"))) const char* ref_host_run(int P, int nx, i
                         os << "\n";
                     }
                 }
-                p.save_mask("partition_mask.nc");
-                p.save_metadata("partition_metadata.nc");
+                p->save_mask("partition_mask.nc");
+                p->save_metadata("partition_metadata.nc");
+                delete p;
             }
             delete grid;
         } catch (const std::exception& e) {
@@ -618,5 +637,40 @@ __attribute__((visibility("default"))) const char* ref_host_run(int P, int nx, i
     g_report = os.str();
     return g_report.c_str();
 }
+} // namespace
+
+#ifdef DDC_WITH_BINDING
+#include "CudaRcbPartitioner.hpp" // integration/reference_binding: the binding a maintainer adds
+#endif
+
+extern "C" {
+// The reference's host path with Zoltan's answers handed in (see the header of this file).
+// order_xy: the caller's `-o xy`; file_order_xy: the mask variable is DECLARED (xdim, ydim) in the file;
+// data_group: dims + variable live in group "data".  boxes == NULL: only Grid is exercised.
+// Returns a text report owned by the library (valid until the next call), NULL on failure
+// (ref_host_error() has the message).
+__attribute__((visibility("default"))) const char* ref_host_run(int P, int nx, int ny, const int* mask, const char* xdim,
+    const char* ydim, const char* maskname, int order_xy, int file_order_xy, int data_group, int ignore_mask, int px,
+    int py, int changes, const int* boxes, const int* pid)
+{
+    const RunArgs a { P, nx, ny, mask, xdim, ydim, maskname, order_xy, file_order_xy, data_group, ignore_mask, px, py };
+    const Given given { changes, boxes, pid };
+    return run_ranks(a, [&](MPI_Comm comm) -> Partitioner* {
+        return boxes ? new GivenBoxesPartitioner(comm, given) : nullptr;
+    });
+}
+#ifdef DDC_WITH_BINDING
+// The same run with the CUDA-backed partitioner of integration/reference_binding in place of Zoltan:
+// reference Grid + binding over the C ABI + reference neighbour discovery + reference writers.
+__attribute__((visibility("default"))) const char* ref_binding_run(int P, int nx, int ny, const int* mask, const char* xdim,
+    const char* ydim, const char* maskname, int ignore_mask, int px, int py, int device)
+{
+    const RunArgs a { P, nx, ny, mask, xdim, ydim, maskname, 0, 0, 0, ignore_mask, px, py };
+    std::string dev = std::to_string(device);
+    char arg0[] = "decomp", arg1[] = "--device";
+    char* argv[] = { arg0, arg1, &dev[0], nullptr };
+    return run_ranks(a, [&](MPI_Comm comm) -> Partitioner* { return CudaRcbPartitioner::create(comm, 3, argv); });
+}
+#endif
 __attribute__((visibility("default"))) const char* ref_host_error(void) { return g_error.c_str(); }
 }
