@@ -1,10 +1,11 @@
 /*
- * ddc_oracle_stub.c -- TEST INFRASTRUCTURE.  The handful of include/ddc.h entry points that
- * integration/reference_binding/CudaRcbPartitioner.cpp calls, answered by the CPU oracle
- * (ddc_oracle.c) instead of the CUDA library.  Linked ONLY into oracle/_ref/libref_binding_cpu.so,
- * so that the binding's own logic (assembling the mask from the ranks' blocks, handing boxes and
- * owners back to the reference's code) can be tested without a GPU; the product library has no
- * such path and is never linked with this file.
+ * ddc_oracle_stub.c -- TEST INFRASTRUCTURE.  The include/ddc.h entry points that the HOST code calls
+ * (integration/reference_binding/CudaRcbPartitioner.cpp and domain_decomp_b200/host/), answered by
+ * the CPU oracle (ddc_oracle.c) instead of the CUDA library.  Linked ONLY into test artefacts under
+ * oracle/_ref/ (libref_binding_cpu.so, decomp_oracle, host_tests_oracle), so that host-side logic
+ * -- assembling the mask, rank views, the writers, the CLI -- can be tested on a machine without a
+ * GPU.  The product (libddc_cuda.so, libdomain_decomp.so, decomp) has no such path and is never
+ * linked with this file.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -14,11 +15,26 @@
 
 int orc_partition(const int32_t* mask, int NX, int NY, int P, int use_hist, int32_t* boxes, int32_t* pid,
     int* changes_out, long* median_iters);
+void orc_neighbours(const int32_t* boxes, int P, int NX, int NY, int px, int py, int32_t* counts,
+    const int64_t* offsets, int32_t* ids, int32_t* halos, int32_t* starts);
+void orc_part_loads(const int32_t* pid, size_t ncell, int P, int64_t* loads);
 
 struct ddc_handle_s {
-    int nx, ny, P;
+    int nx, ny, P, px, py, changes, have_nbr;
+    long iters;
     int32_t *mask, *boxes, *pid;
+    int32_t *counts, *ids, *halos, *starts; /* neighbour tables, 8 lists */
+    int64_t offsets[9];
 };
+static void free_tables(ddc_handle_t h)
+{
+    free(h->counts);
+    free(h->ids);
+    free(h->halos);
+    free(h->starts);
+    h->counts = h->ids = h->halos = h->starts = NULL;
+    h->have_nbr = 0;
+}
 
 const char* ddc_last_error(ddc_handle_t h)
 {
@@ -40,6 +56,7 @@ int ddc_destroy(ddc_handle_t h)
         free(h->mask);
         free(h->boxes);
         free(h->pid);
+        free_tables(h);
         free(h);
     }
     return DDC_OK;
@@ -57,17 +74,85 @@ int ddc_set_mask_host(ddc_handle_t h, const int32_t* rows, int nx, int ny, int y
 }
 int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
 {
-    (void)px;
-    (void)py;
-    (void)flags;
     free(h->boxes);
     free(h->pid);
+    free_tables(h);
     h->P = nparts;
+    h->px = px;
+    h->py = py;
     h->boxes = (int32_t*)malloc(sizeof(int32_t) * 4 * (size_t)nparts);
     h->pid = (int32_t*)malloc(sizeof(int32_t) * (size_t)h->nx * h->ny);
-    int changes;
-    long iters;
-    return orc_partition(h->mask, h->nx, h->ny, nparts, 1, h->boxes, h->pid, &changes, &iters) == 0 ? DDC_OK : DDC_ERR_STATE;
+    if (orc_partition(h->mask, h->nx, h->ny, nparts, 1, h->boxes, h->pid, &h->changes, &h->iters) != 0)
+        return DDC_ERR_STATE;
+    if ((flags & DDC_WANT_NEIGHBOURS) && nparts > 1) { /* P == 1 returns before neighbour discovery */
+        const int P = nparts;
+        h->counts = (int32_t*)calloc(8 * (size_t)P, sizeof(int32_t));
+        orc_neighbours(h->boxes, P, h->nx, h->ny, px, py, h->counts, NULL, NULL, NULL, NULL);
+        h->offsets[0] = 0;
+        for (int l = 0; l < 8; l++) {
+            int64_t t = 0;
+            for (int p = 0; p < P; p++)
+                t += h->counts[(size_t)l * P + p];
+            h->offsets[l + 1] = h->offsets[l] + t;
+        }
+        const size_t n = (size_t)h->offsets[8] + 1;
+        h->ids = (int32_t*)malloc(sizeof(int32_t) * n);
+        h->halos = (int32_t*)malloc(sizeof(int32_t) * n);
+        h->starts = (int32_t*)malloc(sizeof(int32_t) * n);
+        orc_neighbours(h->boxes, P, h->nx, h->ny, px, py, h->counts, h->offsets, h->ids, h->halos, h->starts);
+        h->have_nbr = 1;
+    }
+    return DDC_OK;
+}
+int ddc_get_neighbour_counts(ddc_handle_t h, int edge, int periodic, int32_t* counts)
+{
+    const int l = periodic * 4 + edge;
+    if (!h->have_nbr)
+        memset(counts, 0, sizeof(int32_t) * (size_t)h->P);
+    else
+        memcpy(counts, h->counts + (size_t)l * h->P, sizeof(int32_t) * (size_t)h->P);
+    return DDC_OK;
+}
+int ddc_get_neighbour_total(ddc_handle_t h, int edge, int periodic, int64_t* total)
+{
+    const int l = periodic * 4 + edge;
+    *total = h->have_nbr ? h->offsets[l + 1] - h->offsets[l] : 0;
+    return DDC_OK;
+}
+int ddc_get_neighbours(ddc_handle_t h, int edge, int periodic, int32_t* ids, int32_t* halos, int32_t* starts)
+{
+    const int l = periodic * 4 + edge;
+    if (!h->have_nbr)
+        return DDC_OK;
+    const size_t n = (size_t)(h->offsets[l + 1] - h->offsets[l]), o = (size_t)h->offsets[l];
+    memcpy(ids, h->ids + o, sizeof(int32_t) * n);
+    memcpy(halos, h->halos + o, sizeof(int32_t) * n);
+    memcpy(starts, h->starts + o, sizeof(int32_t) * n);
+    return DDC_OK;
+}
+int ddc_get_stats(ddc_handle_t h, ddc_stats* out)
+{
+    memset(out, 0, sizeof *out);
+    out->nx = h->nx;
+    out->ny = h->ny;
+    out->nparts = h->P;
+    out->changes = h->P > 1 ? h->changes : 0;
+    out->median_iters = (int32_t)h->iters;
+    int64_t* loads = (int64_t*)malloc(sizeof(int64_t) * (size_t)h->P);
+    orc_part_loads(h->pid, (size_t)h->nx * h->ny, h->P, loads);
+    out->load_min = out->load_max = loads[0];
+    for (int p = 0; p < h->P; p++) {
+        out->n_ocean += loads[p];
+        if (loads[p] < out->load_min)
+            out->load_min = loads[p];
+        if (loads[p] > out->load_max)
+            out->load_max = loads[p];
+    }
+    free(loads);
+    for (int l = 0; h->have_nbr && l < 4; l++)
+        for (int64_t k = h->offsets[l]; k < h->offsets[l + 1]; k++)
+            out->edge_cut += h->halos[k];
+    return DDC_OK;
 }
 int ddc_get_boxes(ddc_handle_t h, int32_t* x0, int32_t* y0, int32_t* ex, int32_t* ey)
 {

@@ -1,0 +1,141 @@
+"""The host layer (domain_decomp_b200/host: Grid, Partitioner, CudaRcbPartitioner, the `decomp` CLI) on a machine
+WITHOUT a GPU: oracle/Makefile links the very same host sources with oracle/ddc_oracle_stub.c, i.e. with the CPU
+oracle behind the C ABI, into test binaries under oracle/_ref/.  (The product binaries link libddc_cuda.so and
+have no such path; tests/test_host_cpp.py runs them on the GPU.)  Checked here:
+  * the reference's unit tests re-expressed (host_tests.cpp: test_grid_*, test_zoltan_partitioner_*),
+  * the reference's integration test: CLI output byte-identical to the golden ncdump text,
+  * binary netCDF grids in, partition_mask_<P>.nc out,
+  * on random coastlines: what this host layer writes == what the REFERENCE's own Partitioner.cpp writes
+    (oracle/_ref/libref_hostpath.so) for the same boxes -- rank views, per-edge offsets, zero-length dims."""
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from test_host_cpp import CASES, write_input_cdl
+from test_reference_hostpath import sane_blocks
+
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+DECOMP = os.path.join(REF_DIR, "decomp_oracle")
+HOST_TESTS = os.path.join(REF_DIR, "host_tests_oracle")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built(oracle):
+    oracle.build()
+    if not (os.path.exists(DECOMP) and os.path.exists(HOST_TESTS)):
+        pytest.skip("oracle/_ref host-layer test binaries not built (no reference checkout here)")
+
+
+@pytest.fixture(scope="module")
+def fixture_dir(tmp_path_factory, goldens):
+    d = tmp_path_factory.mktemp("grids_cpu")
+    for name in ("test_0", "test_1", "test_2"):
+        write_input_cdl(os.path.join(d, name + ".cdl"), name, goldens["inputs"][name])
+    return str(d)
+
+
+def test_reference_unit_tests_on_the_host_layer(fixture_dir):
+    out = subprocess.run([HOST_TESTS, fixture_dir], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 failed" in out.stdout
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_cli_integration_goldens(goldens, fixture_dir, tmp_path, case):
+    inp, flags = CASES[case]
+    out = subprocess.run([DECOMP, "-g", os.path.join(fixture_dir, inp + ".cdl"), "--parts", "3"] + flags,
+                         capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stdout + out.stderr
+    G = goldens["integration"][case]
+    for fname, key in (("partition_mask_3.cdl", "mask_cdl_sha256"), ("partition_metadata_3.cdl", "metadata_cdl_sha256")):
+        text = open(os.path.join(tmp_path, fname)).read()
+        assert hashlib.sha256(text.encode()).hexdigest() == G[key], "%s differs from the golden:\n%s" % (fname, text)
+
+
+def parse_cdl(text):
+    dims = {}
+    for mm in re.finditer(r"^\t(\w+) = (\w+) ;(?: // \((\d+) currently\))?$", text, re.M):
+        dims[mm.group(1)] = (0 if mm.group(2) == "UNLIMITED" else int(mm.group(2)), mm.group(2) == "UNLIMITED")
+    data = {}
+    for body in re.split(r"\bdata:\n", text)[1:]:
+        for mm in re.finditer(r"^\s*(\w+) =\s*([-0-9,\s]+?);", body, re.S | re.M):
+            data[mm.group(1)] = [int(v) for v in mm.group(2).replace("\n", " ").split(",")]
+    return dims, data
+
+
+def write_nc(path, mask, version=1):
+    scipy_io = pytest.importorskip("scipy.io")
+    ny, nx = mask.shape
+    f = scipy_io.netcdf_file(path, "w", version=version)
+    f.createDimension("x", nx)
+    f.createDimension("y", ny)
+    f.createVariable("mask", "i4", ("y", "x"))[:] = mask
+    f.close()
+
+
+def test_cli_on_binary_netcdf_and_stats(goldens, tmp_path):
+    scipy_io = pytest.importorskip("scipy.io")
+    inp = goldens["inputs"]["test_1"]
+    write_nc(str(tmp_path / "test_1.nc"), np.asarray(inp["mask"], dtype=np.int32).reshape(inp["ny"], inp["nx"]))
+    out = subprocess.run([DECOMP, "-g", "test_1.nc", "--parts", "3", "--px", "--stats"], capture_output=True, text=True,
+                         timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Total weight of dots = 24" in out.stdout
+    G = goldens["integration"]["test_1_px"]
+    text = open(tmp_path / "partition_metadata_3.cdl").read()
+    assert hashlib.sha256(text.encode()).hexdigest() == G["metadata_cdl_sha256"]
+    m = scipy_io.netcdf_file(str(tmp_path / "partition_mask_3.nc"), "r", mmap=False)
+    assert m.num_processes == 3 and m.variables["pid"].data.ravel().tolist() == list(G["pid"])
+    m.close()
+
+
+def test_cli_errors(fixture_dir, tmp_path):
+    r = subprocess.run([DECOMP], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "'--grid' is required" in r.stderr
+    r = subprocess.run([DECOMP, "-g", os.path.join(fixture_dir, "test_1.cdl"), "-o", "zz"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "must be either 'xy' or 'yx'" in r.stderr
+    r = subprocess.run([DECOMP, "-g", os.path.join(fixture_dir, "test_2.cdl"), "--parts", "2"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1  # default names x / y / mask do not exist in test_2
+    r = subprocess.run([DECOMP, "-g", "/nonexistent/grid.nc"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "ERROR" in r.stderr
+
+
+def test_files_written_by_the_host_layer_equal_the_reference_writers(oracle, tmp_path):
+    """random coastlines through the CLI; the same boxes / owners through the reference's own save_mask and
+    save_metadata (Partitioner.cpp:128-318): dimension lengths (0 => UNLIMITED), every variable, every value"""
+    if oracle.ref_host_lib() is None:
+        pytest.skip("oracle/_ref/libref_hostpath.so not built")
+    rng = np.random.default_rng(77)
+    done = 0
+    while done < 25:
+        nx, ny, P = int(rng.integers(3, 40)), int(rng.integers(3, 40)), int(rng.integers(2, 17))
+        if not sane_blocks(oracle, P, nx, ny):
+            continue
+        mask = (rng.random((ny, nx)) >= rng.random() * 0.7).astype(np.int32)
+        px, py = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        d = tmp_path / ("case%d" % done)
+        d.mkdir()
+        write_nc(str(d / "g.nc"), mask, version=1 + done % 2)
+        cmd = [DECOMP, "-g", "g.nc", "--parts", str(P)] + (["--px"] if px else []) + (["--py"] if py else [])
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=d)
+        assert out.returncode == 0, out.stdout + out.stderr
+        o = oracle.partition(mask, P, px, py, use_hist=True)
+        ref = oracle.ref_host_run(mask, P, px, py, boxes=o.boxes, pid=o.pid, changes=o.changes)
+        # metadata
+        dims, data = parse_cdl(open(d / ("partition_metadata_%d.cdl" % P)).read())
+        rdims = dict(ref["files"]["metadata"]["dims"])
+        assert {k: v[0] for k, v in dims.items()} == rdims, (nx, ny, P)
+        for k, (length, unlimited) in dims.items():
+            assert unlimited == (rdims[k] == 0), (k, "nc_def_dim(len = 0) makes the dimension UNLIMITED")
+        rvars = {name: vals for (grp, name), (vd, vals) in ref["files"]["metadata"]["vars"].items()}
+        assert data == {k: v for k, v in rvars.items() if v}, (nx, ny, P, px, py)
+        # mask
+        mdims, mdata = parse_cdl(open(d / ("partition_mask_%d.cdl" % P)).read())
+        assert {k: v[0] for k, v in mdims.items()} == dict(ref["files"]["mask"]["dims"])
+        assert mdata["pid"] == ref["files"]["mask"]["vars"][("/", "pid")][1]
+        done += 1
