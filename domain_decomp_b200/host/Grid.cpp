@@ -80,11 +80,11 @@ void Grid::load_file(const std::string& filename, const std::string& xdim, const
     if (kind == ddc_host::FileKind::Hdf5)
         throw std::runtime_error("ERROR: NetCDF: '" + filename + "' is a netCDF-4 / HDF5 file; this build reads "
             "netCDF classic files and CDL text (convert with `nccopy -k classic` or `ncdump`)");
-    const ddc_host::CdlFile file = kind == ddc_host::FileKind::NetcdfClassic
-        ? ddc_host::read_netcdf_classic(filename, ignore_mask ? std::string("\x01none") : mask_name)
+    ddc_host::CdlFile file = kind == ddc_host::FileKind::NetcdfClassic
+        ? ddc_host::read_netcdf_classic(filename, ignore_mask ? std::string("\x01none") : mask_name, true)
         : ddc_host::read_cdl(filename);
     // enhanced data model: nextSIM restart files keep everything in group "data" (Grid.cpp:58-62)
-    const ddc_host::CdlGroup* grp = &file.root;
+    ddc_host::CdlGroup* grp = &file.root;
     auto it = file.root.groups.find("data");
     if (it != file.root.groups.end())
         grp = &it->second;
@@ -111,16 +111,21 @@ void Grid::load_file(const std::string& filename, const std::string& xdim, const
     auto v = grp->vars.find(mask_name);
     if (v == grp->vars.end() || !v->second.has_data)
         throw std::runtime_error("ERROR: mask variable '" + mask_name + "' not found in " + filename);
-    const ddc_host::CdlVar& var = v->second;
+    ddc_host::CdlVar& var = v->second;
     // the declared order must be what the caller said (Grid.cpp:104-114)
     if (var.dims.size() != 2 || var.dims[0] != names[order[0]] || var.dims[1] != names[order[1]])
         throw std::runtime_error("Dimension ordering provided does not match ordering in netCDF grid file");
-    if (var.data.size() != n)
-        throw std::runtime_error("ERROR: mask variable holds " + std::to_string(var.data.size())
-            + " values, expected " + std::to_string(n));
+    const size_t have = var.idata.empty() ? var.data.size() : var.idata.size();
+    if (have != n)
+        throw std::runtime_error("ERROR: mask variable holds " + std::to_string(have) + " values, expected "
+            + std::to_string(n));
     // Values arrive in file order and are indexed x-fastest whatever the order says: for
     // (x, y) files this is a raw reinterpretation, as in the reference.
     // Non-integer types convert like nc_get_vara_int does: truncation toward zero.
+    if (!var.idata.empty()) { // binary reader: already ints
+        _global_mask = std::move(var.idata);
+        return;
+    }
     _global_mask.resize(n);
     for (size_t i = 0; i < n; i++)
         _global_mask[i] = (int)var.data[i];

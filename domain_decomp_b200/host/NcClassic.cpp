@@ -274,7 +274,7 @@ FileKind sniff_file_kind(const std::string& path)
     return FileKind::Text;
 }
 
-CdlFile read_netcdf_classic(const std::string& path, const std::string& only_var)
+CdlFile read_netcdf_classic(const std::string& path, const std::string& only_var, bool as_int)
 {
     Reader r(path);
     unsigned char magic[4];
@@ -373,7 +373,10 @@ CdlFile read_netcdf_classic(const std::string& path, const std::string& only_var
             const uint64_t per = slab_elems(v), slabs = v.record ? numrecs : 1;
             if (per * slabs > (uint64_t)std::numeric_limits<int>::max())
                 bad(path, "variable '" + v.name + "' has more values than an int can index");
-            cv.data.reserve((size_t)(per * slabs));
+            if (as_int)
+                cv.idata.reserve((size_t)(per * slabs));
+            else
+                cv.data.reserve((size_t)(per * slabs));
             std::vector<unsigned char> buf;
             const size_t chunk = 1 << 20; // values per read
             for (uint64_t s = 0; s < slabs; s++) {
@@ -382,8 +385,18 @@ CdlFile read_netcdf_classic(const std::string& path, const std::string& only_var
                     const size_t n = (size_t)std::min<uint64_t>(chunk, per - done);
                     buf.resize(n * ts);
                     r.bytes(buf.data(), n * ts);
-                    for (size_t i = 0; i < n; i++)
-                        cv.data.push_back(element(buf.data() + i * ts, v.type));
+                    if (as_int && v.type == NC_INT) { // the common case: a byte swap
+                        for (size_t i = 0; i < n; i++) {
+                            const unsigned char* q = buf.data() + 4 * i;
+                            cv.idata.push_back((int)(((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3]));
+                        }
+                    } else if (as_int) {
+                        for (size_t i = 0; i < n; i++)
+                            cv.idata.push_back((int)element(buf.data() + i * ts, v.type));
+                    } else {
+                        for (size_t i = 0; i < n; i++)
+                            cv.data.push_back(element(buf.data() + i * ts, v.type));
+                    }
                 }
             }
             cv.has_data = true;

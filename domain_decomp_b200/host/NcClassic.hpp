@@ -25,7 +25,9 @@ FileKind sniff_file_kind(const std::string& path);
 
 // Header and data of a classic file as a CdlFile (one root group: classic files have no groups).
 // only_var: when non-empty, only this variable's data is loaded (the others keep has_data = false).
-CdlFile read_netcdf_classic(const std::string& path, const std::string& only_var = "");
+// as_int: values are converted like nc_get_vara_int does (truncation toward zero) and stored in
+// CdlVar::idata instead of CdlVar::data -- half the memory for a mask of 10^9 cells.
+CdlFile read_netcdf_classic(const std::string& path, const std::string& only_var = "", bool as_int = false);
 
 struct NcDim {
     std::string name;

@@ -275,12 +275,16 @@ void Partitioner::save_mask(const std::string& filename) const
     // every rank of the reference writes its slab collectively; here rank 0 holds the whole map
     if (_rank != 0)
         return;
-    write_text(ddc_host::cdl_path_of(filename), mask_cdl(ddc_host::netcdf_name_of(filename)));
-    // a real netCDF file as well when a ".nc" name was asked for: classic format (the reference
-    // writes netCDF-4; dimensions, variable, attribute and values are the same, so `ncdump` prints
-    // the CDL above and every netCDF reader opens it) -- Partitioner.cpp:128-166
-    if (filename.size() > 3 && filename.compare(filename.size() - 3, 3, ".nc") == 0) {
-        const int NX = _global_ext[0], NY = _global_ext[1];
+    // A real netCDF file when a ".nc" name was asked for: classic format (the reference writes
+    // netCDF-4; dimensions, variable, attribute and values are the same, so `ncdump` prints the same
+    // CDL and every netCDF reader opens it) -- Partitioner.cpp:128-166.  The CDL text `ncdump` would
+    // print is written beside it, except for maps of more than 2^24 cells next to a .nc file
+    // (hundreds of MB of text nobody reads).
+    const int NX = _global_ext[0], NY = _global_ext[1];
+    const bool binary = filename.size() > 3 && filename.compare(filename.size() - 3, 3, ".nc") == 0;
+    if (!binary || (size_t)NX * NY <= ((size_t)1 << 24))
+        write_text(ddc_host::cdl_path_of(filename), mask_cdl(ddc_host::netcdf_name_of(filename)));
+    if (binary) {
         ddc_host::write_netcdf_classic(filename, { { "y", (uint64_t)NY }, { "x", (uint64_t)NX } },
             { { "num_processes", _num_parts } }, { { "pid", { 0, 1 }, _pid_global.data() } });
     }
