@@ -1,10 +1,11 @@
 """Host-side logic of the row-sharded (N > 1) path, on CPU with gloo, world_size 2.
 
 The CUDA kernels cannot run here; what can be checked without a GPU is the sharding contract the
-ranks rely on: ddc_shard_rows blocks tile the rows, the SUM-allreduce of per-shard column
-histograms equals the global histogram, and the all-gathered per-strip row histograms in the
-[G][S][Rmax] layout that K4 indexes (rank = y / Rmax, local row = y % Rmax) reproduce the global
-per-strip row histogram -- which, fed to the oracle's histogram RCB, gives the oracle's boxes.
+ranks rely on: ddc_shard_rows blocks tile the rows, the sum over the ranks' column-histogram slots
+equals the global histogram, and the per-strip row histograms -- every rank's block in the chunked
+[row block][S][RB] layout of ddc_kernels.cuh:row_count_index, placed in slot `rank` of every rank's
+exchange buffer, which is what K4 indexes (rank = y / Rmax, local row = y % Rmax) -- reproduce the
+global per-strip row histogram, which, fed to the oracle's histogram RCB, gives the oracle's boxes.
 """
 import os
 import sys
@@ -37,17 +38,30 @@ def _worker(rank, world, port, nx, ny, P, q):
     xs = sorted(set((int(b[0]), int(b[0] + b[2])) for b in o.boxes))
     S = len(xs)
     rmax = -(-ny // world)
-    # exchange step 2: per-strip row histogram, local [S][Rmax] (padding rows are zero)
-    local = np.zeros((S, rmax), dtype=np.int64)
-    for s, (x0, x1) in enumerate(xs):
-        local[s, :yc] = shard[:, x0:x1].sum(axis=1)
-    gathered = [torch.zeros((S, rmax), dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(gathered, torch.from_numpy(local))
-    allg = torch.stack(gathered).numpy()  # [G][S][Rmax]
-    for s, (x0, x1) in enumerate(xs):
-        want = (mask[:, x0:x1] > 0).sum(axis=1)
-        got = np.array([allg[y // rmax, s, y % rmax] for y in range(ny)])
-        ok &= np.array_equal(got, want)
+    # exchange step 2: per-strip row histogram; a rank's block is [row block][S][RB] (RB rows per block of
+    # the kernel that wrote it; rows beyond the shard are written as empty), and every rank ends up with
+    # the block of rank g in slot g (the producers push; an all-gather is the same data movement)
+    for rb_shift in (3, 5):
+        RB = 1 << rb_shift
+        nblk = -(-rmax // RB)
+
+        def index(s, yl):  # row_count_index(s, yl, Scap = S, rb_shift)
+            return (((yl >> rb_shift) * S + s) << rb_shift) + (yl & (RB - 1))
+
+        local = np.zeros(nblk * S * RB, dtype=np.int64)
+        for s, (x0, x1) in enumerate(xs):
+            counts = shard[:, x0:x1].sum(axis=1)
+            for yl in range(yc):
+                local[index(s, yl)] = counts[yl]
+        slots = [torch.zeros(nblk * S * RB, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(slots, torch.from_numpy(local))
+        for s, (x0, x1) in enumerate(xs):
+            want = (mask[:, x0:x1] > 0).sum(axis=1)
+            got = np.array([int(slots[y // rmax][index(s, y % rmax)]) for y in range(ny)])
+            ok &= np.array_equal(got, want)
+        # a block of the kernel (RB rows, all strips) is ONE contiguous chunk of the layout
+        chunk = sorted(index(s, yl) for s in range(S) for yl in range(RB))
+        ok &= chunk == list(range(S * RB))
     # every rank's rows tile [0, ny)
     blocks = [None] * world
     dist.all_gather_object(blocks, (yb, yc))
