@@ -698,6 +698,19 @@ static double find_median_hist(hist_t* H, int c0, int c1, double fractionlo)
     return average_cut(L >= 0, (double)L, U >= 0, (double)U, (double)c0, (double)(c1 + 1));
 }
 
+/* One median of the histogram formulation, for the host fuzz of the DEVICE median code
+   (oracle/emu_median_harness.cpp): the integer boundary ceil(cut) of bins [c0, c1] for a set of
+   num_parts parts whose lower child receives nlo of them (fractionlo as rcb.c forms it). */
+ORC_API int orc_median_boundary(const int64_t* pfx, int n, int c0, int c1, int nlo, int num_parts, long* iters)
+{
+    hist_t H = { pfx, n, 0 };
+    const double fractionlo = (double)nlo / (double)num_parts;
+    const double cut = find_median_hist(&H, c0, c1, fractionlo);
+    if (iters)
+        *iters = H.iters;
+    return (int)ceil(cut);
+}
+
 typedef struct {
     int lo, hi; /* integer cell range [lo, hi) along the cut dimension */
     int partlower, num_parts;

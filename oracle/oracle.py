@@ -26,6 +26,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "ddc_oracle.c")
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_oracle.so"])
+    subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_median_emu.so"])  # make decides what is stale
     if os.path.isdir("/root/reference"):  # make decides what is stale
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"] + (["-B"] if force else []))
     return _LIB
@@ -64,6 +65,17 @@ def ref_lib():
     L = C.CDLL(_REF_LIB)
     L.ref_domain_overlap.argtypes = [C.c_int] * 9
     L.ref_domain_overlap.restype = C.c_int
+    return L
+
+
+def median_emu_lib():
+    """The scalar core of the CUDA cut kernels (csrc/ddc_median.cuh) compiled as host code, with the fuzz
+    driver of oracle/emu_median_harness.cpp."""
+    build()
+    L = C.CDLL(os.path.join(_HERE, "libddc_median_emu.so"))
+    L.emu_fuzz.argtypes = [C.c_uint64, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                           C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.emu_fuzz.restype = C.c_long
     return L
 
 
