@@ -46,7 +46,7 @@ def _stale(target: str, sources: list[str]) -> bool:
 
 def build_cuda_lib(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, "ddc_api.cu")]
-    deps = srcs + [os.path.join(CSRC, "ddc_kernels.cuh"), os.path.join(CSRC, "ddc_median.cuh"),
+    deps = srcs + [os.path.join(CSRC, "ddc_kernels.cuh"), os.path.join(CSRC, "ddc_median.cuh"), os.path.join(CSRC, "ddc_neighbours.cuh"),
                    os.path.join(INCLUDE, "ddc.h"), __file__]
     if force or _stale(CUDA_LIB, deps):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-I", INCLUDE, "-I", CSRC, "-o", CUDA_LIB] + srcs + ["-ldl"]

@@ -12,6 +12,7 @@
 // fast division perturbed by +-2 ulp (the documented accuracy of __fdividef).
 #define DDC_HOST_EMU
 #include "ddc_median.cuh"
+#include "ddc_neighbours.cuh"
 
 #include <cstdint>
 #include <cstdio>
@@ -23,6 +24,8 @@ int g_fdividef_ulps = 0;
 }
 
 extern "C" int orc_median_boundary(const int64_t* pfx, int n, int c0, int c1, int nlo, int num_parts, long* iters);
+extern "C" void orc_neighbours(const int32_t* boxes, int P, int NX, int NY, int px, int py, int32_t* counts,
+    const int64_t* offsets, int32_t* ids, int32_t* halos, int32_t* starts);
 
 namespace {
 struct Rng {
@@ -214,6 +217,143 @@ __attribute__((visibility("default"))) long emu_fuzz(uint64_t seed, long histogr
         }
     }
     *medians_checked = checked;
+    return mism;
+}
+
+// K7's structured search (csrc/ddc_neighbours.cuh, one "thread" per (list, part)) against the oracle's literal
+// O(P^2) discovery on random tilings: x-sorted strips of y-sorted parts.  degenerate: boundaries may coincide
+// (zero-width strips, zero-height parts -- what the cut kernels produce when there are more parts than
+// non-empty columns or rows).  bad[0..5] = {NX, NY, P, list, part, what (1 count, 2 entry, 3 edge cut)}.
+__attribute__((visibility("default"))) long emu_fuzz_neighbours(uint64_t seed, long cases, int maxn, int maxstrips,
+    int maxparts, int degenerate, long long* bad, long long* lists_checked)
+{
+    Rng r { seed * 0x9E3779B97F4A7C15ull + 7 };
+    long mism = 0;
+    long long checked = 0;
+    auto boundaries = [&](int n, int extent, std::vector<int>& out) { // n intervals tiling [0, extent)
+        out.assign((size_t)n + 1, 0);
+        for (int i = 1; i < n; i++)
+            out[i] = (int)r.below((uint64_t)extent + 1);
+        out[n] = extent;
+        std::sort(out.begin(), out.end());
+        if (!degenerate) { // strictly increasing: possible only when n <= extent
+            for (int i = 1; i <= n; i++)
+                out[i] = std::max(out[i], out[i - 1] + 1);
+            for (int i = n; i >= 1; i--)
+                out[i] = std::min(out[i], extent - (n - i));
+        }
+    };
+    for (long t = 0; t < cases; t++) {
+        const int NX = 1 + (int)r.below((uint64_t)maxn), NY = 1 + (int)r.below((uint64_t)maxn);
+        int S = 1 + (int)r.below((uint64_t)maxstrips);
+        if (!degenerate)
+            S = std::min(S, NX);
+        std::vector<int> xb, yb;
+        boundaries(S, NX, xb);
+        std::vector<int> sx0(S), sx1(S), p0(S + 1), bx0, by0, bex, bey;
+        for (int s = 0; s < S; s++) {
+            int n = 1 + (int)r.below((uint64_t)maxparts);
+            if (!degenerate)
+                n = std::min(n, NY);
+            boundaries(n, NY, yb);
+            sx0[s] = xb[s];
+            sx1[s] = xb[s + 1];
+            p0[s] = (int)bx0.size();
+            for (int j = 0; j < n; j++) {
+                bx0.push_back(xb[s]);
+                bex.push_back(xb[s + 1] - xb[s]);
+                by0.push_back(yb[j]);
+                bey.push_back(yb[j + 1] - yb[j]);
+            }
+        }
+        const int P = (int)bx0.size();
+        p0[S] = P;
+        const int px = (int)r.below(2), py = (int)r.below(2);
+        int Sv = S, always = 0;
+        const ddc::StripTable st { sx0.data(), sx1.data(), p0.data(), &Sv, &always };
+        const ddc::BoxTable bx { bx0.data(), by0.data(), bex.data(), bey.data() };
+        // the oracle
+        std::vector<int32_t> aos(4 * (size_t)P), wc(8 * (size_t)P);
+        for (int p = 0; p < P; p++) {
+            aos[4 * p] = bx0[p];
+            aos[4 * p + 1] = by0[p];
+            aos[4 * p + 2] = bex[p];
+            aos[4 * p + 3] = bey[p];
+        }
+        orc_neighbours(aos.data(), P, NX, NY, px, py, wc.data(), nullptr, nullptr, nullptr, nullptr);
+        int64_t woff[9] = { 0 };
+        for (int l = 0; l < 8; l++) {
+            int64_t tot = 0;
+            for (int p = 0; p < P; p++)
+                tot += wc[(size_t)l * P + p];
+            woff[l + 1] = woff[l] + tot;
+        }
+        std::vector<int32_t> wi(woff[8] + 1), wh(woff[8] + 1), ws(woff[8] + 1);
+        orc_neighbours(aos.data(), P, NX, NY, px, py, wc.data(), woff, wi.data(), wh.data(), ws.data());
+        // the device code: count, exclusive scan per list, fill
+        int cap = 1;
+        for (int l = 0; l < 8; l++)
+            cap = std::max<int>(cap, (int)(woff[l + 1] - woff[l]) + 8);
+        std::vector<int> gc(8 * (size_t)P, -1), goff(8 * ((size_t)P + 1), 0), gi(8 * (size_t)cap, -1), gh(8 * (size_t)cap, -1),
+            gs(8 * (size_t)cap, -1);
+        ddc::DevScalars sc {};
+        for (int l = 0; l < 8; l++)
+            for (int me = 0; me < P; me++)
+                ddc::neighbours_structured<false>(bx, P, NX, NY, px, py, st, l, me, gc.data(), nullptr, cap, nullptr, nullptr,
+                    nullptr, &sc);
+        bool ok = true;
+        int badl = -1, badp = -1, what = 0;
+        for (int l = 0; ok && l < 8; l++) {
+            int run = 0;
+            for (int me = 0; me < P; me++) {
+                goff[(size_t)l * (P + 1) + me] = run;
+                if (gc[(size_t)l * P + me] != wc[(size_t)l * P + me]) {
+                    ok = false;
+                    badl = l;
+                    badp = me;
+                    what = 1;
+                    break;
+                }
+                run += gc[(size_t)l * P + me];
+            }
+            goff[(size_t)l * (P + 1) + P] = run;
+        }
+        if (ok) {
+            for (int l = 0; l < 8; l++)
+                for (int me = 0; me < P; me++)
+                    ddc::neighbours_structured<true>(bx, P, NX, NY, px, py, st, l, me, gc.data(), goff.data(), cap, gi.data(),
+                        gh.data(), gs.data(), &sc);
+            unsigned long long cut = 0;
+            for (int l = 0; ok && l < 8; l++) {
+                const int n = (int)(woff[l + 1] - woff[l]);
+                for (int k = 0; k < n; k++) {
+                    const size_t g = (size_t)l * cap + k, w = (size_t)woff[l] + k;
+                    if (gi[g] != wi[w] || gh[g] != wh[w] || gs[g] != ws[w]) {
+                        ok = false;
+                        badl = l;
+                        badp = k;
+                        what = 2;
+                        break;
+                    }
+                    if (l < 4)
+                        cut += (unsigned long long)wh[w];
+                }
+            }
+            if (ok && cut != sc.edge_cut) {
+                ok = false;
+                what = 3;
+            }
+        }
+        checked += 8;
+        if (!ok) {
+            if (!mism) {
+                const long long b[6] = { NX, NY, P, badl, badp, what };
+                std::memcpy(bad, b, sizeof b);
+            }
+            mism++;
+        }
+    }
+    *lists_checked = checked;
     return mism;
 }
 }

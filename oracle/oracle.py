@@ -76,6 +76,9 @@ def median_emu_lib():
     L.emu_fuzz.argtypes = [C.c_uint64, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                            C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.emu_fuzz.restype = C.c_long
+    L.emu_fuzz_neighbours.argtypes = [C.c_uint64, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.emu_fuzz_neighbours.restype = C.c_long
     return L
 
 

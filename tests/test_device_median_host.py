@@ -59,3 +59,18 @@ def test_the_fuzz_sees_a_broken_guard(emu):
     """a division that is wrong by far more than the guard band allows must show up as mismatches"""
     m, n, bad = fuzz(emu, 5, 2000, 40, 3000, 4, 50000, True)
     assert m > 0
+
+
+@pytest.mark.parametrize("degenerate", [0, 1])
+@pytest.mark.parametrize("maxn,maxstrips,maxparts,cases", [(5, 6, 6, 20000), (12, 4, 4, 20000), (40, 8, 8, 10000),
+                                                             (300, 16, 24, 1500)])
+def test_device_neighbour_search_equals_oracle(emu, degenerate, maxn, maxstrips, maxparts, cases):
+    """K7's structured search (csrc/ddc_neighbours.cuh: one thread per (list, part), binary searches over the
+    x-sorted strips and the y-sorted parts) as host code against the oracle's literal O(P^2) discovery: counts,
+    ids, halo sizes, halo starts of all eight lists and the edge cut, on random tilings -- degenerate = 1 lets
+    boundaries coincide (zero-width strips, zero-height parts: more parts than non-empty columns / rows)"""
+    bad = (C.c_longlong * 10)()
+    n = C.c_longlong()
+    m = emu.emu_fuzz_neighbours(11 + degenerate, cases, maxn, maxstrips, maxparts, degenerate, bad, C.byref(n))
+    assert n.value == 8 * cases
+    assert m == 0, "first mismatch {NX, NY, P, list, part, what} = %s" % list(bad)[:6]
