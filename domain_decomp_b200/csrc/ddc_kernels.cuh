@@ -25,11 +25,20 @@
 // column x; rows are padded to NB = 16 * ceil(NX / 128) bytes so that every row is 16-byte aligned.
 // Columns >= NX read as land.
 #pragma once
+#ifndef DDC_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "ddc_median.cuh"
 #include "ddc_neighbours.cuh"
+
+// dynamic shared memory of a kernel (test builds: a buffer of the host emulation, see ddc_host_emu.h)
+#ifdef DDC_HOST_EMU
+#define DDC_DYN_SHARED(T, name) T* name = reinterpret_cast<T*>(ddc_emu_dyn_smem())
+#else
+#define DDC_DYN_SHARED(T, name) extern __shared__ __align__(16) T name[]
+#endif
 
 namespace ddc {
 
@@ -92,6 +101,7 @@ struct PeerPush { // where a producing kernel stores its histogram: dst[q] = MY 
     int n, rank;
     int packed; // column counts only: pushed as 16-bit values (every rank holds < 65536 rows)
 };
+#ifndef DDC_HOST_EMU
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;
@@ -125,6 +135,24 @@ __device__ __forceinline__ bool peer_wait(const PeerSync& ps, int stage, unsigne
     *seen = v;
     return true;
 }
+#else
+// test builds: the emulated ranks run phase by phase, a flag is either there or the test is wrong
+inline unsigned long long global_ns()
+{
+    static unsigned long long t = 0;
+    return t += 1000;
+}
+inline void peer_signal(const PeerSync& ps, int stage, unsigned bit)
+{
+    ps.flags[threadIdx.x][stage * MAX_PEERS + ps.rank] = 2u * ps.step + bit;
+}
+inline bool peer_wait(const PeerSync& ps, int stage, unsigned* seen)
+{
+    const unsigned v = ps.flags[ps.rank][stage * MAX_PEERS + threadIdx.x];
+    *seen = v;
+    return v >= 2u * ps.step;
+}
+#endif
 // Called by the first G threads of a block (thread q talks to rank q).  do_signal: exactly one
 // block per rank sends.
 __device__ __forceinline__ bool peer_barrier(const PeerSync& ps, int stage, unsigned bit, bool do_signal,
@@ -618,7 +646,7 @@ template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
     int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm)
 {
-    extern __shared__ __align__(16) unsigned smem_dyn[];
+    DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
     __shared__ int s_ix, s_iters;
     unsigned* pfx = SMEM ? smem_dyn : pfx_g;
@@ -853,7 +881,7 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     const int* __restrict__ st_x0, const int* __restrict__ st_p0, const Plan* __restrict__ plan, int Scap,
     PeerPush out, int Rmax)
 {
-    extern __shared__ int sm_scan[];
+    DDC_DYN_SHARED(int, sm_scan);
     if (plan->mismatch)
         return;
     static_assert(!FULL || K == 1, "FULL holds one row per warp in registers");
@@ -1047,7 +1075,7 @@ template <typename CT, bool SMEM>
 __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st,
     unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan)
 {
-    extern __shared__ __align__(16) unsigned smem_dyn[];
+    DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
     if (plan->mismatch)
         return;

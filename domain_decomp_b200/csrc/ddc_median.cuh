@@ -9,37 +9,7 @@
 #include <stddef.h>
 
 #ifdef DDC_HOST_EMU
-// ---- host stand-ins of the few device intrinsics used below (test builds only) -------------------
-#include <algorithm>
-#include <cmath>
-#include <cstring>
-#define __device__
-#define __host__
-#define __forceinline__ inline
-namespace ddc {
-using std::max;
-using std::min;
-inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
-inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
-// the device's fast division is accurate to 2 ulp: the harness perturbs the quotient by up to that much
-extern int g_fdividef_ulps;
-inline float __fdividef(float a, float b)
-{
-    float q = a / b;
-    if (g_fdividef_ulps && q > 0.0f && std::isfinite(q)) { // step the bit pattern: +-ulps units in the last place
-        int32_t bits;
-        std::memcpy(&bits, &q, 4);
-        bits += g_fdividef_ulps;
-        std::memcpy(&q, &bits, 4);
-    }
-    return q;
-}
-// correctly rounded double operations (the harness is compiled with -ffp-contract=off)
-inline double __dadd_rn(double a, double b) { return a + b; }
-inline double __dsub_rn(double a, double b) { return a - b; }
-inline double __dmul_rn(double a, double b) { return a * b; }
-inline double __ddiv_rn(double a, double b) { return a / b; }
-} // namespace ddc
+#include "ddc_host_emu.h" // host stand-ins of the device language (test builds only)
 #endif
 
 namespace ddc {

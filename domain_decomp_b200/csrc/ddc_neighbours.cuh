@@ -7,27 +7,7 @@
 #include <stdint.h>
 
 #ifdef DDC_HOST_EMU
-#include <algorithm>
-#ifndef __device__
-#define __device__
-#define __host__
-#define __forceinline__ inline
-#endif
-namespace ddc {
-using std::max;
-using std::min;
-// one "thread" at a time: lane 0 of a warp whose other lanes contribute nothing
-static struct {
-    unsigned x = 0;
-} threadIdx;
-inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long, int) { return 0ull; }
-inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
-{
-    const unsigned long long old = *p;
-    *p += v;
-    return old;
-}
-} // namespace ddc
+#include "ddc_host_emu.h" // host stand-ins of the device language (test builds only)
 #endif
 
 namespace ddc {

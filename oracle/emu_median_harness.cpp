@@ -19,9 +19,21 @@
 #include <cstring>
 #include <vector>
 
-namespace ddc {
-int g_fdividef_ulps = 0;
+// the execution model of a single "thread": no block, no warp
+int ddc_emu_fdividef_ulps = 0;
+ddc_emu_dim threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 }, blockDim = { 1, 1, 1 }, gridDim = { 1, 1, 1 };
+void __syncthreads() { }
+int __syncthreads_or(int p) { return p; }
+const unsigned long long* ddc_emu_warp_gather(unsigned, unsigned long long v, unsigned* present)
+{
+    static unsigned long long lanes[32];
+    for (auto& l : lanes)
+        l = 0ull; // the other lanes of the warp contribute nothing
+    lanes[0] = v;
+    *present = 1u;
+    return lanes;
 }
+void* ddc_emu_dyn_smem() { return nullptr; }
 
 extern "C" int orc_median_boundary(const int64_t* pfx, int n, int c0, int c1, int nlo, int num_parts, long* iters);
 extern "C" void orc_neighbours(const int32_t* boxes, int P, int NX, int NY, int px, int py, int32_t* counts,
@@ -148,7 +160,7 @@ extern "C" {
 __attribute__((visibility("default"))) long emu_fuzz(uint64_t seed, long histograms, int queries, int nmax, int shape,
     int ulps, int use_bitmap, long long* bad, long long* medians_checked)
 {
-    ddc::g_fdividef_ulps = ulps;
+    ddc_emu_fdividef_ulps = ulps;
     Rng r { seed * 0x2545F4914F6CDD1Dull + 1 };
     long mism = 0;
     long long checked = 0;
