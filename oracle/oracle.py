@@ -26,7 +26,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "ddc_oracle.c")
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_oracle.so"])
-    subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_median_emu.so"])  # make decides what is stale
+    subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_median_emu.so", "libddc_emu.so"])  # make decides what is stale
     if os.path.isdir("/root/reference"):  # make decides what is stale
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"] + (["-B"] if force else []))
     return _LIB
@@ -80,6 +80,51 @@ def median_emu_lib():
                                       C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.emu_fuzz_neighbours.restype = C.c_long
     return L
+
+
+_emu = None
+
+
+def emu_partition(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, ranks: int = 1, strip_k: int = 0,
+                  scan_rpc: int = 0, smem_limit: int = 0):
+    """One decomposition through the product's REAL kernels on the host emulation of the CUDA execution model
+    (oracle/emu/), on `ranks` emulated row-sharded ranks.  Returns (Decomposition, info dict)."""
+    global _emu
+    if _emu is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "libddc_emu.so"))
+        i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+        L.emu_partition.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    i32p, i32p, i32p, i32p, C.c_long, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
+        L.emu_partition.restype = C.c_int
+        L.emu_last_error.restype = C.c_char_p
+        _emu = L
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    ny, nx = mask.shape
+    boxes = np.zeros((P, 4), dtype=np.int32)
+    pid = np.zeros((ny, nx), dtype=np.int32)
+    counts = np.zeros(8 * P, dtype=np.int32)
+    cap = 8 * (3 * P + 64)
+    flat = np.zeros(3 * cap, dtype=np.int32)
+    out = np.zeros(8, dtype=np.int64)
+    rc = _emu.emu_partition(mask, nx, ny, P, int(px), int(py), ranks, strip_k, scan_rpc, smem_limit, boxes, pid, counts, flat,
+                            cap, out)
+    if rc != 0:
+        raise RuntimeError("emu_partition: " + _emu.emu_last_error().decode())
+    c = counts.reshape(2, 4, P)
+    totals = counts.reshape(8, P).sum(axis=1)
+    off = np.concatenate([[0], np.cumsum(totals)])
+    sl = lambda k, l: flat[k * cap + off[l]:k * cap + off[l + 1]].copy()
+    nbr = Neighbours(
+        counts=[[c[per, e].copy() for e in range(4)] for per in range(2)],
+        ids=[[sl(0, per * 4 + e) for e in range(4)] for per in range(2)],
+        halos=[[sl(1, per * 4 + e) for e in range(4)] for per in range(2)],
+        starts=[[sl(2, per * 4 + e) for e in range(4)] for per in range(2)],
+    )
+    d = Decomposition(NX=nx, NY=ny, P=P, boxes=boxes, pid=pid, changes=int(out[0]), median_iters=int(out[1]), nbr=nbr)
+    info = dict(n_ocean=int(out[2]), strips=int(out[3]), x_levels=int(out[4]), y_levels=int(out[5]), load_min=int(out[6]),
+                load_max=int(out[7]))
+    return d, info
 
 
 _ref_host = None

@@ -1,0 +1,130 @@
+"""The product's REAL kernels on a machine without a GPU.
+
+oracle/emu/ compiles domain_decomp_b200/csrc/ddc_kernels.cuh as host C++ (-DDDC_HOST_EMU) and runs it on an
+emulation of the CUDA execution model: every thread of a block is a fiber, __syncthreads and the warp
+collectives are rendezvous between fibers, blocks run one after the other; emu_pipeline.cpp launches the
+kernels in the order and with the grids / buffers of ddc_api.cu, for G emulated ranks that exchange their
+histograms through each other's slots exactly as over NVLink.  Whole decompositions of small masks are
+compared with the oracle, bit for bit: boxes, pid, the eight neighbour tables, `changes`, the median
+iteration count.  (The GPU suite checks the same on the device up to 10^9 cells; this suite keeps the kernel
+LOGIC under test in every CPU-only run -- every kernel, both exchange layouts, every variant of the strip
+row-count kernel, the global-memory prefix paths -- and says nothing about speed.)"""
+import numpy as np
+import pytest
+
+from conftest import golden_mask
+
+
+def assert_same(d, o, ctx=""):
+    assert d.boxes.tolist() == o.boxes.tolist(), ctx
+    assert np.array_equal(d.pid, o.pid), ctx
+    assert d.changes == o.changes, ctx
+    assert d.median_iters == o.median_iters, ctx
+    for per in range(2):
+        for e in range(4):
+            assert d.nbr.counts[per][e].tolist() == o.nbr.counts[per][e].tolist(), (ctx, per, e)
+            assert d.nbr.ids[per][e].tolist() == o.nbr.ids[per][e].tolist(), (ctx, per, e)
+            assert d.nbr.halos[per][e].tolist() == o.nbr.halos[per][e].tolist(), (ctx, per, e)
+            assert d.nbr.starts[per][e].tolist() == o.nbr.starts[per][e].tolist(), (ctx, per, e)
+
+
+def test_box_known_answers(goldens, oracle):
+    """the reference's bounding-box known-answer tests (test_zoltan_partitioner_{0,1,2}.cpp) through the kernels"""
+    for kat in goldens["box_kats"]:
+        d, _ = oracle.emu_partition(golden_mask(goldens, kat["input"]), kat["P"])
+        assert d.boxes.tolist() == kat["boxes"], kat["cite"]
+
+
+@pytest.mark.parametrize("case", ["test_1", "test_2", "test_1_px", "test_1_py", "test_1_px_py"])
+def test_integration_goldens(goldens, oracle, case):
+    G = goldens["integration"][case]
+    mask = golden_mask(goldens, G["input"])
+    md = G["metadata"]
+    for ranks in (1, 2):
+        d, _ = oracle.emu_partition(mask, G["P"], bool(G["px"]), bool(G["py"]), ranks=ranks)
+        assert d.pid.ravel().tolist() == list(G["pid"])
+        assert d.boxes[:, 0].tolist() == md["domain_x"] and d.boxes[:, 2].tolist() == md["domain_extent_x"]
+        assert d.boxes[:, 1].tolist() == md["domain_y"] and d.boxes[:, 3].tolist() == md["domain_extent_y"]
+        for per, sfx in ((0, ""), (1, "_periodic")):
+            for e, name in enumerate(("left", "right", "bottom", "top")):
+                assert d.nbr.counts[per][e].tolist() == md[name + "_neighbours" + sfx]
+                assert d.nbr.ids[per][e].tolist() == md.get(name + "_neighbour_ids" + sfx, [])
+                assert d.nbr.halos[per][e].tolist() == md.get(name + "_neighbour_halos" + sfx, [])
+                assert d.nbr.starts[per][e].tolist() == md.get(name + "_neighbour_halo_starts" + sfx, [])
+
+
+def test_rect3030(goldens, oracle):
+    mask = golden_mask(goldens, "rect3030")
+    for P in (2, 4):
+        d, _ = oracle.emu_partition(mask, P)
+        assert_same(d, oracle.partition(mask, P, use_hist=True), "rect3030 P=%d" % P)
+
+
+def test_random_small_masks_one_rank(oracle):
+    """ragged widths (the scalar load / store paths), empty rows and columns, P not a power of two, P > columns"""
+    rng = np.random.default_rng(101)
+    for i in range(14):
+        nx, ny = int(rng.integers(1, 70)), int(rng.integers(1, 50))
+        P = int(rng.integers(1, 20))
+        mask = (rng.random((ny, nx)) >= rng.random() * 0.9).astype(np.int32) * int(rng.integers(1, 4))
+        if i % 5 == 0:
+            mask[:, : nx // 2] = 0
+        px, py = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        d, _ = oracle.emu_partition(mask, P, px, py)
+        assert_same(d, oracle.partition(mask, P, px, py, use_hist=True), (nx, ny, P, px, py))
+
+
+def test_nothing_moved_and_all_land(oracle):
+    """`changes == 0`: the naive blocks are reported and the neighbour tables are rebuilt from them in K5"""
+    for (n, P) in [(64, 4), (60, 6)]:
+        m = np.ones((n, n), dtype=np.int32)
+        d, _ = oracle.emu_partition(m, P, True, True)
+        o = oracle.partition(m, P, True, True, use_hist=True)
+        assert o.changes == 0
+        assert_same(d, o, (n, P))
+    m = np.zeros((12, 18), dtype=np.int32)
+    d, _ = oracle.emu_partition(m, 6)
+    assert_same(d, oracle.partition(m, 6, use_hist=True), "all land")
+
+
+@pytest.mark.parametrize("ranks", [2, 3, 5])
+def test_row_sharded_ranks_exchange_through_their_slots(oracle, ranks):
+    """G emulated ranks: column counts pushed by the last CTA of a column block (16-bit), strip row counts pushed as
+    chunks, `changes` in the flag; a rank without rows (5 ranks, 4 rows) still pushes and signals"""
+    from domain_decomp_b200 import capi
+    cases = [(capi.generate_mask_host(130, 77, 7, 0.5), 12, True, False), (capi.generate_mask_host(64, 4, 2, 0.3), 8, False, False),
+             (np.ones((24, 24), dtype=np.int32), 4, False, True)]
+    for mask, P, px, py in cases:
+        d, _ = oracle.emu_partition(mask, P, px, py, ranks=ranks)
+        assert_same(d, oracle.partition(mask, P, px, py, use_hist=True), (mask.shape, P, ranks))
+
+
+@pytest.mark.parametrize("strip_k", [1, 2, 4, 8, 16])
+def test_strip_row_count_kernel_variants(oracle, strip_k):
+    """rows per warp 1 / 2 / 4, whole row in registers (8), and the kernel for tables beyond shared memory (16)"""
+    from domain_decomp_b200 import capi
+    mask = capi.generate_mask_host(300, 90, 11, 0.45)
+    for ranks in (1, 2):
+        d, _ = oracle.emu_partition(mask, 24, True, False, ranks=ranks, strip_k=strip_k)
+        assert_same(d, oracle.partition(mask, 24, True, False, use_hist=True), (strip_k, ranks))
+
+
+def test_cut_kernels_with_histograms_in_global_memory(oracle):
+    """a shared-memory limit of a few KB forces K2 / K4 onto their global-memory prefix path (no bit map of
+    non-empty bins: binary searches over the prefix sums), as for grids beyond ~55000 columns or rows"""
+    from domain_decomp_b200 import capi
+    mask = capi.generate_mask_host(200, 150, 5, 0.5)
+    for ranks in (1, 2):
+        d, _ = oracle.emu_partition(mask, 16, False, True, ranks=ranks, smem_limit=2048)
+        assert_same(d, oracle.partition(mask, 16, False, True, use_hist=True), ranks)
+
+
+def test_scan_rows_per_cta(oracle):
+    """the mask scan with 8 ... 128 rows per CTA (the host picks by occupancy): several staged flushes per CTA,
+    a last CTA with fewer rows, more than one CTA per column block counting down to the push"""
+    from domain_decomp_b200 import capi
+    mask = capi.generate_mask_host(140, 203, 9, 0.4)
+    o = oracle.partition(mask, 10, use_hist=True)
+    for rpc in (8, 24, 128):
+        d, _ = oracle.emu_partition(mask, 10, ranks=2, scan_rpc=rpc)
+        assert_same(d, o, rpc)
