@@ -278,13 +278,15 @@ __device__ inline unsigned long long block_prefix(F src, int n, unsigned* dst, i
 // data written by other GPUs has to bypass L1, each line crossed the L2 interface 8 times).  The 8
 // sub-tile scans run side by side: 8 independent shuffle chains per thread, then warp q scans the
 // 32 warp totals of sub-tile q.
-// load4(i) returns elements i .. i + 3 (0 beyond n), i a multiple of 4; dst may be shared or global
+// load_tile(base, v) fills v[q] with elements base + q * 4096 .. + 3 (0 beyond n) for the 8 sub-tiles q, base
+// a multiple of 4 -- all of a thread's loads are requested in ONE call, so that a loader that has to visit
+// several buffers can keep 8 independent loads in flight per buffer; dst may be shared or global
 // memory.  bitmap != nullptr: also writes the three-level bit map of the non-empty elements,
 // l0 / l1 / l2 = bitmap + 0 / tiles * 1024 / tiles * (1024 + 32).   ws: >= 8 * 32 + 8 words.
 constexpr int PFX_Q = 8; // sub-tiles of a tile
 constexpr int PFX_WS = PFX_Q * 32 + PFX_Q;
 template <typename F>
-__device__ inline unsigned block_prefix_tiles(F load4, int n, unsigned* dst, unsigned* ws, unsigned* bitmap = nullptr)
+__device__ inline unsigned block_prefix_tiles(F load_tile, int n, unsigned* dst, unsigned* ws, unsigned* bitmap = nullptr)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles = (n + HIST_TILE - 1) / HIST_TILE;
@@ -293,11 +295,7 @@ __device__ inline unsigned block_prefix_tiles(F load4, int n, unsigned* dst, uns
         const int base = t * HIST_TILE + tid * 4;
         uint4 v[PFX_Q];
         unsigned s[PFX_Q], inc[PFX_Q];
-#pragma unroll
-        for (int q = 0; q < PFX_Q; q++) {
-            const int i = base + q * 4096;
-            v[q] = i < n ? load4(i) : make_uint4(0u, 0u, 0u, 0u);
-        }
+        load_tile(base, v);
 #pragma unroll
         for (int q = 0; q < PFX_Q; q++)
             inc[q] = s[q] = v[q].x + v[q].y + v[q].z + v[q].w;
@@ -600,44 +598,56 @@ __device__ __forceinline__ int walk_lanes(int leaves, int threads)
 // ------------------------------------------------------------------------------------------------
 // K2: column prefix sums, preset directions, all x levels, strip table
 // ------------------------------------------------------------------------------------------------
-// 4 consecutive column counts summed over the ranks' slots (one buffer when the counts are already
-// global); one 16-byte load per slot when the chunk is whole and aligned.  ld.global.cg: the slots of
-// the other ranks are written by other GPUs.
-__device__ __forceinline__ uint4 load_counts4(const PeerCols& pc, int i, int n)
+// The column counts of one thread's tile -- 4 consecutive counts in each of the 8 sub-tiles -- summed over the
+// ranks' slots (one buffer when the counts are already global).  Slot by slot: the 8 loads of a slot are
+// independent and requested together, so that summing G slots costs G L2 round trips, not 8 G (with the
+// per-slot loop inside each sub-tile load K2 spent 24 us here on 8 GPUs).  One 16-byte load per slot and
+// sub-tile when the chunk is whole and aligned (8 bytes for 16-bit slots).  ld.global.cg: the slots of the
+// other ranks are written by other GPUs.
+__device__ __forceinline__ uint4 load_slot4(const PeerCols& pc, int g, int i, int n)
 {
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    for (int g = 0; g < pc.n; g++) {
-        if (pc.packed && g != pc.own) {
-            const uint16_t* src = reinterpret_cast<const uint16_t*>(pc.col[g]) + i;
-            if (i + 4 <= n && ((uintptr_t)src & 7) == 0) {
-                const uint2 t = __ldcg(reinterpret_cast<const uint2*>(src));
-                v.x += t.x & 0xffffu;
-                v.y += t.x >> 16;
-                v.z += t.y & 0xffffu;
-                v.w += t.y >> 16;
-            } else {
-                v.x += i < n ? (unsigned)__ldcg(src) : 0u;
-                v.y += i + 1 < n ? (unsigned)__ldcg(src + 1) : 0u;
-                v.z += i + 2 < n ? (unsigned)__ldcg(src + 2) : 0u;
-                v.w += i + 3 < n ? (unsigned)__ldcg(src + 3) : 0u;
-            }
-            continue;
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (i >= n)
+        return t;
+    if (pc.packed && g != pc.own) {
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(pc.col[g]) + i;
+        if (i + 4 <= n && ((uintptr_t)src & 7) == 0) {
+            const uint2 u = __ldcg(reinterpret_cast<const uint2*>(src));
+            return make_uint4(u.x & 0xffffu, u.x >> 16, u.y & 0xffffu, u.y >> 16);
         }
-        const unsigned* src = pc.col[g] + i;
-        if (i + 4 <= n && ((uintptr_t)src & 15) == 0) {
-            const uint4 t = __ldcg(reinterpret_cast<const uint4*>(src));
-            v.x += t.x;
-            v.y += t.y;
-            v.z += t.z;
-            v.w += t.w;
-        } else {
-            v.x += i < n ? __ldcg(src) : 0u;
-            v.y += i + 1 < n ? __ldcg(src + 1) : 0u;
-            v.z += i + 2 < n ? __ldcg(src + 2) : 0u;
-            v.w += i + 3 < n ? __ldcg(src + 3) : 0u;
+        t.x = (unsigned)__ldcg(src);
+        t.y = i + 1 < n ? (unsigned)__ldcg(src + 1) : 0u;
+        t.z = i + 2 < n ? (unsigned)__ldcg(src + 2) : 0u;
+        t.w = i + 3 < n ? (unsigned)__ldcg(src + 3) : 0u;
+        return t;
+    }
+    const unsigned* src = pc.col[g] + i;
+    if (i + 4 <= n && ((uintptr_t)src & 15) == 0)
+        return __ldcg(reinterpret_cast<const uint4*>(src));
+    t.x = __ldcg(src);
+    t.y = i + 1 < n ? __ldcg(src + 1) : 0u;
+    t.z = i + 2 < n ? __ldcg(src + 2) : 0u;
+    t.w = i + 3 < n ? __ldcg(src + 3) : 0u;
+    return t;
+}
+__device__ __forceinline__ void load_counts_tile(const PeerCols& pc, int base, int n, uint4 (&v)[PFX_Q])
+{
+#pragma unroll
+    for (int q = 0; q < PFX_Q; q++)
+        v[q] = make_uint4(0u, 0u, 0u, 0u);
+    for (int g = 0; g < pc.n; g++) {
+        uint4 t[PFX_Q];
+#pragma unroll
+        for (int q = 0; q < PFX_Q; q++)
+            t[q] = load_slot4(pc, g, base + q * 4096, n);
+#pragma unroll
+        for (int q = 0; q < PFX_Q; q++) {
+            v[q].x += t[q].x;
+            v[q].y += t[q].y;
+            v[q].z += t[q].z;
+            v[q].w += t[q].w;
         }
     }
-    return v;
 }
 
 // dynamic shared memory when SMEM: (NX + 1) unsigned, rounded up to 4, + hist_bitmap_words(NX).
@@ -671,7 +681,7 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     if (tid == 0)
         plan->ts[1] = global_ns();
     unsigned* bitmap = SMEM ? smem_dyn + (((size_t)NX + 1 + 3) & ~(size_t)3) : nullptr;
-    block_prefix_tiles([&](int i) { return load_counts4(pc, i, NX); }, NX, pfx, wsum, bitmap);
+    block_prefix_tiles([&](int base, uint4 (&v)[PFX_Q]) { load_counts_tile(pc, base, NX, v); }, NX, pfx, wsum, bitmap);
     if (tid == 0)
         plan->ts[2] = global_ns();
     const Hist H = make_hist(pfx, bitmap, NX);
@@ -1110,7 +1120,14 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
             continue; // K2 already wrote the box of a leaf strip
         __syncthreads(); // previous strip done with pfx
         block_prefix_tiles(
-            [&](int i) { return load_row_counts4<CT>(pr, rl, s, i, NY); }, NY, pfx, wsum, bitmap);
+            [&](int base, uint4 (&v)[PFX_Q]) {
+#pragma unroll
+                for (int q = 0; q < PFX_Q; q++) {
+                    const int i = base + q * 4096;
+                    v[q] = i < NY ? load_row_counts4<CT>(pr, rl, s, i, NY) : make_uint4(0u, 0u, 0u, 0u);
+                }
+            },
+            NY, pfx, wsum, bitmap);
         if (blockIdx.x == 0 && tid == 0)
             plan->ts[8] = global_ns();
         // a group of `lanes` threads walks to the j-th part of the strip (parts come out y-sorted)

@@ -15,6 +15,7 @@
 // GPU (a barrier some live threads never reach) is reported instead of hanging.
 #include "cuda_emu.h"
 
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <cstdio>
@@ -41,16 +42,20 @@ struct Warp {
     unsigned long done_gen = 0, gen = 1;
 };
 
+// A fiber is entered the first time through its ucontext (that is what puts it on its own stack); every later
+// switch is _setjmp / _longjmp, which -- unlike swapcontext -- makes no system call to save the signal mask.
 struct Fiber {
     ucontext_t ctx;
+    jmp_buf jb;
     ddc_emu_dim tid;
-    bool done = false;
+    bool started = false, done = false;
 };
 
 struct BlockState {
     std::vector<Fiber> fibers;
     std::vector<Warp> warps;
     ucontext_t sched;
+    jmp_buf sched_jb;
     int current = -1;
     int alive = 0;
     // block barrier
@@ -70,7 +75,22 @@ void yield()
 {
     BlockState& b = *g_blk;
     Fiber& f = b.fibers[b.current];
-    swapcontext(&f.ctx, &b.sched);
+    if (!_setjmp(f.jb))
+        _longjmp(b.sched_jb, 1);
+}
+// scheduler side: run fiber t until it yields or returns
+void resume(BlockState& b, int t)
+{
+    Fiber& f = b.fibers[t];
+    b.current = t;
+    threadIdx = f.tid;
+    if (!_setjmp(b.sched_jb)) {
+        if (!f.started) {
+            f.started = true;
+            setcontext(&f.ctx);
+        } else
+            _longjmp(f.jb, 1);
+    }
 }
 
 int linear_tid() { return (int)(threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y); }
@@ -100,7 +120,7 @@ void fiber_main()
     w.alive &= ~(1u << (t & 31));
     release_barrier_if_complete(b);
     b.progress++;
-    swapcontext(&f.ctx, &b.sched);
+    _longjmp(b.sched_jb, 1);
 }
 } // namespace
 
@@ -211,9 +231,7 @@ bool launch(Dim3 grid, Dim3 block, size_t dyn_smem, const std::function<void()>&
                         Fiber& f = b.fibers[t];
                         if (f.done)
                             continue;
-                        b.current = t;
-                        threadIdx = f.tid;
-                        swapcontext(&b.sched, &f.ctx);
+                        resume(b, t);
                         ran = true;
                         if (f.done)
                             remaining--;
@@ -225,9 +243,7 @@ bool launch(Dim3 grid, Dim3 block, size_t dyn_smem, const std::function<void()>&
                             Fiber& f = b.fibers[t];
                             if (f.done)
                                 continue;
-                            b.current = t;
-                            threadIdx = f.tid;
-                            swapcontext(&b.sched, &f.ctx);
+                            resume(b, t);
                             if (f.done)
                                 remaining--;
                         }

@@ -128,3 +128,16 @@ def test_scan_rows_per_cta(oracle):
     for rpc in (8, 24, 128):
         d, _ = oracle.emu_partition(mask, 10, ranks=2, scan_rpc=rpc)
         assert_same(d, o, rpc)
+
+
+@pytest.mark.parametrize("nx,ny,P,ranks,kw", [(9000, 6, 5, 2, {}), (33000, 3, 4, 2, {}), (33000, 3, 4, 1, {}),
+                                              (5000, 9, 6, 3, {"smem_limit": 2048}), (70, 9000, 6, 2, {}),
+                                              (40, 33000, 5, 2, {})])
+def test_histograms_of_several_sub_tiles_and_tiles(oracle, nx, ny, P, ranks, kw):
+    """the prefix scan of the cut kernels: a thread owns 4 bins in each of 8 sub-tiles of 4096, a tile is 32768
+    bins -- histograms of 5000 ... 33000 bins reach the later sub-tiles and the second tile, with the slots of
+    several ranks summed in the loader"""
+    from domain_decomp_b200 import capi
+    mask = capi.generate_mask_host(nx, ny, 5, 0.4)
+    d, _ = oracle.emu_partition(mask, P, True, False, ranks=ranks, **kw)
+    assert_same(d, oracle.partition(mask, P, True, False, use_hist=True), (nx, ny, P, ranks))
