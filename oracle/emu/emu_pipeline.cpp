@@ -14,6 +14,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -357,6 +358,11 @@ __attribute__((visibility("default"))) int emu_partition(const int32_t* mask, in
     long nbr_cap, long long* out)
 {
     g_err.clear();
+    if (std::getenv("DDC_EMU_OOB_SELFTEST")) { // proves that an AddressSanitizer build of this library is live
+        std::vector<int> v(4);
+        volatile int* q = v.data();
+        q[4] = 1;
+    }
     if (G < 1 || G > MAX_PEERS || NX < 1 || NY < 1 || P < 1) {
         g_err = "bad arguments";
         return -1;
