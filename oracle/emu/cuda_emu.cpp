@@ -10,7 +10,10 @@
 //     32 values are published and every lane reads what its intrinsic needs;
 //   * `__shared__` variables are function-local statics (one block runs at a time), dynamic shared memory is
 //     one aligned buffer;
-//   * blocks of a grid run one after the other, in x-fastest order.
+//   * blocks of a grid run one after the other, in x-fastest order -- or, with set_schedule_seed(), blocks in a
+//     random order and the threads of a block in a new random order every scheduling round: a kernel whose
+//     result depends on the interleaving (a missing barrier, an assumption about block order) then gives
+//     different results for different seeds.
 // Divergence needs no modelling: every fiber simply executes its own path.  A kernel that would deadlock on a
 // GPU (a barrier some live threads never reach) is reported instead of hanging.
 #include "cuda_emu.h"
@@ -67,6 +70,19 @@ struct BlockState {
 };
 
 BlockState* g_blk = nullptr;
+unsigned long long g_sched_seed = 0; // 0: threads and blocks in index order; else: a different random order every round
+unsigned long long sched_rand()
+{
+    g_sched_seed ^= g_sched_seed << 13;
+    g_sched_seed ^= g_sched_seed >> 7;
+    g_sched_seed ^= g_sched_seed << 17;
+    return g_sched_seed;
+}
+void shuffle(std::vector<int>& v)
+{
+    for (size_t i = v.size(); i > 1; i--)
+        std::swap(v[i - 1], v[sched_rand() % i]);
+}
 std::vector<char> g_stacks; // fibers * STACK_BYTES, reused by every launch
 alignas(64) char g_dyn_smem[DYN_SMEM_BYTES];
 std::string g_error;
@@ -187,6 +203,7 @@ void* ddc_emu_dyn_smem() { return g_dyn_smem; }
 namespace cuda_emu {
 
 const char* last_error() { return g_error.c_str(); }
+void set_schedule_seed(unsigned long long seed) { g_sched_seed = seed; }
 
 bool launch(Dim3 grid, Dim3 block, size_t dyn_smem, const std::function<void()>& body)
 {
@@ -202,9 +219,16 @@ bool launch(Dim3 grid, Dim3 block, size_t dyn_smem, const std::function<void()>&
     BlockState b;
     b.body = &body;
     g_blk = &b;
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++) {
+    std::vector<int> block_order((size_t)grid.x * grid.y * grid.z), thread_order((size_t)nthreads);
+    for (size_t i = 0; i < block_order.size(); i++)
+        block_order[i] = (int)i;
+    for (int t = 0; t < nthreads; t++)
+        thread_order[t] = t;
+    if (g_sched_seed)
+        shuffle(block_order);
+    for (int blk : block_order) {
+                const unsigned bx = (unsigned)blk % grid.x, by = ((unsigned)blk / grid.x) % grid.y,
+                               bz = (unsigned)blk / (grid.x * grid.y);
                 blockIdx = { bx, by, bz };
                 b.fibers.assign((size_t)nthreads, Fiber());
                 b.warps.assign((size_t)(nthreads + 31) / 32, Warp());
@@ -227,7 +251,9 @@ bool launch(Dim3 grid, Dim3 block, size_t dyn_smem, const std::function<void()>&
                 while (remaining > 0) {
                     const unsigned long before = b.progress;
                     bool ran = false;
-                    for (int t = 0; t < nthreads; t++) {
+                    if (g_sched_seed)
+                        shuffle(thread_order);
+                    for (int t : thread_order) {
                         Fiber& f = b.fibers[t];
                         if (f.done)
                             continue;
@@ -239,7 +265,7 @@ bool launch(Dim3 grid, Dim3 block, size_t dyn_smem, const std::function<void()>&
                     if (ran && remaining > 0 && b.progress == before) {
                         // second chance: a round in which fibers only re-checked their conditions
                         const unsigned long again = b.progress;
-                        for (int t = 0; t < nthreads; t++) {
+                        for (int t : thread_order) {
                             Fiber& f = b.fibers[t];
                             if (f.done)
                                 continue;

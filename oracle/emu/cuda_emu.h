@@ -24,4 +24,6 @@ struct Dim3 {
 // false: the launch was refused or deadlocked (last_error() says why)
 bool launch(Dim3 grid, Dim3 block, size_t dyn_smem, const std::function<void()>& body);
 const char* last_error();
+// 0 (default): deterministic index order; otherwise blocks and threads are scheduled in seeded random orders
+void set_schedule_seed(unsigned long long seed);
 } // namespace cuda_emu

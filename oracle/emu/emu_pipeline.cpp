@@ -363,6 +363,10 @@ __attribute__((visibility("default"))) int emu_partition(const int32_t* mask, in
         volatile int* q = v.data();
         q[4] = 1;
     }
+    if (const char* e = std::getenv("DDC_EMU_SCHED_SEED")) // random block / thread schedules (race shaking)
+        cuda_emu::set_schedule_seed(std::strtoull(e, nullptr, 10));
+    else
+        cuda_emu::set_schedule_seed(0);
     if (G < 1 || G > MAX_PEERS || NX < 1 || NY < 1 || P < 1) {
         g_err = "bad arguments";
         return -1;

@@ -141,3 +141,19 @@ def test_histograms_of_several_sub_tiles_and_tiles(oracle, nx, ny, P, ranks, kw)
     mask = capi.generate_mask_host(nx, ny, 5, 0.4)
     d, _ = oracle.emu_partition(mask, P, True, False, ranks=ranks, **kw)
     assert_same(d, oracle.partition(mask, P, True, False, use_hist=True), (nx, ny, P, ranks))
+
+
+def test_results_do_not_depend_on_the_schedule(oracle, monkeypatch):
+    """the emulation can run the blocks of a grid in a random order and the threads of a block in a new random order
+    every scheduling round (DDC_EMU_SCHED_SEED): a missing barrier, an assumption about block order or about
+    which CTA of a column block finishes last would make results differ between seeds"""
+    from domain_decomp_b200 import capi
+    cases = [(capi.generate_mask_host(130, 77, 7, 0.5), 12, True, False, 2), (capi.generate_mask_host(67, 90, 3, 0.4), 9, False, True, 3),
+             (np.ones((24, 24), dtype=np.int32), 4, True, True, 1)]
+    for mask, P, px, py, ranks in cases:
+        o = oracle.partition(mask, P, px, py, use_hist=True)
+        for seed in (1, 2, 3, 99991, 2 ** 40 + 7):
+            monkeypatch.setenv("DDC_EMU_SCHED_SEED", str(seed))
+            d, _ = oracle.emu_partition(mask, P, px, py, ranks=ranks, scan_rpc=16)
+            assert_same(d, o, (mask.shape, P, ranks, seed))
+    monkeypatch.delenv("DDC_EMU_SCHED_SEED")
