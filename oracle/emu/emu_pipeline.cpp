@@ -90,7 +90,7 @@ struct Options {
 };
 
 bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int aix, int aiy, unsigned step,
-    const Options& opt)
+    const Options& opt, int cap)
 {
     const int G = (int)R.size();
     const int NG = (NX + 127) / 128, NB = NG * 16;
@@ -109,7 +109,6 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const int gridx = (NG + 7) / 8;
     const NaiveParams nv = naive_params(P, NX, NY);
     const int par = (int)(step & 1u);
-    const int cap = 3 * P + 64;
     const bool want_nbr = P > 1;
 
     auto tables = [&](Rank& r, StripTable& st, BoxTable& bx) {
@@ -396,11 +395,19 @@ __attribute__((visibility("default"))) int emu_partition(const int32_t* mask, in
     int aix, aiy;
     guess_plan(P, NX, NY, &aix, &aiy);
     unsigned step = 0;
+    int cap = 3 * P + 64; // entries per neighbour list, as the product sizes them
     for (int attempt = 0;; attempt++) {
         step++;
-        if (!run_step(R, NX, NY, P, px, py, aix, aiy, step, opt))
+        if (!run_step(R, NX, NY, P, px, py, aix, aiy, step, opt, cap))
             return -1;
         const Plan& pl = R[0].host_plan;
+        if (!pl.mismatch && R[0].sc.overflow && attempt < 4) {
+            // the bounded lists overflowed (tiny grids cut into many empty parts): the product re-runs the fill
+            // pass with the exact capacity (fetch_totals), the emulation re-runs the step
+            for (int l = 0; l < 8; l++)
+                cap = std::max(cap, R[0].nbr_totals[l] + 1);
+            continue;
+        }
         if (!pl.mismatch)
             break;
         if (pl.mismatch == 3 || attempt >= 2) {
@@ -425,7 +432,6 @@ __attribute__((visibility("default"))) int emu_partition(const int32_t* mask, in
     for (int g = 0; g < G; g++)
         if (R[g].rows > 0)
             std::memcpy(pid + (size_t)R[g].y_begin * NX, R[g].pid.data(), sizeof(int32_t) * (size_t)R[g].rows * NX);
-    const int cap = 3 * P + 64;
     std::memset(nbr_counts, 0, sizeof(int32_t) * 8 * (size_t)P);
     long pos = 0;
     if (P > 1) {

@@ -104,7 +104,7 @@ def emu_partition(mask: np.ndarray, P: int, px: bool = False, py: bool = False, 
     boxes = np.zeros((P, 4), dtype=np.int32)
     pid = np.zeros((ny, nx), dtype=np.int32)
     counts = np.zeros(8 * P, dtype=np.int32)
-    cap = 8 * (3 * P + 64)
+    cap = 8 * (3 * P + 64) + 16 * P * P  # every part can list every other one
     flat = np.zeros(3 * cap, dtype=np.int32)
     out = np.zeros(8, dtype=np.int64)
     rc = _emu.emu_partition(mask, nx, ny, P, int(px), int(py), ranks, strip_k, scan_rpc, smem_limit, boxes, pid, counts, flat,
