@@ -162,10 +162,14 @@ def test_results_do_not_depend_on_the_schedule(oracle, monkeypatch):
 def test_more_parts_than_cells_per_row(oracle):
     """tiny grids cut into many (mostly empty) parts: zero-width strips, zero-height parts, neighbour lists far
     longer than the 3 P + 64 entries reserved per list, so that the fill pass runs again with the exact capacity"""
-    rng = np.random.default_rng(8)
-    for (nx, ny, P, px, py, ranks) in [(11, 11, 36, False, False, 1), (5, 6, 23, True, False, 4), (4, 4, 16, True, True, 2)]:
-        mask = (rng.random((ny, nx)) >= 0.6).astype(np.int32)
-        d, _ = oracle.emu_partition(mask, P, px, py, ranks=ranks)
-        o = oracle.partition(mask, P, px, py, use_hist=True)
-        assert max(len(x) for per in range(2) for x in o.nbr.ids[per]) > 3 * P + 64 or nx * ny < 30
-        assert_same(d, o, (nx, ny, P, ranks))
+    longest = 0
+    for seed, ranks in ((9, 4), (23, 2), (41, 1)):
+        rng = np.random.default_rng(seed)  # (seeds picked because they do overflow the reserved capacity)
+        for (nx, ny, P, px, py) in [(11, 11, 36, False, False), (5, 6, 23, True, False), (4, 4, 16, True, True)]:
+            land = 0.5 + 0.4 * rng.random()
+            mask = (rng.random((ny, nx)) >= land).astype(np.int32)
+            d, _ = oracle.emu_partition(mask, P, px, py, ranks=ranks)
+            o = oracle.partition(mask, P, px, py, use_hist=True)
+            longest = max(longest, max(len(x) - (3 * P + 64) for per in range(2) for x in o.nbr.ids[per]))
+            assert_same(d, o, (seed, nx, ny, P, ranks))
+    assert longest > 0, "no case overflowed the reserved list capacity: the re-run path was not exercised"
