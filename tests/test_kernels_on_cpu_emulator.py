@@ -173,3 +173,16 @@ def test_more_parts_than_cells_per_row(oracle):
             longest = max(longest, max(len(x) - (3 * P + 64) for per in range(2) for x in o.nbr.ids[per]))
             assert_same(d, o, (seed, nx, ny, P, ranks))
     assert longest > 0, "no case overflowed the reserved list capacity: the re-run path was not exercised"
+
+
+def test_assumed_plan_mismatch_reruns_the_step(oracle):
+    """the host sizes the launches after K2 for an ASSUMED number of x / y levels (those of a full-extent bounding
+    box); when the ocean occupies a flat band the real plan has more x levels, K2 flags the mismatch, the later
+    kernels do nothing and the step runs again with the real plan"""
+    mask = np.zeros((64, 64), dtype=np.int32)
+    mask[3:9, :] = 1
+    mask[5, 10:20] = 0
+    for ranks in (1, 2):
+        d, info = oracle.emu_partition(mask, 16, False, False, ranks=ranks)
+        assert (info["x_levels"], info["y_levels"]) == (4, 0)  # a 64 x 64 bounding box would give 2 and 2
+        assert_same(d, oracle.partition(mask, 16, use_hist=True), ranks)
