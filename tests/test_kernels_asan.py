@@ -12,7 +12,9 @@ from conftest import ROOT
 
 
 def run_worker(extra_env=None):
-    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    # the runtime of the compiler oracle/Makefile builds with (the distribution gcc when there is one)
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    asan = subprocess.run([cc, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan not available")
     r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libddc_emu_asan.so"], capture_output=True, text=True)
