@@ -1,0 +1,147 @@
+"""The product's own C-ABI implementation on a machine without a GPU.
+
+oracle/libddc_cuda_emu.so is domain_decomp_b200/csrc/ddc_api.cu itself -- its `<<< >>>` launches rewritten by
+oracle/emu/make_api_emu.py, nothing else -- compiled over a host stand-in of the CUDA runtime
+(oracle/emu/cuda_runtime_fake.h) and the fiber emulation of the execution model.  The GPU parity tests of
+tests/test_gpu_parity.py that fit a CPU (small masks) are run against it unchanged, through the same ctypes
+front-end: besides the kernels this exercises the HOST logic of the library -- the assumed plan and the
+re-run on a mismatch, DDC_ASYNC, the capacity re-run of the neighbour fill pass, reduced flag sets, caller-
+supplied boxes (the all-pairs warp kernel), the error paths.  One rank; several ranks: test_kernels_on_cpu_emulator.
+The product never loads this library: only this test module binds it."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import test_gpu_parity as T
+from conftest import ROOT
+
+
+class EmuCapi:
+    """the parts of domain_decomp_b200.capi the tests use, bound to the emulation library"""
+
+    def __init__(self, real, lib):
+        self._real, self._lib = real, lib
+        for name in ("WANT_PID", "WANT_NEIGHBOURS", "PROFILE", "ASYNC", "DdcError", "generate_mask_host", "LEFT", "RIGHT",
+                     "BOTTOM", "TOP"):
+            setattr(self, name, getattr(real, name))
+        outer = self
+
+        class Handle(real.Handle):
+            def __init__(self, device=0, rank=0, nranks=1, nccl_id=None):
+                self.L = outer._lib
+                self.h = C.c_void_p()
+                rc = self.L.ddc_create(C.byref(self.h), device, rank, nranks, nccl_id)
+                if rc:
+                    raise real.DdcError("ddc_create: %s" % self.L.ddc_last_error(None).decode())
+                self.rank, self.nranks, self.nparts, self.shape, self._keep = rank, nranks, 0, None, None
+
+        self.Handle = Handle
+
+
+@pytest.fixture(scope="module")
+def capi(oracle):
+    from domain_decomp_b200 import capi as real
+    oracle.build()
+    path = os.path.join(ROOT, "oracle", "libddc_cuda_emu.so")
+    assert os.path.exists(path)
+    lib = C.CDLL(path)
+    ref = real.load()
+    for name in real.SYMBOLS:  # same prototypes as the CUDA library's
+        getattr(lib, name).argtypes = getattr(ref, name).argtypes
+        getattr(lib, name).restype = getattr(ref, name).restype
+    return EmuCapi(real, lib)
+
+
+@pytest.fixture()
+def handle(capi):
+    h = capi.Handle(0)
+    yield h
+    h.close()
+
+
+def test_box_known_answers(goldens, handle):
+    T.test_box_known_answers(goldens, handle)
+
+
+@pytest.mark.parametrize("case", ["test_1", "test_2", "test_1_px", "test_1_py", "test_1_px_py"])
+def test_integration_goldens(goldens, handle, case):
+    T.test_integration_goldens(goldens, handle, case)
+
+
+def test_rect3030(goldens, handle, oracle):
+    T.test_rect3030(goldens, handle, oracle)
+
+
+def test_random_small_masks(handle, oracle):
+    """as tests/test_gpu_parity.py::test_random_small_masks, fewer iterations; ONE handle across changing extents"""
+    rng = np.random.default_rng(11)
+    for it in range(40):
+        NX, NY = int(rng.integers(1, 50)), int(rng.integers(1, 50))
+        dens = rng.choice([0.0, 0.02, 0.1, 0.3, 0.6, 0.9, 1.0])
+        m = (rng.random((NY, NX)) < dens).astype(np.int32) * int(rng.integers(1, 5))
+        if rng.random() < 0.3:
+            m[:, rng.integers(0, NX)] = 0
+        if rng.random() < 0.2:
+            m[m == 0] = -int(rng.integers(0, 3))  # land is "<= 0"
+        P = int(rng.integers(1, 24))
+        px, py = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        g = T.run_gpu(handle, m, P, px, py)
+        o = oracle.partition(m, P, px, py, use_hist=bool(it & 1))
+        T.assert_same(g, o, "it=%d NX=%d NY=%d P=%d dens=%s" % (it, NX, NY, P, dens))
+        assert g["loads"].tolist() == oracle.part_loads(o.pid, P).tolist()
+        assert g["stats"]["load_max"] == int(g["loads"].max()) and g["stats"]["load_min"] == int(g["loads"].min())
+
+
+def test_neighbours_from_boxes_random(handle, oracle):
+    T.test_neighbours_from_boxes_random(handle, oracle)
+
+
+def test_flags_and_errors(capi, handle, oracle):
+    m = capi.generate_mask_host(160, 120, seed=9, land_frac=0.4)
+    a = T.run_gpu(handle, m, 12, True, True)
+    handle.set_mask_host(m)
+    handle.partition(12, True, True, flags=0)  # boxes only: no pid, no neighbours
+    assert handle.boxes().tolist() == a["boxes"].tolist()
+    assert handle.stats()["changes"] == a["stats"]["changes"]
+    with pytest.raises(capi.DdcError):
+        handle.pid_host()
+    assert handle.neighbour_counts(0, 0).sum() == 0
+    h2 = capi.Handle(0)
+    with pytest.raises(capi.DdcError, match="no mask set"):
+        h2.partition(4)
+    with pytest.raises(capi.DdcError):
+        h2.boxes()
+    h2.close()
+
+
+def test_async_steps_and_plan_mismatch(capi, handle, oracle):
+    T.test_async_steps_and_plan_mismatch(capi, handle, oracle)
+
+
+@pytest.mark.parametrize("n,P", [(64, 4), (60, 6)])
+def test_nothing_moved_reports_naive_blocks(handle, oracle, n, P):
+    T.test_nothing_moved_reports_naive_blocks(handle, oracle, n, P)
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+def test_strip_row_kernel_variants(capi, oracle, k, monkeypatch):
+    monkeypatch.setenv("DDC_STRIP_K", str(k))
+    h = capi.Handle(0)
+    try:
+        m = capi.generate_mask_host(260, 100, 4, 0.45)
+        T.assert_same(T.run_gpu(h, m, 24, True, False), oracle.partition(m, 24, True, False, use_hist=True), "k=%d" % k)
+    finally:
+        h.close()
+
+
+def test_neighbour_list_capacity_rerun(handle, oracle):
+    """lists longer than the 3 P + 64 entries reserved per list: ddc_get_neighbours runs the fill pass again"""
+    rng = np.random.default_rng(9)
+    for (nx, ny, P, px, py) in [(11, 11, 36, False, False), (5, 6, 23, True, False)]:
+        land = 0.5 + 0.4 * rng.random()
+        m = (rng.random((ny, nx)) >= land).astype(np.int32)
+        o = oracle.partition(m, P, px, py, use_hist=True)
+        T.assert_same(T.run_gpu(handle, m, P, px, py), o, (nx, ny, P))
+    assert max(len(x) for per in range(2) for x in o.nbr.ids[per]) > 3 * 23 + 64
