@@ -23,6 +23,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -207,6 +208,10 @@ void set_schedule_seed(unsigned long long seed) { g_sched_seed = seed; }
 
 bool launch(Dim3 grid, Dim3 block, size_t dyn_smem, const std::function<void()>& body)
 {
+    // one launch at a time: the built-in variables, the `__shared__` statics and the fiber stacks are process-wide
+    // (callers may be several OS threads, e.g. the thread-ranks of oracle/ref_hostpath_shim.cpp)
+    static std::mutex launch_mutex;
+    std::lock_guard<std::mutex> lock(launch_mutex);
     const int nthreads = (int)(block.x * block.y * block.z);
     if (nthreads < 1 || nthreads > 1024 || dyn_smem > DYN_SMEM_BYTES) {
         g_error = "cuda_emu::launch: bad block size or too much dynamic shared memory";

@@ -179,12 +179,14 @@ def _parse_report(out: bytes, P: int) -> dict:
 _ref_binding = {}
 
 
-def ref_binding_lib(cpu: bool):
+def ref_binding_lib(cpu):
     """The reference's host sources + integration/reference_binding (the CudaRcbPartitioner a maintainer adds
-    to the reference tree) -- linked with the CUDA library (cpu=False) or, to test the binding's own logic
-    without a GPU, with the oracle answering its ddc_* calls (cpu=True).  None if not built."""
+    to the reference tree) -- linked with the CUDA library (cpu=False) or, without a GPU, with the oracle
+    answering its ddc_* calls (cpu=True) or with the product's own C ABI and kernels on the host emulation
+    (cpu="emu").  None if not built."""
     if cpu not in _ref_binding:
-        path = os.path.join(_HERE, "_ref", "libref_binding_cpu.so" if cpu else "libref_binding.so")
+        name = {True: "libref_binding_cpu.so", False: "libref_binding.so", "emu": "libref_binding_emu.so"}[cpu]
+        path = os.path.join(_HERE, "_ref", name)
         if not os.path.exists(path):
             return None
         L = C.CDLL(path)
@@ -197,14 +199,14 @@ def ref_binding_lib(cpu: bool):
     return _ref_binding[cpu]
 
 
-def ref_binding_run(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, cpu: bool, xdim: str = "x",
+def ref_binding_run(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, cpu, xdim: str = "x",
                     ydim: str = "y", maskname: str = "mask", ignore_mask: bool = False, device: int = 0) -> dict:
     """Grid::create (reference) -> CudaRcbPartitioner::partition (the binding over the C ABI) -> the
     reference's discover_neighbours, getters, save_mask, save_metadata, on P thread-ranks.  Same report as
     ref_host_run."""
     L = ref_binding_lib(cpu)
     if L is None:
-        raise RuntimeError("oracle/_ref/libref_binding%s.so is not built" % ("_cpu" if cpu else ""))
+        raise RuntimeError("oracle/_ref/libref_binding (%s) is not built" % cpu)
     mask = np.ascontiguousarray(mask, dtype=np.int32)
     ny, nx = mask.shape
     out = L.ref_binding_run(P, nx, ny, mask, xdim.encode(), ydim.encode(), maskname.encode(), int(ignore_mask),

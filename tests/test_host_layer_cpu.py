@@ -1,7 +1,9 @@
 """The host layer (domain_decomp_b200/host: Grid, Partitioner, CudaRcbPartitioner, the `decomp` CLI) on a machine
-WITHOUT a GPU: oracle/Makefile links the very same host sources with oracle/ddc_oracle_stub.c, i.e. with the CPU
-oracle behind the C ABI, into test binaries under oracle/_ref/.  (The product binaries link libddc_cuda.so and
-have no such path; tests/test_host_cpp.py runs them on the GPU.)  Checked here:
+WITHOUT a GPU: oracle/Makefile links the very same host sources into test binaries under oracle/_ref/, with, behind
+the C ABI, either the CPU oracle (oracle/ddc_oracle_stub.c: *_oracle) or the PRODUCT's own C-ABI implementation and
+kernels on the host emulation of CUDA (oracle/libddc_cuda_emu.so: *_emu -- the whole product stack, CLI to
+kernels).  (The product binaries link libddc_cuda.so and have no such path; tests/test_host_cpp.py runs them on
+the GPU.)  Checked here:
   * the reference's unit tests re-expressed (host_tests.cpp: test_grid_*, test_zoltan_partitioner_*),
   * the reference's integration test: CLI output byte-identical to the golden ncdump text,
   * binary netCDF grids in, partition_mask_<P>.nc out,
@@ -21,13 +23,15 @@ from test_reference_hostpath import sane_blocks
 
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 DECOMP = os.path.join(REF_DIR, "decomp_oracle")
+DECOMP_EMU = os.path.join(REF_DIR, "decomp_emu")
 HOST_TESTS = os.path.join(REF_DIR, "host_tests_oracle")
+HOST_TESTS_EMU = os.path.join(REF_DIR, "host_tests_emu")
 
 
 @pytest.fixture(scope="module", autouse=True)
 def built(oracle):
     oracle.build()
-    if not (os.path.exists(DECOMP) and os.path.exists(HOST_TESTS)):
+    if not all(os.path.exists(p) for p in (DECOMP, HOST_TESTS, DECOMP_EMU, HOST_TESTS_EMU)):
         pytest.skip("oracle/_ref host-layer test binaries not built (no reference checkout here)")
 
 
@@ -39,16 +43,18 @@ def fixture_dir(tmp_path_factory, goldens):
     return str(d)
 
 
-def test_reference_unit_tests_on_the_host_layer(fixture_dir):
-    out = subprocess.run([HOST_TESTS, fixture_dir], capture_output=True, text=True, timeout=300)
+@pytest.mark.parametrize("exe", [HOST_TESTS, HOST_TESTS_EMU], ids=["oracle", "emu"])
+def test_reference_unit_tests_on_the_host_layer(fixture_dir, exe):
+    out = subprocess.run([exe, fixture_dir], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 failed" in out.stdout
 
 
+@pytest.mark.parametrize("exe", [DECOMP, DECOMP_EMU], ids=["oracle", "emu"])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_cli_integration_goldens(goldens, fixture_dir, tmp_path, case):
+def test_cli_integration_goldens(goldens, fixture_dir, tmp_path, case, exe):
     inp, flags = CASES[case]
-    out = subprocess.run([DECOMP, "-g", os.path.join(fixture_dir, inp + ".cdl"), "--parts", "3"] + flags,
+    out = subprocess.run([exe, "-g", os.path.join(fixture_dir, inp + ".cdl"), "--parts", "3"] + flags,
                          capture_output=True, text=True, timeout=300, cwd=tmp_path)
     assert out.returncode == 0, out.stdout + out.stderr
     G = goldens["integration"][case]
@@ -78,11 +84,12 @@ def write_nc(path, mask, version=1):
     f.close()
 
 
-def test_cli_on_binary_netcdf_and_stats(goldens, tmp_path):
+@pytest.mark.parametrize("exe", [DECOMP, DECOMP_EMU], ids=["oracle", "emu"])
+def test_cli_on_binary_netcdf_and_stats(goldens, tmp_path, exe):
     scipy_io = pytest.importorskip("scipy.io")
     inp = goldens["inputs"]["test_1"]
     write_nc(str(tmp_path / "test_1.nc"), np.asarray(inp["mask"], dtype=np.int32).reshape(inp["ny"], inp["nx"]))
-    out = subprocess.run([DECOMP, "-g", "test_1.nc", "--parts", "3", "--px", "--stats"], capture_output=True, text=True,
+    out = subprocess.run([exe, "-g", "test_1.nc", "--parts", "3", "--px", "--stats"], capture_output=True, text=True,
                          timeout=300, cwd=tmp_path)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Total weight of dots = 24" in out.stdout
@@ -113,6 +120,7 @@ def test_files_written_by_the_host_layer_equal_the_reference_writers(oracle, tmp
     rng = np.random.default_rng(77)
     done = 0
     while done < 25:
+        exe = DECOMP_EMU if done % 5 == 4 else DECOMP  # every fifth case through the whole product stack
         nx, ny, P = int(rng.integers(3, 40)), int(rng.integers(3, 40)), int(rng.integers(2, 17))
         if not sane_blocks(oracle, P, nx, ny):
             continue
@@ -121,7 +129,7 @@ def test_files_written_by_the_host_layer_equal_the_reference_writers(oracle, tmp
         d = tmp_path / ("case%d" % done)
         d.mkdir()
         write_nc(str(d / "g.nc"), mask, version=1 + done % 2)
-        cmd = [DECOMP, "-g", "g.nc", "--parts", str(P)] + (["--px"] if px else []) + (["--py"] if py else [])
+        cmd = [exe, "-g", "g.nc", "--parts", str(P)] + (["--px"] if px else []) + (["--py"] if py else [])
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=d)
         assert out.returncode == 0, out.stdout + out.stderr
         o = oracle.partition(mask, P, px, py, use_hist=True)

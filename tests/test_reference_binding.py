@@ -1,9 +1,10 @@
 """The drop-in, end to end, on the CPU: the reference's own Grid.cpp / Partitioner.cpp / DomainUtils.cpp (compiled
 where they lie, oracle/_ref) + integration/reference_binding/CudaRcbPartitioner.cpp -- the one file a maintainer
-adds to the reference tree, written against the reference's headers and include/ddc.h -- with the CPU oracle
-answering the binding's ddc_* calls (oracle/ddc_oracle_stub.c).  This checks the BINDING's logic (assembling
-the mask from the ranks' naive blocks, handing box / owners back to the reference's neighbour discovery and
-writers); tests/test_zz_reference_binding.py runs the same thing on a GPU with the real CUDA library."""
+adds to the reference tree, written against the reference's headers and include/ddc.h -- with, behind the C ABI,
+  * backend True:  the CPU oracle answering the binding's ddc_* calls (oracle/ddc_oracle_stub.c), or
+  * backend "emu": the PRODUCT's own C-ABI implementation and kernels on the host emulation of CUDA
+                   (oracle/libddc_cuda_emu.so) -- the whole drop-in stack, reference code on top, without a GPU.
+tests/test_zz_reference_binding.py runs the same thing on a GPU with the real CUDA library."""
 import numpy as np
 import pytest
 
@@ -13,8 +14,8 @@ from test_reference_hostpath import EDGES, per_part, sane_blocks
 
 @pytest.fixture(scope="module")
 def ref(oracle):
-    if oracle.ref_binding_lib(cpu=True) is None:
-        pytest.skip("oracle/_ref/libref_binding_cpu.so not built (no reference checkout here)")
+    if oracle.ref_binding_lib(cpu=True) is None or oracle.ref_binding_lib(cpu="emu") is None:
+        pytest.skip("oracle/_ref/libref_binding_{cpu,emu}.so not built (no reference checkout here)")
     return oracle
 
 
@@ -57,17 +58,19 @@ def check_against_oracle(orc, run, mask, P, px, py):
     assert not r["files"]["metadata"]["unwritten"] and not r["files"]["mask"]["unwritten"]
 
 
+@pytest.mark.parametrize("backend", [True, "emu"])
 @pytest.mark.parametrize("case", ["test_1", "test_2", "test_1_px", "test_1_py", "test_1_px_py"])
-def test_binding_reproduces_the_goldens(goldens, ref, case):
-    check_goldens(goldens, lambda *a, **k: ref.ref_binding_run(*a, cpu=True, **k), case)
+def test_binding_reproduces_the_goldens(goldens, ref, case, backend):
+    check_goldens(goldens, lambda *a, **k: ref.ref_binding_run(*a, cpu=backend, **k), case)
 
 
-def test_binding_random_masks(ref):
+@pytest.mark.parametrize("backend,cases", [(True, 60), ("emu", 6)])
+def test_binding_random_masks(ref, backend, cases):
     rng = np.random.default_rng(41)
-    run = lambda *a, **k: ref.ref_binding_run(*a, cpu=True, **k)
+    run = lambda *a, **k: ref.ref_binding_run(*a, cpu=backend, **k)
     done = 0
-    while done < 60:
-        nx, ny, P = int(rng.integers(2, 40)), int(rng.integers(2, 40)), int(rng.integers(1, 17))
+    while done < cases:
+        nx, ny, P = int(rng.integers(2, 40)), int(rng.integers(2, 40)), int(rng.integers(1, 17 if backend is True else 7))
         if not sane_blocks(ref, P, nx, ny):
             continue
         mask = (rng.random((ny, nx)) >= rng.random() * 0.8).astype(np.int32) * int(rng.integers(1, 3))
