@@ -186,3 +186,14 @@ def test_assumed_plan_mismatch_reruns_the_step(oracle):
         d, info = oracle.emu_partition(mask, 16, False, False, ranks=ranks)
         assert (info["x_levels"], info["y_levels"]) == (4, 0)  # a 64 x 64 bounding box would give 2 and 2
         assert_same(d, oracle.partition(mask, 16, use_hist=True), ranks)
+
+
+def test_rows_of_65536_cells_or_more(oracle):
+    """NX >= 65536 with a y level: 32-bit strip row counts (16-byte stores of 4 counts), three prefix tiles in
+    global memory for the column histogram, ragged width (66001: the scalar load / store paths of K1 and K6)"""
+    from domain_decomp_b200 import capi
+    for (nx, ny, P, kw) in [(65600, 600, 256, {}), (66001, 530, 200, {"strip_k": 16})]:
+        mask = capi.generate_mask_host(nx, ny, 5, 0.4)
+        d, info = oracle.emu_partition(mask, P, True, False, **kw)
+        assert info["x_levels"] == 7 and info["y_levels"] == 1
+        assert_same(d, oracle.partition(mask, P, True, False, use_hist=True), (nx, ny, P))
