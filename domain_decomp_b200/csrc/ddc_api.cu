@@ -139,7 +139,7 @@ struct ddc_handle_s {
     int last_flags = 0, strip_k = 0;
     size_t xcuts_smem = 0, ycuts16_smem = 0, ycuts32_smem = 0; // dynamic smem opt-ins already made
     cudaStream_t side_stream = nullptr; // speculative neighbour tables run beside the labelling
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k2 = nullptr, ev_paint = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // peer exchange (CUDA IPC): one buffer per rank, mapped by all ranks
     //   [flags: PEER_STAGES * MAX_PEERS u32, padded to 256 B][col: 2 parities x G slots][row: 2 parities x G slots]
     //   slot g of a rank's buffer is WRITTEN by rank g (pushed by its producing kernel) and read locally
@@ -373,8 +373,6 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     }
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_k2, cudaEventDisableTiming));
-    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_paint, cudaEventDisableTiming));
     CREATE_TRY(cudaHostAlloc((void**)&h->pin_plan, sizeof(Plan), cudaHostAllocMapped));
     CREATE_TRY(cudaHostGetDevicePointer((void**)&h->pin_plan_dev, h->pin_plan, 0));
     memset(h->pin_plan, 0, sizeof(Plan));
@@ -459,10 +457,6 @@ int ddc_destroy(ddc_handle_t h)
         cudaEventDestroy(h->ev_fork);
     if (h->ev_join)
         cudaEventDestroy(h->ev_join);
-    if (h->ev_k2)
-        cudaEventDestroy(h->ev_k2);
-    if (h->ev_paint)
-        cudaEventDestroy(h->ev_paint);
     if (h->side_stream)
         cudaStreamDestroy(h->side_stream);
     if (h->own_stream)
@@ -810,14 +804,12 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     } else
         k_xcuts<false><<<1, 1024, 0, s>>>(pc, ps, NX, NY, P, h->colpfx.p, yr_off, G, aix, aiy, h->plan.p, t.st,
             t.bx, h->loads.p, h->loadmm.p);
-    // the column -> strip table is only needed by K6: painted on the second stream, beside K3 / K4
-    CUDA_TRY(h, cudaEventRecord(h->ev_k2, s));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_k2, 0));
-    k_paint_strips<<<std::max(1, std::min((Scap + 7) / 8, 148 * 4)), 256, 0, h->side_stream>>>(t.st, h->plan.p,
-        h->strip_of_col.p);
-    CUDA_TRY(h, cudaEventRecord(h->ev_paint, h->side_stream));
     launches++;
-    launches++;
+    // the column -> strip table K6 reads: painted by K4's blocks; without y levels there is no K4
+    if (!ycuts) {
+        k_paint_strips<<<std::max(1, std::min((Scap + 7) / 8, 148 * 4)), 256, 0, s>>>(t.st, h->plan.p, h->strip_of_col.p);
+        launches++;
+    }
     mark(2);
     // ---- K3 + K4: strip row counts, y cuts -----------------------------------------------------
     if (ycuts) {
@@ -887,7 +879,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             opted = yneed;                                                                         \
         }                                                                                          \
         k_ycuts<CT, SM><<<ygrid, 1024, SM ? yneed : 0, s>>>(pr, ps, rl, NY, t.st, h->ypfx.p, t.bx, h->loads.p, \
-            h->loadmm.p, h->plan.p);                                                                \
+            h->loadmm.p, h->plan.p, h->strip_of_col.p);                                                                \
     } while (0)
         if (narrow) {
             if (y_smem)
@@ -927,7 +919,6 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
     }
     // ---- K6: labels + `changes` -----------------------------------------------------------------
-    CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_paint, 0));
     if (rows > 0 && (P > 1 || want_pid)) {
         const bool vecp = want_pid && (NX % 4 == 0) && (((uintptr_t)h->pid.p) % 16 == 0);
 #define LAUNCH_LABEL(V, W)                                                                         \

@@ -782,7 +782,8 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     }
 }
 
-// strip of every column (read by the labelling kernel; runs beside K3 / K4 on the second stream).
+// strip of every column (read by the labelling kernel), for decompositions WITHOUT y levels; with y levels K4
+// paints the table itself.
 // The strips tile [0, NX) in order: one warp paints the column range of one strip; a zero-width
 // strip paints nothing, the strip that follows it owns the shared start column.
 __global__ void __launch_bounds__(256) k_paint_strips(StripTable st, const Plan* __restrict__ plan,
@@ -1083,7 +1084,7 @@ __device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowL
 
 template <typename CT, bool SMEM>
 __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st,
-    unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan)
+    unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan, int* __restrict__ strip_of_col)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
@@ -1092,6 +1093,12 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     const unsigned long long t_start = global_ns();
     if (blockIdx.x == 0 && threadIdx.x == 0)
         plan->ts[6] = t_start;
+    // the column -> strip table the labelling kernel reads: the block of a strip paints the strip's columns
+    // (while the other ranks' row counts are still on their way); a zero-width strip paints nothing, the strip
+    // that follows it owns the shared start column
+    for (int s = blockIdx.x; s < *st.S; s += gridDim.x)
+        for (int x = st.x0[s] + (int)threadIdx.x; x < st.x1[s]; x += (int)blockDim.x)
+            strip_of_col[x] = s;
     // exchange step 2: every rank's strip row counts are written (block 0 says so for this rank)
     if (ps.enabled) {
         bool ok = true;

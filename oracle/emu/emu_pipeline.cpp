@@ -201,8 +201,9 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             LAUNCH(Dim3(1), Dim3(1024), 0,
                 k_xcuts<false>(pc, ps, NX, NY, P, r.colpfx.data(), yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(),
                     r.loadmm.data()));
-        LAUNCH(Dim3(std::max(1, std::min((Scap + 7) / 8, 148 * 4))), Dim3(256), 0,
-            k_paint_strips(st, &r.plan, r.strip_of_col.data()));
+        if (!ycuts) // with y levels K4 paints the column -> strip table
+            LAUNCH(Dim3(std::max(1, std::min((Scap + 7) / 8, 148 * 4))), Dim3(256), 0,
+                k_paint_strips(st, &r.plan, r.strip_of_col.data()));
     }
     // ---- K3: strip row counts (pushed to every rank) ----
     int rb_shift = 5;
@@ -278,7 +279,8 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
 #define YCUTS(CT, SM)                                                                              \
     LAUNCH(Dim3(ygrid), Dim3(1024), SM ? yneed : 0,                                                \
-        (k_ycuts<CT, SM>(pr, ps, rl, NY, st, r.ypfx.data(), bx, r.loads.data(), r.loadmm.data(), &r.plan)))
+        (k_ycuts<CT, SM>(pr, ps, rl, NY, st, r.ypfx.data(), bx, r.loads.data(), r.loadmm.data(), &r.plan,                    \
+            r.strip_of_col.data())))
             if (narrow) {
                 if (y_smem)
                     YCUTS(uint16_t, true);
