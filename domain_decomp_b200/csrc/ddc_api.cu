@@ -137,6 +137,17 @@ struct ddc_handle_s {
     int plan_nx = 0, plan_ny = 0, plan_P = 0, aix = 0, aiy = 0;
     bool pending = false, profiled = false; // a step is enqueued but not yet validated
     int last_flags = 0, strip_k = 0;
+    // what K2 (column counts, scalars) and the scan's last CTA (counters) left clean for a later step: k_init is
+    // only launched when the buffers or the geometry of the step differ (index: parity of the exchange slots)
+    struct CleanSig {
+        const void *col = nullptr, *done = nullptr;
+        int ncol = 0, yr_off = 0, rank = -1, ndone = 0;
+        bool operator==(const CleanSig& o) const
+        {
+            return col == o.col && done == o.done && ncol == o.ncol && yr_off == o.yr_off && rank == o.rank && ndone == o.ndone;
+        }
+    } clean[2];
+    bool clean_p2p = false;
     size_t xcuts_smem = 0, ycuts16_smem = 0, ycuts32_smem = 0; // dynamic smem opt-ins already made
     cudaStream_t side_stream = nullptr; // speculative neighbour tables run beside the labelling
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -773,9 +784,23 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     // ---- K1: mask scan -----------------------------------------------------------------------
     const int gridx = (NG + 7) / 8;
     CUDA_TRY(h, h->done.ensure((size_t)gridx + 1));
-    k_init<<<(ncol + 255) / 256, 256, 0, s>>>(colcount, ncol, yr_off, h->rank, h->sc.p, h->loadmm.p, h->done.p,
-        gridx + 1);
-    launches++;
+    ddc_handle_s::CleanSig sig;
+    sig.col = colcount;
+    sig.done = h->done.p;
+    sig.ncol = ncol;
+    sig.yr_off = yr_off;
+    sig.rank = h->rank;
+    sig.ndone = gridx + 1;
+    const int ci = p2p ? par : 0;
+    if (!(h->clean[ci] == sig) || p2p != h->clean_p2p) { // first use of these buffers with this geometry
+        k_init<<<(ncol + 255) / 256, 256, 0, s>>>(colcount, ncol, yr_off, h->rank, h->sc.p, h->loadmm.p, h->done.p,
+            gridx + 1);
+        launches++;
+        if (p2p != h->clean_p2p)
+            h->clean[0] = h->clean[1] = ddc_handle_s::CleanSig();
+        h->clean_p2p = p2p;
+    }
+    h->clean[ci] = sig; // K2 of this step puts the buffer back into k_init's state
     const bool vec = (NX % 4 == 0) && (((uintptr_t)h->d_mask) % 16 == 0);
     int* yr = reinterpret_cast<int*>(colcount + yr_off + 2 * h->rank);
     if (rows > 0 || p2p) { // an empty shard still has to push its (empty) counts and raise its flag
@@ -800,10 +825,10 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             h->xcuts_smem = xneed;
         }
         k_xcuts<true><<<1, 1024, xneed, s>>>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, h->plan.p, t.st, t.bx,
-            h->loads.p, h->loadmm.p);
+            h->loads.p, h->loadmm.p, h->sc.p, colcount);
     } else
         k_xcuts<false><<<1, 1024, 0, s>>>(pc, ps, NX, NY, P, h->colpfx.p, yr_off, G, aix, aiy, h->plan.p, t.st,
-            t.bx, h->loads.p, h->loadmm.p);
+            t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount);
     launches++;
     // the column -> strip table K6 reads: painted by K4's blocks; without y levels there is no K4
     if (!ycuts) {
@@ -983,11 +1008,13 @@ int validate(ddc_handle_t h)
             break;
         if (pl.mismatch == 3) {
             h->partitioned = false;
+            h->clean[0] = h->clean[1] = ddc_handle_s::CleanSig(); // the step did not run to its end: start clean
             return fail(h, DDC_ERR_PEER, "peer exchange timed out: a rank did not reach the step within %.1f s",
                 (double)PEER_TIMEOUT_NS * 1e-9);
         }
         if (attempt >= 2) {
             h->partitioned = false;
+            h->clean[0] = h->clean[1] = ddc_handle_s::CleanSig();
             return fail(h, DDC_ERR_STATE, "the RCB plan did not settle (x/y levels %d/%d)", pl.ix, pl.iy);
         }
         h->aix = pl.ix;
@@ -1032,8 +1059,10 @@ int ddc_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         return fail(h, DDC_ERR_ARG, "ddc_partition: nparts must be >= 1");
     // (an earlier DDC_ASYNC step that nobody looked at is simply superseded)
     int rc = enqueue_partition(h, nparts, px, py, flags);
-    if (rc)
+    if (rc) {
+        h->clean[0] = h->clean[1] = ddc_handle_s::CleanSig(); // whatever was enqueued may not have run
         return rc;
+    }
     if (flags & DDC_ASYNC)
         return DDC_OK;
     return validate(h);

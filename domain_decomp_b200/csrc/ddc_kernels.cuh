@@ -584,6 +584,10 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
         }
         peer_signal(ps, 0, 0u); // fence.sys, then the flag: the pushes of all blocks come first
     }
+    // every CTA has been counted: the counters are ready for the next step (k_init is then only needed when
+    // the geometry changes)
+    for (unsigned i = threadIdx.x; i <= gridDim.x; i += blockDim.x)
+        done[i] = 0u;
 }
 
 // threads that share one leaf's walk: the largest power of two <= 32 with lanes * leaves <= threads
@@ -654,15 +658,24 @@ __device__ __forceinline__ void load_counts_tile(const PeerCols& pc, int base, i
 // aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
-    int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm)
+    int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm,
+    DevScalars* sc, unsigned* own_col /* this rank's column counts: reset here once they are consumed */)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
     __shared__ int s_ix, s_iters;
     unsigned* pfx = SMEM ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
-    if (tid == 0)
+    if (tid == 0) {
         plan->ts[0] = global_ns();
+        // the per-step scalars: nothing before K2 touches them, everything after K2 accumulates into them
+        sc->changes = 0;
+        sc->changes_all = 0;
+        sc->overflow = 0;
+        sc->edge_cut = 0ull;
+        loadmm[0] = 0x7fffffffffffffffLL;
+        loadmm[1] = -1;
+    }
 
     // 0. exchange step 1: every rank's mask scan has pushed its column counts into my buffer
     if (ps.enabled) {
@@ -732,6 +745,16 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         plan->ts[3] = global_ns();
     }
     __syncthreads();
+    // the column counts and the y-range pairs are consumed: this rank's buffer goes back to the state k_init
+    // leaves it in, ready for the next step that accumulates into it
+    for (int i = tid; i < yr_off + 2 * G; i += blockDim.x) {
+        unsigned v = 0u;
+        if (i == yr_off + 2 * ps.rank)
+            v = 0x80000000u; // -(first ocean row) = INT_MIN
+        if (i == yr_off + 2 * ps.rank + 1)
+            v = 0xffffffffu; // last ocean row = -1
+        own_col[i] = v;
+    }
 
     // 3. the x levels: a group of `lanes` adjacent threads walks to strip i, all of them evaluating
     //    the same medians (the block has more threads than strips; the fewer different medians the

@@ -145,3 +145,22 @@ def test_neighbour_list_capacity_rerun(handle, oracle):
         o = oracle.partition(m, P, px, py, use_hist=True)
         T.assert_same(T.run_gpu(handle, m, P, px, py), o, (nx, ny, P))
     assert max(len(x) for per in range(2) for x in o.nbr.ids[per]) > 3 * 23 + 64
+
+
+def test_repeated_and_alternating_geometries_on_one_handle(capi, handle, oracle):
+    """the host launches k_init only when the buffers or the geometry differ from what the previous steps left
+    clean: the same mask five times, then two geometries in turn (same buffers, other widths), then P changes"""
+    a = capi.generate_mask_host(96, 64, 3, 0.45)
+    b = capi.generate_mask_host(50, 40, 5, 0.3)
+    oa, ob = oracle.partition(a, 12, True, False, use_hist=True), oracle.partition(b, 7, False, True, use_hist=True)
+    launches = []
+    for _ in range(5):
+        g = T.run_gpu(handle, a, 12, True, False)
+        T.assert_same(g, oa, "repeat")
+        launches.append(g["stats"]["gpu_launches"])
+    assert launches[0] == launches[-1] + 1, launches  # only the first step needed k_init
+    for _ in range(3):
+        T.assert_same(T.run_gpu(handle, b, 7, False, True), ob, "alternating b")
+        T.assert_same(T.run_gpu(handle, a, 12, True, False), oa, "alternating a")
+    for P in (5, 12, 3):
+        T.assert_same(T.run_gpu(handle, a, P, True, False), oracle.partition(a, P, True, False, use_hist=True), P)

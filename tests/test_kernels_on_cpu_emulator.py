@@ -197,3 +197,16 @@ def test_rows_of_65536_cells_or_more(oracle):
         d, info = oracle.emu_partition(mask, P, True, False, **kw)
         assert info["x_levels"] == 7 and info["y_levels"] == 1
         assert_same(d, oracle.partition(mask, P, True, False, use_hist=True), (nx, ny, P))
+
+
+@pytest.mark.parametrize("ranks", [1, 2, 3])
+def test_back_to_back_steps_without_k_init(oracle, ranks, monkeypatch):
+    """k_init is only launched for buffers that K2 (column counts, y-range pairs, scalars) and the scan's last CTA
+    (its counters) have not left clean: four more decompositions are enqueued first, from the third step on
+    without k_init, on both parities of the exchange slots"""
+    from domain_decomp_b200 import capi
+    monkeypatch.setenv("DDC_EMU_REPEAT", "4")
+    for mask, P, px, py in [(capi.generate_mask_host(130, 77, 7, 0.5), 12, True, False), (np.ones((24, 24), dtype=np.int32), 4, False, True),
+                            (capi.generate_mask_host(64, 64, 3, 0.97), 8, False, False)]:
+        d, _ = oracle.emu_partition(mask, P, px, py, ranks=ranks)
+        assert_same(d, oracle.partition(mask, P, px, py, use_hist=True), (mask.shape, P, ranks))
