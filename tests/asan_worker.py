@@ -24,10 +24,8 @@ rng = np.random.default_rng(3)
 cases = [(capi.generate_mask_host(130, 40, 7, 0.5), 12, True, False, dict(ranks=2)),
          (capi.generate_mask_host(67, 31, 2, 0.4), 7, False, True, dict(ranks=1)),  # ragged width: scalar paths
          (capi.generate_mask_host(150, 40, 11, 0.45), 12, True, False, dict(ranks=2, strip_k=4)),
-         (capi.generate_mask_host(150, 40, 11, 0.45), 12, True, False, dict(ranks=1, strip_k=16)),
          (capi.generate_mask_host(90, 70, 5, 0.5), 8, False, True, dict(ranks=2, smem_limit=2048)),
          (np.ones((24, 24), dtype=np.int32), 4, True, True, dict(ranks=1)),  # nothing moved: K5 rebuilds the tables
-         (np.zeros((12, 18), dtype=np.int32), 6, False, False, dict(ranks=2)),
          ((rng.random((5, 3)) < 0.5).astype(np.int32), 9, True, True, dict(ranks=1))]  # more parts than columns
 for mask, P, px, py, kw in cases:
     d, _ = orc.emu_partition(mask, P, px, py, **kw)
