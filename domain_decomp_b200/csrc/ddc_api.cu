@@ -549,7 +549,10 @@ int ddc_set_stream(ddc_handle_t h, void* cuda_stream)
 {
     if (!h)
         return DDC_ERR_ARG;
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    if (next != h->stream) // nothing orders the new stream after the old one's last step: start from k_init again
+        h->clean[0] = h->clean[1] = ddc_handle_s::CleanSig();
+    h->stream = next;
     return DDC_OK;
 }
 
