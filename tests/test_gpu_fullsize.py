@@ -205,6 +205,18 @@ def test_c4_arctic1km_4096_parts(capi, oracle):
         assert_same_as_oracle(out, pid, o)
 
 
+@pytest.mark.parametrize("P", [3000, 4097])
+def test_c4_part_counts_that_are_not_powers_of_two(capi, oracle, P):
+    """the same 8192 x 8192 mask into 3000 and 4097 parts: uneven part counts at every level of the RCB tree
+    (ceil(n/2) | floor(n/2) splits, leaves at different depths, targets that are not W/2), both periodic"""
+    nx, ny, land, seed = 8192, 8192, 0.60, 1
+    out = decompose_on_device(capi, nx, ny, P, land, seed, 1, 1)
+    check_properties(out, nx, ny, P, 1, 1)
+    mask = out["d_mask"].cpu().numpy()
+    pid = out["d_pid"].cpu().numpy()
+    assert_same_as_oracle(out, pid, oracle.partition(mask, P, True, True, use_hist=True))
+
+
 def test_c5_1km_global_16384_parts(capi, oracle):
     """BASELINE config 5: 32768 x 32768 (1.07 G cells), 16384 parts, periodic in x"""
     import psutil

@@ -210,3 +210,13 @@ def test_back_to_back_steps_without_k_init(oracle, ranks, monkeypatch):
                             (capi.generate_mask_host(64, 64, 3, 0.97), 8, False, False)][:3 if ranks < 3 else 1]:
         d, _ = oracle.emu_partition(mask, P, px, py, ranks=ranks)
         assert_same(d, oracle.partition(mask, P, px, py, use_hist=True), (mask.shape, P, ranks))
+
+
+@pytest.mark.parametrize("P,ranks", [(77, 1), (100, 2), (129, 1), (255, 1)])
+def test_part_counts_that_are_not_powers_of_two(oracle, P, ranks):
+    """ceil(n/2) | floor(n/2) splits at every level: leaves at different depths, targets that are not W / 2 (the FP64
+    target path of the median), strips with different numbers of parts"""
+    from domain_decomp_b200 import capi
+    mask = capi.generate_mask_host(600, 500, 13, 0.5)
+    d, _ = oracle.emu_partition(mask, P, True, True, ranks=ranks)
+    assert_same(d, oracle.partition(mask, P, True, True, use_hist=True), (P, ranks))
