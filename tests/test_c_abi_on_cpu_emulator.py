@@ -164,3 +164,51 @@ def test_repeated_and_alternating_geometries_on_one_handle(capi, handle, oracle)
         T.assert_same(T.run_gpu(handle, a, 12, True, False), oa, "alternating a")
     for P in (5, 12, 3):
         T.assert_same(T.run_gpu(handle, a, P, True, False), oracle.partition(a, P, True, False, use_hist=True), P)
+
+
+def test_argument_and_state_errors(capi, oracle):
+    """every entry point answers misuse with a status and a message (Utils.hpp / Grid.hpp conventions of the
+    reference: nothing aborts, nothing is silently ignored)"""
+    L = capi._lib
+    h = capi.Handle(0)
+    m = capi.generate_mask_host(40, 30, 1, 0.5)
+    try:
+        # create: rank outside the communicator, ranks > 1 without a NCCL id
+        hh = C.c_void_p()
+        assert L.ddc_create(C.byref(hh), 0, 3, 2, None) < 0 and b"bad arguments" in L.ddc_last_error(None)
+        assert L.ddc_create(C.byref(hh), 0, 0, 2, None) < 0 and b"NCCL unique id" in L.ddc_last_error(None)
+        assert L.ddc_create(C.byref(hh), 7, 0, 1, None) < 0 and b"out of range" in L.ddc_last_error(None)
+        # masks: extents, shard bounds, null pointers
+        assert L.ddc_set_mask_host(h.h, m.ctypes.data, 0, 30, 0, 30) < 0
+        assert L.ddc_set_mask_host(h.h, m.ctypes.data, 40, 30, 0, 29) < 0 and b"must hold rows" in L.ddc_last_error(h.h)
+        assert L.ddc_set_mask_host(h.h, None, 40, 30, 0, 30) < 0
+        assert L.ddc_set_mask_host(h.h, m.ctypes.data, 65536, 65536, 0, 65536) < 0  # more cells than an int can index
+        # partition: before a mask, bad part count
+        with pytest.raises(capi.DdcError, match="no mask set"):
+            h.partition(4)
+        h.set_mask_host(m)
+        with pytest.raises(capi.DdcError, match="nparts"):
+            h.partition(0)
+        # getters before a partition, bad edge
+        with pytest.raises(capi.DdcError, match="ddc_partition"):
+            h.boxes()
+        h.partition(6, True, False)
+        out = np.zeros(6, dtype=np.int32)
+        assert L.ddc_get_neighbour_counts(h.h, 4, 0, out.ctypes.data) < 0 and b"edge" in L.ddc_last_error(h.h)
+        assert L.ddc_get_neighbour_counts(h.h, 0, 2, out.ctypes.data) < 0
+        # a new mask invalidates the old results
+        h.set_mask_host(m)
+        with pytest.raises(capi.DdcError):
+            h.boxes()
+        # P == 1: the reference returns before neighbour discovery (quirk Q4): empty lists, no error
+        h.partition(1, True, True)
+        assert h.boxes().tolist() == [[0, 0, 40, 30]]
+        assert all(len(h.neighbours(e, per)[0]) == 0 for e in range(4) for per in range(2))
+        assert np.array_equal(h.pid_host(), np.where(m > 0, 0, -1))
+        # more parts than cells
+        h.partition(40 * 30 + 5)
+        o = oracle.partition(m, 40 * 30 + 5, use_hist=True)
+        assert h.boxes().tolist() == o.boxes.tolist() and np.array_equal(h.pid_host(), o.pid)
+    finally:
+        h.close()
+    assert L.ddc_destroy(None) == 0 and L.ddc_partition(None, 4, 0, 0, 3) < 0

@@ -147,3 +147,31 @@ def test_files_written_by_the_host_layer_equal_the_reference_writers(oracle, tmp
         assert {k: v[0] for k, v in mdims.items()} == dict(ref["files"]["mask"]["dims"])
         assert mdata["pid"] == ref["files"]["mask"]["vars"][("/", "pid")][1]
         done += 1
+
+
+@pytest.mark.parametrize("exe", [DECOMP, DECOMP_EMU], ids=["oracle", "emu"])
+def test_cli_ignore_mask_and_rect3030(goldens, oracle, fixture_dir, tmp_path, exe):
+    """--ignore-mask (every cell is an object) and the nextSIM restart layout of grids/rect3030.res.cdl: group
+    `data`, a double mask declared (x, y), read with -o xy (BASELINE config 1)"""
+    out = subprocess.run([exe, "-g", os.path.join(fixture_dir, "test_0.cdl"), "--parts", "4", "-i"], capture_output=True,
+                         text=True, timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr
+    _, data = parse_cdl(open(tmp_path / "partition_mask_4.cdl").read())
+    o = oracle.partition(np.ones((4, 6), dtype=np.int32), 4, use_hist=True)  # test_0 is all land: ignored
+    assert data["pid"] == o.pid.ravel().tolist()
+    # rect3030: rebuilt from the golden JSON in the reference's layout
+    inp = goldens["inputs"]["rect3030"]
+    vals = np.asarray(inp["mask"], dtype=np.int32)
+    rows = ",\n".join("  " + ", ".join("%d" % v for v in vals[i * 30:(i + 1) * 30]) for i in range(30))
+    cdl = ("netcdf rect3030 {\n\ngroup: data {\n  dimensions:\n  \tx = 30 ;\n  \ty = 30 ;\n  variables:\n  \tdouble mask(x, y) ;\n"
+           "  data:\n\n   mask =\n%s ;\n  } // group data\n}\n" % rows)
+    (tmp_path / "rect3030.cdl").write_text(cdl)
+    for P in (2, 4):
+        out = subprocess.run([exe, "-g", "rect3030.cdl", "-o", "xy", "--parts", str(P)], capture_output=True, text=True,
+                             timeout=300, cwd=tmp_path)
+        assert out.returncode == 0, out.stderr
+        _, data = parse_cdl(open(tmp_path / ("partition_mask_%d.cdl" % P)).read())
+        o = oracle.partition(vals.reshape(30, 30), P, use_hist=True)
+        assert data["pid"] == o.pid.ravel().tolist()
+        _, meta = parse_cdl(open(tmp_path / ("partition_metadata_%d.cdl" % P)).read())
+        assert meta["domain_x"] == o.boxes[:, 0].tolist() and meta["domain_extent_y"] == o.boxes[:, 3].tolist()
