@@ -33,7 +33,7 @@
 #include "ddc_median.cuh"
 #include "ddc_neighbours.cuh"
 
-// dynamic shared memory of a kernel (test builds: a buffer of the host emulation, see ddc_host_emu.h)
+// dynamic shared memory of a kernel (test builds: a buffer of the host emulation, see oracle/emu/ddc_host_emu.h)
 #ifdef DDC_HOST_EMU
 #define DDC_DYN_SHARED(T, name) T* name = reinterpret_cast<T*>(ddc_emu_dyn_smem())
 #else

@@ -9,7 +9,7 @@
 #include <stddef.h>
 
 #ifdef DDC_HOST_EMU
-#include "ddc_host_emu.h" // host stand-ins of the device language (test builds only)
+#include "ddc_host_emu.h" // oracle/emu: host stand-ins of the device language (test builds only)
 #endif
 
 namespace ddc {

@@ -1,4 +1,4 @@
-// ddc_host_emu.h -- host stand-ins of the CUDA device language, for TEST builds only (-DDDC_HOST_EMU).
+// ddc_host_emu.h -- TEST INFRASTRUCTURE: host stand-ins of the CUDA device language (-DDDC_HOST_EMU builds).
 //
 // With this header the kernel sources (ddc_median.cuh, ddc_neighbours.cuh, ddc_kernels.cuh) compile as
 // plain host C++.  Scalar intrinsics are defined here; the execution model -- thread / block indices,
