@@ -212,3 +212,44 @@ def test_argument_and_state_errors(capi, oracle):
     finally:
         h.close()
     assert L.ddc_destroy(None) == 0 and L.ddc_partition(None, 4, 0, 0, 3) < 0
+
+
+def test_random_call_sequences_on_one_handle(capi, handle, oracle):
+    """the state a handle carries between calls (buffers, the cached plan, which accumulators are clean): a random
+    sequence of decompositions over a pool of masks of different extents -- synchronous, DDC_ASYNC twice in a row,
+    boxes-only followed by a full step on the same mask, caller-supplied boxes in between"""
+    rng = np.random.default_rng(3)
+    pool = []
+    for i in range(5):
+        nx, ny = int(rng.integers(1, 100)), int(rng.integers(1, 100))
+        m = (rng.random((ny, nx)) >= rng.random()).astype(np.int32)
+        if i == 0:
+            m[:] = 1
+        if i == 1:
+            m[:] = 0
+        pool.append(m)
+    for it in range(40):
+        m = pool[int(rng.integers(0, len(pool)))]
+        P = int(rng.integers(1, 30))
+        px, py = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        mode = int(rng.integers(0, 4))
+        o = oracle.partition(m, P, px, py, use_hist=True)
+        ctx = (it, m.shape, P, mode)
+        if mode == 0:
+            T.assert_same(T.run_gpu(handle, m, P, px, py), o, ctx)
+        elif mode == 1:
+            handle.set_mask_host(m)
+            for _ in range(2):
+                handle.partition(P, px, py, flags=capi.WANT_PID | capi.WANT_NEIGHBOURS | capi.ASYNC)
+            assert handle.boxes().tolist() == o.boxes.tolist() and np.array_equal(handle.pid_host(), o.pid), ctx
+        elif mode == 2:
+            handle.set_mask_host(m)
+            handle.partition(P, px, py, flags=0)
+            assert handle.boxes().tolist() == o.boxes.tolist(), ctx
+            handle.partition(P, px, py)
+            assert np.array_equal(handle.pid_host(), o.pid) and handle.stats()["median_iters"] == o.median_iters, ctx
+        else:
+            handle.neighbours_from_boxes(o.boxes, m.shape[1], m.shape[0], px, py)
+            if P > 1:
+                assert handle.neighbours(0, 0)[0].tolist() == o.nbr.ids[0][0].tolist(), ctx
+            T.assert_same(T.run_gpu(handle, m, P, px, py), o, ctx)
