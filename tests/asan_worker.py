@@ -21,10 +21,10 @@ orc._emu = L  # orc.emu_partition() now drives the sanitizer build
 from domain_decomp_b200 import capi  # noqa: E402
 
 rng = np.random.default_rng(3)
-cases = [(capi.generate_mask_host(130, 40, 7, 0.5), 12, True, False, dict(ranks=2)),
+cases = [(capi.generate_mask_host(100, 40, 7, 0.5), 12, True, False, dict(ranks=2)),
          (capi.generate_mask_host(67, 31, 2, 0.4), 7, False, True, dict(ranks=1)),  # ragged width: scalar paths
          (capi.generate_mask_host(150, 40, 11, 0.45), 12, True, False, dict(ranks=2, strip_k=4)),
-         (capi.generate_mask_host(90, 70, 5, 0.5), 8, False, True, dict(ranks=2, smem_limit=2048)),
+         (capi.generate_mask_host(60, 50, 5, 0.5), 8, False, True, dict(ranks=2, smem_limit=2048)),
          (np.ones((24, 24), dtype=np.int32), 4, True, True, dict(ranks=1)),  # nothing moved: K5 rebuilds the tables
          ((rng.random((5, 3)) < 0.5).astype(np.int32), 9, True, True, dict(ranks=1))]  # more parts than columns
 for mask, P, px, py, kw in cases:

@@ -77,7 +77,7 @@ def test_rect3030(goldens, handle, oracle):
 def test_random_small_masks(handle, oracle):
     """as tests/test_gpu_parity.py::test_random_small_masks, fewer iterations; ONE handle across changing extents"""
     rng = np.random.default_rng(11)
-    for it in range(40):
+    for it in range(25):
         NX, NY = int(rng.integers(1, 50)), int(rng.integers(1, 50))
         dens = rng.choice([0.0, 0.02, 0.1, 0.3, 0.6, 0.9, 1.0])
         m = (rng.random((NY, NX)) < dens).astype(np.int32) * int(rng.integers(1, 5))
@@ -228,7 +228,7 @@ def test_random_call_sequences_on_one_handle(capi, handle, oracle):
         if i == 1:
             m[:] = 0
         pool.append(m)
-    for it in range(40):
+    for it in range(25):
         m = pool[int(rng.integers(0, len(pool)))]
         P = int(rng.integers(1, 30))
         px, py = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))

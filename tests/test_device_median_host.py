@@ -33,8 +33,8 @@ def fuzz(emu, seed, histograms, queries, nmax, shape, ulps, bitmap):
 @pytest.mark.parametrize("ulps", [0, 2, -2])
 def test_device_median_equals_oracle_small_histograms(emu, shape, ulps):
     for bitmap in (True, False):
-        m, n, bad = fuzz(emu, 1000 + shape, 6000, 50, 600, shape, ulps, bitmap)
-        assert n > 300000
+        m, n, bad = fuzz(emu, 1000 + shape, 3000, 50, 600, shape, ulps, bitmap)
+        assert n > 150000
         assert m == 0, "%s, ulps %+d, bit map %s: first mismatch {kind,n,c0,c1,nlo,parts,got,want,it,want_it} = %s" % (
             SHAPES[shape], ulps, bitmap, bad)
 
@@ -43,7 +43,7 @@ def test_device_median_equals_oracle_small_histograms(emu, shape, ulps):
 def test_device_median_equals_oracle_multi_tile_histograms(emu, shape):
     """up to 70000 bins: three tiles of the bit map, the sizes of the wide-grid configs"""
     for ulps in (0, 2, -2):
-        m, n, bad = fuzz(emu, 2000 + shape, 600, 80, 70000, shape, ulps, True)
+        m, n, bad = fuzz(emu, 2000 + shape, 300, 80, 70000, shape, ulps, True)
         assert m == 0, (SHAPES[shape], ulps, bad)
 
 
