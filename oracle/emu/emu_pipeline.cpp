@@ -87,6 +87,8 @@ struct Options {
     int strip_k = 0; // 0 auto, 1 / 2 / 4 rows per warp, 8 whole row in registers
     int scan_rpc = 64; // rows per CTA of the mask scan
     int smem_limit = 232448; // bytes of dynamic shared memory a block may use (B200: 227 KB)
+    bool collectives = false; // G > 1: the NCCL fallback of ddc_api.cu (all-reduce / all-gather between the kernels,
+                              // emulated by host loops) instead of the slot exchange inside the kernels
 };
 
 bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int aix, int aiy, unsigned step,
@@ -97,7 +99,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const int yr_off = (NX + 3) & ~3, ncol = yr_off + 2 * G;
     const int Rmax = (NY + G - 1) / G;
     const int Scap = (int)std::min<long long>(P, 1LL << std::min(aix, 30));
-    const bool ycuts = aiy > 0 && P > 1, narrow = NX < 65536, p2p = G > 1;
+    const bool ycuts = aiy > 0 && P > 1, narrow = NX < 65536, p2p = G > 1 && !opt.collectives;
     const size_t rc_elems = (size_t)Scap * (((size_t)Rmax + 31) & ~(size_t)31);
     const size_t rc_words = narrow ? (rc_elems + 1) / 2 : rc_elems;
     const size_t rank_stride = narrow ? rc_words * 2 : rc_words;
@@ -183,6 +185,14 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                         r.done.data(), yr_off));
         }
     }
+    if (G > 1 && !p2p) { // ncclAllReduce(SUM) of the column counts and the y-range pairs, in place on every rank
+        std::vector<unsigned> sum((size_t)ncol, 0u);
+        for (Rank& r : R)
+            for (int i = 0; i < ncol; i++)
+                sum[i] += colslot(r, r.rank)[i];
+        for (Rank& r : R)
+            std::copy(sum.begin(), sum.end(), colslot(r, r.rank));
+    }
     // ---- K2: x cuts ----
     for (Rank& r : R) {
         StripTable st;
@@ -263,6 +273,14 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                         k_strip_rows<unsigned>(r.bits.data(), NB, r.rows, st.x0, st.x1, st.p0, &r.plan, Scap, out, Rmax));
             }
         }
+        std::vector<std::vector<unsigned>> gathered;
+        if (G > 1 && !p2p) { // ncclAllGather of every rank's block: [G][rc_words]
+            gathered.assign(G, std::vector<unsigned>(rc_words * G + 4, 0u));
+            for (Rank& dst : R)
+                for (Rank& src : R)
+                    std::copy(rowslot(src, src.rank), rowslot(src, src.rank) + rc_words,
+                        gathered[dst.rank].begin() + (size_t)src.rank * rc_words);
+        }
         // on the GPU block 0 of every rank's K4 raises the stage-1 flag once its K3 is complete; the ranks of
         // the emulation run one after the other, so the flags are raised here, after ALL K3s
         for (Rank& r : R)
@@ -277,6 +295,8 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             pr.n = p2p ? G : 1;
             for (int q = 0; q < G; q++)
                 pr.row[q] = rowslot(r, p2p ? q : r.rank);
+            if (G > 1 && !p2p)
+                pr.row[0] = gathered[r.rank].data();
             const PeerSync ps = sync_of(r);
             const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
 #define YCUTS(CT, SM)                                                                              \
@@ -331,6 +351,13 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     for (Rank& r : R)
         for (int q = 0; q < G; q++)
             R[q].flags[2 * MAX_PEERS + r.rank] = 2u * step + (r.sc.changes ? 1u : 0u);
+    if (G > 1 && !p2p) { // ncclAllReduce(MAX) of `changes`
+        int any = 0;
+        for (Rank& r : R)
+            any = std::max(any, r.sc.changes);
+        for (Rank& r : R)
+            r.sc.changes = any;
+    }
     // ---- K5 ----
     for (Rank& r : R) {
         StripTable st;
@@ -380,6 +407,7 @@ __attribute__((visibility("default"))) int emu_partition(const int32_t* mask, in
         opt.scan_rpc = scan_rpc;
     if (smem_limit > 0)
         opt.smem_limit = smem_limit;
+    opt.collectives = std::getenv("DDC_EMU_COLLECTIVES") != nullptr;
     // the masks of the ranks: 16-byte aligned copies of their row blocks (like a cudaMalloc'ed shard)
     std::vector<Rank> R(G);
     std::vector<std::vector<int32_t>> shard(G);

@@ -220,3 +220,18 @@ def test_part_counts_that_are_not_powers_of_two(oracle, P, ranks):
     mask = capi.generate_mask_host(600, 500, 13, 0.5)
     d, _ = oracle.emu_partition(mask, P, True, True, ranks=ranks)
     assert_same(d, oracle.partition(mask, P, True, True, use_hist=True), (P, ranks))
+
+
+@pytest.mark.parametrize("ranks", [2, 3, 5])
+def test_row_sharded_ranks_with_collectives(oracle, ranks, monkeypatch):
+    """the NCCL fallback of ddc_api.cu (decompositions that exceed the exported peer buffers): an all-reduce of the
+    column counts + y-range pairs, an all-gather of the strip row counts ([G][rank block], which K4 indexes by
+    rank = y / Rmax) and a MAX of `changes` BETWEEN the kernels, emulated by host loops; the kernels then take
+    their single-buffer paths (pc.n == 1, pr.n == 1) with G > 1.  Twice in a row: the second step without k_init"""
+    from domain_decomp_b200 import capi
+    monkeypatch.setenv("DDC_EMU_COLLECTIVES", "1")
+    monkeypatch.setenv("DDC_EMU_REPEAT", "2")
+    for mask, P, px, py in [(capi.generate_mask_host(130, 77, 7, 0.5), 12, True, False),
+                            (capi.generate_mask_host(64, 4, 2, 0.3), 8, False, False), (np.ones((24, 24), dtype=np.int32), 4, False, True)]:
+        d, _ = oracle.emu_partition(mask, P, px, py, ranks=ranks)
+        assert_same(d, oracle.partition(mask, P, px, py, use_hist=True), (mask.shape, P, ranks))
