@@ -253,3 +253,21 @@ def test_random_call_sequences_on_one_handle(capi, handle, oracle):
             if P > 1:
                 assert handle.neighbours(0, 0)[0].tolist() == o.nbr.ids[0][0].tolist(), ctx
             T.assert_same(T.run_gpu(handle, m, P, px, py), o, ctx)
+
+
+def test_device_mask_generator_and_device_resident_path(capi, handle, oracle):
+    """ddc_generate_mask_device == ddc_generate_mask_host (the benchmark's masks are synthesised on the device), and
+    the device-pointer entry points (borrowed mask in, pid pointer out) -- "device memory" is host memory here"""
+    nx, ny, P = 150, 70, 10
+    d = np.full((ny, nx), -7, dtype=np.int32)
+    handle.generate_mask_device(d.ctypes.data, nx, ny, 25, 0.45)
+    assert np.array_equal(d, capi.generate_mask_host(nx, ny, 25, 0.45))
+    half = np.full((30, nx), -7, dtype=np.int32)  # a row block of the same global mask
+    handle.generate_mask_device(half.ctypes.data, nx, ny, 25, 0.45, y_begin=20, y_count=30)
+    assert np.array_equal(half, d[20:50])
+    handle.set_mask_device(d.ctypes.data, nx, ny)
+    handle.partition(P, True, False)
+    o = oracle.partition(d, P, True, False, use_hist=True)
+    ptr = handle.pid_device()
+    pid = np.ctypeslib.as_array((C.c_int32 * (nx * ny)).from_address(ptr)).reshape(ny, nx)
+    assert np.array_equal(pid, o.pid) and handle.boxes().tolist() == o.boxes.tolist()
