@@ -26,9 +26,9 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "ddc_oracle.c")
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_oracle.so"])
-    subprocess.check_call(["make", "-s", "-C", _HERE, "libddc_median_emu.so", "libddc_emu.so"])  # make decides what is stale
+    subprocess.check_call(["make", "-s", "-j4", "-C", _HERE, "libddc_median_emu.so", "libddc_emu.so", "libddc_cuda_emu.so"])  # make decides what is stale
     if os.path.isdir("/root/reference"):  # make decides what is stale
-        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"] + (["-B"] if force else []))
+        subprocess.check_call(["make", "-s", "-j4", "-C", _HERE, "ref"] + (["-B"] if force else []))
     return _LIB
 
 
