@@ -222,7 +222,7 @@ def test_part_counts_that_are_not_powers_of_two(oracle, P, ranks):
     assert_same(d, oracle.partition(mask, P, True, True, use_hist=True), (P, ranks))
 
 
-@pytest.mark.parametrize("ranks", [2, 3, 5])
+@pytest.mark.parametrize("ranks", [2, 3])
 def test_row_sharded_ranks_with_collectives(oracle, ranks, monkeypatch):
     """the NCCL fallback of ddc_api.cu (decompositions that exceed the exported peer buffers): an all-reduce of the
     column counts + y-range pairs, an all-gather of the strip row counts ([G][rank block], which K4 indexes by
