@@ -38,7 +38,12 @@ WORKLOADS = {
     "C4_8192x8192_p4096": (8192, 8192, 4096, 0.60, 1, 0, 0),
     "C3_4096x4096_p1024": (4096, 4096, 1024, 0.45, 3, 0, 0),
     "C2_528x522_p64": (528, 522, 64, 0.45, 25, 1, 1),
+    # not BASELINE configs: one rank's share of C5 on 2 / 8 GPUs as a mask of its own, for tuning the streaming
+    # kernels at shard size on one GPU
+    "X_shard8_32768x4096_p2048": (32768, 4096, 2048, 0.45, 32, 1, 0),
+    "X_shard2_32768x16384_p8192": (32768, 16384, 8192, 0.45, 32, 1, 0),
 }
+GOLDEN_DIGESTS = os.path.join(ROOT, "tests", "golden", "bench_digests.json")
 DEFAULT_WORKLOAD = "C5_32768x32768_p16384"
 L2_BYTES = 126 * 1000 * 1000
 ALGO_BYTES_PER_CELL = 8  # 4 B int32 mask read + 4 B int32 pid write
@@ -114,21 +119,39 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_sample(workload, threads: int):
-    """a bounded sample of the workload for the CPU legs: the top-left 1/8 x 1/8 window of the SAME
-    mask into 1/64 of the parts (same cells per part), or the whole mask when it is small"""
+def golden_digest(workload):
+    """digest of the decomposition's replicated tables as the CPU oracle computes them (scripts/make_bench_digests.py)"""
+    try:
+        with open(GOLDEN_DIGESTS) as f:
+            return json.load(f)[workload]["digest"]
+    except Exception:
+        return None
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of an int32 device buffer owned by the library"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def cpu_sample(workload, threads: int, whole: bool = False):
+    """the workload for the CPU legs: the whole mask when it is small or `whole` is set, else a bounded sample --
+    the top-left 1/8 x 1/8 window of the SAME mask into 1/64 of the parts (same cells per part).  The mask comes
+    from the oracle's restatement of the generator: the CPU legs never load the CUDA library."""
     nx, ny, P, land, seed, px, py = WORKLOADS[workload]
-    from domain_decomp_b200 import capi
-    if nx * ny > 4096 * 4096:
+    from oracle import oracle as orc
+    if nx * ny > 4096 * 4096 and not whole:
         f = 8
         sx, sy, sp = nx // f, ny // f, max(2, P // (f * f))
         desc = ("top-left %dx%d window of the %dx%d mask into %d parts (same cells per part; %d RCB levels "
                 "instead of %d, which favours the CPU)" % (sx, sy, nx, ny, sp, (sp - 1).bit_length(), (P - 1).bit_length()))
     else:
         sx, sy, sp, desc = nx, ny, P, "the whole %dx%d mask into %d parts" % (nx, ny, P)
-    full = capi.generate_mask_host(nx, ny, seed, land, 0, sy)  # rows [0, sy) of the global mask
+    full = orc.generate_mask(nx, ny, seed, land, 0, sy)  # rows [0, sy) of the global mask
     import numpy as np
-    mask = np.ascontiguousarray(full[:, :sx])
+    mask = full if sx == nx else np.ascontiguousarray(full[:, :sx])
     return mask, sp, px, py, desc
 
 
@@ -152,22 +175,33 @@ def reference_arm(args):
     from oracle import oracle as orc
     orc.build()
     threads = orc.max_threads()
-    mask, sp, px, py, desc = cpu_sample(args.workload, threads)
+    nx, ny, P, land, seed, _, _ = WORKLOADS[args.workload]
+    # the WHOLE workload when the host has the memory for it: the dot-based restatement keeps Zoltan's dot arrays
+    # (24 B per ocean cell) beside the 4 B/cell mask and the 4 B/cell pid
+    need = nx * ny * (4 + 4 + 24 * 0.6) * 1.15
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    whole = args.sample == "whole" or (args.sample == "auto" and avail > need)
+    t0 = time.perf_counter()
+    mask, sp, px, py, desc = cpu_sample(args.workload, threads, whole=whole)
     steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
     # keep the whole run within a few minutes whatever K is
-    t0 = time.perf_counter()
     sec = run_cpu(mask, sp, px, py, threads, 1, 0)
     budget = 150.0
     steps = max(1, min(steps, int(budget / max(sec, 1e-3))))
     sec = run_cpu(mask, sp, px, py, threads, steps, warmup) if steps > 1 else sec
     value = mask.size / sec
-    nx, ny, P, land, seed, _, _ = WORKLOADS[args.workload]
+    same_config = mask.shape == (ny, nx) and sp == P
     line = {
         "impl": "reference", "metric": "mask cells partitioned/sec", "value": value, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
         "config": {"workload": args.workload, "nx": nx, "ny": ny, "parts": P, "land_frac": land, "seed": seed,
                    "periodic_x": px, "periodic_y": py},
+        "same_config": same_config,
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": desc,
                          "note": "CPU port of the reference algorithm (oracle/ddc_oracle.c, dot-based Zoltan RCB "
                                  "restatement + labelling + O(P^2) neighbour discovery); the reference binary "
@@ -187,6 +221,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the result checks (they are outside the timed regions)")
+    ap.add_argument("--sample", default="auto", choices=["auto", "whole", "window"],
+                    help="--impl reference: the whole workload (when the host memory allows: auto) or the bounded window")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU exchange: stores into the peers' memory from inside the kernels (default) or NCCL collectives")
     args = ap.parse_args()
@@ -307,6 +344,39 @@ def main():
         "stage_ms": {k: round(v, 4) for k, v in stage.items()},
     }
 
+    # ---- what was timed is also what is right (outside every timed region) --------------------------
+    # every rank: digest of the replicated tables (boxes, 8 neighbour tables, part loads, `changes`) and its own
+    # pid rows against the labelling rule restated with torch; rank 0: all ranks agree, the digest is the one the CPU
+    # oracle gives for this workload (tests/golden/bench_digests.json), the label counts of all ranks are the loads
+    parity = None
+    if not args.no_verify:
+        from domain_decomp_b200 import verify
+        h.partition(P, px, py, flags)
+        digest = verify.handle_digest(h)
+        d_pid = torch.as_tensor(_DevArray(h.pid_device(), (max(y_count, 1), nx)), device=dev)[:y_count]
+        pid_ok, counts = verify.pid_rows_match_boxes(h.boxes(), nx, ny, d_mask[:y_count], d_pid, y_begin)
+        if world > 1:
+            dist.all_reduce(counts)
+            every = [None] * world
+            dist.all_gather_object(every, (digest, bool(pid_ok)))
+        else:
+            every = [(digest, bool(pid_ok))]
+        loads_ok = bool(torch.equal(counts.cpu(), torch.from_numpy(h.part_loads().astype(np.int64))))
+        golden = golden_digest(args.workload)
+        parity = {"checked": True, "digest": digest, "ranks_agree": all(d == digest for d, _ in every),
+                  "matches_cpu_oracle": (digest == golden) if golden else None,
+                  "pid_rows_are_the_labelling_of_the_boxes": all(ok for _, ok in every),
+                  "label_counts_equal_part_loads": loads_ok,
+                  "what": "sha256 of boxes + 8 neighbour tables + part loads + changes on every rank; golden = CPU oracle "
+                          "(scripts/make_bench_digests.py); pid checked on the device against the labelling rule"}
+        parity["passed"] = bool(parity["ranks_agree"] and parity["matches_cpu_oracle"] is not False
+                                and parity["pid_rows_are_the_labelling_of_the_boxes"] and loads_ok)
+        del d_pid
+        if not parity["passed"]:
+            if rank == 0:
+                print(json.dumps({"parity": parity, "error": "PARITY FAILURE: the timed output is wrong"}), flush=True)
+            raise SystemExit(3)
+
     # ---- end to end through the C ABI with host buffers -----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -370,12 +440,14 @@ def main():
                            ", histograms pushed into the peers' memory over NVLink by the producing kernels, flag barriers in the cut kernels" if st["exchange"] == 2
                            else ", NCCL allreduce + allgather")),
                        "outputs": "boxes + pid + neighbour/halo tables",
+                       "knobs": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("DDC_")},
                        "l2": ("L2 flushed between timed iterations (256 MiB write)" if need_flush else
                               "inputs larger than L2 (%.0f MiB int32 mask + %.0f MiB pid per GPU vs 126 MB L2)"
                               % (shard_bytes / 2**20, shard_bytes / 2**20))},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": st["gpu_launches"] * K * world,
+            "parity": parity,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "result": {"n_ocean": st["n_ocean"], "strips": st["nstrips"], "x_levels": st["n_xlev"],

@@ -102,6 +102,38 @@ struct DevBuf {
         cap = 0;
     }
 };
+
+// One way to launch a kernel.  pdl: programmatic dependent launch -- the kernel may become resident while the
+// kernel before it in the stream is still running and waits for it in its own pdl_wait() (ddc_kernels.cuh).
+// Test builds (DDC_HOST_EMU, oracle/emu) run the kernel on the host emulation instead.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+    Args&&... args)
+{
+#ifdef DDC_HOST_EMU
+    (void)stream;
+    (void)pdl;
+    DDC_EMU_LAUNCH(grid, block, smem, kernel(static_cast<KArgs>(args)...));
+    return cudaSuccess;
+#else
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+#endif
+}
+int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
 } // namespace
 
 struct ddc_handle_s {
@@ -137,6 +169,13 @@ struct ddc_handle_s {
     int plan_nx = 0, plan_ny = 0, plan_P = 0, aix = 0, aiy = 0;
     bool pending = false, profiled = false; // a step is enqueued but not yet validated
     int last_flags = 0, strip_k = 0;
+    // knobs (environment, read once in ddc_create): DDC_PDL=0 plain stream order between the kernels,
+    // DDC_WARM=0 no instruction-cache warm-up in the cut kernels, DDC_FUSE_FIN=0 k_finalize as a kernel of its
+    // own after the labelling kernel, DDC_DEBUG_TS=1 time stamps, DDC_SCAN_RPC / DDC_LABEL_RPC rows per CTA
+    bool use_pdl = true, warm = true, fuse_fin = true, debug_ts = false;
+    int scan_rpc = 0, label_rpc = 0;
+    PeerSync fin_ps {}; // the exchange state of the last step, for a k_finalize launched from validate()
+    size_t xcuts_static = 0, ycuts_static = 0; // static shared memory of the cut kernels (0: not yet asked)
     // what K2 (column counts, scalars) and the scan's last CTA (counters) left clean for a later step: k_init is
     // only launched when the buffers or the geometry of the step differ (index: parity of the exchange slots)
     struct CleanSig {
@@ -279,12 +318,13 @@ int run_neighbours(ddc_handle_t h, int P, int nx, int ny, int px, int py)
     }
     const int warps_per_cta = 8;
     const int grid = (std::max(P, 8) + warps_per_cta - 1) / warps_per_cta; // >= 8 * pad32(P) threads
-    k_neighbours<false><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p, nullptr,
-        nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, nullptr);
-    k_scan_counts<<<8, 1024, 0, s>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p, nullptr);
-    k_neighbours<true><<<grid, 256, 0, s>>>(t.bx, P, nx, ny, px, py, t.st, h->nbr_counts.p,
-        h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
-        h->sc.p, nullptr);
+    CUDA_TRY(h, launch_k(k_neighbours<false>, dim3(grid), dim3(256), 0, s, false, t.bx, P, nx, ny, px, py, t.st,
+        h->nbr_counts.p, nullptr, nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, nullptr));
+    CUDA_TRY(h, launch_k(k_scan_counts, dim3(8), dim3(1024), 0, s, false, h->nbr_counts.p, P, h->nbr_offsets.p,
+        h->nbr_totals.p, nullptr));
+    CUDA_TRY(h, launch_k(k_neighbours<true>, dim3(grid), dim3(256), 0, s, false, t.bx, P, nx, ny, px, py, t.st,
+        h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
+        h->sc.p, nullptr));
     h->stats.gpu_launches += 3;
     CUDA_TRY(h, cudaGetLastError());
     h->totals_valid = false;
@@ -313,9 +353,9 @@ int fetch_totals(ddc_handle_t h)
         CUDA_TRY(h, cudaMemsetAsync(&h->sc.p->edge_cut, 0, sizeof(unsigned long long), h->stream));
         Tables t = tables(h, h->nparts);
         const int grid = (std::max(h->nparts, 8) + 7) / 8;
-        k_neighbours<true><<<grid, 256, 0, h->stream>>>(t.bx, h->nparts, h->nx, h->ny, h->px, h->py, t.st,
-            h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p,
-            h->nbr_halos.p, h->nbr_starts.p, h->sc.p, nullptr);
+        CUDA_TRY(h, launch_k(k_neighbours<true>, dim3(grid), dim3(256), 0, h->stream, false, t.bx, h->nparts, h->nx, h->ny,
+            h->px, h->py, t.st, h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p,
+            h->nbr_halos.p, h->nbr_starts.p, h->sc.p, nullptr));
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaMemcpyAsync(&hs, h->sc.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -368,7 +408,7 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) {                                                                   \
             fail(nullptr, DDC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));           \
-            delete h;                                                                              \
+            ddc_destroy(h); /* releases whatever was created so far */                             \
             return DDC_ERR_CUDA;                                                                   \
         }                                                                                          \
     } while (0)
@@ -398,23 +438,26 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
         const int v = std::max(1, std::min(32, atoi(e)));
         CREATE_TRY(cudaMemcpyToSymbol(g_walk_lanes, &v, sizeof v));
     }
+    h->use_pdl = env_int("DDC_PDL", 1) != 0;
+    h->warm = env_int("DDC_WARM", 1) != 0;
+    h->fuse_fin = env_int("DDC_FUSE_FIN", 1) != 0;
+    h->debug_ts = env_int("DDC_DEBUG_TS", 0) != 0;
+    h->scan_rpc = env_int("DDC_SCAN_RPC", 0);
+    h->label_rpc = env_int("DDC_LABEL_RPC", 0);
     CREATE_TRY(h->sc.ensure(1));
     CREATE_TRY(h->plan.ensure(1));
+    CREATE_TRY(cudaMemset(h->plan.p, 0, sizeof(Plan)));
 #undef CREATE_TRY
-    if (nranks > 1) {
-        if (!nccl_id) {
-            delete h;
-            return fail(nullptr, DDC_ERR_ARG, "ddc_create: nranks > 1 needs a NCCL unique id");
-        }
+    if (nranks > 1 && nccl_id) { // without an id the ranks can only exchange through peer memory (ddc_peer_*)
         if (!g_nccl.load()) {
-            delete h;
+            ddc_destroy(h);
             return fail(nullptr, DDC_ERR_NCCL, "%s", g_nccl.err.c_str());
         }
         ncclUniqueId id;
         memcpy(&id, nccl_id, DDC_NCCL_ID_BYTES);
         int r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
         if (r != ncclSuccess) {
-            delete h;
+            ddc_destroy(h);
             return fail(nullptr, DDC_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
         }
     }
@@ -664,6 +707,20 @@ void guess_plan(int P, int NX, int NY, int* ix, int* iy)
 } // namespace
 static void guess_plan_public(int P, int NX, int NY, int* ix, int* iy) { guess_plan(P, NX, NY, ix, iy); }
 namespace {
+// K5 (one block): `changes` of all ranks; when nothing moved, the naive blocks and the neighbour tables rebuilt
+// from them; the plan into the host's pinned copy.  Uses nparts / px / py / nx / ny of the handle.
+int launch_finalize(ddc_handle_t h, const PeerSync& ps, bool want_nbr)
+{
+    const int P = h->nparts;
+    Tables t = tables(h, P);
+    const NaiveParams nv = naive_params(P, h->nx, h->ny);
+    const NbrTables nb = { h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p,
+        h->nbr_starts.p };
+    CUDA_TRY(h, launch_k(k_finalize, dim3(1), dim3(1024), 0, h->stream, false, ps, P, h->nx, h->ny, h->px, h->py, nv, h->sc.p,
+        h->plan.p, t.st, t.bx, want_nbr ? 1 : 0, nb, h->pin_plan_dev));
+    return DDC_OK;
+}
+
 int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
 {
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -722,7 +779,14 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const size_t xneed = sizeof(unsigned) * ((((size_t)NX + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NX));
     const size_t yneed = sizeof(unsigned) * ((((size_t)NY + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NY));
     const size_t lim = max_dyn_smem(h->device);
-    const int x_smem = xneed + 1024 <= lim, y_smem = yneed + 1024 <= lim;
+    if (!h->xcuts_static) { // what the cut kernels hold statically counts against the same per-block limit
+        cudaFuncAttributes fa;
+        CUDA_TRY(h, cudaFuncGetAttributes(&fa, k_xcuts<true>));
+        h->xcuts_static = fa.sharedSizeBytes + 64;
+        CUDA_TRY(h, cudaFuncGetAttributes(&fa, k_ycuts<uint16_t, true>));
+        h->ycuts_static = fa.sharedSizeBytes + 64;
+    }
+    const int x_smem = xneed + h->xcuts_static <= lim, y_smem = yneed + h->ycuts_static <= lim;
     const int ygrid = std::max(1, std::min(Scap, 148 * 2));
     if (!x_smem)
         CUDA_TRY(h, h->colpfx.ensure((size_t)NX + 1));
@@ -746,7 +810,16 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     // exchange mode: peer memory when the buffers were exchanged and are large enough, else NCCL
     h->step++;
     const bool p2p = G > 1 && h->p2p && (size_t)ncol <= h->x_colcap && (!ycuts || rc_words + 4 <= h->x_rowcap);
+    if (G > 1 && !p2p && !h->comm)
+        return fail(h, DDC_ERR_STATE, "%d ranks but no exchange path: created without a NCCL id and %s", G,
+            h->p2p ? "the decomposition exceeds the exported peer buffers" : "no peer buffers imported");
     const int par = (int)(h->step & 1u);
+    const bool pdl = h->use_pdl && !profile; // (event records between the kernels would break the chain anyway)
+    unsigned long long* dbg = h->debug_ts
+        ? reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(h->plan.p) + offsetof(Plan, ts))
+        : nullptr;
+    if (dbg)
+        CUDA_TRY(h, cudaMemsetAsync(dbg, 0, sizeof(((Plan*)nullptr)->ts), s));
     constexpr size_t XFLAGS = 64; // words reserved for the flags at the head of an exchange buffer
     // slot `slot` (written by rank `slot`) of the buffer of rank q, for this step's parity
     auto xcol = [&](int q, int slot) { return h->xpeer[q] + XFLAGS + ((size_t)par * G + slot) * h->x_colcap; };
@@ -786,18 +859,21 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     mark(0);
     // ---- K1: mask scan -----------------------------------------------------------------------
     const int gridx = (NG + 7) / 8;
-    CUDA_TRY(h, h->done.ensure((size_t)gridx + 1));
+    // counters of the "last block" patterns: [0, gridx] mask scan, [gridx + 1] strip row counts, then the
+    // 64-bit counter of the labelling kernel; all zero between steps (their last blocks reset them)
+    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, ndone = d_label + 2;
+    CUDA_TRY(h, h->done.ensure((size_t)ndone));
     ddc_handle_s::CleanSig sig;
     sig.col = colcount;
     sig.done = h->done.p;
     sig.ncol = ncol;
     sig.yr_off = yr_off;
     sig.rank = h->rank;
-    sig.ndone = gridx + 1;
+    sig.ndone = ndone;
     const int ci = p2p ? par : 0;
     if (!(h->clean[ci] == sig) || p2p != h->clean_p2p) { // first use of these buffers with this geometry
-        k_init<<<(ncol + 255) / 256, 256, 0, s>>>(colcount, ncol, yr_off, h->rank, h->sc.p, h->loadmm.p, h->done.p,
-            gridx + 1);
+        CUDA_TRY(h, launch_k(k_init, dim3((std::max(ncol, ndone) + 255) / 256), dim3(256), 0, s, false, colcount, ncol, yr_off,
+            h->rank, h->sc.p, h->loadmm.p, h->done.p, ndone));
         launches++;
         if (p2p != h->clean_p2p)
             h->clean[0] = h->clean[1] = ddc_handle_s::CleanSig();
@@ -807,15 +883,13 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const bool vec = (NX % 4 == 0) && (((uintptr_t)h->d_mask) % 16 == 0);
     int* yr = reinterpret_cast<int*>(colcount + yr_off + 2 * h->rank);
     if (rows > 0 || p2p) { // an empty shard still has to push its (empty) counts and raise its flag
-        const int rpc = vec ? pick_rows_per_cta(k_scan_mask<true>, std::max(rows, 1), gridx)
-                            : pick_rows_per_cta(k_scan_mask<false>, std::max(rows, 1), gridx);
+        int rpc = vec ? pick_rows_per_cta(k_scan_mask<true>, std::max(rows, 1), gridx)
+                      : pick_rows_per_cta(k_scan_mask<false>, std::max(rows, 1), gridx);
+        if (h->scan_rpc >= 8)
+            rpc = h->scan_rpc & ~7;
         dim3 grid(gridx, std::max(1, (rows + rpc - 1) / rpc));
-        if (vec)
-            k_scan_mask<true><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
-                colcount, yr, push_col, ps, h->done.p, yr_off);
-        else
-            k_scan_mask<false><<<grid, 256, 0, s>>>(h->d_mask, NX, rows, h->y_begin, NB, rpc, h->bits.p,
-                colcount, yr, push_col, ps, h->done.p, yr_off);
+        CUDA_TRY(h, launch_k(vec ? k_scan_mask<true> : k_scan_mask<false>, grid, dim3(256), 0, s, pdl, h->d_mask, NX, rows,
+            h->y_begin, NB, rpc, h->bits.p, colcount, yr, push_col, ps, h->done.p, yr_off, dbg));
         launches++;
     }
     if (G > 1 && !p2p) // the first exchange step: column histogram and every rank's dot y-range in one sum
@@ -827,15 +901,18 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xneed));
             h->xcuts_smem = xneed;
         }
-        k_xcuts<true><<<1, 1024, xneed, s>>>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, h->plan.p, t.st, t.bx,
-            h->loads.p, h->loadmm.p, h->sc.p, colcount);
+        CUDA_TRY(h, launch_k(k_xcuts<true>, dim3(1), dim3(1024), xneed, s, pdl, pc, ps, NX, NY, P, nullptr, yr_off, G, aix,
+            aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, h->warm ? 1 : 0, dbg ? 1 : 0,
+            h->pin_plan_dev));
     } else
-        k_xcuts<false><<<1, 1024, 0, s>>>(pc, ps, NX, NY, P, h->colpfx.p, yr_off, G, aix, aiy, h->plan.p, t.st,
-            t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount);
+        CUDA_TRY(h, launch_k(k_xcuts<false>, dim3(1), dim3(1024), 0, s, pdl, pc, ps, NX, NY, P, h->colpfx.p, yr_off, G, aix,
+            aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, h->warm ? 1 : 0, dbg ? 1 : 0,
+            h->pin_plan_dev));
     launches++;
     // the column -> strip table K6 reads: painted by K4's blocks; without y levels there is no K4
     if (!ycuts) {
-        k_paint_strips<<<std::max(1, std::min((Scap + 7) / 8, 148 * 4)), 256, 0, s>>>(t.st, h->plan.p, h->strip_of_col.p);
+        CUDA_TRY(h, launch_k(k_paint_strips, dim3(std::max(1, std::min((Scap + 7) / 8, 148 * 4))), dim3(256), 0, s, pdl, t.st,
+            h->plan.p, h->strip_of_col.p));
         launches++;
     }
     mark(2);
@@ -856,8 +933,8 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
                 const int grid = (Rmax + 8 * K - 1) / (8 * K);
                 rb_shift = K == 4 ? 5 : (K == 2 ? 4 : 3);
 #define LAUNCH_SCAN(CT, KK, FF)                                                                    \
-    k_strip_rows_scan<CT, KK, FF><<<grid, 256, scan_smem, s>>>(h->bits.p, NB, NX, rows, t.st.x0, t.st.p0, h->plan.p, \
-        Scap, push_row, Rmax)
+    CUDA_TRY(h, launch_k(k_strip_rows_scan<CT, KK, FF>, dim3(grid), dim3(256), scan_smem, s, pdl, h->bits.p, NB, NX, rows, \
+        t.st.x0, t.st.p0, h->plan.p, Scap, push_row, Rmax, ps, h->done.p + d_rows, dbg))
                 // small shards: one row per warp, the whole row requested at once (rows of <= 8 chunks)
                 const bool full = K == 1 && NG <= 256 && h->strip_k != 1;
                 if (narrow) {
@@ -882,12 +959,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
 #undef LAUNCH_SCAN
             } else {
                 dim3 grid((Rmax + 31) / 32, (Scap + 7) / 8);
-                if (narrow)
-                    k_strip_rows<uint16_t><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
-                        h->plan.p, Scap, push_row, Rmax);
-                else
-                    k_strip_rows<unsigned><<<grid, 256, 0, s>>>(h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0,
-                        h->plan.p, Scap, push_row, Rmax);
+                CUDA_TRY(h, launch_k(narrow ? k_strip_rows<uint16_t> : k_strip_rows<unsigned>, grid, dim3(256), 0, s, pdl,
+                    h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0, h->plan.p, Scap, push_row, Rmax, ps, h->done.p + d_rows,
+                    dbg));
             }
             launches++;
         }
@@ -906,8 +980,8 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<CT, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed)); \
             opted = yneed;                                                                         \
         }                                                                                          \
-        k_ycuts<CT, SM><<<ygrid, 1024, SM ? yneed : 0, s>>>(pr, ps, rl, NY, t.st, h->ypfx.p, t.bx, h->loads.p, \
-            h->loadmm.p, h->plan.p, h->strip_of_col.p);                                                                \
+        CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : 0, s, pdl, pr, ps, rl, NY, t.st, \
+            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, h->warm ? 1 : 0, dbg ? 1 : 0)); \
     } while (0)
         if (narrow) {
             if (y_smem)
@@ -931,54 +1005,55 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     h->px = px;
     h->py = py;
     const int ngrid = (std::max(P, 8) + 7) / 8; // >= 8 * pad32(P) threads
-    auto neighbours = [&](cudaStream_t q) {
-        k_neighbours<false><<<ngrid, 256, 0, q>>>(t.bx, P, NX, NY, px, py, t.st, h->nbr_counts.p, nullptr,
-            nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p);
-        k_scan_counts<<<8, 1024, 0, q>>>(h->nbr_counts.p, P, h->nbr_offsets.p, h->nbr_totals.p, h->plan.p);
-        k_neighbours<true><<<ngrid, 256, 0, q>>>(t.bx, P, NX, NY, px, py, t.st, h->nbr_counts.p,
-            h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
-            h->sc.p, h->plan.p);
-        launches += 3;
-    };
     if (want_nbr) {
+        cudaStream_t q = h->side_stream;
         CUDA_TRY(h, cudaEventRecord(h->ev_fork, s));
-        CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-        neighbours(h->side_stream);
-        CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(q, h->ev_fork, 0));
+        CUDA_TRY(h, launch_k(k_neighbours<false>, dim3(ngrid), dim3(256), 0, q, false, t.bx, P, NX, NY, px, py, t.st,
+            h->nbr_counts.p, nullptr, nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p));
+        CUDA_TRY(h, launch_k(k_scan_counts, dim3(8), dim3(1024), 0, q, false, h->nbr_counts.p, P, h->nbr_offsets.p,
+            h->nbr_totals.p, h->plan.p));
+        CUDA_TRY(h, launch_k(k_neighbours<true>, dim3(ngrid), dim3(256), 0, q, false, t.bx, P, NX, NY, px, py, t.st,
+            h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
+            h->sc.p, h->plan.p));
+        launches += 3;
+        CUDA_TRY(h, cudaEventRecord(h->ev_join, q));
     }
     // ---- K6: labels + `changes` -----------------------------------------------------------------
-    if (rows > 0 && (P > 1 || want_pid)) {
+    // The labelling kernel's last block also ends the step (`changes`, exchange step 3, the plan into the host's
+    // pinned copy) unless there is no labelling kernel on this rank or the exchange goes through NCCL.
+    const bool label_runs = rows > 0 && (P > 1 || want_pid);
+    const bool fuse = h->fuse_fin && label_runs && (G == 1 || p2p);
+    h->fin_ps = ps;
+    if (label_runs) {
         const bool vecp = want_pid && (NX % 4 == 0) && (((uintptr_t)h->pid.p) % 16 == 0);
-#define LAUNCH_LABEL(V, W)                                                                         \
-    do {                                                                                           \
-        const int rpc = 32; /* no per-CTA epilogue: many small CTAs keep more stores in flight */  \
-        dim3 grid(gridx, (rows + rpc - 1) / rpc);                                                  \
-        k_label<V, W><<<grid, 256, 0, s>>>(h->bits.p, NX, rows, h->y_begin, NB, rpc,               \
-            h->strip_of_col.p, t.st.p0, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p, h->plan.p);       \
-    } while (0)
-        if (want_pid) {
-            if (vecp)
-                LAUNCH_LABEL(true, true);
-            else
-                LAUNCH_LABEL(false, true);
-        } else
-            LAUNCH_LABEL(false, false);
-#undef LAUNCH_LABEL
+        // no heavy per-CTA epilogue: many small CTAs keep more stores in flight
+        const int rpc = h->label_rpc >= 8 ? (h->label_rpc & ~7) : 32;
+        const dim3 grid(gridx, (rows + rpc - 1) / rpc);
+        LabelEnd fin {};
+        fin.fuse = fuse ? 1 : 0;
+        fin.P = P;
+        fin.ps = ps;
+        fin.counter = reinterpret_cast<unsigned long long*>(h->done.p + d_label);
+        fin.host_plan = h->pin_plan_dev;
+        fin.dbg = dbg;
+        auto kernel = !want_pid ? k_label<false, false> : (vecp ? k_label<true, true> : k_label<false, true>);
+        CUDA_TRY(h, launch_k(kernel, grid, dim3(256), 0, s, false, h->bits.p, NX, rows, h->y_begin, NB, rpc, h->strip_of_col.p,
+            t.st.p0, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p, h->plan.p, fin));
         launches++;
     }
     if (G > 1 && !p2p)
         NCCL_TRY(h, g_nccl.AllReduce(&h->sc.p->changes, &h->sc.p->changes, 1, nccl_Int32, nccl_Max, h->comm, s));
     mark(5);
-    // ---- K5: naive blocks when nothing moved; load statistics -----------------------------------
     if (want_nbr)
-        CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0)); // K5 rewrites the boxes K7 is reading
-    // (one block; when nothing moved it also rebuilds the neighbour tables from the naive blocks, and it
-    //  writes the plan into the host's pinned copy: no separate read-back at the end of the step)
-    const NbrTables nb = { h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p,
-        h->nbr_starts.p };
-    k_finalize<<<1, 1024, 0, s>>>(ps, P, NX, NY, px, py, nv, h->sc.p, h->plan.p, t.st, t.bx, want_nbr ? 1 : 0, nb,
-        h->pin_plan_dev);
-    launches++;
+        CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0)); // the step is over when the neighbour tables are, too
+    // ---- K5 as a kernel of its own (see above; otherwise only from validate(), when nothing moved) ----
+    if (!fuse) {
+        int rc = launch_finalize(h, ps, want_nbr);
+        if (rc)
+            return rc;
+        launches++;
+    }
     mark(6);
     if (want_nbr)
         h->have_nbr = true;
@@ -1030,13 +1105,39 @@ int validate(ddc_handle_t h)
         }
         h->stats.gpu_launches += launches;
     }
+    if (h->pin_plan->fixup) {
+        // nothing moved on this rank: k_finalize collects the other ranks' verdicts and, if nothing moved
+        // anywhere, reports the naive blocks and rebuilds the neighbour tables from them (rare: all land, or
+        // the RCB reproduces the naive block layout)
+        int rc = launch_finalize(h, h->fin_ps, (h->last_flags & DDC_WANT_NEIGHBOURS) && h->nparts > 1);
+        if (rc)
+            return rc;
+        h->stats.gpu_launches++;
+        h->totals_valid = false;
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (h->pin_plan->mismatch == 3) {
+            h->partitioned = false;
+            h->clean[0] = h->clean[1] = ddc_handle_s::CleanSig();
+            return fail(h, DDC_ERR_PEER, "peer exchange timed out: a rank did not reach the end of the step");
+        }
+    }
     const Plan& pl = *h->pin_plan;
-    if (getenv("DDC_DEBUG_TS")) {
+    if (h->debug_ts) {
         const unsigned long long* t = pl.ts;
-        fprintf(stderr, "[ddc] K2 ns: barrier %llu prefix %llu plan %llu walks %llu paint %llu | K4 block 0 ns: barrier %llu "
-                        "prefix %llu walks %llu, longest block %llu | K2 end -> K4 start %llu\n",
-            t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[7] - t[6], t[8] - t[7], t[9] - t[8], t[10],
-            t[6] - t[5]);
+        auto us = [&](int a, int b) { return t[a] && t[b] ? ((double)t[b] - (double)t[a]) * 1e-3 : -1.0; };
+        fprintf(stderr, "[ddc r%d] scan: loop %.1f, last col push +%.1f, flag +%.1f | -> K2 start %.1f | K2: barrier %.1f prefix %.1f "
+                        "plan %.1f walks %.1f end %.1f | -> rows %.1f | rows: %.1f | -> K4 %.1f | K4 b0: barrier %.1f prefix %.1f "
+                        "walks %.1f, longest block %.1f | -> label %.1f | label: loop %.1f, end +%.1f | step %.1f us\n",
+            h->rank, us(11, 12), us(12, 13), us(12, 14), us(12, 0), us(0, 1), us(1, 2), us(2, 3), us(3, 4), us(4, 5),
+            us(5, 15), us(15, 16), us(16, 6), us(6, 7), us(7, 8), us(8, 9), (double)t[10] * 1e-3, us(9, 17), us(17, 18),
+            us(18, 19), us(11, 19));
+        fprintf(stderr, "[ddc r%d] K2 levels (thread 0, us):", h->rank);
+        for (int l = 0; l + 1 < 8 && t[TS_XLEV + l + 1]; l++)
+            fprintf(stderr, " %.2f", us(TS_XLEV + l, TS_XLEV + l + 1));
+        fprintf(stderr, " | K4 block 0 levels:");
+        for (int l = 0; l + 1 < 8 && t[TS_YLEV + l + 1]; l++)
+            fprintf(stderr, " %.2f", us(TS_YLEV + l, TS_YLEV + l + 1));
+        fprintf(stderr, "\n");
     }
     h->stats.nlev = pl.nlev;
     h->stats.n_xlev = pl.ix;
@@ -1300,7 +1401,8 @@ int ddc_generate_mask_device(ddc_handle_t h, int32_t* dev_rows, int nx, int ny, 
     if (y_count) {
         const size_t n = (size_t)nx * y_count;
         const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 32);
-        k_generate_mask<<<grid, 256, 0, h->stream>>>(dev_rows, nx, y_count, y_begin, seed, L1, L2, thresh);
+        CUDA_TRY(h, launch_k(k_generate_mask, dim3(grid), dim3(256), 0, h->stream, false, dev_rows, nx, y_count, y_begin,
+            seed, L1, L2, thresh));
         CUDA_TRY(h, cudaGetLastError());
     }
     return DDC_OK;

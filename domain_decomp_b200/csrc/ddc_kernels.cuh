@@ -49,11 +49,20 @@ struct Plan { // written by K2 (K4 adds iterations), copied into the host's pinn
     int iters; // median iterations (x levels; K4 adds its own atomically)
     int mismatch; // (ix, iy) differ from what the host assumed when it sized the launches: the
                   // kernels after K2 do nothing and the host runs the step again with the real plan
-    // diagnostics (printed by the host when DDC_DEBUG_TS is set): %globaltimer stamps of the phases
-    // of the two cut kernels.  0-5: K2 start, after the exchange barrier, prefix, plan, walks, end;
-    // 6-9: K4 block 0 start, after the barrier, after the prefix, end; 10: longest K4 block (ns)
-    unsigned long long ts[12];
+    int fixup; // written by the kernel that ends the step (the labelling kernel's last CTA, or k_finalize):
+               // 0 the tables are final; 1 nothing moved on any rank, the host has to run k_finalize for the
+               // naive blocks; 2 nothing moved on THIS rank and the other ranks' verdicts were not awaited
+    int pad_;
+    // diagnostics (printed by the host when DDC_DEBUG_TS is set): %globaltimer stamps.
+    //  0-5   K2: start, after the exchange barrier, prefix, plan, walks, end
+    //  6-10  K4 block 0: start, after the barrier, after the prefix, end; 10: longest K4 block (ns)
+    //  11-14 mask scan: first CTA past its dependency wait, last CTA out of its row loop, last column push
+    //        performed, flag raised          15-16 strip rows: first CTA start, last CTA end
+    //  17-19 labelling: first CTA start, last CTA out of its row loop, epilogue done
+    //  20-27 K2 thread 0 after each level of its walk    28-35 the same for K4 block 0
+    unsigned long long ts[36];
 };
+constexpr int TS_SCAN = 11, TS_ROWS = 15, TS_LABEL = 17, TS_XLEV = 20, TS_YLEV = 28;
 
 struct NaiveParams { // Grid.cpp:150-166
     int np0, np1, lx, ly;
@@ -153,6 +162,32 @@ inline bool peer_wait(const PeerSync& ps, int stage, unsigned* seen)
     return v >= 2u * ps.step;
 }
 #endif
+// Programmatic dependent launch: the kernels of a step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel may become resident while its predecessor
+// in the stream is still running.  pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as every CTA
+// of this grid has called it (they then sit in their own pdl_wait()); pdl_wait() returns once the previous
+// grid has completed and its memory operations are visible.  Every kernel of the chain calls pdl_wait() on
+// every path before it touches global memory, so completion is transitive along the chain.  Without the
+// launch attribute both are no-ops.
+#ifndef DDC_HOST_EMU
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+inline void pdl_wait() { }
+inline void pdl_trigger() { }
+#endif
+// diagnostic stamps (dbg == nullptr unless DDC_DEBUG_TS is set; the host zeroes them before the step)
+__device__ __forceinline__ void stamp_first(unsigned long long* dbg, int i)
+{
+    if (dbg && dbg[i] == 0ull)
+        atomicCAS(dbg + i, 0ull, global_ns());
+}
+__device__ __forceinline__ void stamp_last(unsigned long long* dbg, int i)
+{
+    if (dbg)
+        atomicMax(dbg + i, global_ns());
+}
+
 // Called by the first G threads of a block (thread q talks to rank q).  do_signal: exactly one
 // block per rank sends.
 __device__ __forceinline__ bool peer_barrier(const PeerSync& ps, int stage, unsigned bit, bool do_signal,
@@ -409,10 +444,12 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ mask, int NX, int rows,
     int y_begin, int NB, int rows_per_cta, uint8_t* __restrict__ bits, unsigned* __restrict__ colcount,
     int* __restrict__ yr /* this rank's {-(first ocean row), last ocean row}, max-reduced */,
-    PeerPush push, PeerSync ps, unsigned* __restrict__ done /* [gridDim.x + 1], zeroed by k_init */, int yr_off)
+    PeerPush push, PeerSync ps, unsigned* __restrict__ done /* [gridDim.x + 1], zeroed by k_init */, int yr_off,
+    unsigned long long* dbg)
 {
     __shared__ __align__(16) uint8_t sbits[SCAN_STAGE_ROWS][128];
     __shared__ int s_last;
+    pdl_trigger(); // the x-cut kernel may become resident (and warm up) while the scan is still running
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     // warps beyond the last 128-column group (last column block only) have no columns: they
     // load nothing (clamped, masked addresses below) but take part in the CTA barriers
@@ -434,6 +471,11 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
     int4 h0[4], h1[4];
     const int4* pv = reinterpret_cast<const int4*>(mask + (size_t)r0 * NX + xl);
     const bool vec_first = VEC && r0 + 8 <= r1;
+    // the previous step's labelling kernel still reads the bit map, and the mask may come from the caller's
+    // kernel just before this one in the stream
+    pdl_wait();
+    if (threadIdx.x == 0)
+        stamp_first(dbg, TS_SCAN);
     if (vec_first) {
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -534,6 +576,8 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
         if (y1 > yr[1])
             atomicMax(&yr[1], y1);
     }
+    if (threadIdx.x == 0)
+        stamp_last(dbg, TS_SCAN + 1);
     if (push.n <= 1)
         return;
     // Exchange step 1 (several GPUs): the LAST CTA of a column block to finish pushes the block's
@@ -568,6 +612,7 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system(); // the block's stores are performed at the peers before it is counted
+        stamp_last(dbg, TS_SCAN + 2);
         s_last = atomicAdd(&done[gridDim.x], 1u) == gridDim.x - 1;
         if (s_last)
             __threadfence();
@@ -583,6 +628,8 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
             d[1] = (unsigned)__ldcg(yr + 1);
         }
         peer_signal(ps, 0, 0u); // fence.sys, then the flag: the pushes of all blocks come first
+        if (threadIdx.x == 0)
+            stamp_last(dbg, TS_SCAN + 3);
     }
     // every CTA has been counted: the counters are ready for the next step (k_init is then only needed when
     // the geometry changes)
@@ -654,18 +701,70 @@ __device__ __forceinline__ void load_counts_tile(const PeerCols& pc, int base, i
     }
 }
 
+// the plan (levels, mismatch flag, iteration count, fix-up request) goes straight into the host's pinned copy,
+// so that a step ends without a separate device -> host copy; called by all threads of a block (>= 128)
+__device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
+{
+    static_assert(sizeof(Plan) % 4 == 0 && sizeof(Plan) / 4 <= 128, "Plan is copied word by word by one block");
+    if (threadIdx.x < sizeof(Plan) / 4)
+        reinterpret_cast<volatile unsigned*>(host_plan)[threadIdx.x]
+            = reinterpret_cast<const volatile unsigned*>(plan)[threadIdx.x];
+}
+
+// Runs the walk once on a toy histogram in shared memory (64 bins: dots in bins 4-27 and 36-59, a land gap in
+// the middle, empty margins), so that the SM's instruction cache holds the median search before the real
+// histogram has arrived: the cut kernels call it while they wait for the kernel before them (pdl_wait) and for
+// the other ranks' pushes.  A cut kernel runs once per step between kernels that stream gigabytes, so its code
+// is cold every time, and the walks are one long dependent instruction stream.
+constexpr int WARM_WORDS = 72;
+__device__ __forceinline__ void warm_walk(unsigned* toy /* WARM_WORDS of shared memory */, int* sink)
+{
+    const int tid = threadIdx.x;
+    if (tid <= 64) {
+        unsigned c = 0;
+        for (int b = 0; b < tid; b++)
+            c += ((b >= 4 && b < 28) || (b >= 36 && b < 60)) ? 1u + (unsigned)(b % 3) : 0u;
+        toy[tid] = c;
+    }
+    if (tid == 65) {
+        toy[68] = 0x0ffffff0u; // l0: bins 4-27
+        toy[69] = 0x0ffffff0u; //     bins 36-59
+        toy[70] = 3u; // l1
+        toy[71] = 1u; // l2
+    }
+    __syncthreads();
+    Hist H;
+    H.pfx = toy;
+    H.l0 = toy + 68;
+    H.l1 = toy + 70;
+    H.l2 = toy + 71;
+    H.nl2 = 1;
+    const int warp = tid >> 5;
+    const RcbSet root = { 0, 64, 0, 8 + (warp & 3) }; // 8 parts: halves only; 9-11 parts: uneven splits (FP64 targets)
+    const WalkResult r = rcb_walk_shared(H, root, 3, tid & 7, nullptr);
+    if (r.set.lo == -12345) // never: keeps the call alive
+        *sink = r.iters;
+    __syncthreads();
+}
+
 // dynamic shared memory when SMEM: (NX + 1) unsigned, rounded up to 4, + hist_bitmap_words(NX).
 // aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
     int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm,
-    DevScalars* sc, unsigned* own_col /* this rank's column counts: reset here once they are consumed */)
+    DevScalars* sc, unsigned* own_col /* this rank's column counts: reset here once they are consumed */,
+    int warm, int dbg, Plan* host_plan)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
+    __shared__ unsigned toy[WARM_WORDS];
     __shared__ int s_ix, s_iters;
     unsigned* pfx = SMEM ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
+    pdl_trigger(); // the strip row-count kernel may become resident
+    if (warm)
+        warm_walk(toy, &s_iters);
+    pdl_wait(); // the mask scan is complete
     if (tid == 0) {
         plan->ts[0] = global_ns();
         // the per-step scalars: nothing before K2 touches them, everything after K2 accumulates into them
@@ -686,6 +785,8 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         if (__syncthreads_or(!ok)) {
             if (tid == 0)
                 plan->mismatch = 3;
+            __syncthreads();
+            publish_plan(plan, host_plan);
             return;
         }
     }
@@ -740,6 +841,7 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         plan->ymax = ymax;
         plan->W = W;
         plan->mismatch = (ix != aix || iy != aiy) ? 1 : 0;
+        plan->fixup = 0;
         s_ix = ix;
         s_iters = 0;
         plan->ts[3] = global_ns();
@@ -766,11 +868,11 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     long long lmn = 0x7fffffffffffffffLL, lmx = -1;
     for (int i = tid / lanes; i < nstrips; i += blockDim.x / lanes) {
         const RcbSet root = { 0, NX, 0, P };
-        int it = 0;
-        const RcbSet r = rcb_walk(H, root, ix, i, &it);
+        const WalkResult wr = rcb_walk_shared(H, root, ix, i, dbg && tid == 0 ? plan->ts + TS_XLEV : nullptr);
+        const RcbSet r = wr.set;
         if (tid % lanes)
             continue;
-        my_iters += it;
+        my_iters += wr.iters;
         // 4. the strip table, in ascending part order
         st.x0[i] = r.lo;
         st.x1[i] = r.hi;
@@ -802,6 +904,10 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         plan->iters = s_iters;
         plan->ts[5] = global_ns();
         plan->ts[10] = 0ull;
+    }
+    if (plan->mismatch) { // (written by thread 0 before the barrier above) the kernels after this one do nothing:
+        __syncthreads(); //   the host reads the real plan from its pinned copy and runs the step again
+        publish_plan(plan, host_plan);
     }
 }
 
@@ -860,23 +966,47 @@ __device__ __forceinline__ void store_row_count(const PeerPush& out, size_t idx,
             reinterpret_cast<CT*>(out.dst[q])[idx] = v;
 }
 
+// Exchange step 2: the LAST block of a row-count kernel to finish raises this rank's flag at every peer -- the
+// y-cut kernels only wait.  (Raised by the y-cut kernel's first block, the flag left one kernel boundary and a
+// launch later.)  Called by all threads of every block; `done` is a counter that is zero between steps.
+__device__ __forceinline__ void rows_pushed(const PeerSync& ps, unsigned* done, unsigned blocks, int* s_last)
+{
+    if (!ps.enabled)
+        return;
+    __syncthreads(); // every thread's stores are issued ...
+    if (threadIdx.x == 0) {
+        __threadfence_system(); // ... and performed at the peers (cumulative over the barrier) before the block is counted
+        *s_last = atomicAdd(done, 1u) == blocks - 1u;
+    }
+    __syncthreads();
+    if (*s_last) {
+        if ((int)threadIdx.x < ps.G)
+            peer_signal(ps, 1, 0u);
+        if (threadIdx.x == 0)
+            *done = 0u;
+    }
+}
+
 // The grid covers Rmax rows (the rows of the largest shard): rows beyond this rank's `rows` are
 // written as empty, so that a short last shard needs no separate clearing pass.
 template <typename CT /* uint16_t when NX < 65536, else unsigned */>
 __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ bits, int NB, int rows,
     const int* __restrict__ st_x0, const int* __restrict__ st_x1, const int* __restrict__ st_p0,
-    const Plan* __restrict__ plan, int Scap, PeerPush out, int Rmax)
+    const Plan* __restrict__ plan, int Scap, PeerPush out, int Rmax, PeerSync ps, unsigned* __restrict__ done,
+    unsigned long long* dbg)
 {
+    __shared__ int s_last;
+    pdl_trigger();
+    pdl_wait();
     if (plan->mismatch)
         return;
+    if (threadIdx.x == 0)
+        stamp_first(dbg, TS_ROWS);
     const int S = plan->S;
     const int s = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (s >= S || s >= Scap || st_p0[s + 1] - st_p0[s] <= 1)
-        return;
     const int row = blockIdx.x * 32 + lane_id();
-    if (row >= Rmax)
-        return;
-    const int x0 = st_x0[s], x1 = st_x1[s];
+    const bool act = s < S && s < Scap && st_p0[min(s, Scap - 1) + 1] - st_p0[min(s, Scap - 1)] > 1 && row < Rmax;
+    const int x0 = act ? st_x0[s] : 0, x1 = act ? st_x1[s] : 0;
     unsigned cnt = 0;
     if (x1 > x0 && row < rows) {
         const int g0 = x0 >> 7, g1 = (x1 - 1) >> 7;
@@ -891,7 +1021,11 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
                     + __popc(w.z & word_range_mask(a - 64, b - 64)) + __popc(w.w & word_range_mask(a - 96, b - 96));
         }
     }
-    store_row_count<CT>(out, row_count_index(s, row, Scap, 5), (CT)cnt); // 32 consecutive counts per warp
+    if (act)
+        store_row_count<CT>(out, row_count_index(s, row, Scap, 5), (CT)cnt); // 32 consecutive counts per warp
+    rows_pushed(ps, done, gridDim.x * gridDim.y, &s_last);
+    if (threadIdx.x == 0)
+        stamp_last(dbg, TS_ROWS + 1);
 }
 
 // The same counts, coalesced: a block takes 32 consecutive rows and streams them ONCE -- a warp
@@ -913,11 +1047,16 @@ __host__ __device__ inline size_t strip_scan_smem_words(int NG, int S, int K)
 template <typename CT, int K, bool FULL>
 __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restrict__ bits, int NB, int NX, int rows,
     const int* __restrict__ st_x0, const int* __restrict__ st_p0, const Plan* __restrict__ plan, int Scap,
-    PeerPush out, int Rmax)
+    PeerPush out, int Rmax, PeerSync ps, unsigned* __restrict__ done, unsigned long long* dbg)
 {
     DDC_DYN_SHARED(int, sm_scan);
+    __shared__ int s_last;
+    pdl_trigger();
+    pdl_wait();
     if (plan->mismatch)
         return;
+    if (threadIdx.x == 0)
+        stamp_first(dbg, TS_ROWS);
     static_assert(!FULL || K == 1, "FULL holds one row per warp in registers");
     constexpr int RB = 8 * K; // rows per block
     constexpr int KP = (K + 1) / 2; // packed scan registers (two 16-bit running sums each)
@@ -1058,6 +1197,9 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
             o = make_uint4(c[0], c[1 % V], c[2 % V], c[3 % V]);
         store_row_counts16(out, (chunk + e) * sizeof(CT), o);
     }
+    rows_pushed(ps, done, gridDim.x, &s_last);
+    if (tid == 0)
+        stamp_last(dbg, TS_ROWS + 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1107,10 +1249,17 @@ __device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowL
 
 template <typename CT, bool SMEM>
 __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st,
-    unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan, int* __restrict__ strip_of_col)
+    unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan, int* __restrict__ strip_of_col,
+    int warm, int dbg)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
+    __shared__ unsigned toy[WARM_WORDS];
+    __shared__ int s_sink;
+    pdl_trigger(); // (nothing is launched programmatically behind this kernel today; harmless)
+    if (warm)
+        warm_walk(toy, &s_sink);
+    pdl_wait(); // the strip row-count kernel (and with it everything before) is complete
     if (plan->mismatch)
         return;
     const unsigned long long t_start = global_ns();
@@ -1122,12 +1271,12 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     for (int s = blockIdx.x; s < *st.S; s += gridDim.x)
         for (int x = st.x0[s] + (int)threadIdx.x; x < st.x1[s]; x += (int)blockDim.x)
             strip_of_col[x] = s;
-    // exchange step 2: every rank's strip row counts are written (block 0 says so for this rank)
+    // exchange step 2: every rank's strip row counts are written (the last block of its row-count kernel said so)
     if (ps.enabled) {
         bool ok = true;
         unsigned seen;
         if (threadIdx.x < ps.G)
-            ok = peer_barrier(ps, 1, 0u, blockIdx.x == 0, &seen);
+            ok = peer_wait(ps, 1, &seen);
         if (__syncthreads_or(!ok)) {
             if (threadIdx.x == 0)
                 plan->mismatch = 3;
@@ -1165,11 +1314,12 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
         const int lanes = walk_lanes(n, blockDim.x);
         for (int j = tid / lanes; j < n; j += blockDim.x / lanes) {
             const RcbSet root = { 0, NY, plo, n };
-            int it = 0;
-            const RcbSet r = rcb_walk(H, root, ylevels, j, &it);
+            const WalkResult wr
+                = rcb_walk_shared(H, root, ylevels, j, dbg && tid == 0 && blockIdx.x == 0 ? plan->ts + TS_YLEV : nullptr);
+            const RcbSet r = wr.set;
             if (tid % lanes)
                 continue;
-            my_iters += it;
+            my_iters += wr.iters;
             bx.x0[r.plo] = sx0;
             bx.ex[r.plo] = sx1 - sx0;
             bx.y0[r.plo] = r.lo;
@@ -1253,22 +1403,14 @@ __device__ __forceinline__ void store_pid_row(int32_t* __restrict__ q, int x, in
     }
 }
 
+// the rows [r0, r1) of one thread's 4 columns; *s_changed (shared memory) is set when a moved cell is found
 template <bool VEC, bool WRITE>
-__global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bits, int NX, int rows,
-    int y_begin, int NB, int rows_per_cta, const int* __restrict__ strip_of_col,
-    const int* __restrict__ st_p0, const int* __restrict__ box_y0, const int* __restrict__ box_ey,
-    NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc, const Plan* __restrict__ plan)
+__device__ __forceinline__ void label_rows(const uint8_t* __restrict__ bits, int NX, int y_begin, int NB, int g, int r0,
+    int r1, const int* __restrict__ strip_of_col, const int* __restrict__ st_p0, const int* __restrict__ box_y0,
+    const int* __restrict__ box_ey, const NaiveParams& nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc,
+    int* s_changed)
 {
-    if (plan->mismatch)
-        return;
     const int lane = lane_id();
-    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (g * 128 >= NX)
-        return;
-    const int r0 = blockIdx.y * rows_per_cta;
-    const int r1 = min(rows, r0 + rows_per_cta);
-    if (r0 >= r1)
-        return;
     const int x = g * 128 + lane * 4;
 
     int sc4[4], nbx[4];
@@ -1333,8 +1475,10 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
                     }
                 }
                 if (__any_sync(__activemask(), changed)) {
-                    if (changed)
+                    if (changed) {
                         atomicOr(&sc->changes, 1);
+                        *s_changed = 1;
+                    }
                     check = false;
                 }
             }
@@ -1377,12 +1521,81 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
             }
             if (check && changed) {
                 atomicOr(&sc->changes, 1);
+                *s_changed = 1;
                 check = false;
             }
         }
         if (check && (r & 63) == 0)
             check = *reinterpret_cast<volatile int*>(&sc->changes) == 0;
     }
+}
+
+// The end of a step, folded into the labelling kernel (no separate launch behind the largest kernel of the
+// step): every block adds itself -- and, in the upper half of the same 64-bit atomic, whether it found a moved
+// cell -- to a counter; the block that completes the count knows this rank's `changes` without any fence,
+// tells the other ranks (exchange step 3: the verdict rides in the low bit of the flag), and writes the plan
+// into the host's pinned copy.  `changes` is an OR over the ranks, so a rank that found a moved cell knows the
+// global answer already and does not wait for anybody.  Only when NOTHING moved here (all land, or the RCB
+// reproduces the naive blocks) the answer is left open: the host then runs k_finalize (Plan::fixup).
+struct LabelEnd {
+    int fuse; // 0: k_finalize follows as a kernel of its own
+    int P;
+    PeerSync ps;
+    unsigned long long* counter; // zero between steps
+    Plan* host_plan;
+    unsigned long long* dbg;
+};
+
+template <bool VEC, bool WRITE>
+__global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bits, int NX, int rows,
+    int y_begin, int NB, int rows_per_cta, const int* __restrict__ strip_of_col,
+    const int* __restrict__ st_p0, const int* __restrict__ box_y0, const int* __restrict__ box_ey,
+    NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc, Plan* __restrict__ plan, LabelEnd fin)
+{
+    __shared__ int s_changed, s_last;
+    pdl_wait();
+    if (plan->mismatch) { // the host runs the step again with the real plan (or reports the time-out)
+        if (fin.fuse && blockIdx.x == 0 && blockIdx.y == 0)
+            publish_plan(plan, fin.host_plan);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        s_changed = 0;
+        stamp_first(fin.dbg, TS_LABEL);
+    }
+    __syncthreads();
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int r0 = blockIdx.y * rows_per_cta;
+    const int r1 = min(rows, r0 + rows_per_cta);
+    if (g * 128 < NX && r0 < r1)
+        label_rows<VEC, WRITE>(bits, NX, y_begin, NB, g, r0, r1, strip_of_col, st_p0, box_y0, box_ey, nv, pid, sc,
+            &s_changed);
+    if (!fin.fuse)
+        return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        stamp_last(fin.dbg, TS_LABEL + 1);
+        const unsigned long long old
+            = atomicAdd(fin.counter, 1ull | (s_changed ? (1ull << 32) : 0ull));
+        const unsigned blocks = gridDim.x * gridDim.y;
+        s_last = (unsigned)(old & 0xffffffffull) == blocks - 1u;
+        s_changed = (s_changed || (old >> 32) != 0ull) ? 1 : 0; // only meaningful in the last block
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    const int changes = s_changed;
+    if (fin.ps.enabled && (int)threadIdx.x < fin.ps.G)
+        peer_signal(fin.ps, 2, changes ? 1u : 0u);
+    if (threadIdx.x == 0) {
+        *fin.counter = 0ull;
+        sc->changes = changes;
+        sc->changes_all = changes;
+        plan->fixup = (changes || fin.P <= 1) ? 0 : (fin.ps.enabled ? 2 : 1);
+        stamp_last(fin.dbg, TS_LABEL + 2);
+    }
+    __syncthreads();
+    publish_plan(plan, fin.host_plan);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1523,8 +1736,12 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5: the end of a step, ONE block
+// K5: the end of a step as a kernel of its own, ONE block
 // ------------------------------------------------------------------------------------------------
+// Normally the labelling kernel's last block ends the step (LabelEnd above).  This kernel runs
+//  (a) in the stream, when there is no labelling kernel (a rank without rows; one part and no pid wanted) or
+//      when the exchange goes through NCCL, and
+//  (b) from the host's validate(), when the labelling kernel left the verdict open (Plan::fixup != 0).
 //  * exchange step 3: `changes` of every rank (it rides in the low bit of the flag);
 //  * `changes == 0`  =>  the naive blocks are reported (ZoltanPartitioner.cpp:182-187).  The neighbour
 //    tables were built speculatively from the RCB boxes, beside the labelling kernel that was still
@@ -1541,13 +1758,6 @@ struct NbrTables {
     int* halos;
     int* starts;
 };
-__device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
-{
-    static_assert(sizeof(Plan) % 4 == 0, "Plan is copied word by word");
-    if (threadIdx.x < sizeof(Plan) / 4)
-        reinterpret_cast<volatile unsigned*>(host_plan)[threadIdx.x]
-            = reinterpret_cast<const volatile unsigned*>(plan)[threadIdx.x];
-}
 __global__ void __launch_bounds__(1024) k_finalize(PeerSync ps, int P, int NX, int NY, int px, int py, NaiveParams nv,
     DevScalars* __restrict__ sc, Plan* __restrict__ plan, StripTable st, BoxTable bx,
     int want_nbr, NbrTables nb, Plan* __restrict__ host_plan)
@@ -1574,8 +1784,11 @@ __global__ void __launch_bounds__(1024) k_finalize(PeerSync ps, int P, int NX, i
         }
         changes = __syncthreads_or(tid < ps.G && (seen & 1u));
     }
-    if (tid == 0)
+    if (tid == 0) {
         sc->changes_all = changes;
+        plan->fixup = 0; // whatever is left to do is done below
+    }
+    __syncthreads();
     publish_plan(plan, host_plan); // K4 is done: the iteration count is final
     if (P == 1 || changes != 0)
         return;

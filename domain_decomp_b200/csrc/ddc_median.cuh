@@ -10,6 +10,9 @@
 
 #ifdef DDC_HOST_EMU
 #include "ddc_host_emu.h" // oracle/emu: host stand-ins of the device language (test builds only)
+#define DDC_NOINLINE inline
+#else
+#define DDC_NOINLINE __noinline__
 #endif
 
 namespace ddc {
@@ -302,11 +305,25 @@ __device__ __forceinline__ int leaves_below(int n, int levels)
 {
     return levels >= 31 ? n : min(n, 1 << levels);
 }
+#ifndef DDC_HOST_EMU
+__device__ __forceinline__ unsigned long long walk_clock()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#else
+inline unsigned long long walk_clock() { return 0ull; }
+#endif
 // walk `levels` levels down from `set` towards leaf number k (0-based among the leaves below
-// `set`); iterations of a median are counted by the thread whose leaf is the first of its upper child
-__device__ inline RcbSet rcb_walk(const Hist& H, RcbSet set, int levels, int k, int* iters)
+// `set`); iterations of a median are counted by the thread whose leaf is the first of its upper child.
+// lvl_ts (diagnostics, normally nullptr): a time stamp after every level.
+__device__ inline RcbSet rcb_walk(const Hist& H, RcbSet set, int levels, int k, int* iters,
+    unsigned long long* lvl_ts = nullptr)
 {
     for (int l = levels; l > 0 && set.n > 1; l--) {
+        if (lvl_ts && levels - l < 8)
+            lvl_ts[levels - l] = walk_clock(); // start of level (levels - l)
         const int nlo = (set.n - 1) / 2 + 1;
         int it = 0;
         const int cut = median_boundary(H, set.lo, set.hi - 1, nlo, set.n, &it);
@@ -324,6 +341,20 @@ __device__ inline RcbSet rcb_walk(const Hist& H, RcbSet set, int levels, int k, 
         }
     }
     return set;
+}
+// The walk as ONE function in the binary: the cut kernels call it for the real histogram and, before their
+// input has arrived, once for a toy histogram -- the second call only warms the instruction cache if both
+// calls run the same instructions.  Everything crosses the call in registers.
+struct WalkResult {
+    RcbSet set;
+    int iters;
+};
+__device__ DDC_NOINLINE WalkResult rcb_walk_shared(Hist H, RcbSet set, int levels, int k, unsigned long long* lvl_ts)
+{
+    WalkResult r;
+    r.iters = 0;
+    r.set = rcb_walk(H, set, levels, k, &r.iters, lvl_ts);
+    return r;
 }
 
 } // namespace ddc

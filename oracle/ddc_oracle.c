@@ -1070,3 +1070,67 @@ ORC_API void orc_part_loads(const int32_t* pid, size_t ncell, int P, int64_t* lo
         if (pid[i] >= 0 && pid[i] < P)
             loads[pid[i]]++;
 }
+
+/* ------------------------------------------------------------------------- */
+/* bench input: the synthetic land-sea mask of SURVEY 8d                     */
+/* ------------------------------------------------------------------------- */
+/* Not reference code: the benchmark's INPUT generator, restated here so that the CPU legs of bench.py
+ * (`--impl reference`, cpu_baseline) and the golden digests produce the very mask the product generates
+ * (domain_decomp_b200/csrc: synth_value, synth_params) without loading the CUDA library.
+ * tests/test_oracle_golden.py compares the two generators.  Two octaves of integer value noise:
+ * ocean <=> 3 * octave(L1) + octave(L2) >= threshold, the threshold calibrated on a fixed 128 x 128
+ * sample lattice to the requested land fraction. */
+static uint64_t sm64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static uint64_t lat16(uint64_t seed, uint64_t oct, uint64_t ix, uint64_t iy)
+{
+    return sm64(seed ^ sm64((oct << 60) ^ (ix << 30) ^ iy)) >> 48;
+}
+static uint64_t oct16(uint64_t seed, uint64_t oct, uint64_t L, uint64_t x, uint64_t y)
+{
+    const uint64_t cx = x / L, fx = x % L, cy = y / L, fy = y % L;
+    const uint64_t v00 = lat16(seed, oct, cx, cy), v10 = lat16(seed, oct, cx + 1, cy);
+    const uint64_t v01 = lat16(seed, oct, cx, cy + 1), v11 = lat16(seed, oct, cx + 1, cy + 1);
+    const uint64_t top = v00 * (L - fx) + v10 * fx, bot = v01 * (L - fx) + v11 * fx;
+    return (top * (L - fy) + bot * fy) / (L * L);
+}
+static uint32_t synth(uint64_t seed, uint64_t L1, uint64_t L2, uint64_t x, uint64_t y)
+{
+    return (uint32_t)(3 * oct16(seed, 1, L1, x, y) + oct16(seed, 2, L2, x, y));
+}
+static int cmp_u32(const void* a, const void* b)
+{
+    const uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+/* rows [y_begin, y_begin + y_count) of the nx * ny mask; all host threads */
+ORC_API int orc_generate_mask(int32_t* rows, int nx, int ny, int y_begin, int y_count, uint64_t seed, double land_frac)
+{
+    if (nx < 1 || ny < 1 || y_begin < 0 || y_count < 0 || y_begin + y_count > ny || (!rows && y_count))
+        return -1;
+    const uint64_t m = (uint64_t)(nx > ny ? nx : ny);
+    const uint64_t L1 = m / 16 ? m / 16 : 1, L2 = m / 64 ? m / 64 : 1;
+    enum { K = 128 };
+    uint32_t* v = (uint32_t*)malloc(sizeof(uint32_t) * K * K);
+    if (!v)
+        return -1;
+    for (int j = 0; j < K; j++)
+        for (int i = 0; i < K; i++)
+            v[j * K + i] = synth(seed, L1, L2, ((uint64_t)(2 * i + 1) * (uint64_t)nx) / (2 * K),
+                ((uint64_t)(2 * j + 1) * (uint64_t)ny) / (2 * K));
+    qsort(v, K * K, sizeof(uint32_t), cmp_u32);
+    const double f = land_frac < 0 ? 0 : (land_frac > 1 ? 1 : land_frac);
+    const size_t k = (size_t)(f * (double)(K * K));
+    const uint32_t thresh = k >= (size_t)K * K ? 0xffffffffu : (f <= 0 ? 0u : v[k]);
+    free(v);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < y_count; y++)
+        for (int x = 0; x < nx; x++)
+            rows[(size_t)y * nx + x] = synth(seed, L1, L2, (uint64_t)x, (uint64_t)(y + y_begin)) >= thresh ? 1 : 0;
+    return 0;
+}

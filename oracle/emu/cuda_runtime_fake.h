@@ -6,6 +6,7 @@
 // capacity re-run of the neighbour fill pass, DDC_ASYNC, the getters, the error paths -- is exercised by
 // the CPU suite (one rank; several ranks are emulated by emu_pipeline.cpp).  One device, no NCCL, no IPC.
 #pragma once
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -135,6 +136,15 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t)
 }
 template <typename K>
 inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+struct cudaFuncAttributes {
+    size_t sharedSizeBytes;
+};
+template <typename K>
+inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, K)
+{
+    a->sharedSizeBytes = 1400; // about what the cut kernels hold statically
+    return cudaSuccess;
+}
 template <typename K>
 inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t)
 {
@@ -146,7 +156,7 @@ inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cuda
 inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
 
-// kernel<<<grid, block, smem, stream>>>(args) of ddc_api.cu becomes DDC_EMU_LAUNCH(grid, block, smem, kernel(args))
+// launch_k() of ddc_api.cu runs the kernel through DDC_EMU_LAUNCH(grid, block, smem, kernel(args)) in these builds
 #define DDC_EMU_LAUNCH(grid, block, smem, ...)                                                     \
     do {                                                                                           \
         const dim3 g_ = dim3(grid), b_ = dim3(block);                                               \

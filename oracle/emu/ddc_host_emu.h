@@ -130,6 +130,14 @@ inline T atomicMin(T* p, U v)
         *p = (T)v;
     return old;
 }
+template <typename T, typename U, typename V>
+inline T atomicCAS(T* p, U cmp, V v)
+{
+    const T old = *p;
+    if (old == (T)cmp)
+        *p = (T)v;
+    return old;
+}
 template <typename T, typename U>
 inline T atomicOr(T* p, U v)
 {

@@ -109,6 +109,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const bool x_smem = xneed + 1024 <= (size_t)opt.smem_limit, y_smem = yneed + 1024 <= (size_t)opt.smem_limit;
     const int ygrid = std::max(1, std::min(Scap, 148 * 2));
     const int gridx = (NG + 7) / 8;
+    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, ndone = d_label + 2; // ddc_api.cu: the "last block" counters
     const NaiveParams nv = naive_params(P, NX, NY);
     const int par = (int)(step & 1u);
     const bool want_nbr = P > 1;
@@ -143,7 +144,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         r.rowslots.resize(2 * (size_t)G * rowcap, 0xdeadbeefu);
         r.colpfx.resize((size_t)NX + 1);
         r.ypfx.resize((size_t)ygrid * (((size_t)NY + 1 + 3) & ~(size_t)3));
-        r.done.resize((size_t)gridx + 1);
+        r.done.resize((size_t)ndone);
         r.strips.assign((size_t)3 * (P + 1) + 3, 0);
         r.boxes.assign((size_t)4 * P, 0);
         r.strip_of_col.assign(NX, 0);
@@ -161,8 +162,8 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     for (Rank& r : R) {
         unsigned* colcount = colslot(r, r.rank);
         if (!skip_init) // the product launches k_init only for buffers K2 / the scan have not left clean
-            LAUNCH(Dim3((ncol + 255) / 256), Dim3(256), 0,
-                k_init(colcount, ncol, yr_off, r.rank, &r.sc, r.loadmm.data(), r.done.data(), gridx + 1));
+            LAUNCH(Dim3((std::max(ncol, ndone) + 255) / 256), Dim3(256), 0,
+                k_init(colcount, ncol, yr_off, r.rank, &r.sc, r.loadmm.data(), r.done.data(), ndone));
         PeerPush push {};
         push.rank = r.rank;
         push.n = p2p ? G : 1;
@@ -178,11 +179,11 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             if (vec)
                 LAUNCH(grid, Dim3(256), 0,
                     k_scan_mask<true>(r.mask, NX, r.rows, r.y_begin, NB, rpc, r.bits.data(), colcount, yr, push, ps,
-                        r.done.data(), yr_off));
+                        r.done.data(), yr_off, nullptr));
             else
                 LAUNCH(grid, Dim3(256), 0,
                     k_scan_mask<false>(r.mask, NX, r.rows, r.y_begin, NB, rpc, r.bits.data(), colcount, yr, push, ps,
-                        r.done.data(), yr_off));
+                        r.done.data(), yr_off, nullptr));
         }
     }
     if (G > 1 && !p2p) { // ncclAllReduce(SUM) of the column counts and the y-range pairs, in place on every rank
@@ -208,11 +209,11 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         if (x_smem)
             LAUNCH(Dim3(1), Dim3(1024), xneed,
                 k_xcuts<true>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(), r.loadmm.data(),
-                    &r.sc, colslot(r, r.rank)));
+                    &r.sc, colslot(r, r.rank), 1, 0, &r.host_plan));
         else
             LAUNCH(Dim3(1), Dim3(1024), 0,
                 k_xcuts<false>(pc, ps, NX, NY, P, r.colpfx.data(), yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(),
-                    r.loadmm.data(), &r.sc, colslot(r, r.rank)));
+                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 1, 0, &r.host_plan));
         if (!ycuts) // with y levels K4 paints the column -> strip table
             LAUNCH(Dim3(std::max(1, std::min((Scap + 7) / 8, 148 * 4))), Dim3(256), 0,
                 k_paint_strips(st, &r.plan, r.strip_of_col.data()));
@@ -229,6 +230,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             out.n = p2p ? G : 1;
             for (int q = 0; q < G; q++)
                 out.dst[q] = rowslot(R[p2p ? q : r.rank], r.rank);
+            const PeerSync ps = sync_of(r);
             int K = Rmax >= 32 * 4 * 148 ? 4 : (Rmax >= 16 * 4 * 148 ? 2 : 1);
             if (opt.strip_k)
                 K = opt.strip_k == 8 ? 1 : opt.strip_k;
@@ -241,7 +243,8 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                 const bool full = K == 1 && NG <= 256 && opt.strip_k != 1;
 #define SCAN(CT, KK, FF)                                                                           \
     LAUNCH(grid, Dim3(256), scan_smem,                                                             \
-        (k_strip_rows_scan<CT, KK, FF>(r.bits.data(), NB, NX, r.rows, st.x0, st.p0, &r.plan, Scap, out, Rmax)))
+        (k_strip_rows_scan<CT, KK, FF>(r.bits.data(), NB, NX, r.rows, st.x0, st.p0, &r.plan, Scap, out, Rmax, ps,      \
+            r.done.data() + d_rows, nullptr)))
                 if (narrow) {
                     if (K == 4)
                         SCAN(uint16_t, 4, false);
@@ -267,10 +270,12 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                 const Dim3 grid((Rmax + 31) / 32, (Scap + 7) / 8);
                 if (narrow)
                     LAUNCH(grid, Dim3(256), 0,
-                        k_strip_rows<uint16_t>(r.bits.data(), NB, r.rows, st.x0, st.x1, st.p0, &r.plan, Scap, out, Rmax));
+                        k_strip_rows<uint16_t>(r.bits.data(), NB, r.rows, st.x0, st.x1, st.p0, &r.plan, Scap, out, Rmax, ps,
+                            r.done.data() + d_rows, nullptr));
                 else
                     LAUNCH(grid, Dim3(256), 0,
-                        k_strip_rows<unsigned>(r.bits.data(), NB, r.rows, st.x0, st.x1, st.p0, &r.plan, Scap, out, Rmax));
+                        k_strip_rows<unsigned>(r.bits.data(), NB, r.rows, st.x0, st.x1, st.p0, &r.plan, Scap, out, Rmax, ps,
+                            r.done.data() + d_rows, nullptr));
             }
         }
         std::vector<std::vector<unsigned>> gathered;
@@ -281,11 +286,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                     std::copy(rowslot(src, src.rank), rowslot(src, src.rank) + rc_words,
                         gathered[dst.rank].begin() + (size_t)src.rank * rc_words);
         }
-        // on the GPU block 0 of every rank's K4 raises the stage-1 flag once its K3 is complete; the ranks of
-        // the emulation run one after the other, so the flags are raised here, after ALL K3s
-        for (Rank& r : R)
-            for (int q = 0; q < G; q++)
-                R[q].flags[1 * MAX_PEERS + r.rank] = 2u * step;
+        // (the last block of every rank's K3 has raised the rank's stage-1 flag at every peer)
         // ---- K4: y cuts ----
         for (Rank& r : R) {
             StripTable st;
@@ -302,7 +303,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
 #define YCUTS(CT, SM)                                                                              \
     LAUNCH(Dim3(ygrid), Dim3(1024), SM ? yneed : 0,                                                \
         (k_ycuts<CT, SM>(pr, ps, rl, NY, st, r.ypfx.data(), bx, r.loads.data(), r.loadmm.data(), &r.plan,                    \
-            r.strip_of_col.data())))
+            r.strip_of_col.data(), 1, 0)))
             if (narrow) {
                 if (y_smem)
                     YCUTS(uint16_t, true);
@@ -337,20 +338,23 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             const bool vecp = (NX % 4 == 0) && (((uintptr_t)r.pid.data()) % 16 == 0);
             const int rpc = 32;
             const Dim3 grid(gridx, (r.rows + rpc - 1) / rpc);
+            LabelEnd fin {};
+            fin.fuse = (G == 1 || p2p) ? 1 : 0;
+            fin.P = P;
+            fin.ps = sync_of(r);
+            fin.counter = reinterpret_cast<unsigned long long*>(r.done.data() + d_label);
+            fin.host_plan = &r.host_plan;
+            fin.dbg = nullptr;
             if (vecp)
                 LAUNCH(grid, Dim3(256), 0,
                     (k_label<true, true>(r.bits.data(), NX, r.rows, r.y_begin, NB, rpc, r.strip_of_col.data(), st.p0, bx.y0,
-                        bx.ey, nv, r.pid.data(), &r.sc, &r.plan)));
+                        bx.ey, nv, r.pid.data(), &r.sc, &r.plan, fin)));
             else
                 LAUNCH(grid, Dim3(256), 0,
                     (k_label<false, true>(r.bits.data(), NX, r.rows, r.y_begin, NB, rpc, r.strip_of_col.data(), st.p0, bx.y0,
-                        bx.ey, nv, r.pid.data(), &r.sc, &r.plan)));
+                        bx.ey, nv, r.pid.data(), &r.sc, &r.plan, fin)));
         }
     }
-    // stage-2 flags: `changes` of every rank rides in the low bit (raised here for the same reason as stage 1)
-    for (Rank& r : R)
-        for (int q = 0; q < G; q++)
-            R[q].flags[2 * MAX_PEERS + r.rank] = 2u * step + (r.sc.changes ? 1u : 0u);
     if (G > 1 && !p2p) { // ncclAllReduce(MAX) of `changes`
         int any = 0;
         for (Rank& r : R)
@@ -358,8 +362,9 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         for (Rank& r : R)
             r.sc.changes = any;
     }
-    // ---- K5 ----
-    for (Rank& r : R) {
+    // ---- K5: in the stream for ranks without a labelling kernel and for the NCCL exchange; otherwise from
+    //      validate() when the labelling kernel's last block left the verdict open (Plan::fixup) ----
+    auto finalize = [&](Rank& r) {
         StripTable st;
         BoxTable bx;
         tables(r, st, bx);
@@ -368,7 +373,23 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             r.nbr_halos.data(), r.nbr_starts.data() };
         LAUNCH(Dim3(1), Dim3(1024), 0,
             k_finalize(ps, P, NX, NY, px, py, nv, &r.sc, &r.plan, st, bx, want_nbr ? 1 : 0, nb, &r.host_plan));
-    }
+        return true;
+    };
+    // ranks whose K5 is in the stream raise their stage-2 flag there; on the GPU a peer that needs it polls until it
+    // arrives, the emulation runs these ranks first
+    for (Rank& r : R)
+        if (!(r.rows > 0 && (G == 1 || p2p)))
+            if (p2p && r.rows == 0) // (with NCCL there are no flags)
+                for (int q = 0; q < G; q++)
+                    R[q].flags[2 * MAX_PEERS + r.rank] = 2u * step + (r.sc.changes ? 1u : 0u);
+    for (Rank& r : R)
+        if (!(r.rows > 0 && (G == 1 || p2p)))
+            if (!finalize(r))
+                return false;
+    for (Rank& r : R)
+        if (r.rows > 0 && (G == 1 || p2p) && !r.host_plan.mismatch && r.host_plan.fixup)
+            if (!finalize(r))
+                return false;
     return true;
 }
 } // namespace

@@ -332,6 +332,17 @@ def partition(mask: np.ndarray, P: int, px: bool = False, py: bool = False, *, u
     return d
 
 
+def generate_mask(nx: int, ny: int, seed: int, land_frac: float, y_begin: int = 0, y_count: int | None = None) -> np.ndarray:
+    """bench.py's synthetic land-sea mask without the CUDA library: rows [y_begin, y_begin + y_count)"""
+    y_count = ny - y_begin if y_count is None else y_count
+    out = np.empty((y_count, nx), dtype=np.int32)
+    L = lib()
+    L.orc_generate_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_double]
+    if L.orc_generate_mask(out.ctypes.data, nx, ny, y_begin, y_count, seed, float(land_frac)) != 0:
+        raise ValueError("orc_generate_mask: bad arguments")
+    return out
+
+
 def part_loads(pid: np.ndarray, P: int) -> np.ndarray:
     loads = np.zeros(P, dtype=np.int64)
     flat = np.ascontiguousarray(pid, dtype=np.int32).reshape(-1)

@@ -73,6 +73,46 @@ def main():
             print("rank %d/%d %s case %dx%d P=%d: %s" % (rank, world, mode, nx, ny, P, "ok" if ok else "MISMATCH"),
                   flush=True)
             failures += 0 if ok else 1
+    # the BASELINE sizes: the mask is synthesised on the device, the replicated tables are compared with the CPU
+    # oracle's digest (tests/golden/bench_digests.json), the pid rows with the labelling rule restated in torch
+    if "--big" in sys.argv:
+        import json
+        from domain_decomp_b200 import verify
+        with open(os.path.join(ROOT, "tests", "golden", "bench_digests.json")) as f:
+            golden = json.load(f)
+        dev = torch.device("cuda", local)
+        for name in ("C4_8192x8192_p4096", "C5_32768x32768_p16384"):
+            g = golden[name]
+            nx, ny, P, px, py = g["nx"], g["ny"], g["parts"], g["periodic_x"], g["periodic_y"]
+            yb, yc = capi.shard_rows(ny, world, rank)
+            d_mask = torch.empty((max(yc, 1), nx), dtype=torch.int32, device=dev)
+            # a handle of its own, with exchange buffers exported for this size
+            hh = capi.Handle(local, rank, world, None)  # peer-memory exchange only: no NCCL communicator
+            handles = [None] * world
+            dist.all_gather_object(handles, hh.peer_export(nx, ny, P))
+            hh.peer_import(handles)
+            hh.generate_mask_device(d_mask.data_ptr(), nx, ny, g["seed"], g["land_frac"], yb, yc)
+            hh.set_mask_device(d_mask.data_ptr(), nx, ny, yb, yc)
+            for rep in range(3):
+                hh.partition(P, bool(px), bool(py))
+            st = hh.stats()
+            ok = st["exchange"] == 2 and verify.handle_digest(hh) == g["digest"] and st["median_iters"] == g["median_iters"]
+
+            class _Dev:
+                def __init__(self, ptr, shape):
+                    self.__cuda_array_interface__ = {"shape": shape, "typestr": "<i4", "data": (int(ptr), False),
+                                                     "version": 2, "strides": None}
+            d_pid = torch.as_tensor(_Dev(hh.pid_device(), (max(yc, 1), nx)), device=dev)[:yc]
+            pid_ok, counts = verify.pid_rows_match_boxes(hh.boxes(), nx, ny, d_mask[:yc], d_pid, yb)
+            dist.all_reduce(counts)
+            ok &= bool(pid_ok) and counts.cpu().tolist() == hh.part_loads().tolist()
+            print("rank %d/%d peer case %s: %s" % (rank, world, name, "ok" if ok else "MISMATCH"), flush=True)
+            failures += 0 if ok else 1
+            del d_pid
+            hh.peer_close()
+            dist.barrier()
+            hh.close()
+            del d_mask
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
     h.peer_close()

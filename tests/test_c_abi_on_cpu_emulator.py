@@ -176,7 +176,12 @@ def test_argument_and_state_errors(capi, oracle):
         # create: rank outside the communicator, ranks > 1 without a NCCL id
         hh = C.c_void_p()
         assert L.ddc_create(C.byref(hh), 0, 3, 2, None) < 0 and b"bad arguments" in L.ddc_last_error(None)
-        assert L.ddc_create(C.byref(hh), 0, 0, 2, None) < 0 and b"NCCL unique id" in L.ddc_last_error(None)
+        # ranks > 1 without a NCCL id: allowed (peer-memory exchange only), but a step without any exchange path fails
+        assert L.ddc_create(C.byref(hh), 0, 0, 2, None) == 0
+        half = np.ascontiguousarray(m[:15])
+        assert L.ddc_set_mask_host(hh, half.ctypes.data, 40, 30, 0, 15) == 0
+        assert L.ddc_partition(hh, 4, 0, 0, 3) < 0 and b"no exchange path" in L.ddc_last_error(hh)
+        assert L.ddc_destroy(hh) == 0
         assert L.ddc_create(C.byref(hh), 7, 0, 1, None) < 0 and b"out of range" in L.ddc_last_error(None)
         # masks: extents, shard bounds, null pointers
         assert L.ddc_set_mask_host(h.h, m.ctypes.data, 0, 30, 0, 30) < 0
