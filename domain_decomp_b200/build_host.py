@@ -13,7 +13,7 @@ DECOMP = os.path.join(b.PKG, "decomp")
 HOST_TESTS = os.path.join(b.PKG, "host_tests")
 NC_TOOL = os.path.join(b.PKG, "nc_tool")
 
-LIB_SRCS = ["CdlIO.cpp", "NcClassic.cpp", "DomainUtils.cpp", "Grid.cpp", "Partitioner.cpp", "CudaRcbPartitioner.cpp"]
+LIB_SRCS = ["HostBuffer.cpp", "CdlIO.cpp", "NcClassic.cpp", "DomainUtils.cpp", "Grid.cpp", "Partitioner.cpp", "CudaRcbPartitioner.cpp"]
 
 
 def _cxx() -> str:

@@ -29,7 +29,7 @@ SYMBOLS = (
     "ddc_get_boxes", "ddc_get_pid_host", "ddc_get_pid_device", "ddc_get_neighbour_counts",
     "ddc_get_neighbour_total", "ddc_get_neighbours", "ddc_get_part_loads", "ddc_get_stats",
     "ddc_neighbours_from_boxes", "ddc_generate_mask_device", "ddc_generate_mask_host", "ddc_version",
-    "ddc_peer_export", "ddc_peer_import", "ddc_peer_close",
+    "ddc_peer_export", "ddc_peer_import", "ddc_peer_close", "ddc_host_alloc", "ddc_host_free", "ddc_peer_connect",
 )
 
 

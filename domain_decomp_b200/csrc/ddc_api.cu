@@ -196,7 +196,7 @@ struct ddc_handle_s {
     unsigned* xbuf = nullptr; // this rank's buffer
     unsigned* xpeer[MAX_PEERS] = {}; // every rank's buffer as mapped here (xpeer[rank] == xbuf)
     size_t x_colcap = 0, x_rowcap = 0; // capacity of one col / row slot, in 32-bit words
-    bool p2p = false;
+    bool p2p = false, peer_local = false; // peer_local: the peers are handles of this process (ddc_peer_connect)
     unsigned step = 0; // decompositions enqueued so far (the flag value of the exchange barriers)
     int h_totals[8] = { 0 };
     bool totals_valid = false;
@@ -476,7 +476,7 @@ int ddc_destroy(ddc_handle_t h)
     if (h->comm)
         g_nccl.CommDestroy(h->comm);
     for (int q = 0; q < h->nranks && q < MAX_PEERS; q++)
-        if (h->xpeer[q] && q != h->rank)
+        if (h->xpeer[q] && q != h->rank && !h->peer_local)
             cudaIpcCloseMemHandle(h->xpeer[q]);
     if (h->xbuf)
         cudaFree(h->xbuf);
@@ -573,6 +573,44 @@ int ddc_peer_import(ddc_handle_t h, const void* all_handles)
     return DDC_OK;
 }
 
+int ddc_peer_connect(ddc_handle_t* handles, int n, int nx, int ny, int nparts)
+{
+    if (!handles || n < 1 || n > MAX_PEERS || nx < 1 || ny < 1 || nparts < 1)
+        return fail(nullptr, DDC_ERR_ARG, "ddc_peer_connect: bad arguments");
+    for (int q = 0; q < n; q++)
+        if (!handles[q] || handles[q]->nranks != n || handles[q]->rank != q || handles[q]->xbuf)
+            return fail(handles[q], DDC_ERR_ARG, "ddc_peer_connect: handle %d must be rank %d of %d and not yet exported", q, q, n);
+    for (int q = 0; q < n; q++) {
+        ddc_handle_t h = handles[q];
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        for (int r = 0; r < n; r++) {
+            if (handles[r]->device == h->device)
+                continue;
+            int can = 0;
+            CUDA_TRY(h, cudaDeviceCanAccessPeer(&can, h->device, handles[r]->device));
+            if (!can)
+                return fail(h, DDC_ERR_CUDA, "device %d cannot access the memory of device %d", h->device, handles[r]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(handles[r]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled)
+                cudaGetLastError(); // not an error
+            else if (e != cudaSuccess)
+                return fail(h, DDC_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", h->device, handles[r]->device,
+                    cudaGetErrorString(e));
+        }
+        peer_capacity(nx, ny, nparts, n, &h->x_colcap, &h->x_rowcap);
+        const size_t words = 64 + 2 * (size_t)n * (h->x_colcap + h->x_rowcap);
+        CUDA_TRY(h, cudaMalloc((void**)&h->xbuf, words * sizeof(unsigned)));
+        CUDA_TRY(h, cudaMemset(h->xbuf, 0, words * sizeof(unsigned)));
+    }
+    for (int q = 0; q < n; q++) {
+        for (int r = 0; r < n; r++)
+            handles[q]->xpeer[r] = handles[r]->xbuf;
+        handles[q]->p2p = true;
+        handles[q]->peer_local = true;
+    }
+    return DDC_OK;
+}
+
 int ddc_peer_close(ddc_handle_t h)
 {
     if (!h)
@@ -580,11 +618,34 @@ int ddc_peer_close(ddc_handle_t h)
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (int q = 0; q < h->nranks && q < MAX_PEERS; q++) {
-        if (h->xpeer[q] && q != h->rank)
+        if (h->xpeer[q] && q != h->rank && !h->peer_local)
             CUDA_TRY(h, cudaIpcCloseMemHandle(h->xpeer[q]));
         h->xpeer[q] = nullptr;
     }
     h->p2p = false;
+    return DDC_OK;
+}
+
+int ddc_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr)
+        return DDC_ERR_ARG;
+    *ptr = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, DDC_ERR_CUDA, "ddc_host_alloc: no CUDA device");
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess)
+        return fail(nullptr, DDC_ERR_NOMEM, "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    *ptr = p;
+    return DDC_OK;
+}
+
+int ddc_host_free(void* ptr)
+{
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess)
+        return fail(nullptr, DDC_ERR_CUDA, "cudaFreeHost failed");
     return DDC_OK;
 }
 

@@ -6,13 +6,15 @@
 #include <string>
 #include <vector>
 
+#include "HostBuffer.hpp"
+
 namespace ddc_host {
 
 struct CdlVar {
     std::string type;
     std::vector<std::string> dims;
     std::vector<double> data;
-    std::vector<int> idata; // filled INSTEAD of `data` by readers asked for ints (large masks: 4 B/value, not 8)
+    ddc_host::IntBuffer idata; // filled INSTEAD of `data` by readers asked for ints (large masks: 4 B/value, not 8)
     bool has_data = false;
 };
 struct CdlGroup {

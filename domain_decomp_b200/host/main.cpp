@@ -1,10 +1,11 @@
 // main.cpp -- the `decomp` command line tool (same options as the reference's main.cpp:45-56).
 //
-//   decomp -g grid.cdl [--parts N] [-x x] [-y y] [-o yx] [-m mask] [-i] [--px] [--py]
+//   decomp -g grid.cdl [--parts N] [--gpus G] [-x x] [-y y] [-o yx] [-m mask] [-i] [--px] [--py] [--stats]
 //
 // The reference takes the number of parts from `mpirun -n P`; here one process drives the GPU and
 // the number of parts is `--parts N` (default: the communicator size).  Outputs are
 // partition_mask_<P> and partition_metadata_<P> (CDL text unless built with netCDF).
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -38,7 +39,9 @@ void usage(const char* argv0)
                  "  --periodic-x [ --px ]     Periodicity in x-direction\n"
                  "  --periodic-y [ --py ]     Periodicity in y-direction\n"
                  "  -n [ --parts ] arg        Number of parts (the reference uses the MPI world size)\n"
-                 "  --device arg (=0)         CUDA device\n"
+                 "  --device arg (=0)         (first) CUDA device\n"
+                 "  --gpus arg (=1)           Row-shard the mask over this many GPUs of the box (the reference:\n"
+                 "                            mpirun -n)\n"
                  "  --stats                   Print partitioning statistics\n";
 }
 
@@ -83,8 +86,8 @@ bool parse(int argc, char** argv, Options& o)
             if (!need(i, "parts", v))
                 return false;
             o.parts = std::atoi(v.c_str());
-        } else if (a == "--device") {
-            if (!need(i, "device", v))
+        } else if (a == "--device" || a == "--gpus") {
+            if (!need(i, a.substr(2), v))
                 return false; // consumed again by the partitioner from argv
         } else if (a == "--stats")
             o.stats = true;
@@ -127,20 +130,39 @@ int main(int argc, char* argv[])
         partitioner = Partitioner::Factory::create(comm, argc, argv, PartitionerType::Cuda_RCB);
         if (opt.parts > 0)
             partitioner->set_num_parts(opt.parts);
+        else if (partitioner->get_num_parts() == 1)
+            std::cerr << "WARNING: no --parts given and a single-process communicator: decomposing into 1 part "
+                         "(the reference takes the part count from mpirun -n)" << std::endl;
+        CudaRcbPartitioner* cuda = static_cast<CudaRcbPartitioner*>(partitioner);
+        cuda->set_profile(opt.stats);
+        const auto t0 = std::chrono::steady_clock::now();
         partitioner->partition(*grid);
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         const int P = partitioner->get_num_parts();
         partitioner->save_mask("partition_mask_" + std::to_string(P) + ".nc");
         partitioner->save_metadata("partition_metadata_" + std::to_string(P) + ".nc");
         if (opt.stats) {
-            const ddc_stats& s = static_cast<CudaRcbPartitioner*>(partitioner)->stats();
+            // the layout of Zoltan's DEBUG_LEVEL statistics that the reference prints (README.md:165-193), with
+            // what the GPU pipeline has to say: host <-> device copies are inside "Partitioning total time"
+            const ddc_stats& s = cuda->stats();
             const double ave = s.nparts ? (double)s.n_ocean / s.nparts : 0.0;
-            std::cout << "Partitioning Statistics:\n"
+            const double imbal = ave > 0 ? s.load_max / ave : 1.0;
+            static const char* stage[DDC_N_STAGES] = { "Mask scan", "x cuts", "Strip row counts", "y cuts", "Labelling",
+                "Step end", "Neighbours (beside the labelling)", "Device total" };
+            std::cout << "Partitioning total time: " << secs << " (secs)\n"
+                      << "Partitioning Statistics:\n"
+                      << " GPUs = " << cuda->num_gpus() << ", parts = " << s.nparts << ", grid = " << s.nx << " x " << s.ny << "\n"
                       << " Total weight of dots = " << s.n_ocean << "\n"
                       << " Weight on each part: ave = " << ave << ", max = " << s.load_max << ", min = " << s.load_min << "\n"
+                      << " Maximum weight of single dot = 1\n"
                       << " RCB levels: " << s.nlev << " (" << s.n_xlev << " cut x, " << s.n_ylev << " cut y), strips = " << s.nstrips << "\n"
-                      << " Median find iterations (all cuts): " << s.median_iters << "\n"
-                      << " changes = " << s.changes << ", imbalance = " << (ave > 0 ? s.load_max / ave : 1.0)
-                      << ", edge cut = " << s.edge_cut << "\n";
+                      << " Median find iteration counts:\n"
+                      << "     Total for all cuts: " << s.median_iters << "\n";
+            for (int i = 0; i < DDC_N_STAGES; i++)
+                std::cout << " " << stage[i] << " time (secs): " << s.stage_ms[i] * 1e-3 << "\n";
+            std::cout << " Kernel launches: " << s.gpu_launches << ", changes = " << s.changes << ", edge cut = " << s.edge_cut << "\n"
+                      << " STATS Runs 1  bal  CURRENT " << imbal << "  MAX " << imbal << "  MIN " << imbal << "  AVG " << imbal << "\n"
+                      << " STATS DETAIL count:  min " << s.load_min << "  max " << s.load_max << "  avg " << ave << "  imbal " << imbal << "\n";
         }
     } catch (const std::exception& e) {
         std::cerr << e.what() << std::endl;

@@ -24,7 +24,7 @@ struct GivenPartitioner final : Partitioner {
     {
         _num_parts = nparts;
         _global_ext = { nx, ny };
-        _pid_global = std::move(pid);
+        _pid_global.assign(pid.begin(), pid.end());
     }
     void partition(Grid&) override {}
 };

@@ -111,6 +111,18 @@ DDC_API int ddc_peer_import(ddc_handle_t h, const void* all_handles /* nranks * 
    the host synchronises the ranks (a barrier), then every rank calls ddc_destroy(), which frees its
    own buffer -- so that no buffer is freed while another rank still has it mapped. */
 DDC_API int ddc_peer_close(ddc_handle_t h);
+/* The same exchange for handles that live in ONE process (one host thread per GPU instead of one process per
+   GPU; this is what `decomp --gpus G` / CudaRcbPartitioner use): handles[q] must be rank q of n, created on
+   different devices with nccl_id == NULL.  Allocates every handle's exchange buffer for masks up to nx * ny into
+   nparts parts and enables peer access between the devices; no CUDA IPC.  Each handle is then driven by its own
+   thread (ddc_partition blocks in the exchange steps until all ranks have enqueued theirs). */
+DDC_API int ddc_peer_connect(ddc_handle_t* handles, int n, int nx, int ny, int nparts);
+
+/* Page-locked host memory (cudaHostAlloc / cudaFreeHost) for masks and pid maps: ddc_set_mask_host and
+   ddc_get_pid_host move such memory at link speed in asynchronous chunks; pageable memory goes through the
+   driver's staging copies.  No counterpart in the reference (its mask never leaves the host). */
+DDC_API int ddc_host_alloc(void** ptr, size_t bytes);
+DDC_API int ddc_host_free(void* ptr);
 
 /* launch everything on this CUDA stream (a cudaStream_t; NULL = the handle's own stream) */
 DDC_API int ddc_set_stream(ddc_handle_t h, void* cuda_stream);

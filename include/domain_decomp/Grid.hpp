@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "HostBuffer.hpp"
 #include "domain_decomp_export.hpp"
 
 class LIB_EXPORT Grid {
@@ -74,7 +75,7 @@ private:
     int _num_objects = 0;
     int _num_nonzero_objects = 0;
     bool _px = false, _py = false, _ignore_mask = false;
-    std::vector<int> _global_mask; // the whole mask
+    ddc_host::IntBuffer _global_mask; // the whole mask (page-locked when large: it is what crosses PCIe)
     std::vector<int> _land_mask; // the rank's block
     std::vector<int> _local_id, _global_id;
 };

@@ -15,6 +15,7 @@
 
 #include "DomainUtils.hpp"
 #include "Grid.hpp"
+#include "HostBuffer.hpp"
 #include "domain_decomp_export.hpp"
 
 enum class LIB_EXPORT PartitionerType {
@@ -53,7 +54,7 @@ public:
         std::vector<std::vector<int>>& halo_sizes, std::vector<std::vector<int>>& halo_starts) const;
     void get_neighbour_info_periodic(int part, std::vector<std::vector<int>>& ids,
         std::vector<std::vector<int>>& halo_sizes, std::vector<std::vector<int>>& halo_starts) const;
-    const std::vector<int>& get_partition_ids() const { return _pid_global; } // [NY][NX], -1 on land
+    const ddc_host::IntBuffer& get_partition_ids() const { return _pid_global; } // [NY][NX], -1 on land
     // text of the two files exactly as `ncdump <file>` prints them (used by the golden tests)
     std::string mask_cdl(const std::string& netcdf_name) const;
     std::string metadata_cdl(const std::string& netcdf_name) const;
@@ -98,7 +99,7 @@ protected:
     std::vector<std::vector<int>> _nbr_ids = std::vector<std::vector<int>>(2 * NNBRS);
     std::vector<std::vector<int>> _nbr_halos = std::vector<std::vector<int>>(2 * NNBRS);
     std::vector<std::vector<int>> _nbr_starts = std::vector<std::vector<int>>(2 * NNBRS);
-    std::vector<int> _pid_global = {};
+    ddc_host::IntBuffer _pid_global = {}; // page-locked when large: the device writes it over PCIe
 
 public:
     struct LIB_EXPORT Factory {

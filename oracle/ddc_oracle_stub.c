@@ -169,3 +169,38 @@ int ddc_get_pid_host(ddc_handle_t h, int32_t* out)
     memcpy(out, h->pid, sizeof(int32_t) * (size_t)h->nx * h->ny);
     return DDC_OK;
 }
+/* host buffers: there is nothing to pin without a GPU */
+int ddc_host_alloc(void** ptr, size_t bytes)
+{
+    *ptr = malloc(bytes ? bytes : 1);
+    return *ptr ? DDC_OK : DDC_ERR_NOMEM;
+}
+int ddc_host_free(void* ptr)
+{
+    free(ptr);
+    return DDC_OK;
+}
+/* one rank only behind the stub */
+void ddc_shard_rows(int ny, int nranks, int rank, int* y_begin, int* y_count)
+{
+    const int rpr = (ny + nranks - 1) / nranks;
+    int b = rank * rpr < ny ? rank * rpr : ny, e = b + rpr < ny ? b + rpr : ny;
+    if (y_begin)
+        *y_begin = b;
+    if (y_count)
+        *y_count = e - b;
+}
+int ddc_peer_connect(ddc_handle_t* handles, int n, int nx, int ny, int nparts)
+{
+    (void)handles;
+    (void)n;
+    (void)nx;
+    (void)ny;
+    (void)nparts;
+    return DDC_ERR_ARG;
+}
+int ddc_peer_close(ddc_handle_t h)
+{
+    (void)h;
+    return DDC_OK;
+}
