@@ -136,6 +136,27 @@ class _DevArray:
                                          "version": 2, "strides": None}
 
 
+def plugin_e2e(mask, expect_pid, expect_boxes_soa, nx, ny, P, px, py, gpus, reps):
+    """CudaRcbPartitioner::partition through libdomain_decomp.so's ddc_plugin_bench (host/PluginBench.cpp)"""
+    import ctypes as C
+    import numpy as np
+    lib = C.CDLL(os.path.join(ROOT, "domain_decomp_b200", "libdomain_decomp.so"))
+    secs = (C.c_double * reps)()
+    grid_s, same = C.c_double(0.0), C.c_int(0)
+    err = C.create_string_buffer(512)
+    vp = C.c_void_p
+    lib.ddc_plugin_bench.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double), vp, vp, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    rc = lib.ddc_plugin_bench(mask.ctypes.data, nx, ny, P, px, py, 0, gpus, reps, secs, C.byref(grid_s),
+                              expect_pid.ctypes.data, np.ascontiguousarray(expect_boxes_soa, dtype=np.int32).ctypes.data,
+                              C.byref(same), err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    t = list(secs)
+    return {"seconds": sum(t) / len(t), "best_seconds": min(t), "steps": reps, "same": bool(same.value),
+            "grid_seconds": grid_s.value}
+
+
 def cpu_sample(workload, threads: int, whole: bool = False):
     """the workload for the CPU legs: the whole mask when it is small or `whole` is set, else a bounded sample --
     the top-left 1/8 x 1/8 window of the SAME mask into 1/64 of the parts (same cells per part).  The mask comes
@@ -415,9 +436,56 @@ def main():
         e2e = {"value": cells / (e2e_ms * 1e-3), "unit": "cells/s", "ms_per_step": e2e_ms, "steps": ke,
                "h2d_bytes_per_step": shard_bytes * world if world > 1 else shard_bytes,
                "d2h_bytes_per_step": (shard_bytes + small) * world if world > 1 else shard_bytes + small,
+               "path": "C ABI (ddc_set_mask_host, ddc_partition, ddc_get_pid_host, table getters), one process per GPU",
                "note": "pinned host int32 mask -> device, partition, pid + boxes + neighbour tables -> host"}
         h.set_mask_device(d_mask.data_ptr(), nx, ny, y_begin, y_count)
-        del h_mask, h_pid
+        # the same through the reference-facing plugin: Grid + Partitioner::Factory::create + partition(grid)
+        # (main.cpp:84-94 of the reference), one process, one host thread per GPU
+        plugin = None
+        boxes_soa = np.ascontiguousarray(h.boxes().T)  # x0[P] y0[P] ex[P] ey[P]
+        if world > 1:  # rank 0 needs the whole mask / pid on the host: gather the shards through shared memory
+            shm = "/dev/shm/ddc_bench_%s" % os.environ.get("MASTER_PORT", "0")
+            for name, t in (("mask", h_mask), ("pid", h_pid)):
+                mm = np.lib.format.open_memmap if False else None
+                arr = np.memmap("%s_%s.i32" % (shm, name), dtype=np.int32, mode="r+" if rank else "w+", shape=(ny, nx)) \
+                    if rank == 0 else None
+                dist.barrier()
+                if rank != 0:
+                    arr = np.memmap("%s_%s.i32" % (shm, name), dtype=np.int32, mode="r+", shape=(ny, nx))
+                arr[y_begin:y_begin + y_count] = t.numpy()[:y_count]
+                arr.flush()
+                dist.barrier()
+                if name == "mask":
+                    g_mask = arr
+                else:
+                    g_pid = arr
+        else:
+            g_mask, g_pid = h_mask.numpy(), h_pid.numpy()
+        if rank == 0:
+            try:
+                plugin = plugin_e2e(np.ascontiguousarray(g_mask), np.ascontiguousarray(g_pid), boxes_soa, nx, ny, P, px, py,
+                                    world, max(1, min(ke, 5)))
+            except Exception as exc:  # the C ABI number stands
+                plugin = {"error": str(exc)}
+        if world > 1:
+            dist.barrier()
+            if rank == 0:
+                for name in ("mask", "pid"):
+                    try:
+                        os.unlink("%s_%s.i32" % (shm, name))
+                    except OSError:
+                        pass
+        del h_mask, h_pid, g_mask, g_pid
+        if plugin and "error" not in plugin:
+            e2e = {"value": cells / plugin["seconds"], "unit": "cells/s", "ms_per_step": plugin["seconds"] * 1e3,
+                   "steps": plugin["steps"], "h2d_bytes_per_step": cells * 4, "d2h_bytes_per_step": cells * 4 + small,
+                   "path": "plugin: Grid (host mask) -> Partitioner::Factory::create(Cuda_RCB, --gpus %d) -> partition(grid): "
+                           "boxes, neighbour tables and the pid map back in the Partitioner's host memory; one process, one "
+                           "host thread per GPU" % world,
+                   "same_result_as_c_abi": plugin["same"], "grid_build_seconds": plugin["grid_seconds"],
+                   "c_abi": e2e}
+        elif plugin:
+            e2e["plugin_error"] = plugin["error"]
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None

@@ -13,7 +13,7 @@ DECOMP = os.path.join(b.PKG, "decomp")
 HOST_TESTS = os.path.join(b.PKG, "host_tests")
 NC_TOOL = os.path.join(b.PKG, "nc_tool")
 
-LIB_SRCS = ["HostBuffer.cpp", "CdlIO.cpp", "NcClassic.cpp", "DomainUtils.cpp", "Grid.cpp", "Partitioner.cpp", "CudaRcbPartitioner.cpp"]
+LIB_SRCS = ["PluginBench.cpp", "HostBuffer.cpp", "CdlIO.cpp", "NcClassic.cpp", "DomainUtils.cpp", "Grid.cpp", "Partitioner.cpp", "CudaRcbPartitioner.cpp"]
 
 
 def _cxx() -> str:
@@ -25,7 +25,7 @@ def _cxx() -> str:
 
 def build_host(force: bool = False, verbose: bool = False) -> None:
     inc = ["-I", os.path.join(b.INCLUDE, "domain_decomp"), "-I", b.INCLUDE, "-I", b.HOST]
-    flags = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra", "-pedantic"]
+    flags = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra", "-pedantic", "-pthread"]
     srcs = [os.path.join(b.HOST, s) for s in LIB_SRCS]
     hdrs = [os.path.join(b.INCLUDE, "domain_decomp", h) for h in os.listdir(os.path.join(b.INCLUDE, "domain_decomp")) if h.endswith(".hpp")]
     hdrs += [os.path.join(b.HOST, "CdlIO.hpp"), os.path.join(b.HOST, "NcClassic.hpp"), os.path.join(b.INCLUDE, "ddc.h"), __file__]

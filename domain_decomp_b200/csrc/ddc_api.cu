@@ -170,9 +170,10 @@ struct ddc_handle_s {
     bool pending = false, profiled = false; // a step is enqueued but not yet validated
     int last_flags = 0, strip_k = 0;
     // knobs (environment, read once in ddc_create): DDC_PDL=0 plain stream order between the kernels,
-    // DDC_WARM=0 no instruction-cache warm-up in the cut kernels, DDC_FUSE_FIN=0 k_finalize as a kernel of its
-    // own after the labelling kernel, DDC_DEBUG_TS=1 time stamps, DDC_SCAN_RPC / DDC_LABEL_RPC rows per CTA
-    bool use_pdl = true, warm = true, fuse_fin = true, debug_ts = false;
+    // DDC_WARM=1 instruction-cache warm-up in the cut kernels (measured: costs more than it saves), DDC_FUSE_FIN=0
+    // k_finalize as a kernel of its own after the labelling kernel, DDC_SUM_COLS=0 the x-cut block sums the ranks'
+    // column-count slots itself, DDC_DEBUG_TS=1 time stamps, DDC_SCAN_RPC / DDC_LABEL_RPC rows per CTA
+    bool use_pdl = true, warm = false, fuse_fin = true, debug_ts = false, sum_cols = true;
     int scan_rpc = 0, label_rpc = 0;
     PeerSync fin_ps {}; // the exchange state of the last step, for a k_finalize launched from validate()
     size_t xcuts_static = 0, ycuts_static = 0; // static shared memory of the cut kernels (0: not yet asked)
@@ -439,7 +440,8 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
         CREATE_TRY(cudaMemcpyToSymbol(g_walk_lanes, &v, sizeof v));
     }
     h->use_pdl = env_int("DDC_PDL", 1) != 0;
-    h->warm = env_int("DDC_WARM", 1) != 0;
+    h->warm = env_int("DDC_WARM", 0) != 0;
+    h->sum_cols = env_int("DDC_SUM_COLS", 1) != 0;
     h->fuse_fin = env_int("DDC_FUSE_FIN", 1) != 0;
     h->debug_ts = env_int("DDC_DEBUG_TS", 0) != 0;
     h->scan_rpc = env_int("DDC_SCAN_RPC", 0);
@@ -955,6 +957,19 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     }
     if (G > 1 && !p2p) // the first exchange step: column histogram and every rank's dot y-range in one sum
         NCCL_TRY(h, g_nccl.AllReduce(colcount, colcount, ncol, nccl_Uint32, nccl_Sum, h->comm, s));
+    // several GPUs: a grid of blocks waits for the ranks' flags and sums their column-count slots into ONE buffer,
+    // the x-cut block then reads global counts as on one GPU
+    const bool presum = p2p && h->sum_cols;
+    if (presum) {
+        CUDA_TRY(h, launch_k(k_sum_cols, dim3(gridx), dim3(256), 0, s, pdl, pc, ps, NX, yr_off, h->colcount.p, h->plan.p));
+        launches++;
+        pc = PeerCols {};
+        pc.col[0] = h->colcount.p;
+        pc.n = 1;
+    }
+    PeerSync ps_x = ps; // (K2 resets this rank's slot: it needs the rank, not the flags)
+    if (presum)
+        ps_x.enabled = 0;
     mark(1);
     // ---- K2: x cuts ----------------------------------------------------------------------------
     if (x_smem) {
@@ -962,13 +977,13 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xneed));
             h->xcuts_smem = xneed;
         }
-        CUDA_TRY(h, launch_k(k_xcuts<true>, dim3(1), dim3(1024), xneed, s, pdl, pc, ps, NX, NY, P, nullptr, yr_off, G, aix,
+        CUDA_TRY(h, launch_k(k_xcuts<true>, dim3(1), dim3(1024), xneed, s, pdl, pc, ps_x, NX, NY, P, nullptr, yr_off, G, aix,
             aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, h->warm ? 1 : 0, dbg ? 1 : 0,
-            h->pin_plan_dev));
+            h->pin_plan_dev, presum ? 1 : 0));
     } else
-        CUDA_TRY(h, launch_k(k_xcuts<false>, dim3(1), dim3(1024), 0, s, pdl, pc, ps, NX, NY, P, h->colpfx.p, yr_off, G, aix,
+        CUDA_TRY(h, launch_k(k_xcuts<false>, dim3(1), dim3(1024), 0, s, pdl, pc, ps_x, NX, NY, P, h->colpfx.p, yr_off, G, aix,
             aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, h->warm ? 1 : 0, dbg ? 1 : 0,
-            h->pin_plan_dev));
+            h->pin_plan_dev, presum ? 1 : 0));
     launches++;
     // the column -> strip table K6 reads: painted by K4's blocks; without y levels there is no K4
     if (!ycuts) {
@@ -1148,6 +1163,7 @@ int validate(ddc_handle_t h)
         if (pl.mismatch == 3) {
             h->partitioned = false;
             h->clean[0] = h->clean[1] = ddc_handle_s::CleanSig(); // the step did not run to its end: start clean
+            cudaMemsetAsync(h->plan.p, 0, sizeof(Plan), h->stream);
             return fail(h, DDC_ERR_PEER, "peer exchange timed out: a rank did not reach the step within %.1f s",
                 (double)PEER_TIMEOUT_NS * 1e-9);
         }

@@ -328,6 +328,9 @@ __device__ inline unsigned block_prefix_tiles(F load_tile, int n, unsigned* dst,
     unsigned carry = 0;
     for (int t = 0; t < tiles; t++) {
         const int base = t * HIST_TILE + tid * 4;
+        // sub-tiles of this tile that hold elements: a histogram of a few hundred bins (the small grids) pays for
+        // one sub-tile scan, not for eight (the skipped ones are empty: sums 0, bit-map words 0)
+        const int nq = min(PFX_Q, (n - t * HIST_TILE + 4095) >> 12);
         uint4 v[PFX_Q];
         unsigned s[PFX_Q], inc[PFX_Q];
         load_tile(base, v);
@@ -335,17 +338,24 @@ __device__ inline unsigned block_prefix_tiles(F load_tile, int n, unsigned* dst,
         for (int q = 0; q < PFX_Q; q++)
             inc[q] = s[q] = v[q].x + v[q].y + v[q].z + v[q].w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int q = 0; q < PFX_Q; q++) {
+            if (q < nq) { // (uniform over the block)
 #pragma unroll
-            for (int q = 0; q < PFX_Q; q++) {
-                const unsigned u = __shfl_up_sync(0xffffffffu, inc[q], o);
-                if (lane >= o)
-                    inc[q] += u;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned u = __shfl_up_sync(0xffffffffu, inc[q], o);
+                    if (lane >= o)
+                        inc[q] += u;
+                }
             }
         }
         if (bitmap) { // l0: one bit per element; 8 neighbouring lanes make one 32-bit word
 #pragma unroll
             for (int q = 0; q < PFX_Q; q++) {
+                if (q >= nq) {
+                    if ((lane & 7) == 0 && (base + q * 4096) >> 5 < tiles * 1024)
+                        bitmap[(base + q * 4096) >> 5] = 0u;
+                    continue;
+                }
                 unsigned w = ((unsigned)(v[q].x != 0u) | ((unsigned)(v[q].y != 0u) << 1) | ((unsigned)(v[q].z != 0u) << 2)
                                  | ((unsigned)(v[q].w != 0u) << 3))
                     << (4 * (lane & 7));
@@ -380,6 +390,8 @@ __device__ inline unsigned block_prefix_tiles(F load_tile, int n, unsigned* dst,
 #pragma unroll
         for (int q = 0; q < PFX_Q; q++) {
             const int i = base + q * 4096;
+            if (q >= nq) // nothing of this sub-tile lies below n (and its total is 0)
+                continue;
             uint4 o;
             o.x = run + ws[q * 32 + warp] + inc[q] - s[q];
             o.y = o.x + v[q].x;
@@ -747,13 +759,60 @@ __device__ __forceinline__ void warm_walk(unsigned* toy /* WARM_WORDS of shared 
     __syncthreads();
 }
 
+// Several GPUs, exchange step 1 on the consuming side.  The G slots of column counts that the ranks' mask scans
+// pushed into this rank's buffer are summed by a GRID of blocks (one per 1024 columns, every thread requesting the
+// G loads of its 4 columns together), so that the single x-cut block afterwards reads ONE buffer, as on one GPU:
+// summing the slots itself cost that block G dependent round trips to L2 -- 24 us of a 58 us kernel on 8 GPUs.
+// Every block waits for the flags in its prologue (local memory); block 0 also gathers the ranks' dot y-ranges
+// behind the sums (sum[yr_off + 2 g ..], the layout K2 expects of a single global buffer).  A rank that does not
+// show up raises Plan::mismatch to 3; K2 then gives up.
+__global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int NX, int yr_off, unsigned* __restrict__ sum,
+    Plan* plan)
+{
+    pdl_trigger();
+    pdl_wait(); // this rank's mask scan is complete
+    bool ok = true;
+    unsigned seen;
+    if ((int)threadIdx.x < ps.G)
+        ok = peer_wait(ps, 0, &seen);
+    if (__syncthreads_or(!ok)) {
+        if (threadIdx.x == 0)
+            atomicMax(&plan->mismatch, 3);
+        return;
+    }
+    const int c = blockIdx.x * 1024 + threadIdx.x * 4;
+    if (c < yr_off) {
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        for (int g0 = 0; g0 < pc.n; g0 += 8) {
+            uint4 t[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                t[k] = g0 + k < pc.n ? load_slot4(pc, g0 + k, c, NX) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                acc.x += t[k].x;
+                acc.y += t[k].y;
+                acc.z += t[k].z;
+                acc.w += t[k].w;
+            }
+        }
+        *reinterpret_cast<uint4*>(sum + c) = acc; // (elements at and beyond NX are 0: load_slot4)
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < pc.n) {
+        const int g = threadIdx.x;
+        const unsigned* src = pc.col[g] + yr_off + 2 * g;
+        sum[yr_off + 2 * g] = __ldcg(src);
+        sum[yr_off + 2 * g + 1] = __ldcg(src + 1);
+    }
+}
+
 // dynamic shared memory when SMEM: (NX + 1) unsigned, rounded up to 4, + hist_bitmap_words(NX).
 // aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
     int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm,
     DevScalars* sc, unsigned* own_col /* this rank's column counts: reset here once they are consumed */,
-    int warm, int dbg, Plan* host_plan)
+    int warm, int dbg, Plan* host_plan, int presummed /* k_sum_cols ran: pc is ONE buffer of global counts */)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
@@ -764,7 +823,11 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     pdl_trigger(); // the strip row-count kernel may become resident
     if (warm)
         warm_walk(toy, &s_iters);
-    pdl_wait(); // the mask scan is complete
+    pdl_wait(); // the mask scan (and k_sum_cols) is complete
+    if (presummed && plan->mismatch == 3) { // a rank did not show up
+        publish_plan(plan, host_plan);
+        return;
+    }
     if (tid == 0) {
         plan->ts[0] = global_ns();
         // the per-step scalars: nothing before K2 touches them, everything after K2 accumulates into them
@@ -918,6 +981,8 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
 __global__ void __launch_bounds__(256) k_paint_strips(StripTable st, const Plan* __restrict__ plan,
     int* __restrict__ strip_of_col)
 {
+    pdl_trigger();
+    pdl_wait(); // the x-cut kernel is complete
     if (plan->mismatch)
         return;
     const int S = *st.S;

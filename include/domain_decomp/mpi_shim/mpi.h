@@ -17,12 +17,15 @@
 extern "C" {
 #endif
 
-typedef int MPI_Comm;
-#define MPI_COMM_WORLD ((MPI_Comm)0x00010000) /* size 1, rank 0 */
+typedef long long MPI_Comm; /* size in the upper, rank in the lower 32 bits: any int part count fits */
+#define MPI_COMM_WORLD ((MPI_Comm)0x100000000LL) /* size 1, rank 0 */
 #define MPI_SUCCESS 0
 #define MPI_MAX_ERROR_STRING 64
 
-static inline MPI_Comm ddc_shim_comm(int rank, int size) { return (MPI_Comm)((size << 16) | (rank & 0xffff)); }
+static inline MPI_Comm ddc_shim_comm(int rank, int size)
+{
+    return (MPI_Comm)(((unsigned long long)(unsigned)size << 32) | (unsigned long long)(unsigned)rank);
+}
 static inline int MPI_Init(int* argc, char*** argv)
 {
     (void)argc;
@@ -32,12 +35,12 @@ static inline int MPI_Init(int* argc, char*** argv)
 static inline int MPI_Finalize(void) { return MPI_SUCCESS; }
 static inline int MPI_Comm_rank(MPI_Comm comm, int* rank)
 {
-    *rank = (int)(comm & 0xffff);
+    *rank = (int)(unsigned)((unsigned long long)comm & 0xffffffffULL);
     return MPI_SUCCESS;
 }
 static inline int MPI_Comm_size(MPI_Comm comm, int* size)
 {
-    *size = (int)((unsigned)comm >> 16);
+    *size = (int)(unsigned)((unsigned long long)comm >> 32);
     return MPI_SUCCESS;
 }
 

@@ -66,7 +66,7 @@ struct Rank {
     std::vector<uint8_t> bits;
     std::vector<unsigned> flags; // [PEER_STAGES][MAX_PEERS]
     std::vector<unsigned> colslots, rowslots; // G slots each (slot g is written by rank g)
-    std::vector<unsigned> colpfx, ypfx, done;
+    std::vector<unsigned> colpfx, ypfx, done, colsum;
     std::vector<int> strips, boxes, strip_of_col;
     std::vector<long long> loads, loadmm;
     std::vector<int32_t> pid;
@@ -205,15 +205,23 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         pc.packed = p2p && Rmax < 65536 ? 1 : 0;
         for (int q = 0; q < G; q++)
             pc.col[q] = colslot(r, p2p ? q : r.rank);
-        const PeerSync ps = sync_of(r);
+        PeerSync ps = sync_of(r);
+        if (p2p) { // the ranks' slots summed by a grid of blocks first (k_sum_cols), K2 reads one buffer
+            r.colsum.assign((size_t)ncol + 4, 0xdeadbeefu);
+            LAUNCH(Dim3(gridx), Dim3(256), 0, k_sum_cols(pc, ps, NX, yr_off, r.colsum.data(), &r.plan));
+            pc = PeerCols {};
+            pc.col[0] = r.colsum.data();
+            pc.n = 1;
+            ps.enabled = 0;
+        }
         if (x_smem)
             LAUNCH(Dim3(1), Dim3(1024), xneed,
                 k_xcuts<true>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(), r.loadmm.data(),
-                    &r.sc, colslot(r, r.rank), 1, 0, &r.host_plan));
+                    &r.sc, colslot(r, r.rank), 1, 0, &r.host_plan, p2p ? 1 : 0));
         else
             LAUNCH(Dim3(1), Dim3(1024), 0,
                 k_xcuts<false>(pc, ps, NX, NY, P, r.colpfx.data(), yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(),
-                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 1, 0, &r.host_plan));
+                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 1, 0, &r.host_plan, p2p ? 1 : 0));
         if (!ycuts) // with y levels K4 paints the column -> strip table
             LAUNCH(Dim3(std::max(1, std::min((Scap + 7) / 8, 148 * 4))), Dim3(256), 0,
                 k_paint_strips(st, &r.plan, r.strip_of_col.data()));
