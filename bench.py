@@ -438,11 +438,11 @@ def main():
                "d2h_bytes_per_step": (shard_bytes + small) * world if world > 1 else shard_bytes + small,
                "path": "C ABI (ddc_set_mask_host, ddc_partition, ddc_get_pid_host, table getters), one process per GPU",
                "note": "pinned host int32 mask -> device, partition, pid + boxes + neighbour tables -> host"}
+        boxes_soa = np.ascontiguousarray(h.boxes().T)  # x0[P] y0[P] ex[P] ey[P]
         h.set_mask_device(d_mask.data_ptr(), nx, ny, y_begin, y_count)
         # the same through the reference-facing plugin: Grid + Partitioner::Factory::create + partition(grid)
         # (main.cpp:84-94 of the reference), one process, one host thread per GPU
         plugin = None
-        boxes_soa = np.ascontiguousarray(h.boxes().T)  # x0[P] y0[P] ex[P] ey[P]
         if world > 1:  # rank 0 needs the whole mask / pid on the host: gather the shards through shared memory
             shm = "/dev/shm/ddc_bench_%s" % os.environ.get("MASTER_PORT", "0")
             for name, t in (("mask", h_mask), ("pid", h_pid)):

@@ -170,10 +170,10 @@ struct ddc_handle_s {
     bool pending = false, profiled = false; // a step is enqueued but not yet validated
     int last_flags = 0, strip_k = 0;
     // knobs (environment, read once in ddc_create): DDC_PDL=0 plain stream order between the kernels,
-    // DDC_WARM=1 instruction-cache warm-up in the cut kernels (measured: costs more than it saves), DDC_FUSE_FIN=0
+    // DDC_FUSE_FIN=0
     // k_finalize as a kernel of its own after the labelling kernel, DDC_SUM_COLS=0 the x-cut block sums the ranks'
     // column-count slots itself, DDC_DEBUG_TS=1 time stamps, DDC_SCAN_RPC / DDC_LABEL_RPC rows per CTA
-    bool use_pdl = true, warm = false, fuse_fin = true, debug_ts = false, sum_cols = true;
+    bool use_pdl = true, fuse_fin = true, debug_ts = false, sum_cols = true;
     int scan_rpc = 0, label_rpc = 0;
     PeerSync fin_ps {}; // the exchange state of the last step, for a k_finalize launched from validate()
     size_t xcuts_static = 0, ycuts_static = 0; // static shared memory of the cut kernels (0: not yet asked)
@@ -440,7 +440,6 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
         CREATE_TRY(cudaMemcpyToSymbol(g_walk_lanes, &v, sizeof v));
     }
     h->use_pdl = env_int("DDC_PDL", 1) != 0;
-    h->warm = env_int("DDC_WARM", 0) != 0;
     h->sum_cols = env_int("DDC_SUM_COLS", 1) != 0;
     h->fuse_fin = env_int("DDC_FUSE_FIN", 1) != 0;
     h->debug_ts = env_int("DDC_DEBUG_TS", 0) != 0;
@@ -839,8 +838,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             CUDA_TRY(h, h->rowcount_all.ensure(rc_words * G + 4));
     }
     // prefix sums + the bit map of the non-empty bins (ddc_kernels.cuh: Hist)
-    const size_t xneed = sizeof(unsigned) * ((((size_t)NX + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NX));
-    const size_t yneed = sizeof(unsigned) * ((((size_t)NY + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NY));
+    // (+ the sets of two RCB levels, see rcb_levels)
+    const size_t xneed = sizeof(unsigned) * ((((size_t)NX + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NX)) + LEVEL_NODES_BYTES;
+    const size_t yneed = sizeof(unsigned) * ((((size_t)NY + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NY)) + LEVEL_NODES_BYTES;
     const size_t lim = max_dyn_smem(h->device);
     if (!h->xcuts_static) { // what the cut kernels hold statically counts against the same per-block limit
         cudaFuncAttributes fa;
@@ -978,11 +978,11 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             h->xcuts_smem = xneed;
         }
         CUDA_TRY(h, launch_k(k_xcuts<true>, dim3(1), dim3(1024), xneed, s, pdl, pc, ps_x, NX, NY, P, nullptr, yr_off, G, aix,
-            aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, h->warm ? 1 : 0, dbg ? 1 : 0,
+            aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, dbg ? 1 : 0,
             h->pin_plan_dev, presum ? 1 : 0));
     } else
-        CUDA_TRY(h, launch_k(k_xcuts<false>, dim3(1), dim3(1024), 0, s, pdl, pc, ps_x, NX, NY, P, h->colpfx.p, yr_off, G, aix,
-            aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, h->warm ? 1 : 0, dbg ? 1 : 0,
+        CUDA_TRY(h, launch_k(k_xcuts<false>, dim3(1), dim3(1024), LEVEL_NODES_BYTES, s, pdl, pc, ps_x, NX, NY, P, h->colpfx.p, yr_off, G, aix,
+            aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, dbg ? 1 : 0,
             h->pin_plan_dev, presum ? 1 : 0));
     launches++;
     // the column -> strip table K6 reads: painted by K4's blocks; without y levels there is no K4
@@ -999,7 +999,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             // the grid covers the Rmax rows of the largest shard: a short (or empty) shard writes its
             // missing rows as empty, and with the peer exchange every count goes to all ranks
             // rows per warp of the streaming kernel: fewer for small shards, so that the grid fills the SMs
-            int K = Rmax >= 32 * 4 * 148 ? 4 : (Rmax >= 16 * 4 * 148 ? 2 : 1);
+            // (measured at C3 / C4 / one eighth of C5: two rows per warp beat one -- whole row in registers or not --
+            //  by 2-4 us: half the blocks, each amortising its boundary table over twice the rows)
+            int K = Rmax >= 32 * 4 * 148 ? 4 : 2;
             if (h->strip_k) // DDC_STRIP_K: tuning knob (1, 2, 4: rows per warp; 8: one row per warp, whole row at once)
                 K = h->strip_k == 8 ? 1 : h->strip_k;
             while (K > 1 && sizeof(int) * strip_scan_smem_words(NG, Scap, K) > 48 * 1024)
@@ -1012,7 +1014,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     CUDA_TRY(h, launch_k(k_strip_rows_scan<CT, KK, FF>, dim3(grid), dim3(256), scan_smem, s, pdl, h->bits.p, NB, NX, rows, \
         t.st.x0, t.st.p0, h->plan.p, Scap, push_row, Rmax, ps, h->done.p + d_rows, dbg))
                 // small shards: one row per warp, the whole row requested at once (rows of <= 8 chunks)
-                const bool full = K == 1 && NG <= 256 && h->strip_k != 1;
+                const bool full = h->strip_k == 8 && K == 1 && NG <= 256;
                 if (narrow) {
                     if (K == 4)
                         LAUNCH_SCAN(uint16_t, 4, false);
@@ -1056,8 +1058,8 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<CT, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed)); \
             opted = yneed;                                                                         \
         }                                                                                          \
-        CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : 0, s, pdl, pr, ps, rl, NY, t.st, \
-            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, h->warm ? 1 : 0, dbg ? 1 : 0)); \
+        CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : LEVEL_NODES_BYTES, s, pdl, pr, ps, rl, NY, t.st, \
+            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0)); \
     } while (0)
         if (narrow) {
             if (y_smem)

@@ -649,6 +649,71 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
         done[i] = 0u;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The RCB recursion level by level: ONE thread per set
+// ------------------------------------------------------------------------------------------------
+// The sets of one level (cell range [lo, hi) along the cut dimension, parts [plo, plo + n)) sit in shared memory
+// in part order; every set is split by exactly one thread, and the threads that work are spread over the warps
+// (set i -> thread i * spread), so that a level with up to 32 sets runs one median per warp: no divergence, no
+// redundant work.  The barrier-free walks (rcb_walk: every leaf's thread group re-evaluates the medians of its
+// whole path) issued ~7 x the instructions from all 32 warps at once and ran at 13 cycles per dependent
+// instruction (ncu: "wait" stalls, 0.55 IPC); a level here costs one median's latency plus a block barrier.
+// Because Zoltan_Divide_Machine halves the part counts (ceil / floor), the part counts of one level differ by at
+// most one, which gives the position of a set's children in the next level in closed form: 2 i while every set
+// still splits, and plo - root.plo once the sets hold one or two parts (a set of one part is carried down).
+constexpr int LEVEL_NODES = 1024; // sets per level held in shared memory (more leaves: the walks below)
+struct __align__(16) RcbNode {
+    int lo, hi, plo, n;
+};
+constexpr size_t LEVEL_NODES_BYTES = 2 * LEVEL_NODES * sizeof(RcbNode) + 16;
+// all threads of the block call it; returns the final sets (in part order) and their number through *count.
+// iters: this thread's median iterations are added.  lvl_ts (diagnostics): thread 0 stamps the start of a level.
+__device__ inline const RcbNode* rcb_levels(const Hist& H, RcbSet root, int levels, RcbNode* nodes /* [2][LEVEL_NODES] */,
+    int* iters, unsigned long long* lvl_ts, int* count)
+{
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    int cur = 0, cnt = 1;
+    if (tid == 0) {
+        const RcbNode r = { root.lo, root.hi, root.plo, root.n };
+        nodes[0] = r;
+    }
+    __syncthreads();
+    for (int l = 0; l < levels; l++) {
+        // part counts of this level: floor and ceil of root.n / 2^l (uniform over the block)
+        const int minn = l >= 31 ? 0 : root.n >> l;
+        const int maxn = l >= 31 ? 1 : (int)(((long long)root.n + (1LL << l) - 1) >> l);
+        if (maxn <= 1)
+            break;
+        if (lvl_ts && tid == 0 && l < 8)
+            lvl_ts[l] = walk_clock();
+        int spread = 1;
+        while (spread < 32 && 2 * spread * cnt <= nthreads)
+            spread <<= 1;
+        const RcbNode* src = nodes + cur * LEVEL_NODES;
+        RcbNode* dst = nodes + (cur ^ 1) * LEVEL_NODES;
+        const int i = tid / spread;
+        if (tid % spread == 0 && i < cnt) {
+            const RcbNode sset = src[i];
+            const int off = minn >= 2 ? 2 * i : sset.plo - root.plo;
+            if (sset.n > 1) {
+                const int nlo = (sset.n - 1) / 2 + 1;
+                int it = 0;
+                const int cut = median_boundary(H, sset.lo, sset.hi - 1, nlo, sset.n, &it);
+                *iters += it;
+                const RcbNode a = { sset.lo, cut, sset.plo, nlo }, b = { cut, sset.hi, sset.plo + nlo, sset.n - nlo };
+                dst[off] = a;
+                dst[off + 1] = b;
+            } else
+                dst[off] = sset;
+        }
+        cnt = minn >= 2 ? 2 * cnt : root.n;
+        cur ^= 1;
+        __syncthreads();
+    }
+    *count = cnt;
+    return nodes + cur * LEVEL_NODES;
+}
+
 // threads that share one leaf's walk: the largest power of two <= 32 with lanes * leaves <= threads
 __device__ int g_walk_lanes = 32; // upper bound (tuning knob, set by the host)
 __device__ __forceinline__ int walk_lanes(int leaves, int threads)
@@ -723,42 +788,6 @@ __device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
             = reinterpret_cast<const volatile unsigned*>(plan)[threadIdx.x];
 }
 
-// Runs the walk once on a toy histogram in shared memory (64 bins: dots in bins 4-27 and 36-59, a land gap in
-// the middle, empty margins), so that the SM's instruction cache holds the median search before the real
-// histogram has arrived: the cut kernels call it while they wait for the kernel before them (pdl_wait) and for
-// the other ranks' pushes.  A cut kernel runs once per step between kernels that stream gigabytes, so its code
-// is cold every time, and the walks are one long dependent instruction stream.
-constexpr int WARM_WORDS = 72;
-__device__ __forceinline__ void warm_walk(unsigned* toy /* WARM_WORDS of shared memory */, int* sink)
-{
-    const int tid = threadIdx.x;
-    if (tid <= 64) {
-        unsigned c = 0;
-        for (int b = 0; b < tid; b++)
-            c += ((b >= 4 && b < 28) || (b >= 36 && b < 60)) ? 1u + (unsigned)(b % 3) : 0u;
-        toy[tid] = c;
-    }
-    if (tid == 65) {
-        toy[68] = 0x0ffffff0u; // l0: bins 4-27
-        toy[69] = 0x0ffffff0u; //     bins 36-59
-        toy[70] = 3u; // l1
-        toy[71] = 1u; // l2
-    }
-    __syncthreads();
-    Hist H;
-    H.pfx = toy;
-    H.l0 = toy + 68;
-    H.l1 = toy + 70;
-    H.l2 = toy + 71;
-    H.nl2 = 1;
-    const int warp = tid >> 5;
-    const RcbSet root = { 0, 64, 0, 8 + (warp & 3) }; // 8 parts: halves only; 9-11 parts: uneven splits (FP64 targets)
-    const WalkResult r = rcb_walk_shared(H, root, 3, tid & 7, nullptr);
-    if (r.set.lo == -12345) // never: keeps the call alive
-        *sink = r.iters;
-    __syncthreads();
-}
-
 // Several GPUs, exchange step 1 on the consuming side.  The G slots of column counts that the ranks' mask scans
 // pushed into this rank's buffer are summed by a GRID of blocks (one per 1024 columns, every thread requesting the
 // G loads of its 4 columns together), so that the single x-cut block afterwards reads ONE buffer, as on one GPU:
@@ -812,17 +841,14 @@ template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
     int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm,
     DevScalars* sc, unsigned* own_col /* this rank's column counts: reset here once they are consumed */,
-    int warm, int dbg, Plan* host_plan, int presummed /* k_sum_cols ran: pc is ONE buffer of global counts */)
+    int dbg, Plan* host_plan, int presummed /* k_sum_cols ran: pc is ONE buffer of global counts */)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
-    __shared__ unsigned toy[WARM_WORDS];
     __shared__ int s_ix, s_iters;
     unsigned* pfx = SMEM ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
     pdl_trigger(); // the strip row-count kernel may become resident
-    if (warm)
-        warm_walk(toy, &s_iters);
     pdl_wait(); // the mask scan (and k_sum_cols) is complete
     if (presummed && plan->mismatch == 3) { // a rank did not show up
         publish_plan(plan, host_plan);
@@ -926,16 +952,34 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     //    lanes of a warp work on, the less a warp waits for the slowest of them)
     const int ix = s_ix;
     const int nstrips = leaves_below(P, ix);
-    const int lanes = walk_lanes(nstrips, blockDim.x);
+    const bool by_level = nstrips <= LEVEL_NODES;
+    const int lanes = by_level ? 1 : walk_lanes(nstrips, blockDim.x);
     int my_iters = 0;
     long long lmn = 0x7fffffffffffffffLL, lmx = -1;
-    for (int i = tid / lanes; i < nstrips; i += blockDim.x / lanes) {
+    const RcbNode* fin = nullptr;
+    if (by_level) { // the sets of a level side by side, one thread each
+        RcbNode* nodes = reinterpret_cast<RcbNode*>(
+            (reinterpret_cast<uintptr_t>(SMEM ? bitmap + hist_bitmap_words(NX) : smem_dyn) + 15) & ~(uintptr_t)15);
         const RcbSet root = { 0, NX, 0, P };
-        const WalkResult wr = rcb_walk_shared(H, root, ix, i, dbg && tid == 0 ? plan->ts + TS_XLEV : nullptr);
-        const RcbSet r = wr.set;
-        if (tid % lanes)
-            continue;
-        my_iters += wr.iters;
+        int cnt;
+        fin = rcb_levels(H, root, ix, nodes, &my_iters, dbg ? plan->ts + TS_XLEV : nullptr, &cnt);
+    }
+    for (int i = tid / lanes; i < nstrips; i += blockDim.x / lanes) {
+        RcbSet r;
+        if (by_level) {
+            const RcbNode f = fin[i];
+            r.lo = f.lo;
+            r.hi = f.hi;
+            r.plo = f.plo;
+            r.n = f.n;
+        } else {
+            const RcbSet root = { 0, NX, 0, P };
+            int it = 0;
+            r = rcb_walk(H, root, ix, i, &it, dbg && tid == 0 ? plan->ts + TS_XLEV : nullptr);
+            if (tid % lanes)
+                continue;
+            my_iters += it;
+        }
         // 4. the strip table, in ascending part order
         st.x0[i] = r.lo;
         st.x1[i] = r.hi;
@@ -1315,15 +1359,11 @@ __device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowL
 template <typename CT, bool SMEM>
 __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st,
     unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan, int* __restrict__ strip_of_col,
-    int warm, int dbg)
+    int dbg)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
-    __shared__ unsigned toy[WARM_WORDS];
-    __shared__ int s_sink;
     pdl_trigger(); // (nothing is launched programmatically behind this kernel today; harmless)
-    if (warm)
-        warm_walk(toy, &s_sink);
     pdl_wait(); // the strip row-count kernel (and with it everything before) is complete
     if (plan->mismatch)
         return;
@@ -1376,15 +1416,32 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
             plan->ts[8] = global_ns();
         // a group of `lanes` threads walks to the j-th part of the strip (parts come out y-sorted)
         const int sx0 = st.x0[s], sx1 = st.x1[s];
-        const int lanes = walk_lanes(n, blockDim.x);
-        for (int j = tid / lanes; j < n; j += blockDim.x / lanes) {
-            const RcbSet root = { 0, NY, plo, n };
-            const WalkResult wr
-                = rcb_walk_shared(H, root, ylevels, j, dbg && tid == 0 && blockIdx.x == 0 ? plan->ts + TS_YLEV : nullptr);
-            const RcbSet r = wr.set;
-            if (tid % lanes)
-                continue;
-            my_iters += wr.iters;
+        const int nleaves = leaves_below(n, ylevels);
+        const bool by_level = nleaves <= LEVEL_NODES;
+        const int lanes = by_level ? 1 : walk_lanes(nleaves, blockDim.x);
+        const RcbSet root = { 0, NY, plo, n };
+        const RcbNode* fin = nullptr;
+        if (by_level) {
+            RcbNode* nodes = reinterpret_cast<RcbNode*>(
+                (reinterpret_cast<uintptr_t>(SMEM ? bitmap + hist_bitmap_words(NY) : smem_dyn) + 15) & ~(uintptr_t)15);
+            int cnt;
+            fin = rcb_levels(H, root, ylevels, nodes, &my_iters, dbg && blockIdx.x == 0 ? plan->ts + TS_YLEV : nullptr, &cnt);
+        }
+        for (int j = tid / lanes; j < nleaves; j += blockDim.x / lanes) {
+            RcbSet r;
+            if (by_level) {
+                const RcbNode f = fin[j];
+                r.lo = f.lo;
+                r.hi = f.hi;
+                r.plo = f.plo;
+                r.n = f.n;
+            } else {
+                int it = 0;
+                r = rcb_walk(H, root, ylevels, j, &it, dbg && tid == 0 && blockIdx.x == 0 ? plan->ts + TS_YLEV : nullptr);
+                if (tid % lanes)
+                    continue;
+                my_iters += it;
+            }
             bx.x0[r.plo] = sx0;
             bx.ex[r.plo] = sx1 - sx0;
             bx.y0[r.plo] = r.lo;

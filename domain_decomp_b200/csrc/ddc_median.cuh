@@ -10,9 +10,6 @@
 
 #ifdef DDC_HOST_EMU
 #include "ddc_host_emu.h" // oracle/emu: host stand-ins of the device language (test builds only)
-#define DDC_NOINLINE inline
-#else
-#define DDC_NOINLINE __noinline__
 #endif
 
 namespace ddc {
@@ -342,19 +339,4 @@ __device__ inline RcbSet rcb_walk(const Hist& H, RcbSet set, int levels, int k, 
     }
     return set;
 }
-// The walk as ONE function in the binary: the cut kernels call it for the real histogram and, before their
-// input has arrived, once for a toy histogram -- the second call only warms the instruction cache if both
-// calls run the same instructions.  Everything crosses the call in registers.
-struct WalkResult {
-    RcbSet set;
-    int iters;
-};
-__device__ DDC_NOINLINE WalkResult rcb_walk_shared(Hist H, RcbSet set, int levels, int k, unsigned long long* lvl_ts)
-{
-    WalkResult r;
-    r.iters = 0;
-    r.set = rcb_walk(H, set, levels, k, &r.iters, lvl_ts);
-    return r;
-}
-
 } // namespace ddc

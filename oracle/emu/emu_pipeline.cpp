@@ -104,8 +104,8 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const size_t rc_words = narrow ? (rc_elems + 1) / 2 : rc_elems;
     const size_t rank_stride = narrow ? rc_words * 2 : rc_words;
     const size_t colcap = (((size_t)ncol + 3) & ~(size_t)3), rowcap = (rc_words + 4 + 3) & ~(size_t)3;
-    const size_t xneed = sizeof(unsigned) * ((((size_t)NX + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NX));
-    const size_t yneed = sizeof(unsigned) * ((((size_t)NY + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NY));
+    const size_t xneed = sizeof(unsigned) * ((((size_t)NX + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NX)) + LEVEL_NODES_BYTES;
+    const size_t yneed = sizeof(unsigned) * ((((size_t)NY + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NY)) + LEVEL_NODES_BYTES;
     const bool x_smem = xneed + 1024 <= (size_t)opt.smem_limit, y_smem = yneed + 1024 <= (size_t)opt.smem_limit;
     const int ygrid = std::max(1, std::min(Scap, 148 * 2));
     const int gridx = (NG + 7) / 8;
@@ -217,11 +217,11 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         if (x_smem)
             LAUNCH(Dim3(1), Dim3(1024), xneed,
                 k_xcuts<true>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(), r.loadmm.data(),
-                    &r.sc, colslot(r, r.rank), 1, 0, &r.host_plan, p2p ? 1 : 0));
+                    &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0));
         else
-            LAUNCH(Dim3(1), Dim3(1024), 0,
+            LAUNCH(Dim3(1), Dim3(1024), LEVEL_NODES_BYTES,
                 k_xcuts<false>(pc, ps, NX, NY, P, r.colpfx.data(), yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(),
-                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 1, 0, &r.host_plan, p2p ? 1 : 0));
+                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0));
         if (!ycuts) // with y levels K4 paints the column -> strip table
             LAUNCH(Dim3(std::max(1, std::min((Scap + 7) / 8, 148 * 4))), Dim3(256), 0,
                 k_paint_strips(st, &r.plan, r.strip_of_col.data()));
@@ -239,7 +239,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             for (int q = 0; q < G; q++)
                 out.dst[q] = rowslot(R[p2p ? q : r.rank], r.rank);
             const PeerSync ps = sync_of(r);
-            int K = Rmax >= 32 * 4 * 148 ? 4 : (Rmax >= 16 * 4 * 148 ? 2 : 1);
+            int K = Rmax >= 32 * 4 * 148 ? 4 : 2;
             if (opt.strip_k)
                 K = opt.strip_k == 8 ? 1 : opt.strip_k;
             while (K > 1 && sizeof(int) * strip_scan_smem_words(NG, Scap, K) > 48 * 1024)
@@ -248,7 +248,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             if (scan_smem <= 48 * 1024 && opt.strip_k != 16) {
                 const Dim3 grid((Rmax + 8 * K - 1) / (8 * K));
                 rb_shift = K == 4 ? 5 : (K == 2 ? 4 : 3);
-                const bool full = K == 1 && NG <= 256 && opt.strip_k != 1;
+                const bool full = opt.strip_k == 8 && K == 1 && NG <= 256;
 #define SCAN(CT, KK, FF)                                                                           \
     LAUNCH(grid, Dim3(256), scan_smem,                                                             \
         (k_strip_rows_scan<CT, KK, FF>(r.bits.data(), NB, NX, r.rows, st.x0, st.p0, &r.plan, Scap, out, Rmax, ps,      \
@@ -309,9 +309,9 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             const PeerSync ps = sync_of(r);
             const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
 #define YCUTS(CT, SM)                                                                              \
-    LAUNCH(Dim3(ygrid), Dim3(1024), SM ? yneed : 0,                                                \
+    LAUNCH(Dim3(ygrid), Dim3(1024), SM ? yneed : LEVEL_NODES_BYTES,                                                \
         (k_ycuts<CT, SM>(pr, ps, rl, NY, st, r.ypfx.data(), bx, r.loads.data(), r.loadmm.data(), &r.plan,                    \
-            r.strip_of_col.data(), 1, 0)))
+            r.strip_of_col.data(), 0)))
             if (narrow) {
                 if (y_smem)
                     YCUTS(uint16_t, true);
