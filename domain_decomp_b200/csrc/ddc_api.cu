@@ -171,10 +171,9 @@ struct ddc_handle_s {
     int last_flags = 0, strip_k = 0;
     // knobs (environment, read once in ddc_create): DDC_PDL=0 plain stream order between the kernels,
     // DDC_FUSE_FIN=0
-    // k_finalize as a kernel of its own after the labelling kernel, DDC_SUM_COLS=0 the x-cut block sums the ranks'
-    // column-count slots itself, DDC_DEBUG_TS=1 time stamps, DDC_SCAN_RPC / DDC_LABEL_RPC rows per CTA
-    bool use_pdl = true, fuse_fin = true, debug_ts = false, sum_cols = true;
-    int scan_rpc = 0, label_rpc = 0;
+    // k_finalize as a kernel of its own after the labelling kernel, DDC_DEBUG_TS=1 time stamps, DDC_SCAN_RPC / DDC_LABEL_RPC rows per CTA
+    bool use_pdl = true, fuse_fin = true, debug_ts = false;
+    int scan_rpc = 0, label_rpc = 0, scan_tail = 25;
     PeerSync fin_ps {}; // the exchange state of the last step, for a k_finalize launched from validate()
     size_t xcuts_static = 0, ycuts_static = 0; // static shared memory of the cut kernels (0: not yet asked)
     // what K2 (column counts, scalars) and the scan's last CTA (counters) left clean for a later step: k_init is
@@ -440,10 +439,10 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
         CREATE_TRY(cudaMemcpyToSymbol(g_walk_lanes, &v, sizeof v));
     }
     h->use_pdl = env_int("DDC_PDL", 1) != 0;
-    h->sum_cols = env_int("DDC_SUM_COLS", 1) != 0;
     h->fuse_fin = env_int("DDC_FUSE_FIN", 1) != 0;
     h->debug_ts = env_int("DDC_DEBUG_TS", 0) != 0;
     h->scan_rpc = env_int("DDC_SCAN_RPC", 0);
+    h->scan_tail = std::max(0, std::min(90, env_int("DDC_SCAN_TAIL", 25)));
     h->label_rpc = env_int("DDC_LABEL_RPC", 0);
     CREATE_TRY(h->sc.ensure(1));
     CREATE_TRY(h->plan.ensure(1));
@@ -950,16 +949,23 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
                       : pick_rows_per_cta(k_scan_mask<false>, std::max(rows, 1), gridx);
         if (h->scan_rpc >= 8)
             rpc = h->scan_rpc & ~7;
-        dim3 grid(gridx, std::max(1, (rows + rpc - 1) / rpc));
+        // the last `scan_tail` percent of the rows go in chunks of a quarter of the size (see the kernel)
+        const int small = std::max(8, (rpc / 4) & ~7);
+        int nbig = (rows + rpc - 1) / rpc, nsmall = 0;
+        if (h->scan_tail > 0 && small < rpc && rows >= 4 * rpc) {
+            nbig = (int)((long long)rows * (100 - h->scan_tail) / 100) / rpc;
+            nsmall = (rows - nbig * rpc + small - 1) / small;
+        }
+        dim3 grid(gridx, std::max(1, nbig + nsmall));
         CUDA_TRY(h, launch_k(vec ? k_scan_mask<true> : k_scan_mask<false>, grid, dim3(256), 0, s, pdl, h->d_mask, NX, rows,
-            h->y_begin, NB, rpc, h->bits.p, colcount, yr, push_col, ps, h->done.p, yr_off, dbg));
+            h->y_begin, NB, rpc, h->bits.p, colcount, yr, push_col, ps, h->done.p, yr_off, dbg, nbig, small));
         launches++;
     }
     if (G > 1 && !p2p) // the first exchange step: column histogram and every rank's dot y-range in one sum
         NCCL_TRY(h, g_nccl.AllReduce(colcount, colcount, ncol, nccl_Uint32, nccl_Sum, h->comm, s));
     // several GPUs: a grid of blocks waits for the ranks' flags and sums their column-count slots into ONE buffer,
     // the x-cut block then reads global counts as on one GPU
-    const bool presum = p2p && h->sum_cols;
+    const bool presum = p2p;
     if (presum) {
         CUDA_TRY(h, launch_k(k_sum_cols, dim3(gridx), dim3(256), 0, s, pdl, pc, ps, NX, yr_off, h->colcount.p, h->plan.p));
         launches++;

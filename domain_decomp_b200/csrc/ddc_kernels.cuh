@@ -453,11 +453,12 @@ __device__ __forceinline__ unsigned ocean_nibble(const int4& v)
 constexpr int SCAN_STAGE_ROWS = 64; // bit-map rows staged in shared memory between flushes (power of 2)
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ mask, int NX, int rows,
+__global__ void __launch_bounds__(256, 4) k_scan_mask(const int32_t* __restrict__ mask, int NX, int rows,
     int y_begin, int NB, int rows_per_cta, uint8_t* __restrict__ bits, unsigned* __restrict__ colcount,
     int* __restrict__ yr /* this rank's {-(first ocean row), last ocean row}, max-reduced */,
     PeerPush push, PeerSync ps, unsigned* __restrict__ done /* [gridDim.x + 1], zeroed by k_init */, int yr_off,
-    unsigned long long* dbg)
+    unsigned long long* dbg, int nbig /* row chunks of rows_per_cta rows; the chunks after them hold rows_small */,
+    int rows_small)
 {
     __shared__ __align__(16) uint8_t sbits[SCAN_STAGE_ROWS][128];
     __shared__ int s_last;
@@ -467,8 +468,12 @@ __global__ void __launch_bounds__(256) k_scan_mask(const int32_t* __restrict__ m
     // load nothing (clamped, masked addresses below) but take part in the CTA barriers
     const int g = min(blockIdx.x * 8 + warp, NB / 16 - 1);
     const bool warp_valid = blockIdx.x * 8 + warp < NB / 16;
-    const int r0 = blockIdx.y * rows_per_cta;
-    const int r1 = min(rows, r0 + rows_per_cta);
+    // Blocks are scheduled in index order, and the last blocks of a grid run on a half-empty machine that no longer
+    // saturates HBM: the last rows are therefore cut into smaller chunks (a fine-grained tail), the bulk into large
+    // ones (fewer column atomics).
+    const int big = (int)blockIdx.y < nbig;
+    const int r0 = big ? blockIdx.y * rows_per_cta : nbig * rows_per_cta + ((int)blockIdx.y - nbig) * rows_small;
+    const int r1 = min(rows, r0 + (big ? rows_per_cta : rows_small));
     const int x = g * 128 + lane * 4;
     unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     int ylo = 0x7fffffff, yhi = -1;
@@ -668,9 +673,14 @@ struct __align__(16) RcbNode {
 constexpr size_t LEVEL_NODES_BYTES = 2 * LEVEL_NODES * sizeof(RcbNode) + 16;
 // all threads of the block call it; returns the final sets (in part order) and their number through *count.
 // iters: this thread's median iterations are added.  lvl_ts (diagnostics): thread 0 stamps the start of a level.
+// FAST: the histogram is in shared memory with a bit map and at most FAST_HIST_BINS bins (median_boundary_fast)
+template <bool FAST>
 __device__ inline const RcbNode* rcb_levels(const Hist& H, RcbSet root, int levels, RcbNode* nodes /* [2][LEVEL_NODES] */,
     int* iters, unsigned long long* lvl_ts, int* count)
 {
+    FastHist F {};
+    if (FAST)
+        F = make_fast_hist(H);
     const int tid = threadIdx.x, nthreads = blockDim.x;
     int cur = 0, cnt = 1;
     if (tid == 0) {
@@ -698,7 +708,8 @@ __device__ inline const RcbNode* rcb_levels(const Hist& H, RcbSet root, int leve
             if (sset.n > 1) {
                 const int nlo = (sset.n - 1) / 2 + 1;
                 int it = 0;
-                const int cut = median_boundary(H, sset.lo, sset.hi - 1, nlo, sset.n, &it);
+                const int cut = FAST ? median_boundary_fast(F, sset.lo, sset.hi - 1, nlo, sset.n, &it)
+                                     : median_boundary(H, sset.lo, sset.hi - 1, nlo, sset.n, &it);
                 *iters += it;
                 const RcbNode a = { sset.lo, cut, sset.plo, nlo }, b = { cut, sset.hi, sset.plo + nlo, sset.n - nlo };
                 dst[off] = a;
@@ -758,26 +769,6 @@ __device__ __forceinline__ uint4 load_slot4(const PeerCols& pc, int g, int i, in
     t.w = i + 3 < n ? __ldcg(src + 3) : 0u;
     return t;
 }
-__device__ __forceinline__ void load_counts_tile(const PeerCols& pc, int base, int n, uint4 (&v)[PFX_Q])
-{
-#pragma unroll
-    for (int q = 0; q < PFX_Q; q++)
-        v[q] = make_uint4(0u, 0u, 0u, 0u);
-    for (int g = 0; g < pc.n; g++) {
-        uint4 t[PFX_Q];
-#pragma unroll
-        for (int q = 0; q < PFX_Q; q++)
-            t[q] = load_slot4(pc, g, base + q * 4096, n);
-#pragma unroll
-        for (int q = 0; q < PFX_Q; q++) {
-            v[q].x += t[q].x;
-            v[q].y += t[q].y;
-            v[q].z += t[q].z;
-            v[q].w += t[q].w;
-        }
-    }
-}
-
 // the plan (levels, mismatch flag, iteration count, fix-up request) goes straight into the host's pinned copy,
 // so that a step ends without a separate device -> host copy; called by all threads of a block (>= 128)
 __device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
@@ -884,7 +875,18 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     if (tid == 0)
         plan->ts[1] = global_ns();
     unsigned* bitmap = SMEM ? smem_dyn + (((size_t)NX + 1 + 3) & ~(size_t)3) : nullptr;
-    block_prefix_tiles([&](int base, uint4 (&v)[PFX_Q]) { load_counts_tile(pc, base, NX, v); }, NX, pfx, wsum, bitmap);
+    // (ONE buffer of global counts: this GPU's own, an all-reduced one, or the sum k_sum_cols made of the ranks' slots;
+    //  16-byte aligned, zero between NX and yr_off = NX rounded up to 4)
+    const uint4* gcol = reinterpret_cast<const uint4*>(pc.col[0]);
+    block_prefix_tiles(
+        [&](int base, uint4 (&v)[PFX_Q]) {
+#pragma unroll
+            for (int q = 0; q < PFX_Q; q++) {
+                const int i = base + q * 4096;
+                v[q] = i < yr_off ? __ldcg(gcol + (i >> 2)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        },
+        NX, pfx, wsum, bitmap);
     if (tid == 0)
         plan->ts[2] = global_ns();
     const Hist H = make_hist(pfx, bitmap, NX);
@@ -962,7 +964,9 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
             (reinterpret_cast<uintptr_t>(SMEM ? bitmap + hist_bitmap_words(NX) : smem_dyn) + 15) & ~(uintptr_t)15);
         const RcbSet root = { 0, NX, 0, P };
         int cnt;
-        fin = rcb_levels(H, root, ix, nodes, &my_iters, dbg ? plan->ts + TS_XLEV : nullptr, &cnt);
+        fin = SMEM && NX <= FAST_HIST_BINS
+            ? rcb_levels<true>(H, root, ix, nodes, &my_iters, dbg ? plan->ts + TS_XLEV : nullptr, &cnt)
+            : rcb_levels<false>(H, root, ix, nodes, &my_iters, dbg ? plan->ts + TS_XLEV : nullptr, &cnt);
     }
     for (int i = tid / lanes; i < nstrips; i += blockDim.x / lanes) {
         RcbSet r;
@@ -1425,7 +1429,9 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
             RcbNode* nodes = reinterpret_cast<RcbNode*>(
                 (reinterpret_cast<uintptr_t>(SMEM ? bitmap + hist_bitmap_words(NY) : smem_dyn) + 15) & ~(uintptr_t)15);
             int cnt;
-            fin = rcb_levels(H, root, ylevels, nodes, &my_iters, dbg && blockIdx.x == 0 ? plan->ts + TS_YLEV : nullptr, &cnt);
+            fin = SMEM && NY <= FAST_HIST_BINS
+                ? rcb_levels<true>(H, root, ylevels, nodes, &my_iters, dbg && blockIdx.x == 0 ? plan->ts + TS_YLEV : nullptr, &cnt)
+                : rcb_levels<false>(H, root, ylevels, nodes, &my_iters, dbg && blockIdx.x == 0 ? plan->ts + TS_YLEV : nullptr, &cnt);
         }
         for (int j = tid / lanes; j < nleaves; j += blockDim.x / lanes) {
             RcbSet r;

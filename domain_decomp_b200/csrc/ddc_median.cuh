@@ -10,6 +10,9 @@
 
 #ifdef DDC_HOST_EMU
 #include "ddc_host_emu.h" // oracle/emu: host stand-ins of the device language (test builds only)
+#define DDC_NOINLINE
+#else
+#define DDC_NOINLINE __noinline__
 #endif
 
 namespace ddc {
@@ -195,7 +198,10 @@ __device__ __forceinline__ int guess_bin(int vmin, int range, unsigned Ti, float
 // m < T, where the subtraction is exact because m is a multiple of ulp(T)) <=> m >= ceil(T) - 1.
 // FP64 is only touched for the tie rule that ends a search, for an ambiguous guess, and to form
 // the targets when the part counts are not split in half (fractionlo != 0.5).
-__device__ inline int median_boundary(const Hist& H, int c0, int c1, int nlo, int num_parts,
+// (Out of line: the general form serves the configurations off the fast path -- histograms in global memory or
+//  beyond 32768 bins, more than 1024 leaves -- from one copy of the code; median_boundary_fast below is the one
+//  the benchmark grids run.)
+__device__ DDC_NOINLINE inline int median_boundary(const Hist& H, int c0, int c1, int nlo, int num_parts,
     int* iters)
 {
     const unsigned* pfx = H.pfx;
@@ -283,6 +289,212 @@ __device__ inline int median_boundary(const Hist& H, int c0, int c1, int nlo, in
     if (L >= 0)
         return L + 1; // policy Q2
     return U; // policy Q2 (U >= 0 because Wn > 0)
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same search for the case every benchmark grid is in: prefix sums and bit map in SHARED memory and at
+// most 32768 bins (one tile of the bit map: its third level is ONE word, kept in a register).
+// ------------------------------------------------------------------------------------------------
+// median_boundary above costs ~660 SASS instructions per median (ncu, r2c: 86 branches, generic-pointer address
+// arithmetic, FP64 tie rules, both the bit-map and the binary-search paths compiled in) and a median is one
+// dependent chain: a cut kernel is 7 such chains in a row.  Here the accesses are 32-bit ld.shared, the bit-map
+// queries are straight-line, and when the part counts split in half (always, for a power-of-two part count) the
+// targets are W / 2 and Zoltan's FP64 tie rules become exact integer comparisons: (moved - T) < (T - cum) <=>
+// moved + cum < W (every term is a multiple of 1/2 below 2^32, so the doubles were exact).  Same boundaries, same
+// iteration counts: fuzzed against the oracle next to median_boundary (tests/test_device_median_host.py).
+#ifndef DDC_HOST_EMU
+typedef unsigned sm_ptr; // a shared-memory address
+__device__ __forceinline__ unsigned sm_ld(sm_ptr base, int i)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + 4u * (unsigned)i));
+    return v;
+}
+__device__ __forceinline__ sm_ptr sm_addr(const unsigned* p) { return (sm_ptr)__cvta_generic_to_shared(p); }
+#else
+typedef const unsigned* sm_ptr;
+inline unsigned sm_ld(sm_ptr base, int i) { return base[i]; }
+inline sm_ptr sm_addr(const unsigned* p) { return p; }
+#endif
+struct FastHist {
+    sm_ptr pfx, l0, l1;
+    unsigned l2;
+};
+// Zoltan's guess evaluated exactly (the real IEEE sequence in FP64): out of line, it is rarely needed
+__device__ DDC_NOINLINE inline int guess_bin_exact(int vmin, int range, double T, unsigned wlo, unsigned den, int alo, int ahi)
+{
+    const double tmp = __dadd_rn((double)vmin, __dmul_rn(__ddiv_rn(__dsub_rn(T, (double)wlo), (double)den), (double)range));
+    if (tmp < (double)alo)
+        return alo - 1;
+    if (tmp >= (double)ahi)
+        return ahi;
+    return (int)floor(tmp);
+}
+// guess_bin with the exact evaluation out of line; Wn / half: the target is Wn / 2 when half, else T
+__device__ __forceinline__ int guess_bin_fast(int vmin, int range, unsigned Ti, float Tfrac, double T, bool half, unsigned Wn,
+    unsigned wlo, unsigned den, int alo, int ahi)
+{
+    if (range < (1 << 22) && den != 0u) {
+        const float numf = (float)(Ti - wlo) + Tfrac;
+        const float rangef = (float)range;
+        const float off = __fdividef(numf, (float)den) * rangef;
+        const float fl = floorf(off), fr = off - fl;
+        const float guard = rangef * 0x1p-20f + 0x1p-18f;
+        if (fr > guard && fr < 1.0f - guard)
+            return min(max(vmin + (int)fl, alo - 1), ahi);
+    }
+    return guess_bin_exact(vmin, range, half ? 0.5 * (double)Wn : T, wlo, den, alo, ahi);
+}
+constexpr int FAST_HIST_BINS = 32768;
+// H must have a bit map and at most FAST_HIST_BINS bins; call after the histogram is complete
+__device__ __forceinline__ FastHist make_fast_hist(const Hist& H)
+{
+    FastHist F;
+    F.pfx = sm_addr(H.pfx);
+    F.l0 = sm_addr(H.l0);
+    F.l1 = sm_addr(H.l1);
+    F.l2 = H.l2[0];
+    return F;
+}
+// largest non-empty bin in [a, t], -1 if none
+__device__ __forceinline__ int fast_prev(const FastHist& F, int a, int t)
+{
+    if (t < a)
+        return -1;
+    int w = t >> 5;
+    unsigned m = sm_ld(F.l0, w) & (0xffffffffu >> (31 - (t & 31)));
+    if (!m) {
+        int w1 = w >> 5;
+        unsigned m1 = sm_ld(F.l1, w1) & ((1u << (w & 31)) - 1u);
+        if (!m1) {
+            const unsigned m2 = F.l2 & ((1u << w1) - 1u);
+            if (!m2)
+                return -1;
+            w1 = 31 - __clz(m2);
+            m1 = sm_ld(F.l1, w1);
+        }
+        w = (w1 << 5) + 31 - __clz(m1);
+        m = sm_ld(F.l0, w);
+    }
+    const int j = (w << 5) + 31 - __clz(m);
+    return j >= a ? j : -1;
+}
+// smallest non-empty bin in [t, b], -1 if none
+__device__ __forceinline__ int fast_next(const FastHist& F, int t, int b)
+{
+    if (t > b)
+        return -1;
+    int w = t >> 5;
+    unsigned m = sm_ld(F.l0, w) & (0xffffffffu << (t & 31));
+    if (!m) {
+        int w1 = w >> 5;
+        unsigned m1 = (w & 31) == 31 ? 0u : sm_ld(F.l1, w1) & (0xffffffffu << ((w & 31) + 1));
+        if (!m1) {
+            const unsigned m2 = w1 == 31 ? 0u : F.l2 & (0xffffffffu << (w1 + 1));
+            if (!m2)
+                return -1;
+            w1 = __ffs(m2) - 1;
+            m1 = sm_ld(F.l1, w1);
+        }
+        w = (w1 << 5) + __ffs(m1) - 1;
+        m = sm_ld(F.l0, w);
+    }
+    const int j = (w << 5) + __ffs(m) - 1;
+    return j <= b ? j : -1;
+}
+__device__ inline int median_boundary_fast(const FastHist& F, int c0, int c1, int nlo, int num_parts, int* iters)
+{
+    const unsigned base = sm_ld(F.pfx, c0);
+    const unsigned Wn = c1 < c0 ? 0u : sm_ld(F.pfx, c1 + 1) - base;
+    if (Wn == 0u) { // no dot at all: integer midpoint of the inherited range (policy Q2)
+        *iters += 1;
+        return c0 + ((c1 + 1 - c0) >> 1);
+    }
+    const bool half = 2 * nlo == num_parts;
+    double T = 0.0, Thi = 0.0;
+    unsigned Ti, ceilT, ceilThi;
+    float Tfrac;
+    if (half) { // fractionlo = 0.5: both targets are W / 2 exactly
+        Ti = Wn >> 1;
+        Tfrac = (Wn & 1u) ? 0.5f : 0.0f;
+        ceilT = ceilThi = (Wn + 1u) >> 1;
+    } else {
+        T = __dmul_rn(__ddiv_rn((double)nlo, (double)num_parts), (double)Wn);
+        Thi = __dsub_rn((double)Wn, T);
+        const double fT = floor(T);
+        Ti = (unsigned)fT;
+        Tfrac = (float)(T - fT);
+        ceilT = (unsigned)ceil(T);
+        ceilThi = (unsigned)ceil(Thi);
+    }
+    const int first = fast_next(F, c0, c1), last = fast_prev(F, c0, c1);
+    int vmin = first, vmax = last, alo = first, ahi = last;
+    int B;
+    unsigned wlo = 0, whi = 0;
+    int it = 0;
+    for (;;) {
+        const int t = guess_bin_fast(vmin, vmax - vmin, Ti, Tfrac, T, half, Wn, wlo, Wn - wlo - whi, alo, ahi);
+        it++;
+        B = t;
+        const unsigned cum = sm_ld(F.pfx, t + 1) - base; // dots in [c0, t] = weightlo + totallo
+        if (cum < ceilT) { // lower half TOO SMALL
+            const int vhi = fast_next(F, t + 1, ahi);
+            if (vhi < 0)
+                break;
+            const unsigned moved = sm_ld(F.pfx, vhi + 1) - base; // weightlo + wthi
+            if (moved >= ceilT) { // the bin that crosses the target: Zoltan's tie rules
+                bool move;
+                if (half) // (moved - W/2) < (W/2 - cum) <=> moved + cum < W: exact in integers as it was in FP64
+                    move = moved - cum == 1u ? moved + cum < Wn : !(moved + cum > Wn);
+                else {
+                    const double over = __dsub_rn((double)moved, T), under = __dsub_rn(T, (double)cum);
+                    move = moved - cum == 1u ? over < under : !(over > under);
+                }
+                if (move)
+                    B = vhi;
+                break;
+            }
+            B = vhi;
+            wlo = moved;
+            if (moved >= ceilT - 1u)
+                break;
+            vmin = vhi;
+            alo = vhi + 1;
+        } else {
+            const unsigned above = Wn - cum; // dots in (t, c1] = weighthi + totalhi
+            if (above >= ceilThi)
+                break;
+            const int vlo = fast_prev(F, alo, t);
+            if (vlo < 0)
+                break;
+            const unsigned moved = Wn - (sm_ld(F.pfx, vlo) - base); // weighthi + wtlo = dots in [vlo, c1]
+            if (moved >= ceilThi) {
+                bool move;
+                if (half)
+                    move = moved - above == 1u ? moved + above < Wn : !(moved + above > Wn);
+                else {
+                    const double over = __dsub_rn((double)moved, Thi), under = __dsub_rn(Thi, (double)above);
+                    move = moved - above == 1u ? over < under : !(over > under);
+                }
+                if (move)
+                    B = vlo - 1;
+                break;
+            }
+            B = vlo - 1;
+            whi = moved;
+            if (moved >= ceilThi - 1u)
+                break;
+            vmax = vlo;
+            ahi = vlo - 1;
+        }
+    }
+    *iters += it;
+    const int L = fast_prev(F, c0, B), U = fast_next(F, B + 1, c1);
+    if (L >= 0 && U >= 0)
+        return (L + U + 1) >> 1;
+    if (L >= 0)
+        return L + 1;
+    return U;
 }
 
 // The RCB recursion without level barriers.  A set is the cell range [lo, hi) along the cut

@@ -175,15 +175,21 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         int* yr = reinterpret_cast<int*>(colcount + yr_off + 2 * r.rank);
         if (r.rows > 0 || p2p) {
             const int rpc = opt.scan_rpc;
-            const Dim3 grid(gridx, std::max(1, (r.rows + rpc - 1) / rpc));
+            const int small = std::max(8, (rpc / 4) & ~7); // ddc_api.cu: the last quarter of the rows in smaller chunks
+            int nbig = (r.rows + rpc - 1) / rpc, nsmall = 0;
+            if (small < rpc && r.rows >= 4 * rpc) {
+                nbig = (int)((long long)r.rows * 75 / 100) / rpc;
+                nsmall = (r.rows - nbig * rpc + small - 1) / small;
+            }
+            const Dim3 grid(gridx, std::max(1, nbig + nsmall));
             if (vec)
                 LAUNCH(grid, Dim3(256), 0,
                     k_scan_mask<true>(r.mask, NX, r.rows, r.y_begin, NB, rpc, r.bits.data(), colcount, yr, push, ps,
-                        r.done.data(), yr_off, nullptr));
+                        r.done.data(), yr_off, nullptr, nbig, small));
             else
                 LAUNCH(grid, Dim3(256), 0,
                     k_scan_mask<false>(r.mask, NX, r.rows, r.y_begin, NB, rpc, r.bits.data(), colcount, yr, push, ps,
-                        r.done.data(), yr_off, nullptr));
+                        r.done.data(), yr_off, nullptr, nbig, small));
         }
     }
     if (G > 1 && !p2p) { // ncclAllReduce(SUM) of the column counts and the y-range pairs, in place on every rank

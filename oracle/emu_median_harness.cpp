@@ -201,6 +201,19 @@ __attribute__((visibility("default"))) long emu_fuzz(uint64_t seed, long histogr
                 }
                 mism++;
             }
+            if (use_bitmap && n <= ddc::FAST_HIST_BINS) { // the shared-memory variant of the cut kernels
+                const ddc::FastHist F = ddc::make_fast_hist(H);
+                int fit = 0;
+                const int fgot = ddc::median_boundary_fast(F, c0, c1, nlo, np, &fit);
+                checked++;
+                if (fgot != want || fit != wit) {
+                    if (!mism) {
+                        const long long b[10] = { 3, n, c0, c1, nlo, np, fgot, want, fit, wit };
+                        std::memcpy(bad, b, sizeof b);
+                    }
+                    mism++;
+                }
+            }
         }
         // the barrier-free walk: every leaf reached on its own must be the oracle's recursion
         {
