@@ -95,6 +95,24 @@ def test_rect3030(goldens, handle, oracle):
         assert_same(run_gpu(handle, mask, P), oracle.partition(mask, P), "rect3030 P=%d" % P)
 
 
+@pytest.mark.parametrize("P", [2, 4])
+def test_rect3030_equals_the_reference_pictures(goldens, handle, P):
+    """the GPU's pid map against the part map read off the reference's own img/partition_{2,4}.png (not via the
+    oracle): see tests/test_oracle_golden.py::test_rect3030_equals_the_reference_pictures"""
+    from test_oracle_golden import png_part_map
+    want = png_part_map(P)
+    pid = run_gpu(handle, golden_mask(goldens, "rect3030"), P)["pid"]
+    trusted = want > -2
+    assert int(trusted.sum()) >= 820 and np.array_equal(pid[trusted], want[trusted])
+
+
+def test_readme_sample_balance(goldens, handle):
+    """README.md:165-192 of the reference: test_2 on 2 ranks -> 6 / 6 dots, imbalance 1.0"""
+    g = run_gpu(handle, golden_mask(goldens, "test_2"), 2)
+    loads = np.bincount(g["pid"][g["pid"] >= 0].ravel(), minlength=2)
+    assert loads.tolist() == [6, 6]
+
+
 def test_random_small_masks(handle, oracle):
     """ragged extents, empty rows/columns, all-land, all-ocean, P not a power of two, P > columns"""
     rng = np.random.default_rng(11)

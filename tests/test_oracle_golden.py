@@ -93,3 +93,48 @@ def test_rect3030_two_and_four_parts(goldens, oracle):
         assert a.changes == b.changes
         loads = oracle.part_loads(a.pid, P)
         assert loads.sum() == 456
+
+
+def png_part_map(P):
+    """the part map read off the reference's own picture of rect3030 into P parts (scripts/make_golden_png.py), in
+    the decomposer's frame: want[y][x], -2 where the picture cannot be trusted (blended colours, clipped column)"""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rect3030_png_parts.json")) as f:
+        G = json.load(f)
+    v = np.asarray(G["partition_%d.png" % P]["value"])  # [picture row j][column i]
+    part = np.rint(v).astype(int)
+    part[np.abs(v - np.rint(v)) > 0.25] = -2
+    part[:, 29] = -2  # clipped by the plot frame
+    if P == 4 and G["swap_1_2_in_partition_4"]:  # the picture predates REMAP=0 numbering (SURVEY 2)
+        one, two = part == 1, part == 2
+        part[one], part[two] = 2, 1
+    return part.T  # picture (j, i) = decomposer (x, y)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_rect3030_equals_the_reference_pictures(goldens, oracle, P):
+    """a4 pinned on an irregular coastline: every cell of img/partition_{2,4}.png whose colour can be read carries the
+    part the restatement gives it -- 861 / 825 of 900 cells; the rest are the clipped last column and cells
+    whose colour is blended with the land (or the other part) next to them.  In the pictures' frame the cuts are x = 15.5 (2 parts) and
+    y = 14.5 then x = 14.5 / 16.5 (4 parts): the direction count of RCB_SET_DIRECTIONS and the "all cuts of the first
+    direction, then the second" order of the restatement."""
+    mask = golden_mask(goldens, "rect3030")
+    want = png_part_map(P)
+    for use_hist in (False, True):
+        pid = oracle.partition(mask, P, use_hist=use_hist).pid
+        trusted = want > -2
+        assert int(trusted.sum()) >= 820  # 861 (2 parts) and 825 (4 parts) of 900 cells read cleanly
+        assert np.array_equal(pid[trusted], want[trusted]), np.argwhere((pid != want) & trusted)[:10]
+    boxes = oracle.partition(mask, P).boxes.tolist()
+    assert boxes == ([[0, 0, 30, 16], [0, 16, 30, 14]] if P == 2 else
+                     [[0, 0, 15, 15], [0, 15, 15, 15], [15, 0, 15, 17], [15, 17, 15, 13]])
+
+
+def test_readme_sample_balance(goldens, oracle):
+    """README.md:165-192 of the reference: test_2 on 2 ranks -- 12 dots, 6 on each part, imbalance 1.0"""
+    mask = golden_mask(goldens, "test_2")
+    o = oracle.partition(mask, 2)
+    loads = oracle.part_loads(o.pid, 2)
+    assert int((mask > 0).sum()) == 12 and loads.tolist() == [6, 6]
+    assert loads.max() / loads.mean() == 1.0
