@@ -5,6 +5,13 @@
 #include "ddc.h"
 #include "ddc_kernels.cuh"
 
+#ifndef DDC_HOST_EMU
+#include <nvtx3/nvToolsExt.h> // header-only; ranges show up in Nsight Systems timelines, cost nothing otherwise
+#else
+inline void nvtxRangePushA(const char*) { }
+inline void nvtxRangePop() { }
+#endif
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -797,10 +804,30 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     h->totals_valid = false;
     memset(&h->stats, 0, sizeof h->stats);
     int launches = 0;
+    // stage i begins: a CUDA event when profiling, and an NVTX range (the host-side enqueue of the stage; Nsight
+    // Systems projects it onto the kernels) -- SURVEY 5 "profiling hooks"; the reference has Zoltan's timers
+    static const char* const stage_name[DDC_N_STAGES] = { "ddc:mask_scan", "ddc:x_cuts", "ddc:strip_rows", "ddc:y_cuts",
+        "ddc:neighbours+label", "ddc:step_end", "ddc:done", "ddc:done" };
+    int open_range = -1;
     auto mark = [&](int i) {
         if (profile)
             cudaEventRecord(h->ev[i], s);
+        if (open_range >= 0)
+            nvtxRangePop();
+        open_range = i < 6 ? i : -1;
+        if (open_range >= 0)
+            nvtxRangePushA(stage_name[i]);
     };
+    struct RangeGuard { // error returns leave no range open
+        int* open;
+        ~RangeGuard()
+        {
+            if (*open >= 0)
+                nvtxRangePop();
+            nvtxRangePop();
+        }
+    } range_guard { &open_range };
+    nvtxRangePushA("ddc_partition");
 
     // the assumed plan
     if (h->plan_nx != NX || h->plan_ny != NY || h->plan_P != P) {

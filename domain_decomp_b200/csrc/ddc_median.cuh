@@ -334,6 +334,12 @@ __device__ DDC_NOINLINE inline int guess_bin_exact(int vmin, int range, double T
 __device__ __forceinline__ int guess_bin_fast(int vmin, int range, unsigned Ti, float Tfrac, double T, bool half, unsigned Wn,
     unsigned wlo, unsigned den, int alo, int ahi)
 {
+    // As much weight set aside below as above (always so in the first iteration) with targets of W / 2: the
+    // quotient (W/2 - wlo) / (W - 2 wlo) is 0.5 EXACTLY in IEEE double, so tmp = vmin + range / 2 without any
+    // rounding and its floor is an integer expression.  (This case used to fall to the exact FP64 evaluation
+    // whenever range was even: the FP32 estimate of an exact integer is never "sure".)
+    if (half && Wn - wlo - wlo == den && den != 0u)
+        return min(max(vmin + (range >> 1), alo - 1), ahi);
     if (range < (1 << 22) && den != 0u) {
         const float numf = (float)(Ti - wlo) + Tfrac;
         const float rangef = (float)range;
