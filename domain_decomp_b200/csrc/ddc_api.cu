@@ -164,6 +164,8 @@ struct ddc_handle_s {
     DevBuf<uint8_t> bits;
     DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx, done;
     DevBuf<DevScalars> sc;
+    DevBuf<unsigned> gate; // the word the gate kernel of the second stream waits for (see BoxGate)
+    bool use_gate = true;
     DevBuf<Plan> plan;
     DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
     DevBuf<int> boxes; // x0 y0 ex ey, P each
@@ -451,6 +453,9 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     h->scan_rpc = env_int("DDC_SCAN_RPC", 0);
     h->scan_tail = std::max(0, std::min(90, env_int("DDC_SCAN_TAIL", 25)));
     h->label_rpc = env_int("DDC_LABEL_RPC", 0);
+    h->use_gate = env_int("DDC_GATE", 1) != 0;
+    CREATE_TRY(h->gate.ensure(1));
+    CREATE_TRY(cudaMemset(h->gate.p, 0, sizeof(unsigned)));
     CREATE_TRY(h->sc.ensure(1));
     CREATE_TRY(h->plan.ensure(1));
     CREATE_TRY(cudaMemset(h->plan.p, 0, sizeof(Plan)));
@@ -496,6 +501,7 @@ int ddc_destroy(ddc_handle_t h)
     h->ypfx.release();
     h->done.release();
     h->sc.release();
+    h->gate.release();
     h->plan.release();
     h->strips.release();
     h->boxes.release();
@@ -950,7 +956,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const int gridx = (NG + 7) / 8;
     // counters of the "last block" patterns: [0, gridx] mask scan, [gridx + 1] strip row counts, then the
     // 64-bit counter of the labelling kernel; all zero between steps (their last blocks reset them)
-    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, ndone = d_label + 2;
+    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, ndone = d_ycuts + 1;
     CUDA_TRY(h, h->done.ensure((size_t)ndone));
     ddc_handle_s::CleanSig sig;
     sig.col = colcount;
@@ -1000,7 +1006,11 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         pc.col[0] = h->colcount.p;
         pc.n = 1;
     }
-    PeerSync ps_x = ps; // (K2 resets this rank's slot: it needs the rank, not the flags)
+    // who puts this rank's column-count slot back to zero once it is consumed: the labelling kernel when the slot is
+    // peer-mapped memory (see k_xcuts), else the x-cut block
+    const bool label_runs = rows > 0 && (P > 1 || want_pid);
+    const bool reset_in_label = presum && label_runs;
+    PeerSync ps_x = ps; // (K2 needs the rank, not the flags)
     if (presum)
         ps_x.enabled = 0;
     mark(1);
@@ -1012,11 +1022,11 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         }
         CUDA_TRY(h, launch_k(k_xcuts<true>, dim3(1), dim3(1024), xneed, s, pdl, pc, ps_x, NX, NY, P, nullptr, yr_off, G, aix,
             aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, dbg ? 1 : 0,
-            h->pin_plan_dev, presum ? 1 : 0));
+            h->pin_plan_dev, presum ? 1 : 0, reset_in_label ? 0 : 1));
     } else
         CUDA_TRY(h, launch_k(k_xcuts<false>, dim3(1), dim3(1024), LEVEL_NODES_BYTES, s, pdl, pc, ps_x, NX, NY, P, h->colpfx.p, yr_off, G, aix,
             aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, dbg ? 1 : 0,
-            h->pin_plan_dev, presum ? 1 : 0));
+            h->pin_plan_dev, presum ? 1 : 0, reset_in_label ? 0 : 1));
     launches++;
     // the column -> strip table K6 reads: painted by K4's blocks; without y levels there is no K4
     if (!ycuts) {
@@ -1025,6 +1035,15 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         launches++;
     }
     mark(2);
+    // the second stream (neighbour tables beside the labelling kernel) is forked by a device-side gate when K4 runs
+    // and nothing else has to sit between K4 and the labelling kernel (no profiling events)
+    const bool gated = h->use_gate && want_nbr && ycuts && !profile;
+    BoxGate gate {};
+    if (gated) {
+        gate.word = h->gate.p;
+        gate.done = h->done.p + d_ycuts;
+        gate.step = h->step;
+    }
     // ---- K3 + K4: strip row counts, y cuts -----------------------------------------------------
     if (ycuts) {
         int rb_shift = 5; // log2(rows per block) of the kernel that writes the row counts
@@ -1085,6 +1104,10 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         }
         mark(3);
         const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
+        if (gated) { // the second stream waits in a one-warp kernel until K4's last block says the boxes are in place
+            CUDA_TRY(h, launch_k(k_gate, dim3(1), dim3(32), 0, h->side_stream, false, h->gate.p, h->step, h->plan.p));
+            launches++;
+        }
 #define LAUNCH_YCUTS(CT, SM, opted)                                                                \
     do {                                                                                           \
         if (SM && opted < yneed) {                                                                 \
@@ -1092,7 +1115,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             opted = yneed;                                                                         \
         }                                                                                          \
         CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : LEVEL_NODES_BYTES, s, pdl, pr, ps, rl, NY, t.st, \
-            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0)); \
+            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0, gate)); \
     } while (0)
         if (narrow) {
             if (y_smem)
@@ -1118,8 +1141,10 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const int ngrid = (std::max(P, 8) + 7) / 8; // >= 8 * pad32(P) threads
     if (want_nbr) {
         cudaStream_t q = h->side_stream;
-        CUDA_TRY(h, cudaEventRecord(h->ev_fork, s));
-        CUDA_TRY(h, cudaStreamWaitEvent(q, h->ev_fork, 0));
+        if (!gated) {
+            CUDA_TRY(h, cudaEventRecord(h->ev_fork, s));
+            CUDA_TRY(h, cudaStreamWaitEvent(q, h->ev_fork, 0));
+        }
         CUDA_TRY(h, launch_k(k_neighbours<false>, dim3(ngrid), dim3(256), 0, q, false, t.bx, P, NX, NY, px, py, t.st,
             h->nbr_counts.p, nullptr, nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p));
         CUDA_TRY(h, launch_k(k_scan_counts, dim3(8), dim3(1024), 0, q, false, h->nbr_counts.p, P, h->nbr_offsets.p,
@@ -1133,7 +1158,6 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     // ---- K6: labels + `changes` -----------------------------------------------------------------
     // The labelling kernel's last block also ends the step (`changes`, exchange step 3, the plan into the host's
     // pinned copy) unless there is no labelling kernel on this rank or the exchange goes through NCCL.
-    const bool label_runs = rows > 0 && (P > 1 || want_pid);
     const bool fuse = h->fuse_fin && label_runs && (G == 1 || p2p);
     h->fin_ps = ps;
     if (label_runs) {
@@ -1148,8 +1172,12 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         fin.counter = reinterpret_cast<unsigned long long*>(h->done.p + d_label);
         fin.host_plan = h->pin_plan_dev;
         fin.dbg = dbg;
+        fin.reset_col = reset_in_label ? colcount : nullptr;
+        fin.reset_n = ncol;
+        fin.yr_off = yr_off;
         auto kernel = !want_pid ? k_label<false, false> : (vecp ? k_label<true, true> : k_label<false, true>);
-        CUDA_TRY(h, launch_k(kernel, grid, dim3(256), 0, s, false, h->bits.p, NX, rows, h->y_begin, NB, rpc, h->strip_of_col.p,
+        // (behind K4 without a stream operation in between when the second stream is gated: programmatic launch)
+        CUDA_TRY(h, launch_k(kernel, grid, dim3(256), 0, s, pdl && (gated || !want_nbr), h->bits.p, NX, rows, h->y_begin, NB, rpc, h->strip_of_col.p,
             t.st.p0, t.bx.y0, t.bx.ey, nv, h->pid.p, h->sc.p, h->plan.p, fin));
         launches++;
     }

@@ -826,13 +826,24 @@ __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int 
     }
 }
 
+// the state a rank's column-count slot accumulates from: counts 0, its own y-range pair "no dot yet"
+__device__ __forceinline__ unsigned column_slot_reset_value(int i, int yr_off, int rank)
+{
+    if (i == yr_off + 2 * rank)
+        return 0x80000000u; // -(first ocean row) = INT_MIN
+    if (i == yr_off + 2 * rank + 1)
+        return 0xffffffffu; // last ocean row = -1
+    return 0u;
+}
+
 // dynamic shared memory when SMEM: (NX + 1) unsigned, rounded up to 4, + hist_bitmap_words(NX).
 // aix / aiy: the numbers of x / y levels the host assumed when it sized the launches that follow.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX, int NY, int P, unsigned* pfx_g,
     int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm,
     DevScalars* sc, unsigned* own_col /* this rank's column counts: reset here once they are consumed */,
-    int dbg, Plan* host_plan, int presummed /* k_sum_cols ran: pc is ONE buffer of global counts */)
+    int dbg, Plan* host_plan, int presummed /* k_sum_cols ran: pc is ONE buffer of global counts */,
+    int reset_own /* put this rank's column counts back to zero here (else: the labelling kernel does it) */)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
@@ -940,14 +951,11 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     __syncthreads();
     // the column counts and the y-range pairs are consumed: this rank's buffer goes back to the state k_init
     // leaves it in, ready for the next step that accumulates into it
-    for (int i = tid; i < yr_off + 2 * G; i += blockDim.x) {
-        unsigned v = 0u;
-        if (i == yr_off + 2 * ps.rank)
-            v = 0x80000000u; // -(first ocean row) = INT_MIN
-        if (i == yr_off + 2 * ps.rank + 1)
-            v = 0xffffffffu; // last ocean row = -1
-        own_col[i] = v;
-    }
+    // (With the peer exchange this rank's slot lives in memory the other GPUs map; a kernel that writes there
+    //  completes microseconds later -- measured: 6.7 instead of 1.5 us until the next kernel of the chain runs.
+    //  The labelling kernel, far off the critical path, resets the slot then.)
+    for (int i = tid; reset_own && i < yr_off + 2 * G; i += blockDim.x)
+        own_col[i] = column_slot_reset_value(i, yr_off, ps.rank);
 
     // 3. the x levels: a group of `lanes` adjacent threads walks to strip i, all of them evaluating
     //    the same medians (the block has more threads than strips; the fewer different medians the
@@ -1316,6 +1324,63 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// The gate between the cut kernels and the neighbour kernels on the second stream
+// ------------------------------------------------------------------------------------------------
+// The neighbour tables are built beside the labelling kernel, on a second stream.  Forking that stream with an
+// event recorded behind K4 puts a stream operation between K4 and the labelling kernel: no programmatic launch
+// there, and the largest kernel of the step started 6-7 us after the boxes were done.  Instead the second stream
+// holds, from the start of the step, a one-warp kernel that waits for a word in device memory; the last block
+// of K4 to finish writes the step number there once every box is in place.  Blocks of K4 that leave early (plan
+// mismatch, exchange time-out) count themselves too, so the gate always opens.
+struct BoxGate {
+    unsigned* word; // nullptr: no gate (the stream is forked with an event)
+    unsigned* done; // block counter, zero between steps
+    unsigned step;
+};
+// called by all threads of a block of K4 on every path out
+__device__ __forceinline__ void boxes_ready(const BoxGate& g)
+{
+    if (!g.word)
+        return;
+    __syncthreads(); // the block's boxes are written ...
+    if (threadIdx.x == 0) {
+        __threadfence(); // ... and visible to the device before the block is counted
+        if (atomicAdd(g.done, 1u) == gridDim.x - 1u) {
+            *g.done = 0u;
+            __threadfence();
+#ifndef DDC_HOST_EMU
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(g.word), "r"(g.step) : "memory");
+#else
+            *g.word = g.step;
+#endif
+        }
+    }
+}
+__global__ void __launch_bounds__(32) k_gate(const unsigned* word, unsigned step, Plan* plan)
+{
+    if (threadIdx.x != 0)
+        return;
+#ifndef DDC_HOST_EMU
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
+        if ((int)(v - step) >= 0)
+            return;
+        if (global_ns() - t0 > 4 * PEER_TIMEOUT_NS) { // the cut kernels never ran to their end
+            atomicMax(&plan->mismatch, 3);
+            return;
+        }
+        __nanosleep(100);
+    }
+#else
+    (void)word;
+    (void)step;
+    (void)plan;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: y levels, one CTA per strip (grid-stride), boxes out
 // ------------------------------------------------------------------------------------------------
 // Row counts of rank g: the block [row block][Scap][RB] described above (row_count_index); the blocks
@@ -1363,14 +1428,16 @@ __device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowL
 template <typename CT, bool SMEM>
 __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st,
     unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan, int* __restrict__ strip_of_col,
-    int dbg)
+    int dbg, BoxGate gate)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
-    pdl_trigger(); // (nothing is launched programmatically behind this kernel today; harmless)
+    pdl_trigger(); // the labelling kernel may become resident
     pdl_wait(); // the strip row-count kernel (and with it everything before) is complete
-    if (plan->mismatch)
+    if (plan->mismatch) {
+        boxes_ready(gate); // (the kernels behind the gate look at the mismatch themselves)
         return;
+    }
     const unsigned long long t_start = global_ns();
     if (blockIdx.x == 0 && threadIdx.x == 0)
         plan->ts[6] = t_start;
@@ -1389,6 +1456,7 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
         if (__syncthreads_or(!ok)) {
             if (threadIdx.x == 0)
                 plan->mismatch = 3;
+            boxes_ready(gate);
             return;
         }
     }
@@ -1468,6 +1536,7 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
             plan->ts[9] = t_end;
         atomicMax(&plan->ts[10], t_end - t_start);
     }
+    boxes_ready(gate);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1672,6 +1741,8 @@ struct LabelEnd {
     unsigned long long* counter; // zero between steps
     Plan* host_plan;
     unsigned long long* dbg;
+    unsigned* reset_col; // != nullptr: this rank's column-count slot, consumed by k_sum_cols: zeroed here for the next step
+    int reset_n, yr_off;
 };
 
 template <bool VEC, bool WRITE>
@@ -1690,6 +1761,11 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
     if (threadIdx.x == 0) {
         s_changed = 0;
         stamp_first(fin.dbg, TS_LABEL);
+    }
+    if (fin.reset_col) { // (the first blocks of the grid take 256 entries each)
+        const long long stride = (long long)gridDim.x * gridDim.y * blockDim.x;
+        for (long long i = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < fin.reset_n; i += stride)
+            fin.reset_col[i] = column_slot_reset_value((int)i, fin.yr_off, fin.ps.rank);
     }
     __syncthreads();
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);

@@ -282,6 +282,14 @@ void Partitioner::save_mask(const std::string& filename) const
     // (hundreds of MB of text nobody reads).
     const int NX = _global_ext[0], NY = _global_ext[1];
     const bool binary = filename.size() > 3 && filename.compare(filename.size() - 3, 3, ".nc") == 0;
+#ifdef HAVE_NETCDF
+    if (binary) { // the reference's own format: netCDF-4 through netCDF-C
+        if (_pid_global.size() != (size_t)NX * NY)
+            throw std::runtime_error("ERROR: no partition (call partition() first)");
+        ddc_host::nc_write_mask(filename, NX, NY, _num_parts, _pid_global.data());
+        return;
+    }
+#endif
     if (!binary || (size_t)NX * NY <= ((size_t)1 << 24))
         write_text(ddc_host::cdl_path_of(filename), mask_cdl(ddc_host::netcdf_name_of(filename)));
     if (binary) {
@@ -294,5 +302,21 @@ void Partitioner::save_metadata(const std::string& filename) const
 {
     if (_rank != 0)
         return;
-    write_text(ddc_host::cdl_path_of(filename), metadata_cdl(ddc_host::netcdf_name_of(filename)));
+#ifdef HAVE_NETCDF
+    if (filename.size() > 3 && filename.compare(filename.size() - 3, 3, ".nc") == 0) {
+        // netCDF-4 with the groups bounding_boxes / connectivity, as nextSIM-DG reads it (Partitioner.cpp:168-318)
+        if (_boxes[0].empty())
+            throw std::runtime_error("ERROR: no partition (call partition() first)");
+        ddc_host::nc_write_metadata(filename, _global_ext[0], _global_ext[1], _boxes, _nbr_counts, _nbr_ids, _nbr_halos,
+            _nbr_starts);
+        return;
+    }
+#endif
+    // Groups need netCDF-4 / HDF5, which this build does not have: the CDL text `ncdump` prints for the reference's
+    // file goes to <name>.cdl; `ncgen -k nc4 -b <name>.cdl` turns it into the file nextSIM-DG opens.
+    const std::string cdl = ddc_host::cdl_path_of(filename);
+    write_text(cdl, metadata_cdl(ddc_host::netcdf_name_of(filename)));
+    if (cdl != filename)
+        std::cerr << "NOTE: built without netCDF-C: wrote " << cdl << " (CDL text) instead of " << filename
+                  << "; convert with `ncgen -k nc4 -b " << cdl << "` or rebuild with -DDDC_WITH_NETCDF=ON" << std::endl;
 }

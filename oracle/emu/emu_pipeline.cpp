@@ -72,6 +72,7 @@ struct Rank {
     std::vector<int32_t> pid;
     std::vector<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
     DevScalars sc {};
+    unsigned gate_word = 0;
     Plan plan {}, host_plan {};
 };
 
@@ -109,7 +110,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const bool x_smem = xneed + 1024 <= (size_t)opt.smem_limit, y_smem = yneed + 1024 <= (size_t)opt.smem_limit;
     const int ygrid = std::max(1, std::min(Scap, 148 * 2));
     const int gridx = (NG + 7) / 8;
-    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, ndone = d_label + 2; // ddc_api.cu: the "last block" counters
+    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, ndone = d_ycuts + 1; // ddc_api.cu: the "last block" counters
     const NaiveParams nv = naive_params(P, NX, NY);
     const int par = (int)(step & 1u);
     const bool want_nbr = P > 1;
@@ -223,11 +224,11 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         if (x_smem)
             LAUNCH(Dim3(1), Dim3(1024), xneed,
                 k_xcuts<true>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(), r.loadmm.data(),
-                    &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0));
+                    &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0, (p2p && r.rows > 0) ? 0 : 1));
         else
             LAUNCH(Dim3(1), Dim3(1024), LEVEL_NODES_BYTES,
                 k_xcuts<false>(pc, ps, NX, NY, P, r.colpfx.data(), yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(),
-                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0));
+                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0, (p2p && r.rows > 0) ? 0 : 1));
         if (!ycuts) // with y levels K4 paints the column -> strip table
             LAUNCH(Dim3(std::max(1, std::min((Scap + 7) / 8, 148 * 4))), Dim3(256), 0,
                 k_paint_strips(st, &r.plan, r.strip_of_col.data()));
@@ -314,10 +315,14 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                 pr.row[0] = gathered[r.rank].data();
             const PeerSync ps = sync_of(r);
             const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
+            BoxGate gate {}; // as in ddc_api.cu: K4's last block opens the gate of the second stream
+            gate.word = &r.gate_word;
+            gate.done = r.done.data() + d_ycuts;
+            gate.step = step;
 #define YCUTS(CT, SM)                                                                              \
     LAUNCH(Dim3(ygrid), Dim3(1024), SM ? yneed : LEVEL_NODES_BYTES,                                                \
         (k_ycuts<CT, SM>(pr, ps, rl, NY, st, r.ypfx.data(), bx, r.loads.data(), r.loadmm.data(), &r.plan,                    \
-            r.strip_of_col.data(), 0)))
+            r.strip_of_col.data(), 0, gate)))
             if (narrow) {
                 if (y_smem)
                     YCUTS(uint16_t, true);
@@ -339,6 +344,13 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         tables(r, st, bx);
         const int ngrid = (std::max(P, 8) + 7) / 8;
         if (want_nbr) {
+            if (ycuts) {
+                if (r.gate_word != step) {
+                    g_err = "K4 did not open the gate of the second stream";
+                    return false;
+                }
+                LAUNCH(Dim3(1), Dim3(32), 0, k_gate(&r.gate_word, step, &r.plan));
+            }
             LAUNCH(Dim3(ngrid), Dim3(256), 0,
                 k_neighbours<false>(bx, P, NX, NY, px, py, st, r.nbr_counts.data(), nullptr, nullptr, cap, nullptr, nullptr,
                     nullptr, &r.sc, &r.plan));
@@ -359,6 +371,9 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             fin.counter = reinterpret_cast<unsigned long long*>(r.done.data() + d_label);
             fin.host_plan = &r.host_plan;
             fin.dbg = nullptr;
+            fin.reset_col = p2p ? colslot(r, r.rank) : nullptr;
+            fin.reset_n = ncol;
+            fin.yr_off = yr_off;
             if (vecp)
                 LAUNCH(grid, Dim3(256), 0,
                     (k_label<true, true>(r.bits.data(), NX, r.rows, r.y_begin, NB, rpc, r.strip_of_col.data(), st.p0, bx.y0,
