@@ -9,6 +9,7 @@
 
 #include "CdlIO.hpp"
 #include "NcClassic.hpp"
+#include "NcLibrary.hpp"
 
 #include <cmath>
 #include <stdexcept>
@@ -73,6 +74,23 @@ void Grid::load_file(const std::string& filename, const std::string& xdim, const
 {
     if (order.size() != 2 || !((order[0] == 1 && order[1] == 0) || (order[0] == 0 && order[1] == 1)))
         throw std::runtime_error("ERROR: dim_order must be {1, 0} (yx) or {0, 1} (xy)");
+#ifdef HAVE_NETCDF
+    // built with netCDF-C: every netCDF file -- classic or netCDF-4 / HDF5 -- goes through the library, as in the
+    // reference (Grid.cpp:51-130); only CDL text (*.cdl) is still read by the in-tree parser below
+    if (!(filename.size() > 4 && filename.compare(filename.size() - 4, 4, ".cdl") == 0)) {
+        ddc_host::NcGridMask g = ddc_host::nc_read_grid(filename, xdim, ydim, order, mask_name, ignore_mask);
+        _global_ext[0] = g.nx;
+        _global_ext[1] = g.ny;
+        if (g.nx < 1 || g.ny < 1)
+            throw std::runtime_error("ERROR: grid extents must be positive");
+        _ignore_mask = ignore_mask;
+        if (ignore_mask)
+            _global_mask.assign((size_t)g.nx * g.ny, 1);
+        else
+            _global_mask = std::move(g.mask); // file order, indexed x-fastest
+        return;
+    }
+#endif
     // netCDF classic files (CDF-1 / CDF-2 / CDF-5: what `ncgen -b` makes of the reference's test
     // inputs) are read directly; netCDF-4 needs HDF5, which this build does not have; anything else
     // is taken as CDL text (`ncdump grid.nc > grid.cdl`)

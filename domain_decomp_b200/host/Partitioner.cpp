@@ -8,6 +8,7 @@
 
 #include "CdlIO.hpp"
 #include "NcClassic.hpp"
+#include "NcLibrary.hpp"
 #include "CudaRcbPartitioner.hpp"
 
 #include <fstream>

@@ -25,6 +25,10 @@ extern "C" {
 #define NC_ENOENT 2
 
 const char* nc_strerror(int err);
+/* serial open / create: what THIS repository's host layer calls (one process drives the GPUs); the reference uses
+   the parallel variants of netcdf_par.h */
+int nc_open(const char* path, int mode, int* ncidp);
+int nc_create(const char* path, int cmode, int* ncidp);
 int nc_close(int ncid);
 int nc_enddef(int ncid);
 int nc_inq_ncid(int ncid, const char* name, int* grp_ncid);
