@@ -408,6 +408,29 @@ __device__ __forceinline__ int fast_next(const FastHist& F, int t, int b)
     const int j = (w << 5) + __ffs(m) - 1;
     return j <= b ? j : -1;
 }
+// Both neighbours of a guess at once: the largest non-empty bin in [a, t] and the smallest one in [t2, b].  The two
+// l0 words are requested before either result is looked at -- a warp issues in order, so a branch on the first
+// load would hold the second one back for a shared-memory round trip; a median is one dependent chain, and the
+// round trips are what it is made of.
+__device__ __forceinline__ void fast_prev_next(const FastHist& F, int a, int t, int t2, int b, int* prev, int* next)
+{
+    const bool hp = t >= a, hn = t2 <= b;
+    const int wp = hp ? t >> 5 : 0, wn = hn ? t2 >> 5 : 0;
+    unsigned mp = sm_ld(F.l0, wp), mn = sm_ld(F.l0, wn);
+    mp = hp ? mp & (0xffffffffu >> (31 - (t & 31))) : 0u;
+    mn = hn ? mn & (0xffffffffu << (t2 & 31)) : 0u;
+    int p, n;
+    if (mp)
+        p = (wp << 5) + 31 - __clz(mp);
+    else
+        p = hp ? fast_prev(F, a, (wp << 5) - 1) : -1; // (continues below this word: l1 / l2)
+    if (mn)
+        n = (wn << 5) + __ffs(mn) - 1;
+    else
+        n = hn ? fast_next(F, (wn << 5) + 32, b) : -1;
+    *prev = p >= a ? p : -1;
+    *next = (n >= 0 && n <= b) ? n : -1;
+}
 __device__ inline int median_boundary_fast(const FastHist& F, int c0, int c1, int nlo, int num_parts, int* iters)
 {
     const unsigned base = sm_ld(F.pfx, c0);
@@ -433,7 +456,8 @@ __device__ inline int median_boundary_fast(const FastHist& F, int c0, int c1, in
         ceilT = (unsigned)ceil(T);
         ceilThi = (unsigned)ceil(Thi);
     }
-    const int first = fast_next(F, c0, c1), last = fast_prev(F, c0, c1);
+    int first, last;
+    fast_prev_next(F, c0, c1, c0, c1, &last, &first);
     int vmin = first, vmax = last, alo = first, ahi = last;
     int B;
     unsigned wlo = 0, whi = 0;
@@ -442,12 +466,17 @@ __device__ inline int median_boundary_fast(const FastHist& F, int c0, int c1, in
         const int t = guess_bin_fast(vmin, vmax - vmin, Ti, Tfrac, T, half, Wn, wlo, Wn - wlo - whi, alo, ahi);
         it++;
         B = t;
+        // everything that depends on the guess only is requested together: the dots up to t and BOTH neighbours of
+        // the guess (which one is needed depends on the dots up to t) ...
         const unsigned cum = sm_ld(F.pfx, t + 1) - base; // dots in [c0, t] = weightlo + totallo
+        int vlo, vhi;
+        fast_prev_next(F, alo, t, t + 1, ahi, &vlo, &vhi);
+        // ... and so are the dots up to both neighbours
+        const unsigned p_hi = sm_ld(F.pfx, (vhi >= 0 ? vhi : t) + 1), p_lo = sm_ld(F.pfx, vlo >= 0 ? vlo : c0);
         if (cum < ceilT) { // lower half TOO SMALL
-            const int vhi = fast_next(F, t + 1, ahi);
             if (vhi < 0)
                 break;
-            const unsigned moved = sm_ld(F.pfx, vhi + 1) - base; // weightlo + wthi
+            const unsigned moved = p_hi - base; // weightlo + wthi
             if (moved >= ceilT) { // the bin that crosses the target: Zoltan's tie rules
                 bool move;
                 if (half) // (moved - W/2) < (W/2 - cum) <=> moved + cum < W: exact in integers as it was in FP64
@@ -470,10 +499,9 @@ __device__ inline int median_boundary_fast(const FastHist& F, int c0, int c1, in
             const unsigned above = Wn - cum; // dots in (t, c1] = weighthi + totalhi
             if (above >= ceilThi)
                 break;
-            const int vlo = fast_prev(F, alo, t);
             if (vlo < 0)
                 break;
-            const unsigned moved = Wn - (sm_ld(F.pfx, vlo) - base); // weighthi + wtlo = dots in [vlo, c1]
+            const unsigned moved = Wn - (p_lo - base); // weighthi + wtlo = dots in [vlo, c1]
             if (moved >= ceilThi) {
                 bool move;
                 if (half)
@@ -495,7 +523,8 @@ __device__ inline int median_boundary_fast(const FastHist& F, int c0, int c1, in
         }
     }
     *iters += it;
-    const int L = fast_prev(F, c0, B), U = fast_next(F, B + 1, c1);
+    int L, U;
+    fast_prev_next(F, c0, B, B + 1, c1, &L, &U);
     if (L >= 0 && U >= 0)
         return (L + U + 1) >> 1;
     if (L >= 0)

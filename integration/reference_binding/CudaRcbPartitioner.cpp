@@ -2,14 +2,14 @@
  * @file CudaRcbPartitioner.cpp
  * @brief Partitioner of the reference tree backed by the B200 library (see CudaRcbPartitioner.hpp).
  *
- * Mode of operation: "every rank asks its GPU".  The reference runs one MPI rank per part; the GPU
- * library computes ALL parts from the whole mask in about a millisecond, so every rank assembles the
- * global mask from the ranks' naive blocks (two collectives), runs the decomposition on its GPU and
- * keeps its own part.  What Zoltan used to deliver -- this rank's box, `changes`, the new owner of
- * every cell of this rank's block -- comes from the library; neighbour discovery and both writers
- * stay the reference's own code.  (One rank per GPU with a row-sharded mask and NCCL / peer-memory
- * exchange is the other mode the C ABI offers; it needs the mask read as row blocks, see
- * INTEGRATION.md.)
+ * Mode of operation: "rank 0 asks the GPU".  The reference runs one MPI rank per part; the GPU library
+ * computes ALL parts from the whole mask in about a millisecond.  So the ranks' naive blocks of the mask are
+ * gathered on rank 0 (MPI_Gatherv), rank 0 -- the only rank that ever touches the GPU -- runs the
+ * decomposition once, the P boxes are broadcast (MPI_Bcast) and every rank receives the owners of the cells
+ * of its own block (MPI_Scatterv).  What Zoltan used to deliver -- this rank's box, `changes`, the new owner of
+ * every cell of this rank's block -- comes from the library; neighbour discovery and both writers stay the
+ * reference's own code.  (One rank per GPU with a row-sharded mask and the peer-memory / NCCL exchange is the
+ * other mode the C ABI offers; it needs the mask read as row blocks, see INTEGRATION.md.)
  */
 #include "CudaRcbPartitioner.hpp"
 
@@ -43,11 +43,14 @@ CudaRcbPartitioner* CudaRcbPartitioner::create(MPI_Comm comm, int argc, char** a
 CudaRcbPartitioner::CudaRcbPartitioner(MPI_Comm comm, int device)
     : Partitioner(comm)
 {
-    // replaces Zoltan_Initialize + new Zoltan(comm) (ZoltanPartitioner.cpp:69-86); one GPU, no NCCL
-    ddc_handle_t h = nullptr;
-    if (ddc_create(&h, device, 0, 1, nullptr) != DDC_OK)
-        throw std::runtime_error(std::string("ERROR: ddc_create: ") + ddc_last_error(nullptr));
-    _ddc = h;
+    // replaces Zoltan_Initialize + new Zoltan(comm) (ZoltanPartitioner.cpp:69-86); one GPU, no NCCL: only rank 0
+    // holds a handle
+    if (_rank == 0) {
+        ddc_handle_t h = nullptr;
+        if (ddc_create(&h, device, 0, 1, nullptr) != DDC_OK)
+            throw std::runtime_error(std::string("ERROR: ddc_create: ") + ddc_last_error(nullptr));
+        _ddc = h;
+    }
 }
 
 CudaRcbPartitioner::~CudaRcbPartitioner() { ddc_destroy(_ddc); }
@@ -76,7 +79,7 @@ void CudaRcbPartitioner::partition(Grid& grid)
         return;
     }
 
-    // 1. every rank's naive block (Grid.cpp:150-166) and its slab of the mask -> the whole mask
+    // 1. every rank's naive block (Grid.cpp:150-166) and its slab of the mask -> the whole mask, on rank 0
     int mine[4] = { _global[0], _global[1], _local_ext[0], _local_ext[1] };
     std::vector<int> blocks(4 * (size_t)P);
     CHECK_MPI(MPI_Allgather(mine, 4, MPI_INT, blocks.data(), 4, MPI_INT, _comm));
@@ -91,35 +94,51 @@ void CudaRcbPartitioner::partition(Grid& grid)
     std::vector<int> slab(n_own, 1);
     if (masked)
         slab.assign(grid.get_land_mask(), grid.get_land_mask() + n_own);
-    std::vector<int> slabs(total);
-    CHECK_MPI(MPI_Allgatherv(slab.data(), n_own, MPI_INT, slabs.data(), counts.data(), displs.data(), MPI_INT, _comm));
-    std::vector<int> mask((size_t)NX * NY, 0);
-    for (int r = 0; r < P; r++) {
-        const int x0 = blocks[4 * r], y0 = blocks[4 * r + 1], ex = blocks[4 * r + 2], ey = blocks[4 * r + 3];
-        for (int j = 0; j < ey; j++)
-            std::memcpy(&mask[(size_t)(y0 + j) * NX + x0], &slabs[(size_t)displs[r] + (size_t)j * ex], sizeof(int) * ex);
-    }
+    std::vector<int> slabs(_rank == 0 ? total : 0);
+    CHECK_MPI(MPI_Gatherv(slab.data(), n_own, MPI_INT, slabs.data(), counts.data(), displs.data(), MPI_INT, 0, _comm));
 
-    // 2. the decomposition: replaces Set_Param x14, the four callbacks, LB_Partition and RCB_Box
-    //    (ZoltanPartitioner.cpp:125-195; the ceil / clamp of the boxes and the `changes == 0`
-    //    fallback to the naive blocks happen inside the library)
-    ddc_check(_ddc, ddc_set_mask_host(_ddc, mask.data(), NX, NY, 0, NY), "ddc_set_mask_host");
-    ddc_check(_ddc, ddc_partition(_ddc, P, _px, _py, DDC_WANT_PID), "ddc_partition");
-    std::vector<int> bx(P), by(P), bex(P), bey(P);
-    ddc_check(_ddc, ddc_get_boxes(_ddc, bx.data(), by.data(), bex.data(), bey.data()), "ddc_get_boxes");
-    _global_new = { bx[_rank], by[_rank] };
-    _local_ext_new = { bex[_rank], bey[_rank] };
+    // 2. the decomposition, once, on rank 0: replaces Set_Param x14, the four callbacks, LB_Partition and RCB_Box
+    //    (ZoltanPartitioner.cpp:125-195; the ceil / clamp of the boxes and the `changes == 0` fallback to the
+    //    naive blocks happen inside the library).  boxes[4 P] = x0[P] y0[P] ex[P] ey[P]; `status` travels in front
+    //    so that a failure on rank 0 is an exception on every rank
+    std::vector<int> boxes(1 + 4 * (size_t)P, 0), pid_blocks(_rank == 0 ? total : 0);
+    std::string failure;
+    if (_rank == 0) {
+        try {
+            std::vector<int> mask((size_t)NX * NY, 0);
+            for (int r = 0; r < P; r++) {
+                const int x0 = blocks[4 * r], y0 = blocks[4 * r + 1], ex = blocks[4 * r + 2], ey = blocks[4 * r + 3];
+                for (int j = 0; j < ey; j++)
+                    std::memcpy(&mask[(size_t)(y0 + j) * NX + x0], &slabs[(size_t)displs[r] + (size_t)j * ex], sizeof(int) * ex);
+            }
+            ddc_check(_ddc, ddc_set_mask_host(_ddc, mask.data(), NX, NY, 0, NY), "ddc_set_mask_host");
+            ddc_check(_ddc, ddc_partition(_ddc, P, _px, _py, DDC_WANT_PID), "ddc_partition");
+            int* b = boxes.data() + 1;
+            ddc_check(_ddc, ddc_get_boxes(_ddc, b, b + P, b + 2 * P, b + 3 * P), "ddc_get_boxes");
+            // the owner map (-1 on land), cut into the ranks' ORIGINAL blocks: what MPI_Scatterv hands out
+            std::vector<int>& pid = mask; // (the mask is consumed: reuse its storage)
+            ddc_check(_ddc, ddc_get_pid_host(_ddc, pid.data()), "ddc_get_pid_host");
+            for (int r = 0; r < P; r++) {
+                const int x0 = blocks[4 * r], y0 = blocks[4 * r + 1], ex = blocks[4 * r + 2], ey = blocks[4 * r + 3];
+                for (int j = 0; j < ey; j++)
+                    std::memcpy(&pid_blocks[(size_t)displs[r] + (size_t)j * ex], &pid[(size_t)(y0 + j) * NX + x0], sizeof(int) * ex);
+            }
+            boxes[0] = 1;
+        } catch (const std::exception& e) {
+            failure = e.what();
+        }
+    }
+    CHECK_MPI(MPI_Bcast(boxes.data(), 1 + 4 * P, MPI_INT, 0, _comm));
+    if (boxes[0] != 1)
+        throw std::runtime_error(_rank == 0 ? failure : std::string("ERROR: the decomposition failed on rank 0"));
+    _global_new = { boxes[1 + _rank], boxes[1 + P + _rank] };
+    _local_ext_new = { boxes[1 + 2 * P + _rank], boxes[1 + 3 * P + _rank] };
 
     // 3. Find my neighbours: the reference's own code (Partitioner.cpp:329-435)
     discover_neighbours();
 
     // 4. the process ids of the grid points of my ORIGINAL block (payload of save_mask,
-    //    ZoltanPartitioner.cpp:201-219): the library's owner map, -1 on land
-    std::vector<int> pid((size_t)NX * NY);
-    ddc_check(_ddc, ddc_get_pid_host(_ddc, pid.data()), "ddc_get_pid_host");
+    //    ZoltanPartitioner.cpp:201-219)
     _proc_id.resize(n_own);
-    for (int i = 0; i < n_own; i++) {
-        const int x = _global[0] + i % _local_ext[0], y = _global[1] + i / _local_ext[0];
-        _proc_id[i] = pid[(size_t)y * NX + x];
-    }
+    CHECK_MPI(MPI_Scatterv(pid_blocks.data(), counts.data(), displs.data(), MPI_INT, _proc_id.data(), n_own, MPI_INT, 0, _comm));
 }

@@ -114,6 +114,64 @@ int MPI_Allgatherv(const void* sendbuf, int, MPI_Datatype, void* recvbuf, const 
     w.barrier(); // every rank has copied before any send buffer goes away
     return MPI_SUCCESS;
 }
+// rooted collectives (integration/reference_binding): every rank publishes its buffer pointer, the data is copied
+// between the barriers
+int MPI_Gatherv(const void* sendbuf, int, MPI_Datatype, void* recvbuf, const int* recvcounts, const int* displs,
+    MPI_Datatype, int root, MPI_Comm c)
+{
+    World& w = *c->world;
+    {
+        std::lock_guard<std::mutex> lk(w.m);
+        w.sendptr.resize(w.size);
+    }
+    w.barrier();
+    w.sendptr[c->rank] = static_cast<const int*>(sendbuf);
+    w.barrier();
+    if (c->rank == root)
+        for (int r = 0; r < w.size; r++)
+            std::copy(w.sendptr[r], w.sendptr[r] + recvcounts[r], static_cast<int*>(recvbuf) + displs[r]);
+    w.barrier();
+    return MPI_SUCCESS;
+}
+int MPI_Scatterv(const void* sendbuf, const int* sendcounts, const int* displs, MPI_Datatype, void* recvbuf, int recvcount,
+    MPI_Datatype, int root, MPI_Comm c)
+{
+    World& w = *c->world;
+    {
+        std::lock_guard<std::mutex> lk(w.m);
+        w.sendptr.resize(w.size);
+        w.slots.resize(2 * (size_t)w.size);
+    }
+    w.barrier();
+    if (c->rank == root) {
+        w.sendptr[0] = static_cast<const int*>(sendbuf);
+        for (int r = 0; r < w.size; r++) {
+            w.slots[2 * r] = sendcounts[r];
+            w.slots[2 * r + 1] = displs[r];
+        }
+    }
+    w.barrier();
+    const int n = std::min(recvcount, w.slots[2 * c->rank]);
+    std::copy(w.sendptr[0] + w.slots[2 * c->rank + 1], w.sendptr[0] + w.slots[2 * c->rank + 1] + n, static_cast<int*>(recvbuf));
+    w.barrier();
+    return MPI_SUCCESS;
+}
+int MPI_Bcast(void* buffer, int count, MPI_Datatype, int root, MPI_Comm c)
+{
+    World& w = *c->world;
+    {
+        std::lock_guard<std::mutex> lk(w.m);
+        w.sendptr.resize(w.size);
+    }
+    w.barrier();
+    if (c->rank == root)
+        w.sendptr[0] = static_cast<const int*>(buffer);
+    w.barrier();
+    if (c->rank != root)
+        std::copy(w.sendptr[0], w.sendptr[0] + count, static_cast<int*>(buffer));
+    w.barrier();
+    return MPI_SUCCESS;
+}
 int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype, MPI_Op, MPI_Comm c)
 {
     exchange(c, static_cast<const int*>(sendbuf), count, [&](const std::vector<int>& t) {

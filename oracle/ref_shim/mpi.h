@@ -1,7 +1,7 @@
 /* mpi.h -- TEST INFRASTRUCTURE.  A miniature MPI for compiling the REFERENCE's own Grid.cpp /
  * Partitioner.cpp where they lie (oracle/Makefile target `ref`): P "ranks" are P threads of one
  * process, a communicator is a (world, rank) pair, and the few collectives the reference's host
- * path uses (Grid.cpp:142-146, Partitioner.cpp:85-86,190-205,378-388; MPI_Allgatherv for integration/reference_binding) are implemented over a
+ * path uses (Grid.cpp:142-146, Partitioner.cpp:85-86,190-205,378-388; MPI_Gatherv / MPI_Bcast / MPI_Scatterv for integration/reference_binding) are implemented over a
  * generation barrier in oracle/ref_hostpath_shim.cpp.  Not part of the product. */
 #ifndef DDC_REF_SHIM_MPI_H
 #define DDC_REF_SHIM_MPI_H
@@ -28,6 +28,11 @@ int MPI_Allgather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, voi
     MPI_Datatype recvtype, MPI_Comm comm);
 int MPI_Allgatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, const int* recvcounts,
     const int* displs, MPI_Datatype recvtype, MPI_Comm comm);
+int MPI_Gatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, const int* recvcounts,
+    const int* displs, MPI_Datatype recvtype, int root, MPI_Comm comm);
+int MPI_Scatterv(const void* sendbuf, const int* sendcounts, const int* displs, MPI_Datatype sendtype, void* recvbuf,
+    int recvcount, MPI_Datatype recvtype, int root, MPI_Comm comm);
+int MPI_Bcast(void* buffer, int count, MPI_Datatype type, int root, MPI_Comm comm);
 int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm);
 int MPI_Exscan(const void* sendbuf, void* recvbuf, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm);
 int MPI_Error_string(int errorcode, char* string, int* resultlen);
