@@ -29,7 +29,7 @@ SYMBOLS = (
     "ddc_get_boxes", "ddc_get_pid_host", "ddc_get_pid_device", "ddc_get_neighbour_counts",
     "ddc_get_neighbour_total", "ddc_get_neighbours", "ddc_get_part_loads", "ddc_get_stats",
     "ddc_neighbours_from_boxes", "ddc_generate_mask_device", "ddc_generate_mask_host", "ddc_version",
-    "ddc_peer_export", "ddc_peer_import", "ddc_peer_close", "ddc_host_alloc", "ddc_host_free", "ddc_peer_connect",
+    "ddc_peer_export", "ddc_peer_import", "ddc_peer_close", "ddc_host_alloc", "ddc_host_free", "ddc_peer_connect", "ddc_halo_tile_offsets", "ddc_halo_exchange_f64",
 )
 
 
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     L.ddc_get_part_loads.argtypes = [vp, vp]
     L.ddc_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.ddc_neighbours_from_boxes.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, i32]
+    L.ddc_halo_tile_offsets.argtypes = [vp, vp]
+    L.ddc_halo_exchange_f64.argtypes = [vp, vp, i32]
     L.ddc_generate_mask_device.argtypes = [vp, vp, i32, i32, i32, i32, C.c_uint64, C.c_double]
     L.ddc_generate_mask_host.argtypes = [vp, i32, i32, i32, i32, C.c_uint64, C.c_double]
     _lib = L
@@ -229,6 +231,15 @@ class Handle:
         p = C.c_void_p()
         self._ck(self.L.ddc_get_pid_device(self.h, C.byref(p)), "ddc_get_pid_device")
         return p.value
+
+    def halo_tile_offsets(self) -> np.ndarray:
+        """element offsets of the framed tiles of all parts in one buffer (ddc_halo_tile_offsets)"""
+        out = np.empty(self.nparts + 1, dtype=np.int64)
+        self._ck(self.L.ddc_halo_tile_offsets(self.h, out.ctypes.data), "ddc_halo_tile_offsets")
+        return out
+
+    def halo_exchange_f64(self, tiles_dev_ptr: int, periodic: bool = False):
+        self._ck(self.L.ddc_halo_exchange_f64(self.h, tiles_dev_ptr, int(periodic)), "ddc_halo_exchange_f64")
 
     def neighbour_counts(self, edge: int, periodic: int) -> np.ndarray:
         out = np.empty(self.nparts, dtype=np.int32)

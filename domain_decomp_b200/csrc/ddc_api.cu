@@ -164,6 +164,8 @@ struct ddc_handle_s {
     DevBuf<uint8_t> bits;
     DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx, done;
     DevBuf<DevScalars> sc;
+    DevBuf<long long> halo_off; // tile offsets of the halo exchange (ddc_halo_tile_offsets)
+    int halo_parts = 0;
     DevBuf<unsigned> gate; // the word the gate kernel of the second stream waits for (see BoxGate)
     bool use_gate = true;
     DevBuf<Plan> plan;
@@ -502,6 +504,7 @@ int ddc_destroy(ddc_handle_t h)
     h->done.release();
     h->sc.release();
     h->gate.release();
+    h->halo_off.release();
     h->plan.release();
     h->strips.release();
     h->boxes.release();
@@ -808,6 +811,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     h->have_pid = false;
     h->have_nbr = false;
     h->totals_valid = false;
+    h->halo_parts = 0;
     memset(&h->stats, 0, sizeof h->stats);
     int launches = 0;
     // stage i begins: a CUDA event when profiling, and an NVTX range (the host-side enqueue of the stage; Nsight
@@ -1500,6 +1504,57 @@ int ddc_neighbours_from_boxes(ddc_handle_t h, int nparts, int nx, int ny, const 
     CUDA_TRY(h, cudaMemsetAsync(h->loads.p, 0, sizeof(long long) * P, s));
     CUDA_TRY(h, cudaMemsetAsync(h->loadmm.p, 0, sizeof(long long) * 2, s));
     CUDA_TRY(h, cudaMemsetAsync(h->plan.p, 0, sizeof(Plan), s));
+    return DDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo exchange (a consumer of the neighbour tables)
+// ------------------------------------------------------------------------------------------------
+int ddc_halo_tile_offsets(ddc_handle_t h, int64_t* offsets)
+{
+    NEED_PARTITION(h);
+    if (!offsets)
+        return fail(h, DDC_ERR_ARG, "ddc_halo_tile_offsets: null output");
+    const int P = h->nparts;
+    std::vector<int32_t> ex(P), ey(P);
+    int rc = ddc_get_boxes(h, nullptr, nullptr, ex.data(), ey.data());
+    if (rc)
+        return rc;
+    std::vector<long long> off((size_t)P + 1);
+    long long run = 0;
+    for (int p = 0; p < P; p++) {
+        off[p] = run;
+        run += (long long)(std::max(ex[p], 0) + 2) * (std::max(ey[p], 0) + 2);
+    }
+    off[P] = run;
+    CUDA_TRY(h, h->halo_off.ensure((size_t)P + 1));
+    CUDA_TRY(h, cudaMemcpyAsync(h->halo_off.p, off.data(), sizeof(long long) * ((size_t)P + 1), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->halo_parts = P;
+    for (int p = 0; p <= P; p++)
+        offsets[p] = off[p];
+    return DDC_OK;
+}
+
+int ddc_halo_exchange_f64(ddc_handle_t h, double* tiles_dev, int periodic)
+{
+    NEED_PARTITION(h);
+    if (!tiles_dev)
+        return fail(h, DDC_ERR_ARG, "ddc_halo_exchange_f64: null tiles");
+    if (h->halo_parts != h->nparts)
+        return fail(h, DDC_ERR_STATE, "ddc_halo_exchange_f64: call ddc_halo_tile_offsets() for this decomposition first");
+    if (!h->have_nbr)
+        return DDC_OK; // one part (or no tables asked for): nothing to exchange
+    int rc = fetch_totals(h); // (re-runs the fill pass with the exact capacity if the bounded one overflowed)
+    if (rc)
+        return rc;
+    const int P = h->nparts;
+    Tables t = tables(h, P);
+    const long long warps = 8LL * P;
+    CUDA_TRY(h, launch_k(k_halo_exchange<double>, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, h->stream, false, t.bx, P,
+        h->nbr_counts.p, h->nbr_offsets.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p, h->halo_off.p, tiles_dev,
+        periodic ? 0xffu : 0x0fu));
+    CUDA_TRY(h, cudaGetLastError());
     return DDC_OK;
 }
 

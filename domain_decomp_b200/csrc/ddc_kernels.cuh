@@ -2094,6 +2094,62 @@ __global__ void __launch_bounds__(256) k_init(unsigned* __restrict__ colcount, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Halo exchange: a consumer of the neighbour tables
+// ------------------------------------------------------------------------------------------------
+// The reference's only in-tree consumer of get_neighbour_info is examples/zoltan_comm.cpp:84-246: every rank
+// holds its box as a (ext + 2)^2-framed array, builds one MPI subarray type per neighbour from the halo sizes and
+// exchanges the frames with MPI_Neighbor_alltoallw.  Here all parts of a decomposition live in one device buffer
+// -- tile p is a row-major (ext_y + 2) x (ext_x + 2) array with a ghost frame of one cell, at tiles[off[p]] -- and one
+// warp per (edge list, part) walks the part's CSR entries: neighbour id, halo size and halo START (the index of
+// the first shared cell in the neighbour's flattened box, Partitioner.cpp:55-80) locate the source cells, the
+// overlap of the two boxes the ghost cells.  Corners are not exchanged (a corner-touching box is no neighbour,
+// DomainUtils.cpp:15-35).  lists: bit l set = use list l (l = periodic * 4 + edge).
+template <typename T>
+__global__ void __launch_bounds__(256) k_halo_exchange(BoxTable bx, int P, const int* __restrict__ counts,
+    const int* __restrict__ offsets, int cap, const int* __restrict__ ids, const int* __restrict__ halos,
+    const int* __restrict__ starts, const long long* __restrict__ off, T* __restrict__ tiles, unsigned lists)
+{
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = lane_id();
+    if (w >= 8LL * P)
+        return;
+    const int l = (int)(w / P), p = (int)(w % P);
+    if (!((lists >> l) & 1u))
+        return;
+    const int edge = l & 3;
+    const int px0 = bx.x0[p], py0 = bx.y0[p], pex = bx.ex[p], pey = bx.ey[p];
+    T* mine = tiles + off[p];
+    const int n = counts[l * P + p], first = offsets[l * (P + 1) + p];
+    for (int k = 0; k < n; k++) {
+        const size_t e = (size_t)l * cap + first + k;
+        const int q = ids[e], h = halos[e], st = starts[e];
+        const int qw = bx.ex[q];
+        const T* theirs = tiles + off[q];
+        const bool lr = edge < 2; // left / right: the shared cells run along y
+        const int along = lr ? max(py0, bx.y0[q]) - py0 : max(px0, bx.x0[q]) - px0; // first shared cell along my edge
+        for (int i = lane; i < h; i += 32) {
+            const int s = st + (lr ? i * qw : i); // the neighbour's cell, in its flattened box
+            const T v = theirs[(size_t)(s / qw + 1) * (qw + 2) + (s % qw + 1)];
+            int row, col; // my ghost cell
+            if (edge == 0) {
+                row = along + i + 1;
+                col = 0;
+            } else if (edge == 1) {
+                row = along + i + 1;
+                col = pex + 1;
+            } else if (edge == 2) {
+                row = 0;
+                col = along + i + 1;
+            } else {
+                row = pey + 1;
+                col = along + i + 1;
+            }
+            mine[(size_t)row * (pex + 2) + col] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // synthetic land-sea mask: two octaves of integer value noise (bit-identical on host and device)
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline uint64_t splitmix64(uint64_t z)

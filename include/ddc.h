@@ -176,6 +176,15 @@ DDC_API int ddc_get_stats(ddc_handle_t h, ddc_stats* out);
 DDC_API int ddc_neighbours_from_boxes(ddc_handle_t h, int nparts, int nx, int ny, const int32_t* x0,
     const int32_t* y0, const int32_t* ext_x, const int32_t* ext_y, int periodic_x, int periodic_y);
 
+/* Halo exchange driven by the neighbour tables of the last decomposition -- the consumer side, what
+   examples/zoltan_comm.cpp:84-246 of the reference does with MPI subarray types and MPI_Neighbor_alltoallw.  All
+   parts live in ONE device buffer: tile p is a row-major (ext_y[p] + 2) x (ext_x[p] + 2) array with a ghost frame of
+   one cell around the part's box, starting at element offsets[p] (ddc_halo_tile_offsets: offsets[nparts] = total
+   elements).  ddc_halo_exchange_f64 fills every ghost cell that faces a neighbour with that neighbour's adjacent
+   interior cell (interior lists; periodic != 0: the periodic lists too).  Corners are not exchanged. */
+DDC_API int ddc_halo_tile_offsets(ddc_handle_t h, int64_t* offsets /* nparts + 1 */);
+DDC_API int ddc_halo_exchange_f64(ddc_handle_t h, double* tiles_dev, int periodic);
+
 /* ---- synthetic masks: deterministic value-noise land-sea mask, generated directly
    into device memory so that no 4 GiB file is needed for the large configurations.
    land_frac in [0,1] is the target land fraction; rows as in ddc_set_mask_device. */

@@ -204,3 +204,17 @@ int ddc_peer_close(ddc_handle_t h)
     (void)h;
     return DDC_OK;
 }
+/* the halo exchange runs on the device only */
+int ddc_halo_tile_offsets(ddc_handle_t h, int64_t* offsets)
+{
+    (void)h;
+    (void)offsets;
+    return DDC_ERR_STATE;
+}
+int ddc_halo_exchange_f64(ddc_handle_t h, double* tiles_dev, int periodic)
+{
+    (void)h;
+    (void)tiles_dev;
+    (void)periodic;
+    return DDC_ERR_STATE;
+}

@@ -276,3 +276,30 @@ def test_device_mask_generator_and_device_resident_path(capi, handle, oracle):
     ptr = handle.pid_device()
     pid = np.ctypeslib.as_array((C.c_int32 * (nx * ny)).from_address(ptr)).reshape(ny, nx)
     assert np.array_equal(pid, o.pid) and handle.boxes().tolist() == o.boxes.tolist()
+
+
+def test_halo_exchange_consumes_the_neighbour_tables(capi, handle):
+    """ddc_halo_exchange_f64 (the GPU analogue of examples/zoltan_comm.cpp:84-246 of the reference) on the emulation:
+    after the exchange every ghost cell that faces a neighbour holds that neighbour's id, derived independently from
+    the boxes (tests/halo_check.py) -- interior and periodic lists, ragged coastlines, part counts that are not
+    powers of two"""
+    import halo_check
+    rng = np.random.default_rng(21)
+    done = 0
+    while done < 12:
+        nx, ny, P = int(rng.integers(6, 60)), int(rng.integers(6, 60)), int(rng.integers(2, 14))
+        px, py = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        mask = (rng.random((ny, nx)) < 0.8).astype(np.int32)
+        handle.set_mask_host(mask)
+        handle.partition(P, px, py)
+        boxes = handle.boxes()
+        if (boxes[:, 2:] <= 0).any():
+            continue  # an empty part has no tile to exchange with
+        off = handle.halo_tile_offsets()
+        for periodic in (False, True):
+            tiles = halo_check.initial_tiles(boxes, off)
+            handle.halo_exchange_f64(tiles.ctypes.data, periodic)  # (emulation: "device" memory is host memory)
+            handle.L.ddc_synchronize(handle.h)
+            want = halo_check.expected_tiles(boxes, off, nx, ny, px, py, periodic)
+            assert np.array_equal(tiles, want), (nx, ny, P, px, py, periodic)
+        done += 1

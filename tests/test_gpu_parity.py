@@ -270,3 +270,25 @@ def test_strip_row_kernel_variants(capi, oracle, k, monkeypatch):
                         "k=%d %dx%d" % (k, nx, ny))
     finally:
         h.close()
+
+
+def test_halo_exchange_consumes_the_neighbour_tables(capi, handle):
+    """ddc_halo_exchange_f64 (the GPU analogue of examples/zoltan_comm.cpp:84-246 of the reference): every ghost cell
+    facing a neighbour ends up with that neighbour's id -- expected values from the boxes alone (tests/halo_check.py);
+    528 x 522 into 64 parts with both directions periodic, and a 2048 x 1536 coastline into 1000 parts"""
+    import halo_check
+    import torch
+    for (nx, ny, P, land, seed, px, py) in ((528, 522, 64, 0.45, 25, True, True), (2048, 1536, 1000, 0.4, 5, True, False)):
+        mask = capi.generate_mask_host(nx, ny, seed, land)
+        handle.set_mask_host(mask)
+        handle.partition(P, px, py)
+        boxes = handle.boxes()
+        assert (boxes[:, 2:] > 0).all()
+        off = handle.halo_tile_offsets()
+        for periodic in (False, True):
+            tiles = torch.from_numpy(halo_check.initial_tiles(boxes, off)).cuda()
+            handle.halo_exchange_f64(tiles.data_ptr(), periodic)
+            handle.L.ddc_synchronize(handle.h)
+            torch.cuda.synchronize()
+            want = halo_check.expected_tiles(boxes, off, nx, ny, px, py, periodic)
+            assert np.array_equal(tiles.cpu().numpy(), want), (nx, ny, P, periodic)
