@@ -1108,10 +1108,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         }
         mark(3);
         const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
-        if (gated) { // the second stream waits in a one-warp kernel until K4's last block says the boxes are in place
-            CUDA_TRY(h, launch_k(k_gate, dim3(1), dim3(32), 0, h->side_stream, false, h->gate.p, h->step, h->plan.p));
-            launches++;
-        }
+
 #define LAUNCH_YCUTS(CT, SM, opted)                                                                \
     do {                                                                                           \
         if (SM && opted < yneed) {                                                                 \
@@ -1134,6 +1131,12 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         }
 #undef LAUNCH_YCUTS
         launches++;
+        if (gated) { // the second stream waits in a one-warp kernel until K4's last block says the boxes are in place
+            // (launched AFTER K4: tools that serialise kernels in launch order -- ncu, CUDA_LAUNCH_BLOCKING -- then run
+            //  K4 first and the gate finds itself open)
+            CUDA_TRY(h, launch_k(k_gate, dim3(1), dim3(32), 0, h->side_stream, false, h->gate.p, h->step, h->plan.p));
+            launches++;
+        }
     } else
         mark(3);
     mark(4);
