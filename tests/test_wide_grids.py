@@ -65,3 +65,23 @@ def test_histogram_of_exactly_one_tile_and_one_more(capi, oracle):
     """32768 bins is one prefix tile, 32769 two; 49152 still fits shared memory with two tiles"""
     for nx, ny, P in [(32768, 20, 16), (32769, 20, 16), (49152, 12, 8), (16, 32769, 8)]:
         run_and_compare(capi, oracle, nx, ny, P, False, False, 3, 0.3)
+
+
+def test_around_the_shared_memory_limit_of_the_cut_kernels(capi, oracle):
+    """The cut kernels keep the prefix sums, the bit map and the sets of two RCB levels in dynamic shared memory and a
+    little more statically; the library asks the kernel for its static size (cudaFuncGetAttributes) before it chooses
+    the shared-memory variant.  Extents just below and above the limit -- in x and in y -- must both decompose
+    (round 1 reserved a fixed 1024 bytes and failed to launch in a window of a few columns)."""
+    lim, static = 232448, 1056 + 64
+
+    def need(n):
+        tiles = (n + 32767) // 32768
+        return 4 * ((((n + 1) + 3) & ~3) + tiles * (1024 + 32 + 1)) + (2 * 1024 * 16 + 16)
+
+    n = 40000
+    while need(n) + static <= lim:
+        n += 1
+    for nx in (n - 9, n - 3, n - 1, n, n + 2, n + 8):
+        run_and_compare(capi, oracle, nx, 12, 8, False, False, 5, 0.3)
+    for ny in (n - 2, n + 1):
+        run_and_compare(capi, oracle, 16, ny, 8, False, False, 7, 0.3)
