@@ -163,7 +163,7 @@ def cpu_sample(workload, threads: int, whole: bool = False):
     from the oracle's restatement of the generator: the CPU legs never load the CUDA library."""
     nx, ny, P, land, seed, px, py = WORKLOADS[workload]
     from oracle import oracle as orc
-    if nx * ny > 4096 * 4096 and not whole:
+    if nx * ny > 8192 * 8192 and not whole:
         f = 8
         sx, sy, sp = nx // f, ny // f, max(2, P // (f * f))
         desc = ("top-left %dx%d window of the %dx%d mask into %d parts (same cells per part; %d RCB levels "
