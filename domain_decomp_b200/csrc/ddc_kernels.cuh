@@ -696,13 +696,13 @@ __device__ inline const RcbNode* rcb_levels(const Hist& H, RcbSet root, int leve
             break;
         if (lvl_ts && tid == 0 && l < 8)
             lvl_ts[l] = walk_clock();
-        int spread = 1;
-        while (spread < 32 && 2 * spread * cnt <= nthreads)
-            spread <<= 1;
+        int shift = 0; // set i -> thread i << shift: the largest spread (<= 32) that still fits the block
+        while (shift < 5 && (2 << shift) * cnt <= nthreads)
+            shift++;
         const RcbNode* src = nodes + cur * LEVEL_NODES;
         RcbNode* dst = nodes + (cur ^ 1) * LEVEL_NODES;
-        const int i = tid / spread;
-        if (tid % spread == 0 && i < cnt) {
+        const int i = tid >> shift;
+        if ((tid & ((1 << shift) - 1)) == 0 && i < cnt) {
             const RcbNode sset = src[i];
             const int off = minn >= 2 ? 2 * i : sset.plo - root.plo;
             if (sset.n > 1) {
@@ -1434,7 +1434,12 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     __shared__ unsigned wsum[PFX_WS];
     pdl_trigger(); // the labelling kernel may become resident
     pdl_wait(); // the strip row-count kernel (and with it everything before) is complete
-    if (plan->mismatch) {
+    // everything the block needs to know about its first strip is requested at once: one trip to L2 instead of a chain
+    // of four (mismatch -> S -> p0 -> x0) in front of the row counts
+    const int mism = plan->mismatch, S = *st.S, ylevels = plan->iy;
+    const int first_plo = st.p0[blockIdx.x], first_pend = st.p0[blockIdx.x + 1];
+    const int first_x0 = st.x0[blockIdx.x], first_x1 = st.x1[blockIdx.x];
+    if (mism) {
         boxes_ready(gate); // (the kernels behind the gate look at the mismatch themselves)
         return;
     }
@@ -1444,9 +1449,12 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     // the column -> strip table the labelling kernel reads: the block of a strip paints the strip's columns
     // (while the other ranks' row counts are still on their way); a zero-width strip paints nothing, the strip
     // that follows it owns the shared start column
-    for (int s = blockIdx.x; s < *st.S; s += gridDim.x)
-        for (int x = st.x0[s] + (int)threadIdx.x; x < st.x1[s]; x += (int)blockDim.x)
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const bool f = s == (int)blockIdx.x;
+        const int xa = f ? first_x0 : st.x0[s], xb = f ? first_x1 : st.x1[s];
+        for (int x = xa + (int)threadIdx.x; x < xb; x += (int)blockDim.x)
             strip_of_col[x] = s;
+    }
     // exchange step 2: every rank's strip row counts are written (the last block of its row-count kernel said so)
     if (ps.enabled) {
         bool ok = true;
@@ -1466,12 +1474,11 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     unsigned* bitmap = SMEM ? smem_dyn + (((size_t)NY + 1 + 3) & ~(size_t)3) : nullptr;
     const Hist H = make_hist(pfx, bitmap, NY);
     const int tid = threadIdx.x;
-    const int S = *st.S;
-    const int ylevels = plan->iy;
     int my_iters = 0;
     long long lmn = 0x7fffffffffffffffLL, lmx = -1;
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
-        const int plo = st.p0[s], n = st.p0[s + 1] - plo;
+        const bool f = s == (int)blockIdx.x;
+        const int plo = f ? first_plo : st.p0[s], n = (f ? first_pend : st.p0[s + 1]) - plo;
         if (n <= 1)
             continue; // K2 already wrote the box of a leaf strip
         __syncthreads(); // previous strip done with pfx
@@ -1487,7 +1494,7 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
         if (blockIdx.x == 0 && tid == 0)
             plan->ts[8] = global_ns();
         // a group of `lanes` threads walks to the j-th part of the strip (parts come out y-sorted)
-        const int sx0 = st.x0[s], sx1 = st.x1[s];
+        const int sx0 = f ? first_x0 : st.x0[s], sx1 = f ? first_x1 : st.x1[s];
         const int nleaves = leaves_below(n, ylevels);
         const bool by_level = nleaves <= LEVEL_NODES;
         const int lanes = by_level ? 1 : walk_lanes(nleaves, blockDim.x);
