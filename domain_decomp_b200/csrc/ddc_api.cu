@@ -171,7 +171,7 @@ struct ddc_handle_s {
     DevBuf<Plan> plan;
     DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
     DevBuf<int> boxes; // x0 y0 ex ey, P each
-    DevBuf<int> strip_of_col;
+    DevBuf<int> strip_of_col, part_at; // part_at: [strips][ceil(NY / 32)] row -> part table K4 leaves for the labelling kernel
     DevBuf<long long> loads, loadmm;
     DevBuf<int32_t> pid;
     DevBuf<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
@@ -509,6 +509,7 @@ int ddc_destroy(ddc_handle_t h)
     h->strips.release();
     h->boxes.release();
     h->strip_of_col.release();
+    h->part_at.release();
     h->loads.release();
     h->loadmm.release();
     h->pid.release();
@@ -861,6 +862,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
     CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
     CUDA_TRY(h, h->strip_of_col.ensure(NX));
+    const int nchunk = (NY + 31) / 32;
+    if (ycuts)
+        CUDA_TRY(h, h->part_at.ensure((size_t)Scap * nchunk));
     CUDA_TRY(h, h->loads.ensure(P));
     CUDA_TRY(h, h->loadmm.ensure(2));
     if (want_pid)
@@ -1116,7 +1120,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             opted = yneed;                                                                         \
         }                                                                                          \
         CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : LEVEL_NODES_BYTES, s, pdl, pr, ps, rl, NY, t.st, \
-            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0, gate)); \
+            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0, gate, h->part_at.p, nchunk)); \
     } while (0)
         if (narrow) {
             if (y_smem)
@@ -1179,6 +1183,8 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         fin.counter = reinterpret_cast<unsigned long long*>(h->done.p + d_label);
         fin.host_plan = h->pin_plan_dev;
         fin.dbg = dbg;
+        fin.part_at.table = ycuts ? h->part_at.p : nullptr;
+        fin.part_at.nchunk = nchunk;
         fin.reset_col = reset_in_label ? colcount : nullptr;
         fin.reset_n = ncol;
         fin.yr_off = yr_off;

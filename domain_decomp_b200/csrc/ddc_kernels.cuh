@@ -1428,7 +1428,8 @@ __device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowL
 template <typename CT, bool SMEM>
 __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st,
     unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan, int* __restrict__ strip_of_col,
-    int dbg, BoxGate gate)
+    int dbg, BoxGate gate, int* __restrict__ part_at /* [S][nchunk]: the part of a strip owning row 32 j (PartAt) */,
+    int nchunk)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
@@ -1479,8 +1480,11 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
         const bool f = s == (int)blockIdx.x;
         const int plo = f ? first_plo : st.p0[s], n = (f ? first_pend : st.p0[s + 1]) - plo;
-        if (n <= 1)
-            continue; // K2 already wrote the box of a leaf strip
+        if (n <= 1) { // K2 already wrote the box of a leaf strip: its one part owns every row
+            for (int j = tid; j < nchunk; j += blockDim.x)
+                part_at[(size_t)s * nchunk + j] = plo;
+            continue;
+        }
         __syncthreads(); // previous strip done with pfx
         block_prefix_tiles(
             [&](int base, uint4 (&v)[PFX_Q]) {
@@ -1531,6 +1535,23 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
             loads[r.plo] = w;
             lmn = w < lmn ? w : lmn;
             lmx = w > lmx ? w : lmx;
+        }
+        // the row -> part table of the strip for the labelling kernel: the first part whose rows end after row 32 j
+        // (the last part if none does), exactly what seat_cursor's search over the boxes would find
+        if (!by_level)
+            __syncthreads(); // the boxes of this strip, written above by this block, are read back below
+        for (int j = tid; j < nchunk; j += blockDim.x) {
+            const int y = j << 5;
+            int lo = 0, hi = nleaves - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const int yend = by_level ? fin[mid].hi : bx.y0[plo + mid] + bx.ey[plo + mid];
+                if (y < yend)
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            part_at[(size_t)s * nchunk + j] = plo + lo;
         }
     }
     reduce_load_extremes(lmn, lmx, loadmm);
@@ -1607,40 +1628,61 @@ __device__ __forceinline__ void store_pid_row(int32_t* __restrict__ q, int x, in
     }
 }
 
-// the rows [r0, r1) of one thread's 4 columns; *s_changed (shared memory) is set when a moved cell is found
+// The part of strip s that owns row y, for the start of a block's rows.  K4 leaves a table: part_at[s * nchunk + j] = the
+// part of strip s owning row 32 j (PartAt below); from there the cursor steps forward (a block starts at most 31 rows
+// further).  Without the table (no y levels) a binary search over the y-sorted parts.
+struct PartAt {
+    const int* table; // nullptr: search
+    int nchunk; // = ceil(NY / 32)
+};
+__device__ __forceinline__ LabelCursor seat_cursor_at(const PartAt& pa, const int* __restrict__ st_p0,
+    const int* __restrict__ box_y0, const int* __restrict__ box_ey, int s, int y)
+{
+    if (!pa.table)
+        return seat_cursor(st_p0, box_y0, box_ey, s, y);
+    LabelCursor c;
+    c.part = pa.table[(size_t)s * pa.nchunk + (y >> 5)];
+    c.last = st_p0[s + 1] - 1;
+    c.yend = box_y0[c.part] + box_ey[c.part];
+    advance_cursor(c, box_y0, box_ey, y);
+    return c;
+}
+
+// the rows [r0, r1) of one thread's 4 columns; returns whether a moved cell was found
 template <bool VEC, bool WRITE>
-__device__ __forceinline__ void label_rows(const uint8_t* __restrict__ bits, int NX, int y_begin, int NB, int g, int r0,
+__device__ __forceinline__ bool label_rows(const uint8_t* __restrict__ bits, int NX, int y_begin, int NB, int g, int r0,
     int r1, const int* __restrict__ strip_of_col, const int* __restrict__ st_p0, const int* __restrict__ box_y0,
     const int* __restrict__ box_ey, const NaiveParams& nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc,
-    int* s_changed)
+    const PartAt& pa)
 {
     const int lane = lane_id();
     const int x = g * 128 + lane * 4;
-
+    bool found = false;
+    // everything that does not depend on anything else is requested first, together: the strips of my columns, the
+    // first batch of bit-map bytes, the `changes` flag (a block lives for a few microseconds; a chain of dependent
+    // trips to L2 at its start was a third of that)
     int sc4[4], nbx[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const int xc = min(x + c, NX - 1);
-        sc4[c] = strip_of_col[xc];
-        nbx[c] = min(xc / nv.lx, nv.np0 - 1) * nv.np1;
-    }
-    // columns 1, 2 belong to the strip of column 0 or of column 3 unless the thread spans > 2 strips
-    const bool two = (sc4[1] == sc4[0] || sc4[1] == sc4[3]) && (sc4[2] == sc4[0] || sc4[2] == sc4[3]);
-    const bool b1 = sc4[1] != sc4[0], b2 = sc4[2] != sc4[0], b3 = sc4[3] != sc4[0];
-    LabelCursor A = seat_cursor(st_p0, box_y0, box_ey, sc4[0], y_begin + r0);
-    LabelCursor B = b3 ? seat_cursor(st_p0, box_y0, box_ey, sc4[3], y_begin + r0) : A;
+    for (int c = 0; c < 4; c++)
+        sc4[c] = strip_of_col[min(x + c, NX - 1)];
     const uint8_t* brow = bits + (size_t)g * 16 + (lane >> 1);
     const int sh = (lane & 1) * 4;
-    int by = min((y_begin + r0) / nv.ly, nv.np1 - 1);
-    int by_next = (by == nv.np1 - 1) ? 0x7fffffff : (by + 1) * nv.ly;
-    // `changes` only ever goes 0 -> 1: stop looking as soon as anyone has found a moved cell
-    bool check = *reinterpret_cast<volatile int*>(&sc->changes) == 0;
-
-    // the bit-map bytes of the next batch are requested before the current batch is stored
     unsigned nb[8];
 #pragma unroll
     for (int k = 0; k < 8; k++)
         nb[k] = r0 + k < r1 ? (unsigned)__ldg(brow + (size_t)(r0 + k) * NB) : 0u;
+    // `changes` only ever goes 0 -> 1: stop looking as soon as anyone has found a moved cell
+    bool check = *reinterpret_cast<volatile int*>(&sc->changes) == 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        nbx[c] = min(min(x + c, NX - 1) / nv.lx, nv.np0 - 1) * nv.np1;
+    // columns 1, 2 belong to the strip of column 0 or of column 3 unless the thread spans > 2 strips
+    const bool two = (sc4[1] == sc4[0] || sc4[1] == sc4[3]) && (sc4[2] == sc4[0] || sc4[2] == sc4[3]);
+    const bool b1 = sc4[1] != sc4[0], b2 = sc4[2] != sc4[0], b3 = sc4[3] != sc4[0];
+    LabelCursor A = seat_cursor_at(pa, st_p0, box_y0, box_ey, sc4[0], y_begin + r0);
+    LabelCursor B = b3 ? seat_cursor_at(pa, st_p0, box_y0, box_ey, sc4[3], y_begin + r0) : A;
+    int by = min((y_begin + r0) / nv.ly, nv.np1 - 1);
+    int by_next = (by == nv.np1 - 1) ? 0x7fffffff : (by + 1) * nv.ly;
     for (int r = r0; r < r1; r += 8) {
         const int y = y_begin + r;
         const int nrow = min(8, r1 - r);
@@ -1681,7 +1723,7 @@ __device__ __forceinline__ void label_rows(const uint8_t* __restrict__ bits, int
                 if (__any_sync(__activemask(), changed)) {
                     if (changed) {
                         atomicOr(&sc->changes, 1);
-                        *s_changed = 1;
+                        found = true;
                     }
                     check = false;
                 }
@@ -1725,13 +1767,14 @@ __device__ __forceinline__ void label_rows(const uint8_t* __restrict__ bits, int
             }
             if (check && changed) {
                 atomicOr(&sc->changes, 1);
-                *s_changed = 1;
+                found = true;
                 check = false;
             }
         }
         if (check && (r & 63) == 0)
             check = *reinterpret_cast<volatile int*>(&sc->changes) == 0;
     }
+    return found;
 }
 
 // The end of a step, folded into the labelling kernel (no separate launch behind the largest kernel of the
@@ -1748,6 +1791,7 @@ struct LabelEnd {
     unsigned long long* counter; // zero between steps
     Plan* host_plan;
     unsigned long long* dbg;
+    PartAt part_at; // the row -> part table K4 left (table == nullptr: none)
     unsigned* reset_col; // != nullptr: this rank's column-count slot, consumed by k_sum_cols: zeroed here for the next step
     int reset_n, yr_off;
 };
@@ -1765,32 +1809,29 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
             publish_plan(plan, fin.host_plan);
         return;
     }
-    if (threadIdx.x == 0) {
-        s_changed = 0;
+    if (threadIdx.x == 0)
         stamp_first(fin.dbg, TS_LABEL);
-    }
     if (fin.reset_col) { // (the first blocks of the grid take 256 entries each)
         const long long stride = (long long)gridDim.x * gridDim.y * blockDim.x;
         for (long long i = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < fin.reset_n; i += stride)
             fin.reset_col[i] = column_slot_reset_value((int)i, fin.yr_off, fin.ps.rank);
     }
-    __syncthreads();
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(rows, r0 + rows_per_cta);
+    bool found = false;
     if (g * 128 < NX && r0 < r1)
-        label_rows<VEC, WRITE>(bits, NX, y_begin, NB, g, r0, r1, strip_of_col, st_p0, box_y0, box_ey, nv, pid, sc,
-            &s_changed);
+        found = label_rows<VEC, WRITE>(bits, NX, y_begin, NB, g, r0, r1, strip_of_col, st_p0, box_y0, box_ey, nv, pid, sc,
+            fin.part_at);
     if (!fin.fuse)
         return;
-    __syncthreads();
+    const int any = __syncthreads_or(found ? 1 : 0); // (the one barrier of a block: its warps are done)
     if (threadIdx.x == 0) {
         stamp_last(fin.dbg, TS_LABEL + 1);
-        const unsigned long long old
-            = atomicAdd(fin.counter, 1ull | (s_changed ? (1ull << 32) : 0ull));
+        const unsigned long long old = atomicAdd(fin.counter, 1ull | (any ? (1ull << 32) : 0ull));
         const unsigned blocks = gridDim.x * gridDim.y;
         s_last = (unsigned)(old & 0xffffffffull) == blocks - 1u;
-        s_changed = (s_changed || (old >> 32) != 0ull) ? 1 : 0; // only meaningful in the last block
+        s_changed = (any || (old >> 32) != 0ull) ? 1 : 0; // only meaningful in the last block
     }
     __syncthreads();
     if (!s_last)

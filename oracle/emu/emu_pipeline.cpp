@@ -67,7 +67,7 @@ struct Rank {
     std::vector<unsigned> flags; // [PEER_STAGES][MAX_PEERS]
     std::vector<unsigned> colslots, rowslots; // G slots each (slot g is written by rank g)
     std::vector<unsigned> colpfx, ypfx, done, colsum;
-    std::vector<int> strips, boxes, strip_of_col;
+    std::vector<int> strips, boxes, strip_of_col, part_at;
     std::vector<long long> loads, loadmm;
     std::vector<int32_t> pid;
     std::vector<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
@@ -112,6 +112,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const int gridx = (NG + 7) / 8;
     const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, ndone = d_ycuts + 1; // ddc_api.cu: the "last block" counters
     const NaiveParams nv = naive_params(P, NX, NY);
+    const int nchunk = (NY + 31) / 32;
     const int par = (int)(step & 1u);
     const bool want_nbr = P > 1;
 
@@ -149,6 +150,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         r.strips.assign((size_t)3 * (P + 1) + 3, 0);
         r.boxes.assign((size_t)4 * P, 0);
         r.strip_of_col.assign(NX, 0);
+        r.part_at.assign((size_t)std::max(Scap, 1) * nchunk, -12345);
         r.loads.assign(P, 0);
         r.loadmm.assign(2, 0);
         r.pid.assign((size_t)std::max(r.rows, 1) * NX, INT_MIN);
@@ -322,7 +324,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
 #define YCUTS(CT, SM)                                                                              \
     LAUNCH(Dim3(ygrid), Dim3(1024), SM ? yneed : LEVEL_NODES_BYTES,                                                \
         (k_ycuts<CT, SM>(pr, ps, rl, NY, st, r.ypfx.data(), bx, r.loads.data(), r.loadmm.data(), &r.plan,                    \
-            r.strip_of_col.data(), 0, gate)))
+            r.strip_of_col.data(), 0, gate, r.part_at.data(), nchunk)))
             if (narrow) {
                 if (y_smem)
                     YCUTS(uint16_t, true);
@@ -371,6 +373,8 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             fin.counter = reinterpret_cast<unsigned long long*>(r.done.data() + d_label);
             fin.host_plan = &r.host_plan;
             fin.dbg = nullptr;
+            fin.part_at.table = ycuts ? r.part_at.data() : nullptr;
+            fin.part_at.nchunk = nchunk;
             fin.reset_col = p2p ? colslot(r, r.rank) : nullptr;
             fin.reset_n = ncol;
             fin.yr_off = yr_off;
