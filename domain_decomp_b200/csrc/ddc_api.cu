@@ -20,6 +20,7 @@ inline void nvtxRangePop() { }
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -136,6 +137,26 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 #endif
 }
+// Dynamic shared memory a kernel has been opted in for (cudaFuncAttributeMaxDynamicSharedMemorySize), per device.
+// The attribute belongs to the FUNCTION, not to a handle: it is only ever raised, and the bookkeeping is shared by
+// all handles of the process (a second handle that set a smaller value used to leave the first one launching
+// with more than the function allowed: "invalid argument").
+constexpr int MAX_DEVICES = 64;
+std::mutex g_optin_mutex;
+size_t g_optin[MAX_DEVICES][3]; // x cuts, y cuts (16-bit counts), y cuts (32-bit counts)
+template <typename K>
+cudaError_t opt_in_smem(K kernel, int device, int which, size_t need)
+{
+    std::lock_guard<std::mutex> lk(g_optin_mutex);
+    size_t& have = g_optin[device % MAX_DEVICES][which];
+    if (need <= have)
+        return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e == cudaSuccess)
+        have = need;
+    return e;
+}
+
 int env_int(const char* name, int dflt)
 {
     const char* e = getenv(name);
@@ -198,7 +219,6 @@ struct ddc_handle_s {
         }
     } clean[2];
     bool clean_p2p = false;
-    size_t xcuts_smem = 0, ycuts16_smem = 0, ycuts32_smem = 0; // dynamic smem opt-ins already made
     cudaStream_t side_stream = nullptr; // speculative neighbour tables run beside the labelling
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // peer exchange (CUDA IPC): one buffer per rank, mapped by all ranks
@@ -1024,10 +1044,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     mark(1);
     // ---- K2: x cuts ----------------------------------------------------------------------------
     if (x_smem) {
-        if (h->xcuts_smem < xneed) {
-            CUDA_TRY(h, cudaFuncSetAttribute(k_xcuts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xneed));
-            h->xcuts_smem = xneed;
-        }
+        CUDA_TRY(h, opt_in_smem(k_xcuts<true>, h->device, 0, std::max<size_t>(xneed, 48 * 1024)));
         CUDA_TRY(h, launch_k(k_xcuts<true>, dim3(1), dim3(1024), xneed, s, pdl, pc, ps_x, NX, NY, P, nullptr, yr_off, G, aix,
             aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, dbg ? 1 : 0,
             h->pin_plan_dev, presum ? 1 : 0, reset_in_label ? 0 : 1));
@@ -1113,25 +1130,23 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         mark(3);
         const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
 
-#define LAUNCH_YCUTS(CT, SM, opted)                                                                \
+#define LAUNCH_YCUTS(CT, SM, which)                                                                \
     do {                                                                                           \
-        if (SM && opted < yneed) {                                                                 \
-            CUDA_TRY(h, cudaFuncSetAttribute(k_ycuts<CT, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yneed)); \
-            opted = yneed;                                                                         \
-        }                                                                                          \
+        if (SM)                                                                                    \
+            CUDA_TRY(h, opt_in_smem(k_ycuts<CT, SM>, h->device, which, std::max<size_t>(yneed, 48 * 1024))); \
         CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : LEVEL_NODES_BYTES, s, pdl, pr, ps, rl, NY, t.st, \
             h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0, gate, h->part_at.p, nchunk)); \
     } while (0)
         if (narrow) {
             if (y_smem)
-                LAUNCH_YCUTS(uint16_t, true, h->ycuts16_smem);
+                LAUNCH_YCUTS(uint16_t, true, 1);
             else
-                LAUNCH_YCUTS(uint16_t, false, h->ycuts16_smem);
+                LAUNCH_YCUTS(uint16_t, false, 1);
         } else {
             if (y_smem)
-                LAUNCH_YCUTS(unsigned, true, h->ycuts32_smem);
+                LAUNCH_YCUTS(unsigned, true, 2);
             else
-                LAUNCH_YCUTS(unsigned, false, h->ycuts32_smem);
+                LAUNCH_YCUTS(unsigned, false, 2);
         }
 #undef LAUNCH_YCUTS
         launches++;

@@ -292,3 +292,17 @@ def test_halo_exchange_consumes_the_neighbour_tables(capi, handle):
             torch.cuda.synchronize()
             want = halo_check.expected_tiles(boxes, off, nx, ny, px, py, periodic)
             assert np.array_equal(tiles.cpu().numpy(), want), (nx, ny, P, periodic)
+
+
+def test_two_handles_with_different_shared_memory_needs(capi, oracle):
+    """the dynamic shared memory a cut kernel is opted in for is a property of the FUNCTION: a second handle with a
+    small grid must not lower what a first handle with a large one relies on (round 2: 'invalid argument')"""
+    big = capi.generate_mask_host(300, 30000, 9, 0.4)
+    small = capi.generate_mask_host(64, 48, 2, 0.3)
+    a, b = capi.Handle(0), capi.Handle(0)
+    try:
+        for h, m, P in ((a, big, 32), (b, small, 6), (a, big, 32), (b, small, 6), (a, big, 24)):
+            assert_same(run_gpu(h, m, P), oracle.partition(m, P, use_hist=True), "P=%d" % P)
+    finally:
+        a.close()
+        b.close()
