@@ -12,6 +12,7 @@
 #include "NcLibrary.hpp"
 
 #include <cmath>
+#include <cstring>
 #include <stdexcept>
 
 namespace {
@@ -64,7 +65,8 @@ Grid* Grid::create_from_mask(MPI_Comm comm, const int* mask, int nx, int ny, boo
         throw std::runtime_error("ERROR: Grid::create_from_mask needs a non-empty mask");
     Grid* g = new Grid(comm, px, py);
     g->_global_ext = { nx, ny };
-    g->_global_mask.assign(mask, mask + (size_t)nx * ny);
+    g->_global_mask.resize((size_t)nx * ny); // (page-locked, not value-initialised)
+    std::memcpy(g->_global_mask.data(), mask, sizeof(int) * (size_t)nx * ny);
     g->build_block();
     return g;
 }
@@ -163,11 +165,21 @@ void Grid::build_block()
     if (by == _num_procs[1] - 1)
         _local_ext[1] = _global_ext[1] - _global[1];
     _num_objects = _local_ext[0] * _local_ext[1];
-
+    // The block's own copies (mask slab, ocean id lists) are built when a getter first asks for them: the CUDA
+    // partitioner works from the global mask, and for a single-rank communicator the "block" is the whole grid --
+    // 4 GiB of mask and 5 GiB of id lists at 32768^2 that nobody may ever read.
     _land_mask.clear();
     _local_id.clear();
     _global_id.clear();
     _num_nonzero_objects = 0;
+    _block_built = false;
+}
+
+void Grid::build_block_arrays() const
+{
+    if (_block_built)
+        return;
+    _block_built = true;
     if (_num_objects <= 0)
         return;
     const int NX = _global_ext[0];
@@ -188,16 +200,32 @@ void Grid::build_block()
 }
 
 int Grid::get_num_objects() const { return _num_objects; }
-int Grid::get_num_nonzero_objects() const { return _num_nonzero_objects; }
+int Grid::get_num_nonzero_objects() const
+{
+    build_block_arrays();
+    return _num_nonzero_objects;
+}
 bool Grid::get_px() const { return _px; }
 bool Grid::get_py() const { return _py; }
 std::vector<int> Grid::get_num_procs() const { return _num_procs; }
 std::vector<int> Grid::get_global_ext() const { return _global_ext; }
 std::vector<int> Grid::get_local_ext() const { return _local_ext; }
 std::vector<int> Grid::get_global() const { return _global; }
-const int* Grid::get_land_mask() const { return _land_mask.data(); }
-const int* Grid::get_sparse_to_dense() const { return _local_id.data(); }
-const int* Grid::get_nonzero_object_ids() const { return _global_id.data(); }
+const int* Grid::get_land_mask() const
+{
+    build_block_arrays();
+    return _land_mask.data();
+}
+const int* Grid::get_sparse_to_dense() const
+{
+    build_block_arrays();
+    return _local_id.data();
+}
+const int* Grid::get_nonzero_object_ids() const
+{
+    build_block_arrays();
+    return _global_id.data();
+}
 const int* Grid::get_global_land_mask() const { return _global_mask.data(); }
 
 void Grid::get_bounding_box(int& global_0, int& global_1, int& local_ext_0, int& local_ext_1) const

@@ -147,9 +147,10 @@ void Partitioner::publish_rank_view()
         _global_new = { 0, 0 };
         _local_ext_new = { 0, 0 };
     }
-    // pid slab of this rank's naive block, the payload of the reference's save_mask
+    // pid slab of this rank's naive block, the payload of the reference's save_mask (save_mask here writes from the
+    // global map; for a single-rank communicator the slab IS the global map and is not copied: 4 GiB at 32768^2)
     _proc_id.clear();
-    if (!_pid_global.empty() && _local_ext[0] > 0 && _local_ext[1] > 0) {
+    if (_total_num_procs > 1 && !_pid_global.empty() && _local_ext[0] > 0 && _local_ext[1] > 0) {
         const int NX = _global_ext[0], NY = _global_ext[1];
         _proc_id.reserve((size_t)_local_ext[0] * _local_ext[1]);
         for (int j = 0; j < _local_ext[1]; j++)

@@ -64,6 +64,7 @@ private:
     void load_file(const std::string& filename, const std::string& xdim, const std::string& ydim,
         const std::vector<int>& order, const std::string& mask_name, bool ignore_mask);
     void build_block();
+    void build_block_arrays() const; // the block's mask slab and ocean id lists, on first use
 
     MPI_Comm _comm;
     int _rank = -1;
@@ -73,9 +74,10 @@ private:
     std::vector<int> _local_ext = std::vector<int>(NDIMS, 0);
     std::vector<int> _global = std::vector<int>(NDIMS, -1);
     int _num_objects = 0;
-    int _num_nonzero_objects = 0;
+    mutable int _num_nonzero_objects = 0;
+    mutable bool _block_built = false;
     bool _px = false, _py = false, _ignore_mask = false;
     ddc_host::IntBuffer _global_mask; // the whole mask (page-locked when large: it is what crosses PCIe)
-    std::vector<int> _land_mask; // the rank's block
-    std::vector<int> _local_id, _global_id;
+    mutable std::vector<int> _land_mask; // the rank's block (built on first use)
+    mutable std::vector<int> _local_id, _global_id;
 };
