@@ -1399,10 +1399,11 @@ struct RowLayout {
     int Rmax, Scap, rb_shift;
 };
 // 4 consecutive row counts of strip s starting at global row i (a multiple of 4)
+// (g, yl): the rank holding global row i and the row's index there -- the caller keeps them up to date from one load
+// of a thread to the next instead of dividing by Rmax for each of them
 template <typename CT>
-__device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowLayout& rl, int s, int i, int NY)
+__device__ __forceinline__ uint4 load_row_counts4(const PeerRows& pr, const RowLayout& rl, int s, int i, int NY, int g, int yl)
 {
-    const int g = i / rl.Rmax, yl = i - g * rl.Rmax;
     const CT* src = row_segment<CT>(pr, rl.rank_stride, g) + row_count_index(s, yl, rl.Scap, rl.rb_shift);
     if (i + 4 <= NY && yl + 4 <= rl.Rmax && (yl & 3) == 0 && ((uintptr_t)src & (4 * sizeof(CT) - 1)) == 0) {
         // the chunk lies inside one rank's rows and inside one row block (RB is a multiple of 4)
@@ -1488,10 +1489,18 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
         __syncthreads(); // previous strip done with pfx
         block_prefix_tiles(
             [&](int base, uint4 (&v)[PFX_Q]) {
+                int g = base / rl.Rmax, yl = base - g * rl.Rmax; // one division per thread and tile
 #pragma unroll
                 for (int q = 0; q < PFX_Q; q++) {
                     const int i = base + q * 4096;
-                    v[q] = i < NY ? load_row_counts4<CT>(pr, rl, s, i, NY) : make_uint4(0u, 0u, 0u, 0u);
+                    v[q] = i < NY ? load_row_counts4<CT>(pr, rl, s, i, NY, g, yl) : make_uint4(0u, 0u, 0u, 0u);
+                    if (i + 4096 < NY) { // the next sub-tile's rows: a few ranks further when the ranks hold few rows
+                        yl += 4096;
+                        while (yl >= rl.Rmax) {
+                            yl -= rl.Rmax;
+                            g++;
+                        }
+                    }
                 }
             },
             NY, pfx, wsum, bitmap);
