@@ -189,6 +189,8 @@ struct ddc_handle_s {
     int halo_parts = 0;
     DevBuf<unsigned> gate; // the word the gate kernel of the second stream waits for (see BoxGate)
     bool use_gate = true;
+    int early = 0; // DDC_EARLY, bit mask: which kernels poll a flag / word instead of waiting for the previous kernel's
+                   // completion (ChainWord): 1 k_sum_cols, 2 K4, 4 labelling kernel, 8 row counts, 16 K2
     DevBuf<Plan> plan;
     DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
     DevBuf<int> boxes; // x0 y0 ex ey, P each
@@ -476,8 +478,9 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     h->scan_tail = std::max(0, std::min(90, env_int("DDC_SCAN_TAIL", 25)));
     h->label_rpc = env_int("DDC_LABEL_RPC", 0);
     h->use_gate = env_int("DDC_GATE", 1) != 0;
-    CREATE_TRY(h->gate.ensure(1));
-    CREATE_TRY(cudaMemset(h->gate.p, 0, sizeof(unsigned)));
+    h->early = env_int("DDC_EARLY", 0);
+    CREATE_TRY(h->gate.ensure(4)); // [0] K4 -> labelling kernel / second stream, [1] k_sum_cols -> K2, [2] K2 -> K3 (ChainWord)
+    CREATE_TRY(cudaMemset(h->gate.p, 0, 4 * sizeof(unsigned)));
     CREATE_TRY(h->sc.ensure(1));
     CREATE_TRY(h->plan.ensure(1));
     CREATE_TRY(cudaMemset(h->plan.p, 0, sizeof(Plan)));
@@ -984,7 +987,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const int gridx = (NG + 7) / 8;
     // counters of the "last block" patterns: [0, gridx] mask scan, [gridx + 1] strip row counts, then the
     // 64-bit counter of the labelling kernel; all zero between steps (their last blocks reset them)
-    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, ndone = d_ycuts + 1;
+    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, d_sum = d_ycuts + 1, ndone = d_sum + 1;
     CUDA_TRY(h, h->done.ensure((size_t)ndone));
     ddc_handle_s::CleanSig sig;
     sig.col = colcount;
@@ -1027,8 +1030,15 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     // several GPUs: a grid of blocks waits for the ranks' flags and sums their column-count slots into ONE buffer,
     // the x-cut block then reads global counts as on one GPU
     const bool presum = p2p;
+    // words polled in place of a kernel boundary (ChainWord; only between programmatic launches)
+    ChainWord w_none { nullptr, 0u }, w_sum = w_none, w_strips = w_none;
+    if (pdl && presum && (h->early & 16))
+        w_sum = ChainWord { h->gate.p + 1, h->step };
+    if (pdl && (h->early & 8))
+        w_strips = ChainWord { h->gate.p + 2, h->step };
     if (presum) {
-        CUDA_TRY(h, launch_k(k_sum_cols, dim3(gridx), dim3(256), 0, s, pdl, pc, ps, NX, yr_off, h->colcount.p, h->plan.p));
+        CUDA_TRY(h, launch_k(k_sum_cols, dim3(gridx), dim3(256), 0, s, pdl, pc, ps, NX, yr_off, h->colcount.p, h->plan.p,
+            pdl && (h->early & 1) ? 1 : 0, h->done.p + d_sum, w_sum));
         launches++;
         pc = PeerCols {};
         pc.col[0] = h->colcount.p;
@@ -1047,11 +1057,11 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         CUDA_TRY(h, opt_in_smem(k_xcuts<true>, h->device, 0, std::max<size_t>(xneed, 48 * 1024)));
         CUDA_TRY(h, launch_k(k_xcuts<true>, dim3(1), dim3(1024), xneed, s, pdl, pc, ps_x, NX, NY, P, nullptr, yr_off, G, aix,
             aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, dbg ? 1 : 0,
-            h->pin_plan_dev, presum ? 1 : 0, reset_in_label ? 0 : 1));
+            h->pin_plan_dev, presum ? 1 : 0, reset_in_label ? 0 : 1, w_sum, ycuts ? w_strips : w_none));
     } else
         CUDA_TRY(h, launch_k(k_xcuts<false>, dim3(1), dim3(1024), LEVEL_NODES_BYTES, s, pdl, pc, ps_x, NX, NY, P, h->colpfx.p, yr_off, G, aix,
             aiy, h->plan.p, t.st, t.bx, h->loads.p, h->loadmm.p, h->sc.p, colcount, dbg ? 1 : 0,
-            h->pin_plan_dev, presum ? 1 : 0, reset_in_label ? 0 : 1));
+            h->pin_plan_dev, presum ? 1 : 0, reset_in_label ? 0 : 1, w_sum, ycuts ? w_strips : w_none));
     launches++;
     // the column -> strip table K6 reads: painted by K4's blocks; without y levels there is no K4
     if (!ycuts) {
@@ -1063,8 +1073,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     // the second stream (neighbour tables beside the labelling kernel) is forked by a device-side gate when K4 runs
     // and nothing else has to sit between K4 and the labelling kernel (no profiling events)
     const bool gated = h->use_gate && want_nbr && ycuts && !profile;
+    const bool label_polls = pdl && ycuts && (h->early & 4); // the labelling kernel polls the same word
     BoxGate gate {};
-    if (gated) {
+    if (gated || label_polls) {
         gate.word = h->gate.p;
         gate.done = h->done.p + d_ycuts;
         gate.step = h->step;
@@ -1089,7 +1100,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
                 rb_shift = K == 4 ? 5 : (K == 2 ? 4 : 3);
 #define LAUNCH_SCAN(CT, KK, FF)                                                                    \
     CUDA_TRY(h, launch_k(k_strip_rows_scan<CT, KK, FF>, dim3(grid), dim3(256), scan_smem, s, pdl, h->bits.p, NB, NX, rows, \
-        t.st.x0, t.st.p0, h->plan.p, Scap, push_row, Rmax, ps, h->done.p + d_rows, dbg))
+        t.st.x0, t.st.p0, h->plan.p, Scap, push_row, Rmax, ps, h->done.p + d_rows, dbg, w_strips))
                 // small shards: one row per warp, the whole row requested at once (rows of <= 8 chunks)
                 const bool full = h->strip_k == 8 && K == 1 && NG <= 256;
                 if (narrow) {
@@ -1116,7 +1127,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
                 dim3 grid((Rmax + 31) / 32, (Scap + 7) / 8);
                 CUDA_TRY(h, launch_k(narrow ? k_strip_rows<uint16_t> : k_strip_rows<unsigned>, grid, dim3(256), 0, s, pdl,
                     h->bits.p, NB, rows, t.st.x0, t.st.x1, t.st.p0, h->plan.p, Scap, push_row, Rmax, ps, h->done.p + d_rows,
-                    dbg));
+                    dbg, w_strips));
             }
             launches++;
         }
@@ -1135,7 +1146,8 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         if (SM)                                                                                    \
             CUDA_TRY(h, opt_in_smem(k_ycuts<CT, SM>, h->device, which, std::max<size_t>(yneed, 48 * 1024))); \
         CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : LEVEL_NODES_BYTES, s, pdl, pr, ps, rl, NY, t.st, \
-            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0, gate, h->part_at.p, nchunk)); \
+            h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0, gate, h->part_at.p, nchunk, \
+            pdl && p2p && (h->early & 2) ? 1 : 0)); \
     } while (0)
         if (narrow) {
             if (y_smem)
@@ -1203,6 +1215,8 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         fin.reset_col = reset_in_label ? colcount : nullptr;
         fin.reset_n = ncol;
         fin.yr_off = yr_off;
+        if (label_polls)
+            fin.prev = ChainWord { h->gate.p, h->step };
         auto kernel = !want_pid ? k_label<false, false> : (vecp ? k_label<true, true> : k_label<false, true>);
         // (behind K4 without a stream operation in between when the second stream is gated: programmatic launch)
         CUDA_TRY(h, launch_k(kernel, grid, dim3(256), 0, s, pdl && (gated || !want_nbr), h->bits.p, NX, rows, h->y_begin, NB, rpc, h->strip_of_col.p,

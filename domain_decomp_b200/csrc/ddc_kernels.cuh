@@ -188,6 +188,68 @@ __device__ __forceinline__ void stamp_last(unsigned long long* dbg, int i)
         atomicMax(dbg + i, global_ns());
 }
 
+// Flags instead of kernel boundaries.  griddepcontrol.wait returns when the previous GRID has completed and its memory
+// is flushed -- 1.5 us after its last block on one GPU, but 5-8 us once the device maps peer memory (measured on 2 and
+// 8 GPUs at every boundary of the chain, also behind kernels that store nothing remotely).  A consumer can do
+// without the completion when the producer's LAST block publishes "my outputs are written" itself: it stores the step
+// number into a word of device memory (release, gpu scope, after a barrier + fence that order the block's and -- through
+// the block counter -- the grid's writes before it), and every block of the consumer polls that word (acquire) in
+// place of griddepcontrol.wait.  Causality is cumulative, so whatever the producer had acquired (the completion of ITS
+// predecessor, the peers' flags) is ordered before the consumer as well.  The consumer's blocks may be resident and
+// polling while the producer runs; that is safe because a dependent grid is only launched once every block of the
+// primary is resident (they all have executed griddepcontrol.launch_dependents).  word == nullptr: kernel boundary.
+struct ChainWord {
+    unsigned* word;
+    unsigned step;
+};
+#ifndef DDC_HOST_EMU
+// one thread, after a __syncthreads() behind the writes of its block
+__device__ __forceinline__ void chain_signal(const ChainWord& c)
+{
+    if (!c.word)
+        return;
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(c.word), "r"(c.step) : "memory");
+}
+// all threads of a block, first thing.  (Steps only grow and a word belongs to one boundary of one handle, so "==" and
+// ">=" are the same; a word that never comes -- the producer died -- falls back to the kernel boundary.)
+__device__ __forceinline__ void chain_wait(const ChainWord& c)
+{
+    if (!c.word) {
+        pdl_wait();
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = global_ns();
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.word) : "memory");
+            if (v == c.step)
+                break;
+            if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+                pdl_wait();
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+#else
+inline void chain_signal(const ChainWord& c)
+{
+    if (c.word)
+        *c.word = c.step;
+}
+inline void chain_wait(const ChainWord& c)
+{
+    if (c.word && *c.word != c.step) // (the emulated launches run one after the other: the word must be there)
+    {
+        fprintf(stderr, "chain_wait: the producer did not publish its word (%u, step %u)\n", *c.word, c.step);
+        abort();
+    }
+}
+#endif
+
 // Called by the first G threads of a block (thread q talks to rank q).  do_signal: exactly one
 // block per rank sends.
 __device__ __forceinline__ bool peer_barrier(const PeerSync& ps, int stage, unsigned bit, bool do_signal,
@@ -787,21 +849,26 @@ __device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
 // behind the sums (sum[yr_off + 2 g ..], the layout K2 expects of a single global buffer).  A rank that does not
 // show up raises Plan::mismatch to 3; K2 then gives up.
 __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int NX, int yr_off, unsigned* __restrict__ sum,
-    Plan* plan)
+    Plan* plan, int early /* the flags stand in for the completion of the mask scan (see ChainWord) */,
+    unsigned* __restrict__ done /* block counter, zero between steps */, ChainWord next)
 {
+    __shared__ int s_last;
     pdl_trigger();
-    pdl_wait(); // this rank's mask scan is complete
+    if (!early)
+        pdl_wait(); // this rank's mask scan is complete
     bool ok = true;
     unsigned seen;
     if ((int)threadIdx.x < ps.G)
         ok = peer_wait(ps, 0, &seen);
-    if (__syncthreads_or(!ok)) {
+    const bool timed_out = __syncthreads_or(!ok);
+    if (timed_out) {
+        if (early)
+            pdl_wait();
         if (threadIdx.x == 0)
             atomicMax(&plan->mismatch, 3);
-        return;
     }
     const int c = blockIdx.x * 1024 + threadIdx.x * 4;
-    if (c < yr_off) {
+    if (!timed_out && c < yr_off) {
         uint4 acc = make_uint4(0u, 0u, 0u, 0u);
         for (int g0 = 0; g0 < pc.n; g0 += 8) {
             uint4 t[8];
@@ -818,11 +885,23 @@ __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int 
         }
         *reinterpret_cast<uint4*>(sum + c) = acc; // (elements at and beyond NX are 0: load_slot4)
     }
-    if (blockIdx.x == 0 && (int)threadIdx.x < pc.n) {
+    if (!timed_out && blockIdx.x == 0 && (int)threadIdx.x < pc.n) {
         const int g = threadIdx.x;
         const unsigned* src = pc.col[g] + yr_off + 2 * g;
         sum[yr_off + 2 * g] = __ldcg(src);
         sum[yr_off + 2 * g + 1] = __ldcg(src + 1);
+    }
+    if (!next.word)
+        return;
+    // the last block to finish tells the x-cut block that the sums are in place
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1u;
+        if (s_last) {
+            *done = 0u;
+            chain_signal(next);
+        }
     }
 }
 
@@ -843,7 +922,8 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     int yr_off, int G, int aix, int aiy, Plan* plan, StripTable st, BoxTable bx, long long* loads, long long* loadmm,
     DevScalars* sc, unsigned* own_col /* this rank's column counts: reset here once they are consumed */,
     int dbg, Plan* host_plan, int presummed /* k_sum_cols ran: pc is ONE buffer of global counts */,
-    int reset_own /* put this rank's column counts back to zero here (else: the labelling kernel does it) */)
+    int reset_own /* put this rank's column counts back to zero here (else: the labelling kernel does it) */,
+    ChainWord prev /* published by k_sum_cols */, ChainWord next /* polled by the row-count kernel */)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
@@ -851,9 +931,12 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     unsigned* pfx = SMEM ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
     pdl_trigger(); // the strip row-count kernel may become resident
-    pdl_wait(); // the mask scan (and k_sum_cols) is complete
+    chain_wait(prev); // the mask scan (and k_sum_cols) is complete
     if (presummed && plan->mismatch == 3) { // a rank did not show up
         publish_plan(plan, host_plan);
+        __syncthreads();
+        if (tid == 0)
+            chain_signal(next);
         return;
     }
     if (tid == 0) {
@@ -878,6 +961,9 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
                 plan->mismatch = 3;
             __syncthreads();
             publish_plan(plan, host_plan);
+            __syncthreads();
+            if (tid == 0)
+                chain_signal(next);
             return;
         }
     }
@@ -1028,6 +1114,11 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         __syncthreads(); //   the host reads the real plan from its pinned copy and runs the step again
         publish_plan(plan, host_plan);
     }
+    if (next.word) { // strip table, leaf boxes and plan are written: the row-count kernel's blocks may go
+        __syncthreads();
+        if (tid == 0)
+            chain_signal(next);
+    }
 }
 
 // strip of every column (read by the labelling kernel), for decompositions WITHOUT y levels; with y levels K4
@@ -1114,13 +1205,15 @@ template <typename CT /* uint16_t when NX < 65536, else unsigned */>
 __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ bits, int NB, int rows,
     const int* __restrict__ st_x0, const int* __restrict__ st_x1, const int* __restrict__ st_p0,
     const Plan* __restrict__ plan, int Scap, PeerPush out, int Rmax, PeerSync ps, unsigned* __restrict__ done,
-    unsigned long long* dbg)
+    unsigned long long* dbg, ChainWord prev /* published by the x-cut block */)
 {
     __shared__ int s_last;
     pdl_trigger();
-    pdl_wait();
-    if (plan->mismatch)
+    chain_wait(prev);
+    if (plan->mismatch) { // (the flag is raised all the same: the y-cut kernel may wait for it before it looks at the plan)
+        rows_pushed(ps, done, gridDim.x * gridDim.y, &s_last);
         return;
+    }
     if (threadIdx.x == 0)
         stamp_first(dbg, TS_ROWS);
     const int S = plan->S;
@@ -1168,14 +1261,17 @@ __host__ __device__ inline size_t strip_scan_smem_words(int NG, int S, int K)
 template <typename CT, int K, bool FULL>
 __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restrict__ bits, int NB, int NX, int rows,
     const int* __restrict__ st_x0, const int* __restrict__ st_p0, const Plan* __restrict__ plan, int Scap,
-    PeerPush out, int Rmax, PeerSync ps, unsigned* __restrict__ done, unsigned long long* dbg)
+    PeerPush out, int Rmax, PeerSync ps, unsigned* __restrict__ done, unsigned long long* dbg,
+    ChainWord prev /* published by the x-cut block */)
 {
     DDC_DYN_SHARED(int, sm_scan);
     __shared__ int s_last;
     pdl_trigger();
-    pdl_wait();
-    if (plan->mismatch)
+    chain_wait(prev);
+    if (plan->mismatch) { // (the flag is raised all the same: the y-cut kernel may wait for it before it looks at the plan)
+        rows_pushed(ps, done, gridDim.x, &s_last);
         return;
+    }
     if (threadIdx.x == 0)
         stamp_first(dbg, TS_ROWS);
     static_assert(!FULL || K == 1, "FULL holds one row per warp in registers");
@@ -1430,12 +1526,31 @@ template <typename CT, bool SMEM>
 __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLayout rl, int NY, StripTable st,
     unsigned* pfx_g, BoxTable bx, long long* loads, long long* loadmm, Plan* plan, int* __restrict__ strip_of_col,
     int dbg, BoxGate gate, int* __restrict__ part_at /* [S][nchunk]: the part of a strip owning row 32 j (PartAt) */,
-    int nchunk)
+    int nchunk, int early /* the flags of exchange step 2 stand in for the completion of the row-count kernel */)
 {
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
     pdl_trigger(); // the labelling kernel may become resident
-    pdl_wait(); // the strip row-count kernel (and with it everything before) is complete
+    // Flags instead of a kernel boundary: a kernel that has stored into peer-mapped memory completes late -- the grid
+    // is only done once every posted NVLink store is acknowledged -- and its successor in the stream starts 6-8 us
+    // after its last block instead of 1.5 us.  This kernel needs nothing from that completion that the flags do not
+    // give: this rank's own flag is raised by the last block of ITS row-count kernel (release, cumulative over the
+    // block counter), which ran after the x-cut kernel had completed, so acquiring all G flags orders every input of
+    // this kernel before it.  (The blocks may then be resident, polling, while the row counts are still written.)
+    if (ps.enabled && early) {
+        bool ok = true;
+        unsigned seen;
+        if (threadIdx.x < ps.G)
+            ok = peer_wait(ps, 1, &seen);
+        if (__syncthreads_or(!ok)) {
+            pdl_wait();
+            if (threadIdx.x == 0)
+                plan->mismatch = 3;
+            boxes_ready(gate);
+            return;
+        }
+    } else
+        pdl_wait(); // the strip row-count kernel (and with it everything before) is complete
     // everything the block needs to know about its first strip is requested at once: one trip to L2 instead of a chain
     // of four (mismatch -> S -> p0 -> x0) in front of the row counts
     const int mism = plan->mismatch, S = *st.S, ylevels = plan->iy;
@@ -1458,7 +1573,7 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
             strip_of_col[x] = s;
     }
     // exchange step 2: every rank's strip row counts are written (the last block of its row-count kernel said so)
-    if (ps.enabled) {
+    if (ps.enabled && !early) {
         bool ok = true;
         unsigned seen;
         if (threadIdx.x < ps.G)
@@ -1803,6 +1918,7 @@ struct LabelEnd {
     PartAt part_at; // the row -> part table K4 left (table == nullptr: none)
     unsigned* reset_col; // != nullptr: this rank's column-count slot, consumed by k_sum_cols: zeroed here for the next step
     int reset_n, yr_off;
+    ChainWord prev; // the gate word the last block of K4 writes (boxes_ready), polled instead of the kernel boundary
 };
 
 template <bool VEC, bool WRITE>
@@ -1812,7 +1928,7 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
     NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc, Plan* __restrict__ plan, LabelEnd fin)
 {
     __shared__ int s_changed, s_last;
-    pdl_wait();
+    chain_wait(fin.prev);
     if (plan->mismatch) { // the host runs the step again with the real plan (or reports the time-out)
         if (fin.fuse && blockIdx.x == 0 && blockIdx.y == 0)
             publish_plan(plan, fin.host_plan);

@@ -73,6 +73,7 @@ struct Rank {
     std::vector<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
     DevScalars sc {};
     unsigned gate_word = 0;
+    unsigned chain_words[2] = { 0u, 0u }; // k_sum_cols -> K2, K2 -> K3 (ChainWord)
     Plan plan {}, host_plan {};
 };
 
@@ -110,7 +111,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const bool x_smem = xneed + 1024 <= (size_t)opt.smem_limit, y_smem = yneed + 1024 <= (size_t)opt.smem_limit;
     const int ygrid = std::max(1, std::min(Scap, 148 * 2));
     const int gridx = (NG + 7) / 8;
-    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, ndone = d_ycuts + 1; // ddc_api.cu: the "last block" counters
+    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, d_sum = d_ycuts + 1, ndone = d_sum + 1; // ddc_api.cu: the "last block" counters
     const NaiveParams nv = naive_params(P, NX, NY);
     const int nchunk = (NY + 31) / 32;
     const int par = (int)(step & 1u);
@@ -203,6 +204,10 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         for (Rank& r : R)
             std::copy(sum.begin(), sum.end(), colslot(r, r.rank));
     }
+    // every other step polls words in place of the kernel boundaries, as DDC_EARLY does on the device
+    const bool chained = (step & 1u) != 0u;
+    const ChainWord w_none { nullptr, 0u };
+    auto w_strips_of = [&](Rank& r) { return chained && ycuts ? ChainWord { &r.chain_words[1], step } : w_none; };
     // ---- K2: x cuts ----
     for (Rank& r : R) {
         StripTable st;
@@ -215,9 +220,12 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         for (int q = 0; q < G; q++)
             pc.col[q] = colslot(r, p2p ? q : r.rank);
         PeerSync ps = sync_of(r);
+        const ChainWord w_sum = chained && p2p ? ChainWord { &r.chain_words[0], step } : w_none;
+        const ChainWord w_strips = w_strips_of(r);
         if (p2p) { // the ranks' slots summed by a grid of blocks first (k_sum_cols), K2 reads one buffer
             r.colsum.assign((size_t)ncol + 4, 0xdeadbeefu);
-            LAUNCH(Dim3(gridx), Dim3(256), 0, k_sum_cols(pc, ps, NX, yr_off, r.colsum.data(), &r.plan));
+            LAUNCH(Dim3(gridx), Dim3(256), 0,
+                k_sum_cols(pc, ps, NX, yr_off, r.colsum.data(), &r.plan, chained ? 1 : 0, r.done.data() + d_sum, w_sum));
             pc = PeerCols {};
             pc.col[0] = r.colsum.data();
             pc.n = 1;
@@ -226,11 +234,11 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         if (x_smem)
             LAUNCH(Dim3(1), Dim3(1024), xneed,
                 k_xcuts<true>(pc, ps, NX, NY, P, nullptr, yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(), r.loadmm.data(),
-                    &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0, (p2p && r.rows > 0) ? 0 : 1));
+                    &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0, (p2p && r.rows > 0) ? 0 : 1, w_sum, w_strips));
         else
             LAUNCH(Dim3(1), Dim3(1024), LEVEL_NODES_BYTES,
                 k_xcuts<false>(pc, ps, NX, NY, P, r.colpfx.data(), yr_off, G, aix, aiy, &r.plan, st, bx, r.loads.data(),
-                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0, (p2p && r.rows > 0) ? 0 : 1));
+                    r.loadmm.data(), &r.sc, colslot(r, r.rank), 0, &r.host_plan, p2p ? 1 : 0, (p2p && r.rows > 0) ? 0 : 1, w_sum, w_strips));
         if (!ycuts) // with y levels K4 paints the column -> strip table
             LAUNCH(Dim3(std::max(1, std::min((Scap + 7) / 8, 148 * 4))), Dim3(256), 0,
                 k_paint_strips(st, &r.plan, r.strip_of_col.data()));
@@ -261,7 +269,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
 #define SCAN(CT, KK, FF)                                                                           \
     LAUNCH(grid, Dim3(256), scan_smem,                                                             \
         (k_strip_rows_scan<CT, KK, FF>(r.bits.data(), NB, NX, r.rows, st.x0, st.p0, &r.plan, Scap, out, Rmax, ps,      \
-            r.done.data() + d_rows, nullptr)))
+            r.done.data() + d_rows, nullptr, w_strips_of(r))))
                 if (narrow) {
                     if (K == 4)
                         SCAN(uint16_t, 4, false);
@@ -288,11 +296,11 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                 if (narrow)
                     LAUNCH(grid, Dim3(256), 0,
                         k_strip_rows<uint16_t>(r.bits.data(), NB, r.rows, st.x0, st.x1, st.p0, &r.plan, Scap, out, Rmax, ps,
-                            r.done.data() + d_rows, nullptr));
+                            r.done.data() + d_rows, nullptr, w_strips_of(r)));
                 else
                     LAUNCH(grid, Dim3(256), 0,
                         k_strip_rows<unsigned>(r.bits.data(), NB, r.rows, st.x0, st.x1, st.p0, &r.plan, Scap, out, Rmax, ps,
-                            r.done.data() + d_rows, nullptr));
+                            r.done.data() + d_rows, nullptr, w_strips_of(r)));
             }
         }
         std::vector<std::vector<unsigned>> gathered;
@@ -324,7 +332,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
 #define YCUTS(CT, SM)                                                                              \
     LAUNCH(Dim3(ygrid), Dim3(1024), SM ? yneed : LEVEL_NODES_BYTES,                                                \
         (k_ycuts<CT, SM>(pr, ps, rl, NY, st, r.ypfx.data(), bx, r.loads.data(), r.loadmm.data(), &r.plan,                    \
-            r.strip_of_col.data(), 0, gate, r.part_at.data(), nchunk)))
+            r.strip_of_col.data(), 0, gate, r.part_at.data(), nchunk, p2p ? (int)(step & 1u) : 0)))
             if (narrow) {
                 if (y_smem)
                     YCUTS(uint16_t, true);
@@ -378,6 +386,8 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             fin.reset_col = p2p ? colslot(r, r.rank) : nullptr;
             fin.reset_n = ncol;
             fin.yr_off = yr_off;
+            if (chained && ycuts)
+                fin.prev = ChainWord { &r.gate_word, step };
             if (vecp)
                 LAUNCH(grid, Dim3(256), 0,
                     (k_label<true, true>(r.bits.data(), NX, r.rows, r.y_begin, NB, rpc, r.strip_of_col.data(), st.p0, bx.y0,

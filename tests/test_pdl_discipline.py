@@ -2,7 +2,8 @@
 
 A kernel launched with the PDL attribute may start while the kernel before it in the stream is still running; it
 is only correct if every thread executes griddepcontrol.wait (pdl_wait()) before it touches global memory -- and
-that holds transitively only if EVERY kernel of the chain does so on every path.  The CPU emulation cannot see a
+that holds transitively only if EVERY kernel of the chain does so on every path (or, instead, acquires a flag / word
+that the previous kernel's last block released once its outputs were written: chain_wait(), the peer flags).  The CPU emulation cannot see a
 violation (its launches run one after the other), a GPU run only sometimes: round 2 shipped k_paint_strips without
 the wait for one GPU run and got stale strip tables.  So the rule is checked on the sources: every kernel that
 ddc_api.cu launches with a `pdl` argument that can be true calls pdl_wait() before its first `if (...) return`.
@@ -60,8 +61,11 @@ def test_every_pdl_launched_kernel_waits_first():
         for name in set(re.findall(r"\bk_\w+", kernel_expr)):
             seen.add(name)
             body = _kernel_body(name)
-            w = body.find("pdl_wait()")
-            assert w >= 0, "%s is launched with PDL but never calls pdl_wait()" % name
+            # chain_wait(word) polls the word the previous kernel's last block publishes and falls back to pdl_wait()
+            # ("flags instead of kernel boundaries")
+            waits = [body.find(w) for w in ("pdl_wait()", "chain_wait(") if w in body]
+            assert waits, "%s is launched with PDL but never calls pdl_wait() / chain_wait()" % name
+            w = min(waits)
             r = re.search(r"\breturn\b", body)
             assert r is None or w < r.start(), "%s can return before pdl_wait(): breaks the transitive completion" % name
             # nothing of global memory before the wait: no pointer dereference / index into a kernel parameter
