@@ -1038,7 +1038,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         w_strips = ChainWord { h->gate.p + 2, h->step };
     if (presum) {
         CUDA_TRY(h, launch_k(k_sum_cols, dim3(gridx), dim3(256), 0, s, pdl, pc, ps, NX, yr_off, h->colcount.p, h->plan.p,
-            pdl && (h->early & 1) ? 1 : 0, h->done.p + d_sum, w_sum));
+            pdl && (h->early & 1) ? 1 : 0, h->done.p + d_sum, w_sum, dbg));
         launches++;
         pc = PeerCols {};
         pc.col[0] = h->colcount.p;
@@ -1313,6 +1313,11 @@ int validate(ddc_handle_t h)
             h->rank, us(11, 12), us(12, 13), us(12, 14), us(12, 0), us(0, 1), us(1, 2), us(2, 3), us(3, 4), us(4, 5),
             us(5, 15), us(15, 16), us(16, 6), us(6, 7), us(7, 8), us(8, 9), (double)t[10] * 1e-3, us(9, 17), us(17, 18),
             us(18, 19), us(11, 19));
+        // when the first block of each kernel was on an SM (before its wait), relative to the end of the scan's row loop
+        fprintf(stderr, "[ddc r%d] resident at (us after the scan's loop): sum %.1f (flags seen %.1f, done %.1f) K2 %.1f rows %.1f "
+                        "K4 %.1f label %.1f | K2 start %.1f rows start %.1f K4 start %.1f label start %.1f\n",
+            h->rank, us(12, TS_RES), us(12, TS_RES + 5), us(12, TS_RES + 6), us(12, TS_RES + 1), us(12, TS_RES + 2),
+            us(12, TS_RES + 3), us(12, TS_RES + 4), us(12, 0), us(12, 15), us(12, 6), us(12, 17));
         fprintf(stderr, "[ddc r%d] K2 levels (thread 0, us):", h->rank);
         for (int l = 0; l + 1 < 8 && t[TS_XLEV + l + 1]; l++)
             fprintf(stderr, " %.2f", us(TS_XLEV + l, TS_XLEV + l + 1));

@@ -60,9 +60,10 @@ struct Plan { // written by K2 (K4 adds iterations), copied into the host's pinn
     //        performed, flag raised          15-16 strip rows: first CTA start, last CTA end
     //  17-19 labelling: first CTA start, last CTA out of its row loop, epilogue done
     //  20-27 K2 thread 0 after each level of its walk    28-35 the same for K4 block 0
-    unsigned long long ts[36];
+    unsigned long long ts[44]; // 36-42: first block of k_sum_cols / K2 / row counts / K4 / labelling kernel on an SM (before its wait),
+                               //        k_sum_cols past the flags, k_sum_cols done
 };
-constexpr int TS_SCAN = 11, TS_ROWS = 15, TS_LABEL = 17, TS_XLEV = 20, TS_YLEV = 28;
+constexpr int TS_SCAN = 11, TS_ROWS = 15, TS_LABEL = 17, TS_XLEV = 20, TS_YLEV = 28, TS_RES = 36;
 
 struct NaiveParams { // Grid.cpp:150-166
     int np0, np1, lx, ly;
@@ -850,10 +851,12 @@ __device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
 // show up raises Plan::mismatch to 3; K2 then gives up.
 __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int NX, int yr_off, unsigned* __restrict__ sum,
     Plan* plan, int early /* the flags stand in for the completion of the mask scan (see ChainWord) */,
-    unsigned* __restrict__ done /* block counter, zero between steps */, ChainWord next)
+    unsigned* __restrict__ done /* block counter, zero between steps */, ChainWord next, unsigned long long* dbg)
 {
     __shared__ int s_last;
     pdl_trigger();
+    if (dbg && threadIdx.x == 0)
+        stamp_first(dbg, TS_RES);
     if (!early)
         pdl_wait(); // this rank's mask scan is complete
     bool ok = true;
@@ -861,6 +864,8 @@ __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int 
     if ((int)threadIdx.x < ps.G)
         ok = peer_wait(ps, 0, &seen);
     const bool timed_out = __syncthreads_or(!ok);
+    if (dbg && threadIdx.x == 0)
+        stamp_first(dbg, TS_RES + 5);
     if (timed_out) {
         if (early)
             pdl_wait();
@@ -891,6 +896,8 @@ __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int 
         sum[yr_off + 2 * g] = __ldcg(src);
         sum[yr_off + 2 * g + 1] = __ldcg(src + 1);
     }
+    if (dbg && threadIdx.x == 0)
+        stamp_last(dbg, TS_RES + 6);
     if (!next.word)
         return;
     // the last block to finish tells the x-cut block that the sums are in place
@@ -931,6 +938,8 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
     unsigned* pfx = SMEM ? smem_dyn : pfx_g;
     const int tid = threadIdx.x;
     pdl_trigger(); // the strip row-count kernel may become resident
+    if (dbg && tid == 0)
+        plan->ts[TS_RES + 1] = global_ns(); // (diagnostic only: the one word written before the wait)
     chain_wait(prev); // the mask scan (and k_sum_cols) is complete
     if (presummed && plan->mismatch == 3) { // a rank did not show up
         publish_plan(plan, host_plan);
@@ -1209,6 +1218,8 @@ __global__ void __launch_bounds__(256) k_strip_rows(const uint8_t* __restrict__ 
 {
     __shared__ int s_last;
     pdl_trigger();
+    if (threadIdx.x == 0)
+        stamp_first(dbg, TS_RES + 2);
     chain_wait(prev);
     if (plan->mismatch) { // (the flag is raised all the same: the y-cut kernel may wait for it before it looks at the plan)
         rows_pushed(ps, done, gridDim.x * gridDim.y, &s_last);
@@ -1267,6 +1278,8 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
     DDC_DYN_SHARED(int, sm_scan);
     __shared__ int s_last;
     pdl_trigger();
+    if (threadIdx.x == 0)
+        stamp_first(dbg, TS_RES + 2);
     chain_wait(prev);
     if (plan->mismatch) { // (the flag is raised all the same: the y-cut kernel may wait for it before it looks at the plan)
         rows_pushed(ps, done, gridDim.x, &s_last);
@@ -1531,6 +1544,8 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     DDC_DYN_SHARED(unsigned, smem_dyn);
     __shared__ unsigned wsum[PFX_WS];
     pdl_trigger(); // the labelling kernel may become resident
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0)
+        plan->ts[TS_RES + 3] = global_ns(); // (diagnostic only)
     // Flags instead of a kernel boundary: a kernel that has stored into peer-mapped memory completes late -- the grid
     // is only done once every posted NVLink store is acknowledged -- and its successor in the stream starts 6-8 us
     // after its last block instead of 1.5 us.  This kernel needs nothing from that completion that the flags do not
@@ -1928,6 +1943,8 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
     NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc, Plan* __restrict__ plan, LabelEnd fin)
 {
     __shared__ int s_changed, s_last;
+    if (threadIdx.x == 0)
+        stamp_first(fin.dbg, TS_RES + 4);
     chain_wait(fin.prev);
     if (plan->mismatch) { // the host runs the step again with the real plan (or reports the time-out)
         if (fin.fuse && blockIdx.x == 0 && blockIdx.y == 0)

@@ -225,7 +225,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
         if (p2p) { // the ranks' slots summed by a grid of blocks first (k_sum_cols), K2 reads one buffer
             r.colsum.assign((size_t)ncol + 4, 0xdeadbeefu);
             LAUNCH(Dim3(gridx), Dim3(256), 0,
-                k_sum_cols(pc, ps, NX, yr_off, r.colsum.data(), &r.plan, chained ? 1 : 0, r.done.data() + d_sum, w_sum));
+                k_sum_cols(pc, ps, NX, yr_off, r.colsum.data(), &r.plan, chained ? 1 : 0, r.done.data() + d_sum, w_sum, nullptr));
             pc = PeerCols {};
             pc.col[0] = r.colsum.data();
             pc.n = 1;
