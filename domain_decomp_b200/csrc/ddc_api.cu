@@ -567,7 +567,10 @@ static void peer_capacity(int nx, int ny, int nparts, int G, size_t* colcap, siz
     const size_t Scap = (size_t)std::min<long long>(nparts, 1LL << std::min(ix, 30));
     const size_t Rmax = ((size_t)ny + G - 1) / G;
     const size_t elems = iy > 0 ? Scap * ((Rmax + 31) & ~(size_t)31) : 0; // whole row blocks (row_count_index)
-    *colcap = ((((size_t)nx + 3) & ~(size_t)3) + 2 * (size_t)G + 4 + 3) & ~(size_t)3;
+    // a slot holds either the rank's own 32-bit counts + the G y-range pairs, or a peer's data + flag words
+    // (ll_word: at most one 8-byte word per column, two for the y-range)
+    const size_t yr_off = ((size_t)nx + 3) & ~(size_t)3;
+    *colcap = (std::max(yr_off + 2 * (size_t)G, 2 * (yr_off + 2)) + 4 + 3) & ~(size_t)3;
     *rowcap = ((nx < 65536 ? (elems + 1) / 2 : elems) + 4 + 3) & ~(size_t)3;
 }
 
@@ -935,7 +938,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
 
     // exchange mode: peer memory when the buffers were exchanged and are large enough, else NCCL
     h->step++;
-    const bool p2p = G > 1 && h->p2p && (size_t)ncol <= h->x_colcap && (!ycuts || rc_words + 4 <= h->x_rowcap);
+    const int col_packed = Rmax < 65536 ? 1 : 0; // a rank's column counts fit 16 bits: two per data + flag word
+    const size_t col_need = std::max<size_t>(ncol, 2 * (ll_column_words(yr_off, col_packed) + 2));
+    const bool p2p = G > 1 && h->p2p && col_need <= h->x_colcap && (!ycuts || rc_words + 4 <= h->x_rowcap);
     if (G > 1 && !p2p && !h->comm)
         return fail(h, DDC_ERR_STATE, "%d ranks but no exchange path: created without a NCCL id and %s", G,
             h->p2p ? "the decomposition exceeds the exported peer buffers" : "no peer buffers imported");
@@ -973,7 +978,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         }
         pc.n = pr.n = push_col.n = push_row.n = G;
         pc.own = h->rank;
-        pc.packed = push_col.packed = Rmax < 65536 ? 1 : 0; // a rank's column counts fit 16 bits
+        pc.packed = push_col.packed = col_packed;
     } else {
         pc.col[0] = colcount;
         pc.n = pr.n = 1;

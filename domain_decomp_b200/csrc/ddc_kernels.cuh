@@ -120,14 +120,29 @@ __device__ __forceinline__ unsigned long long global_ns()
 }
 // thread q of a block tells rank q that this rank has reached `stage` of the current step.  The
 // caller makes sure (fences + barriers) that everything pushed for the stage is ordered before.
+// (st.release.sys is the fence: cumulative over the barriers and block counters the caller went through)
 __device__ __forceinline__ void peer_signal(const PeerSync& ps, int stage, unsigned bit)
 {
     const int q = threadIdx.x;
-    __threadfence_system();
     unsigned* dst = ps.flags[q] + stage * MAX_PEERS + ps.rank;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(2u * ps.step + bit) : "memory");
 }
+// the same for a stage whose flag IS the message (exchange step 3: the `changes` bit): nothing was pushed before it, so
+// nothing has to be ordered before it -- the labelling kernel's last block does not wait for a round trip over NVLink
+__device__ __forceinline__ void peer_signal_relaxed(const PeerSync& ps, int stage, unsigned bit)
+{
+    const int q = threadIdx.x;
+    unsigned* dst = ps.flags[q] + stage * MAX_PEERS + ps.rank;
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(2u * ps.step + bit) : "memory");
+}
 // thread q waits until rank q has reached `stage`.  Returns false on timeout; *seen = its flag value.
+// this rank's own flag of a stage, for a consumer on the same GPU (one thread)
+__device__ __forceinline__ void peer_signal_local(const PeerSync& ps, int stage)
+{
+    __threadfence();
+    unsigned* dst = ps.flags[ps.rank] + stage * MAX_PEERS + ps.rank;
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(dst), "r"(2u * ps.step) : "memory");
+}
 __device__ __forceinline__ bool peer_wait(const PeerSync& ps, int stage, unsigned* seen)
 {
     const int q = threadIdx.x;
@@ -156,6 +171,11 @@ inline void peer_signal(const PeerSync& ps, int stage, unsigned bit)
 {
     ps.flags[threadIdx.x][stage * MAX_PEERS + ps.rank] = 2u * ps.step + bit;
 }
+inline void peer_signal_relaxed(const PeerSync& ps, int stage, unsigned bit) { peer_signal(ps, stage, bit); }
+inline void peer_signal_local(const PeerSync& ps, int stage)
+{
+    ps.flags[ps.rank][stage * MAX_PEERS + ps.rank] = 2u * ps.step;
+}
 inline bool peer_wait(const PeerSync& ps, int stage, unsigned* seen)
 {
     const unsigned v = ps.flags[ps.rank][stage * MAX_PEERS + threadIdx.x];
@@ -163,6 +183,74 @@ inline bool peer_wait(const PeerSync& ps, int stage, unsigned* seen)
     return v >= 2u * ps.step;
 }
 #endif
+// Exchange step 1 travels as "data + flag" words (the LL protocol of collective libraries): every 8-byte word a rank
+// stores into a peer's slot carries 32 bits of counts and, in its upper half, the step number.  An aligned 8-byte
+// store is single-copy atomic, so the consumer polls the word itself -- data and "it has arrived" come together, and
+// the producer needs no fence.sys before a separate flag (two of them sat on the critical path of every step: one
+// per column block, one before the flag -- 10-14 us between the end of the scan and the flag on 8 GPUs, now the one-way
+// latency of a store).  Steps only grow and a slot alternates by step parity, so a stale word is simply "not yet".
+//   packed (every rank holds < 65536 rows): word i = { count[2 i] | count[2 i + 1] << 16, step }
+//   else:                                   word i = { count[i], step }
+//   behind the nw column words: the rank's dot y-range, { -(first ocean row), step } and { last ocean row, step }
+__host__ __device__ __forceinline__ unsigned long long ll_word(unsigned data, unsigned step)
+{
+    return (unsigned long long)data | ((unsigned long long)step << 32);
+}
+__host__ __device__ __forceinline__ size_t ll_column_words(int yr_off, int packed) // yr_off = NX rounded up to 4
+{
+    return packed ? (size_t)yr_off / 2 : (size_t)yr_off;
+}
+#ifndef DDC_HOST_EMU
+__device__ __forceinline__ void ll_store2(unsigned long long* dst, unsigned long long a, unsigned long long b)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ll_store1(unsigned long long* dst, unsigned long long a)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(a) : "memory");
+}
+__device__ __forceinline__ void ll_load2(const unsigned long long* src, unsigned long long& a, unsigned long long& b)
+{
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load1(const unsigned long long* src)
+{
+    unsigned long long a;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
+    return a;
+}
+#else
+inline void ll_store2(unsigned long long* dst, unsigned long long a, unsigned long long b)
+{
+    dst[0] = a;
+    dst[1] = b;
+}
+inline void ll_store1(unsigned long long* dst, unsigned long long a) { *dst = a; }
+inline void ll_load2(const unsigned long long* src, unsigned long long& a, unsigned long long& b)
+{
+    a = src[0];
+    b = src[1];
+}
+inline unsigned long long ll_load1(const unsigned long long* src) { return *src; }
+#endif
+// two / one words whose step halves must both read `step`; false: timed out
+__device__ __forceinline__ bool ll_wait2(const unsigned long long* src, unsigned step, unsigned& d0, unsigned& d1)
+{
+    unsigned long long a, b;
+    ll_load2(src, a, b);
+    if ((unsigned)(a >> 32) != step || (unsigned)(b >> 32) != step) {
+        const unsigned long long t0 = global_ns();
+        do {
+            if (global_ns() - t0 > PEER_TIMEOUT_NS)
+                return false;
+            ll_load2(src, a, b);
+        } while ((unsigned)(a >> 32) != step || (unsigned)(b >> 32) != step);
+    }
+    d0 = (unsigned)a;
+    d1 = (unsigned)b;
+    return true;
+}
+
 // Programmatic dependent launch: the kernels of a step are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel may become resident while its predecessor
 // in the stream is still running.  pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as every CTA
@@ -660,11 +748,11 @@ __global__ void __launch_bounds__(256, 4) k_scan_mask(const int32_t* __restrict_
         stamp_last(dbg, TS_SCAN + 1);
     if (push.n <= 1)
         return;
-    // Exchange step 1 (several GPUs): the LAST CTA of a column block to finish pushes the block's
-    // final counts into this rank's slot of every peer's exchange buffer, and the last column
-    // block to have done so pushes the dot y-range and raises this rank's flag at every peer --
-    // so the counts travel while the rest of the scan is still running and the x-cut kernel of
-    // every rank finds all of them in its own memory.
+    // Exchange step 1 (several GPUs): the LAST CTA of a column block to finish pushes the block's final counts into
+    // this rank's slot of every peer's exchange buffer as data + flag words (ll_word: no fence, the peers poll the
+    // words themselves) -- so the counts travel while the rest of the scan is still running.  The last column block
+    // to have done so sends the dot y-range the same way and tells this rank's own summing kernel (a flag in local
+    // memory) that the local counts are final.
     __syncthreads(); // every thread's atomics are issued ...
     if (threadIdx.x == 0) {
         __threadfence(); // ... and performed (cumulative over the barrier) before this CTA is counted as done
@@ -678,36 +766,39 @@ __global__ void __launch_bounds__(256, 4) k_scan_mask(const int32_t* __restrict_
     const int c = blockIdx.x * 1024 + threadIdx.x * 4;
     if (c < yr_off) {
         const uint4 v = __ldcg(reinterpret_cast<const uint4*>(colcount + c));
-        if (push.packed) { // a rank holds < 65536 rows: its counts travel (and are read) as 16-bit values
-            const uint2 w = make_uint2(v.x | (v.y << 16), v.z | (v.w << 16));
+        if (push.packed) { // a rank holds < 65536 rows: two counts per word
+            const unsigned long long w0 = ll_word(v.x | (v.y << 16), ps.step), w1 = ll_word(v.z | (v.w << 16), ps.step);
             for (int q = 0; q < push.n; q++)
                 if (q != push.rank)
-                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(push.dst[q]) + c) = w;
+                    ll_store2(reinterpret_cast<unsigned long long*>(push.dst[q]) + (c >> 1), w0, w1);
         } else {
+            const unsigned long long w0 = ll_word(v.x, ps.step), w1 = ll_word(v.y, ps.step), w2 = ll_word(v.z, ps.step),
+                                     w3 = ll_word(v.w, ps.step);
             for (int q = 0; q < push.n; q++)
-                if (q != push.rank)
-                    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned*>(push.dst[q]) + c) = v;
+                if (q != push.rank) {
+                    unsigned long long* d = reinterpret_cast<unsigned long long*>(push.dst[q]) + c;
+                    ll_store2(d, w0, w1);
+                    ll_store2(d + 2, w2, w3);
+                }
         }
     }
-    __syncthreads();
+    __syncthreads(); // (s_last is about to be written again)
     if (threadIdx.x == 0) {
-        __threadfence_system(); // the block's stores are performed at the peers before it is counted
         stamp_last(dbg, TS_SCAN + 2);
-        s_last = atomicAdd(&done[gridDim.x], 1u) == gridDim.x - 1;
+        s_last = atomicAdd(&done[gridDim.x], 1u) == gridDim.x - 1; // (this block has seen all CTAs of its columns)
         if (s_last)
             __threadfence();
     }
     __syncthreads();
     if (!s_last)
         return;
-    if (threadIdx.x < push.n) {
+    if ((int)threadIdx.x < push.n) {
         const int q = threadIdx.x;
         if (q != push.rank) {
-            unsigned* d = reinterpret_cast<unsigned*>(push.dst[q]) + yr_off + 2 * push.rank;
-            d[0] = (unsigned)__ldcg(yr);
-            d[1] = (unsigned)__ldcg(yr + 1);
-        }
-        peer_signal(ps, 0, 0u); // fence.sys, then the flag: the pushes of all blocks come first
+            unsigned long long* d = reinterpret_cast<unsigned long long*>(push.dst[q]) + ll_column_words(yr_off, push.packed);
+            ll_store2(d, ll_word((unsigned)__ldcg(yr), ps.step), ll_word((unsigned)__ldcg(yr + 1), ps.step));
+        } else
+            peer_signal_local(ps, 0); // this rank's own counts: read in place by its summing kernel
         if (threadIdx.x == 0)
             stamp_last(dbg, TS_SCAN + 3);
     }
@@ -846,11 +937,12 @@ __device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
 // pushed into this rank's buffer are summed by a GRID of blocks (one per 1024 columns, every thread requesting the
 // G loads of its 4 columns together), so that the single x-cut block afterwards reads ONE buffer, as on one GPU:
 // summing the slots itself cost that block G dependent round trips to L2 -- 24 us of a 58 us kernel on 8 GPUs.
-// Every block waits for the flags in its prologue (local memory); block 0 also gathers the ranks' dot y-ranges
-// behind the sums (sum[yr_off + 2 g ..], the layout K2 expects of a single global buffer).  A rank that does not
-// show up raises Plan::mismatch to 3; K2 then gives up.
+// The peers' slots hold data + flag words (ll_word): a thread polls exactly the words it sums; this rank's own
+// counts are plain 32-bit values in local memory, final once its scan has raised the local stage-0 flag.  Block 0
+// also gathers the ranks' dot y-ranges behind the sums (sum[yr_off + 2 g ..], the layout K2 expects of a single
+// global buffer).  A rank that does not show up raises Plan::mismatch to 3; K2 then gives up.
 __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int NX, int yr_off, unsigned* __restrict__ sum,
-    Plan* plan, int early /* the flags stand in for the completion of the mask scan (see ChainWord) */,
+    Plan* plan, int early /* the local flag stands in for the completion of the mask scan (see ChainWord) */,
     unsigned* __restrict__ done /* block counter, zero between steps */, ChainWord next, unsigned long long* dbg)
 {
     __shared__ int s_last;
@@ -860,41 +952,61 @@ __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int 
     if (!early)
         pdl_wait(); // this rank's mask scan is complete
     bool ok = true;
-    unsigned seen;
-    if ((int)threadIdx.x < ps.G)
+    if ((int)threadIdx.x == ps.rank) { // (only the own flag: the peers' words are polled one by one below)
+        unsigned seen;
         ok = peer_wait(ps, 0, &seen);
-    const bool timed_out = __syncthreads_or(!ok);
+    }
+    bool timed_out = __syncthreads_or(!ok);
     if (dbg && threadIdx.x == 0)
         stamp_first(dbg, TS_RES + 5);
+    const int c = blockIdx.x * 1024 + threadIdx.x * 4;
+    if (!timed_out && c < yr_off) {
+        uint4 acc = __ldcg(reinterpret_cast<const uint4*>(pc.col[pc.own] + c)); // (zero between NX and yr_off)
+        for (int g = 0; g < pc.n; g++) {
+            if (g == pc.own)
+                continue;
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(pc.col[g]);
+            unsigned d0, d1, d2, d3;
+            if (pc.packed) {
+                if (!ll_wait2(src + (c >> 1), ps.step, d0, d1)) {
+                    ok = false;
+                    break;
+                }
+                acc.x += d0 & 0xffffu;
+                acc.y += d0 >> 16;
+                acc.z += d1 & 0xffffu;
+                acc.w += d1 >> 16;
+            } else {
+                if (!ll_wait2(src + c, ps.step, d0, d1) || !ll_wait2(src + c + 2, ps.step, d2, d3)) {
+                    ok = false;
+                    break;
+                }
+                acc.x += d0;
+                acc.y += d1;
+                acc.z += d2;
+                acc.w += d3;
+            }
+        }
+        *reinterpret_cast<uint4*>(sum + c) = acc;
+    }
+    if (!timed_out && blockIdx.x == 0 && (int)threadIdx.x < pc.n) {
+        const int g = threadIdx.x;
+        unsigned a = 0u, b = 0u;
+        if (g == pc.own) {
+            a = __ldcg(pc.col[g] + yr_off + 2 * g);
+            b = __ldcg(pc.col[g] + yr_off + 2 * g + 1);
+        } else if (!ll_wait2(reinterpret_cast<const unsigned long long*>(pc.col[g]) + ll_column_words(yr_off, pc.packed), ps.step,
+                       a, b))
+            ok = false;
+        sum[yr_off + 2 * g] = a;
+        sum[yr_off + 2 * g + 1] = b;
+    }
+    timed_out = __syncthreads_or(!ok) || timed_out;
     if (timed_out) {
         if (early)
             pdl_wait();
         if (threadIdx.x == 0)
             atomicMax(&plan->mismatch, 3);
-    }
-    const int c = blockIdx.x * 1024 + threadIdx.x * 4;
-    if (!timed_out && c < yr_off) {
-        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-        for (int g0 = 0; g0 < pc.n; g0 += 8) {
-            uint4 t[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                t[k] = g0 + k < pc.n ? load_slot4(pc, g0 + k, c, NX) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                acc.x += t[k].x;
-                acc.y += t[k].y;
-                acc.z += t[k].z;
-                acc.w += t[k].w;
-            }
-        }
-        *reinterpret_cast<uint4*>(sum + c) = acc; // (elements at and beyond NX are 0: load_slot4)
-    }
-    if (!timed_out && blockIdx.x == 0 && (int)threadIdx.x < pc.n) {
-        const int g = threadIdx.x;
-        const unsigned* src = pc.col[g] + yr_off + 2 * g;
-        sum[yr_off + 2 * g] = __ldcg(src);
-        sum[yr_off + 2 * g + 1] = __ldcg(src + 1);
     }
     if (dbg && threadIdx.x == 0)
         stamp_last(dbg, TS_RES + 6);
@@ -1980,7 +2092,7 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
         return;
     const int changes = s_changed;
     if (fin.ps.enabled && (int)threadIdx.x < fin.ps.G)
-        peer_signal(fin.ps, 2, changes ? 1u : 0u);
+        peer_signal_relaxed(fin.ps, 2, changes ? 1u : 0u);
     if (threadIdx.x == 0) {
         *fin.counter = 0ull;
         sc->changes = changes;

@@ -105,7 +105,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const size_t rc_elems = (size_t)Scap * (((size_t)Rmax + 31) & ~(size_t)31);
     const size_t rc_words = narrow ? (rc_elems + 1) / 2 : rc_elems;
     const size_t rank_stride = narrow ? rc_words * 2 : rc_words;
-    const size_t colcap = (((size_t)ncol + 3) & ~(size_t)3), rowcap = (rc_words + 4 + 3) & ~(size_t)3;
+    const size_t colcap = ((std::max<size_t>(ncol, 2 * ((size_t)yr_off + 2)) + 3) & ~(size_t)3), rowcap = (rc_words + 4 + 3) & ~(size_t)3;
     const size_t xneed = sizeof(unsigned) * ((((size_t)NX + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NX)) + LEVEL_NODES_BYTES;
     const size_t yneed = sizeof(unsigned) * ((((size_t)NY + 1 + 3) & ~(size_t)3) + hist_bitmap_words(NY)) + LEVEL_NODES_BYTES;
     const bool x_smem = xneed + 1024 <= (size_t)opt.smem_limit, y_smem = yneed + 1024 <= (size_t)opt.smem_limit;

@@ -143,6 +143,16 @@ def test_histograms_of_several_sub_tiles_and_tiles(oracle, nx, ny, P, ranks, kw)
     assert_same(d, oracle.partition(mask, P, True, False, use_hist=True), (nx, ny, P, ranks))
 
 
+def test_column_counts_travel_as_data_and_flag_words(oracle):
+    """exchange step 1 (ll_word): two 16-bit counts per word while every rank holds < 65536 rows, one 32-bit count per
+    word beyond that; several column blocks (every one pushes its own words), columns that are not a multiple of 4"""
+    from domain_decomp_b200 import capi
+    for nx, ny, P, ranks in ((12, 131080, 3, 2), (2501, 40, 6, 3), (1030, 17, 4, 2)):
+        mask = capi.generate_mask_host(nx, ny, 5, 0.4)
+        d, _ = oracle.emu_partition(mask, P, True, False, ranks=ranks)
+        assert_same(d, oracle.partition(mask, P, True, False, use_hist=True), (nx, ny, P, ranks))
+
+
 def test_results_do_not_depend_on_the_schedule(oracle, monkeypatch):
     """the emulation can run the blocks of a grid in a random order and the threads of a block in a new random order
     every scheduling round (DDC_EMU_SCHED_SEED): a missing barrier, an assumption about block order or about
