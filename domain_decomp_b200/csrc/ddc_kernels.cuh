@@ -962,30 +962,54 @@ __global__ void __launch_bounds__(256) k_sum_cols(PeerCols pc, PeerSync ps, int 
     const int c = blockIdx.x * 1024 + threadIdx.x * 4;
     if (!timed_out && c < yr_off) {
         uint4 acc = __ldcg(reinterpret_cast<const uint4*>(pc.col[pc.own] + c)); // (zero between NX and yr_off)
-        for (int g = 0; g < pc.n; g++) {
-            if (g == pc.own)
-                continue;
-            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(pc.col[g]);
-            unsigned d0, d1, d2, d3;
-            if (pc.packed) {
-                if (!ll_wait2(src + (c >> 1), ps.step, d0, d1)) {
-                    ok = false;
-                    break;
+        // all peers' words are requested together (one trip to L2); only a word that has not arrived is polled
+        for (int g0 = 0; g0 < pc.n; g0 += 8) {
+            unsigned long long w[8][4];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int g = g0 + k;
+                if (g >= pc.n || g == pc.own)
+                    continue;
+                const unsigned long long* src = reinterpret_cast<const unsigned long long*>(pc.col[g]);
+                if (pc.packed)
+                    ll_load2(src + (c >> 1), w[k][0], w[k][1]);
+                else {
+                    ll_load2(src + c, w[k][0], w[k][1]);
+                    ll_load2(src + c + 2, w[k][2], w[k][3]);
                 }
-                acc.x += d0 & 0xffffu;
-                acc.y += d0 >> 16;
-                acc.z += d1 & 0xffffu;
-                acc.w += d1 >> 16;
-            } else {
-                if (!ll_wait2(src + c, ps.step, d0, d1) || !ll_wait2(src + c + 2, ps.step, d2, d3)) {
-                    ok = false;
-                    break;
-                }
-                acc.x += d0;
-                acc.y += d1;
-                acc.z += d2;
-                acc.w += d3;
             }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int g = g0 + k;
+                if (g >= pc.n || g == pc.own)
+                    continue;
+                const unsigned long long* src = reinterpret_cast<const unsigned long long*>(pc.col[g]);
+                unsigned d0 = (unsigned)w[k][0], d1 = (unsigned)w[k][1], d2 = 0u, d3 = 0u;
+                if (pc.packed) {
+                    if (((unsigned)(w[k][0] >> 32) != ps.step || (unsigned)(w[k][1] >> 32) != ps.step)
+                        && !ll_wait2(src + (c >> 1), ps.step, d0, d1))
+                        ok = false;
+                    acc.x += d0 & 0xffffu;
+                    acc.y += d0 >> 16;
+                    acc.z += d1 & 0xffffu;
+                    acc.w += d1 >> 16;
+                } else {
+                    d2 = (unsigned)w[k][2];
+                    d3 = (unsigned)w[k][3];
+                    if (((unsigned)(w[k][0] >> 32) != ps.step || (unsigned)(w[k][1] >> 32) != ps.step)
+                        && !ll_wait2(src + c, ps.step, d0, d1))
+                        ok = false;
+                    if (((unsigned)(w[k][2] >> 32) != ps.step || (unsigned)(w[k][3] >> 32) != ps.step)
+                        && !ll_wait2(src + c + 2, ps.step, d2, d3))
+                        ok = false;
+                    acc.x += d0;
+                    acc.y += d1;
+                    acc.z += d2;
+                    acc.w += d3;
+                }
+            }
+            if (!ok)
+                break;
         }
         *reinterpret_cast<uint4*>(sum + c) = acc;
     }
