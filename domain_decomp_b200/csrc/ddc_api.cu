@@ -189,6 +189,7 @@ struct ddc_handle_s {
     int halo_parts = 0;
     DevBuf<unsigned> gate; // the word the gate kernel of the second stream waits for (see BoxGate)
     bool use_gate = true;
+    bool row_flags = true; // DDC_ROW_FLAGS: exchange step 2 with one flag per block of the row-count kernel
     int early = 0; // DDC_EARLY, bit mask: which kernels poll a flag / word instead of waiting for the previous kernel's
                    // completion (ChainWord): 1 k_sum_cols, 2 K4, 4 labelling kernel, 8 row counts, 16 K2
     DevBuf<Plan> plan;
@@ -229,6 +230,7 @@ struct ddc_handle_s {
     unsigned* xbuf = nullptr; // this rank's buffer
     unsigned* xpeer[MAX_PEERS] = {}; // every rank's buffer as mapped here (xpeer[rank] == xbuf)
     size_t x_colcap = 0, x_rowcap = 0; // capacity of one col / row slot, in 32-bit words
+    size_t x_flagcap = 0; // per-block flags of the row-count kernel, per rank
     bool p2p = false, peer_local = false; // peer_local: the peers are handles of this process (ddc_peer_connect)
     unsigned step = 0; // decompositions enqueued so far (the flag value of the exchange barriers)
     int h_totals[8] = { 0 };
@@ -479,6 +481,7 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     h->label_rpc = env_int("DDC_LABEL_RPC", 0);
     h->use_gate = env_int("DDC_GATE", 1) != 0;
     h->early = env_int("DDC_EARLY", 0);
+    h->row_flags = env_int("DDC_ROW_FLAGS", 1) != 0;
     CREATE_TRY(h->gate.ensure(4)); // [0] K4 -> labelling kernel / second stream, [1] k_sum_cols -> K2, [2] K2 -> K3 (ChainWord)
     CREATE_TRY(cudaMemset(h->gate.p, 0, 4 * sizeof(unsigned)));
     CREATE_TRY(h->sc.ensure(1));
@@ -560,7 +563,7 @@ int ddc_destroy(ddc_handle_t h)
 }
 
 static void guess_plan_public(int P, int NX, int NY, int* ix, int* iy);
-static void peer_capacity(int nx, int ny, int nparts, int G, size_t* colcap, size_t* rowcap)
+static void peer_capacity(int nx, int ny, int nparts, int G, size_t* colcap, size_t* rowcap, size_t* flagcap)
 {
     int ix, iy;
     guess_plan_public(nparts, nx, ny, &ix, &iy);
@@ -572,6 +575,12 @@ static void peer_capacity(int nx, int ny, int nparts, int G, size_t* colcap, siz
     const size_t yr_off = ((size_t)nx + 3) & ~(size_t)3;
     *colcap = (std::max(yr_off + 2 * (size_t)G, 2 * (yr_off + 2)) + 4 + 3) & ~(size_t)3;
     *rowcap = ((nx < 65536 ? (elems + 1) / 2 : elems) + 4 + 3) & ~(size_t)3;
+    *flagcap = iy > 0 ? ((Rmax + 7) / 8 + 4 + 3) & ~(size_t)3 : 0; // one flag per block of the row-count kernel (>= 8 rows each)
+}
+// words of one rank's exchange buffer: [flags][col: 2 parities x G slots][row: 2 parities x G slots][row flags: G x flagcap]
+static size_t peer_words(int G, size_t colcap, size_t rowcap, size_t flagcap)
+{
+    return 64 + 2 * (size_t)G * (colcap + rowcap) + (size_t)G * flagcap;
 }
 
 int ddc_peer_export(ddc_handle_t h, int nx, int ny, int nparts, void* ipc_handle_out)
@@ -583,8 +592,8 @@ int ddc_peer_export(ddc_handle_t h, int nx, int ny, int nparts, void* ipc_handle
     if (h->xbuf)
         return fail(h, DDC_ERR_STATE, "ddc_peer_export: already exported");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    peer_capacity(nx, ny, nparts, h->nranks, &h->x_colcap, &h->x_rowcap);
-    const size_t words = 64 + 2 * (size_t)h->nranks * (h->x_colcap + h->x_rowcap);
+    peer_capacity(nx, ny, nparts, h->nranks, &h->x_colcap, &h->x_rowcap, &h->x_flagcap);
+    const size_t words = peer_words(h->nranks, h->x_colcap, h->x_rowcap, h->x_flagcap);
     CUDA_TRY(h, cudaMalloc((void**)&h->xbuf, words * sizeof(unsigned)));
     CUDA_TRY(h, cudaMemset(h->xbuf, 0, words * sizeof(unsigned)));
     cudaIpcMemHandle_t ipc;
@@ -640,8 +649,8 @@ int ddc_peer_connect(ddc_handle_t* handles, int n, int nx, int ny, int nparts)
                 return fail(h, DDC_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", h->device, handles[r]->device,
                     cudaGetErrorString(e));
         }
-        peer_capacity(nx, ny, nparts, n, &h->x_colcap, &h->x_rowcap);
-        const size_t words = 64 + 2 * (size_t)n * (h->x_colcap + h->x_rowcap);
+        peer_capacity(nx, ny, nparts, n, &h->x_colcap, &h->x_rowcap, &h->x_flagcap);
+        const size_t words = peer_words(n, h->x_colcap, h->x_rowcap, h->x_flagcap);
         CUDA_TRY(h, cudaMalloc((void**)&h->xbuf, words * sizeof(unsigned)));
         CUDA_TRY(h, cudaMemset(h->xbuf, 0, words * sizeof(unsigned)));
     }
@@ -1086,6 +1095,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         gate.step = h->step;
     }
     // ---- K3 + K4: strip row counts, y cuts -----------------------------------------------------
+    PeerSync ps_rows = ps; // (+ the per-block flags of exchange step 2, when the streaming row-count kernel runs)
     if (ycuts) {
         int rb_shift = 5; // log2(rows per block) of the kernel that writes the row counts
         {
@@ -1102,10 +1112,17 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             const size_t scan_smem = sizeof(int) * strip_scan_smem_words(NG, Scap, K);
             if (scan_smem <= 48 * 1024) { // the streaming kernel: boundary table in shared memory
                 const int grid = (Rmax + 8 * K - 1) / (8 * K);
+                if (p2p && h->row_flags && (size_t)grid <= h->x_flagcap) { // one flag per block (row_flags_raise)
+                    const size_t off = peer_words(G, h->x_colcap, h->x_rowcap, 0);
+                    for (int q = 0; q < G; q++)
+                        ps_rows.rowflag[q] = h->xpeer[q] + off;
+                    ps_rows.flagcap = (int)h->x_flagcap;
+                    ps_rows.rowblocks = grid;
+                }
                 rb_shift = K == 4 ? 5 : (K == 2 ? 4 : 3);
 #define LAUNCH_SCAN(CT, KK, FF)                                                                    \
     CUDA_TRY(h, launch_k(k_strip_rows_scan<CT, KK, FF>, dim3(grid), dim3(256), scan_smem, s, pdl, h->bits.p, NB, NX, rows, \
-        t.st.x0, t.st.p0, h->plan.p, Scap, push_row, Rmax, ps, h->done.p + d_rows, dbg, w_strips))
+        t.st.x0, t.st.p0, h->plan.p, Scap, push_row, Rmax, ps_rows, h->done.p + d_rows, dbg, w_strips))
                 // small shards: one row per warp, the whole row requested at once (rows of <= 8 chunks)
                 const bool full = h->strip_k == 8 && K == 1 && NG <= 256;
                 if (narrow) {
@@ -1150,7 +1167,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     do {                                                                                           \
         if (SM)                                                                                    \
             CUDA_TRY(h, opt_in_smem(k_ycuts<CT, SM>, h->device, which, std::max<size_t>(yneed, 48 * 1024))); \
-        CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : LEVEL_NODES_BYTES, s, pdl, pr, ps, rl, NY, t.st, \
+        CUDA_TRY(h, launch_k(k_ycuts<CT, SM>, dim3(ygrid), dim3(1024), SM ? yneed : LEVEL_NODES_BYTES, s, pdl, pr, ps_rows, rl, NY, t.st, \
             h->ypfx.p, t.bx, h->loads.p, h->loadmm.p, h->plan.p, h->strip_of_col.p, dbg ? 1 : 0, gate, h->part_at.p, nchunk, \
             pdl && p2p && (h->early & 2) ? 1 : 0)); \
     } while (0)

@@ -93,6 +93,10 @@ struct PeerSync {
     unsigned* flags[MAX_PEERS]; // rank q's flag array [PEER_STAGES][MAX_PEERS], as mapped here
     int rank, G, enabled;
     unsigned step;
+    // exchange step 2 with one flag per BLOCK of the row-count kernel (row_flags_*): rank q's array [G][flagcap], as
+    // mapped here; rowflag[0] == nullptr: one flag per rank (stage 1 of `flags`), raised by the kernel's last block
+    unsigned* rowflag[MAX_PEERS];
+    int flagcap, rowblocks;
 };
 struct PeerCols { // column counts of every rank: slot g of MY exchange buffer (pushed there by rank g);
                   // n == 1: col[0] already holds global counts (single GPU, or after an all-reduce)
@@ -1344,6 +1348,49 @@ __device__ __forceinline__ void rows_pushed(const PeerSync& ps, unsigned* done, 
     }
 }
 
+// The same with one flag per block: a block of the row-count kernel tells every rank "my chunk is there" itself (the
+// release store orders the block's pushes -- all threads', through the barrier -- before the flag), and the y-cut
+// kernel polls the G x blocks flags.  No block counter, no last block that has to notice it is the last and then pay a
+// second fence: the flags of a rank arrive as its blocks finish.
+__device__ __forceinline__ void row_flags_raise(const PeerSync& ps)
+{
+    __syncthreads(); // every thread's stores are issued
+    if ((int)threadIdx.x < ps.G) {
+        unsigned* dst = ps.rowflag[threadIdx.x] + (size_t)ps.rank * ps.flagcap + blockIdx.x;
+#ifndef DDC_HOST_EMU
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(ps.step) : "memory");
+#else
+        *dst = ps.step;
+#endif
+    }
+}
+// all threads of a block; false: a flag did not arrive in time
+__device__ __forceinline__ bool row_flags_wait(const PeerSync& ps)
+{
+    bool ok = true;
+    const int n = ps.G * ps.rowblocks;
+    for (int i = threadIdx.x; i < n && ok; i += blockDim.x) {
+        const int g = i / ps.rowblocks, b = i - g * ps.rowblocks;
+        const unsigned* src = ps.rowflag[ps.rank] + (size_t)g * ps.flagcap + b;
+#ifndef DDC_HOST_EMU
+        const unsigned long long t0 = global_ns();
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if (v == ps.step)
+                break;
+            if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+                ok = false;
+                break;
+            }
+        }
+#else
+        ok = *src == ps.step;
+#endif
+    }
+    return !__syncthreads_or(!ok);
+}
+
 // The grid covers Rmax rows (the rows of the largest shard): rows beyond this rank's `rows` are
 // written as empty, so that a short last shard needs no separate clearing pass.
 template <typename CT /* uint16_t when NX < 65536, else unsigned */>
@@ -1418,7 +1465,10 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
         stamp_first(dbg, TS_RES + 2);
     chain_wait(prev);
     if (plan->mismatch) { // (the flag is raised all the same: the y-cut kernel may wait for it before it looks at the plan)
-        rows_pushed(ps, done, gridDim.x, &s_last);
+        if (ps.enabled && ps.rowflag[0])
+            row_flags_raise(ps);
+        else
+            rows_pushed(ps, done, gridDim.x, &s_last);
         return;
     }
     if (threadIdx.x == 0)
@@ -1563,7 +1613,10 @@ __global__ void __launch_bounds__(256) k_strip_rows_scan(const uint8_t* __restri
             o = make_uint4(c[0], c[1 % V], c[2 % V], c[3 % V]);
         store_row_counts16(out, (chunk + e) * sizeof(CT), o);
     }
-    rows_pushed(ps, done, gridDim.x, &s_last);
+    if (ps.enabled && ps.rowflag[0])
+        row_flags_raise(ps);
+    else
+        rows_pushed(ps, done, gridDim.x, &s_last);
     if (tid == 0)
         stamp_last(dbg, TS_ROWS + 1);
 }
@@ -1691,7 +1744,9 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     if (ps.enabled && early) {
         bool ok = true;
         unsigned seen;
-        if (threadIdx.x < ps.G)
+        if (ps.rowflag[0])
+            ok = row_flags_wait(ps);
+        else if (threadIdx.x < ps.G)
             ok = peer_wait(ps, 1, &seen);
         if (__syncthreads_or(!ok)) {
             pdl_wait();
@@ -1727,7 +1782,9 @@ __global__ void __launch_bounds__(1024) k_ycuts(PeerRows pr, PeerSync ps, RowLay
     if (ps.enabled && !early) {
         bool ok = true;
         unsigned seen;
-        if (threadIdx.x < ps.G)
+        if (ps.rowflag[0])
+            ok = row_flags_wait(ps);
+        else if (threadIdx.x < ps.G)
             ok = peer_wait(ps, 1, &seen);
         if (__syncthreads_or(!ok)) {
             if (threadIdx.x == 0)

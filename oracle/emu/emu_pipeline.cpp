@@ -65,6 +65,7 @@ struct Rank {
     const int32_t* mask = nullptr;
     std::vector<uint8_t> bits;
     std::vector<unsigned> flags; // [PEER_STAGES][MAX_PEERS]
+    std::vector<unsigned> rowflags; // [G][flagcap]: one flag per block of the row-count kernel
     std::vector<unsigned> colslots, rowslots; // G slots each (slot g is written by rank g)
     std::vector<unsigned> colpfx, ypfx, done, colsum;
     std::vector<int> strips, boxes, strip_of_col, part_at;
@@ -89,6 +90,7 @@ struct Options {
     int strip_k = 0; // 0 auto, 1 / 2 / 4 rows per warp, 8 whole row in registers
     int scan_rpc = 64; // rows per CTA of the mask scan
     int smem_limit = 232448; // bytes of dynamic shared memory a block may use (B200: 227 KB)
+    bool row_flags = true; // exchange step 2 with one flag per block of the row-count kernel (DDC_ROW_FLAGS)
     bool collectives = false; // G > 1: the NCCL fallback of ddc_api.cu (all-reduce / all-gather between the kernels,
                               // emulated by host loops) instead of the slot exchange inside the kernels
 };
@@ -129,6 +131,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     };
     auto colslot = [&](Rank& r, int slot) { return r.colslots.data() + ((size_t)par * G + slot) * colcap; };
     auto rowslot = [&](Rank& r, int slot) { return r.rowslots.data() + ((size_t)par * G + slot) * rowcap; };
+    const size_t flagcap = (size_t)(Rmax + 7) / 8 + 4;
     auto sync_of = [&](Rank& r) {
         PeerSync ps {};
         ps.rank = r.rank;
@@ -143,6 +146,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     for (Rank& r : R) { // buffers
         r.bits.resize((size_t)std::max(r.rows, 1) * NB);
         r.flags.resize((size_t)PEER_STAGES * MAX_PEERS, 0u);
+        r.rowflags.resize((size_t)G * flagcap, 0u);
         r.colslots.resize(2 * (size_t)G * colcap, 0xdeadbeefu);
         r.rowslots.resize(2 * (size_t)G * rowcap, 0xdeadbeefu);
         r.colpfx.resize((size_t)NX + 1);
@@ -244,7 +248,13 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                 k_paint_strips(st, &r.plan, r.strip_of_col.data()));
     }
     // ---- K3: strip row counts (pushed to every rank) ----
-    int rb_shift = 5;
+    int rb_shift = 5, row_blocks = 0;
+    auto row_sync = [&](PeerSync& ps) {
+        for (int q = 0; q < G; q++)
+            ps.rowflag[q] = R[q].rowflags.data();
+        ps.flagcap = (int)flagcap;
+        ps.rowblocks = row_blocks;
+    };
     if (ycuts) {
         for (Rank& r : R) {
             StripTable st;
@@ -255,7 +265,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             out.n = p2p ? G : 1;
             for (int q = 0; q < G; q++)
                 out.dst[q] = rowslot(R[p2p ? q : r.rank], r.rank);
-            const PeerSync ps = sync_of(r);
+            PeerSync ps = sync_of(r);
             int K = Rmax >= 32 * 4 * 148 ? 4 : 2;
             if (opt.strip_k)
                 K = opt.strip_k == 8 ? 1 : opt.strip_k;
@@ -265,6 +275,10 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             if (scan_smem <= 48 * 1024 && opt.strip_k != 16) {
                 const Dim3 grid((Rmax + 8 * K - 1) / (8 * K));
                 rb_shift = K == 4 ? 5 : (K == 2 ? 4 : 3);
+                if (p2p && opt.row_flags) { // one flag per block instead of one per rank (row_flags_raise)
+                    row_blocks = (int)grid.x;
+                    row_sync(ps);
+                }
                 const bool full = opt.strip_k == 8 && K == 1 && NG <= 256;
 #define SCAN(CT, KK, FF)                                                                           \
     LAUNCH(grid, Dim3(256), scan_smem,                                                             \
@@ -323,7 +337,9 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
                 pr.row[q] = rowslot(r, p2p ? q : r.rank);
             if (G > 1 && !p2p)
                 pr.row[0] = gathered[r.rank].data();
-            const PeerSync ps = sync_of(r);
+            PeerSync ps = sync_of(r);
+            if (row_blocks)
+                row_sync(ps);
             const RowLayout rl = { rank_stride, Rmax, Scap, rb_shift };
             BoxGate gate {}; // as in ddc_api.cu: K4's last block opens the gate of the second stream
             gate.word = &r.gate_word;
@@ -472,6 +488,8 @@ __attribute__((visibility("default"))) int emu_partition(const int32_t* mask, in
     if (smem_limit > 0)
         opt.smem_limit = smem_limit;
     opt.collectives = std::getenv("DDC_EMU_COLLECTIVES") != nullptr;
+    if (const char* e = std::getenv("DDC_ROW_FLAGS"))
+        opt.row_flags = std::atoi(e) != 0;
     // the masks of the ranks: 16-byte aligned copies of their row blocks (like a cudaMalloc'ed shard)
     std::vector<Rank> R(G);
     std::vector<std::vector<int32_t>> shard(G);
