@@ -183,14 +183,15 @@ struct ddc_handle_s {
 
     // device buffers
     DevBuf<uint8_t> bits;
-    DevBuf<unsigned> colcount, colpfx, rowcount, rowcount_all, ypfx, done;
+    DevBuf<unsigned> colcount, colsum, colpfx, rowcount, rowcount_all, ypfx, done;
     DevBuf<DevScalars> sc;
     DevBuf<long long> halo_off; // tile offsets of the halo exchange (ddc_halo_tile_offsets)
     int halo_parts = 0;
     DevBuf<unsigned> gate; // the word the gate kernel of the second stream waits for (see BoxGate)
     bool use_gate = true;
-    bool row_flags = true; // DDC_ROW_FLAGS: exchange step 2 with one flag per block of the row-count kernel
-    int early = 0; // DDC_EARLY, bit mask: which kernels poll a flag / word instead of waiting for the previous kernel's
+    bool row_flags = true; // DDC_ROW_FLAGS: exchange step 2 with one flag per block of the row-count kernel (default: 2 ranks
+                           // only -- measured -2.4 us on 2 GPUs, +4 us on 8, where a block has 8 flags to send)
+    int early = 17; // DDC_EARLY, bit mask (default 1 + 16): which kernels poll a flag / word instead of waiting for the previous kernel's
                    // completion (ChainWord): 1 k_sum_cols, 2 K4, 4 labelling kernel, 8 row counts, 16 K2
     DevBuf<Plan> plan;
     DevBuf<int> strips; // x0[P+1] x1[P+1] p0[P+2] S always
@@ -455,7 +456,10 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
         // kernel still has tens of thousands of CTAs queued
         int least = 0, greatest = 0;
         CREATE_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        CREATE_TRY(cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, greatest));
+        // (DDC_SIDE_PRIO=0: the priority of a default stream -- on several GPUs every rank builds ALL neighbour tables
+        //  beside a labelling kernel that has only 1 / G of the cells)
+        CREATE_TRY(cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking,
+            env_int("DDC_SIDE_PRIO", 1) ? greatest : least));
     }
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -480,8 +484,8 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     h->scan_tail = std::max(0, std::min(90, env_int("DDC_SCAN_TAIL", 25)));
     h->label_rpc = env_int("DDC_LABEL_RPC", 0);
     h->use_gate = env_int("DDC_GATE", 1) != 0;
-    h->early = env_int("DDC_EARLY", 0);
-    h->row_flags = env_int("DDC_ROW_FLAGS", 1) != 0;
+    h->early = env_int("DDC_EARLY", 17);
+    h->row_flags = env_int("DDC_ROW_FLAGS", nranks <= 2 ? 1 : 0) != 0;
     CREATE_TRY(h->gate.ensure(4)); // [0] K4 -> labelling kernel / second stream, [1] k_sum_cols -> K2, [2] K2 -> K3 (ChainWord)
     CREATE_TRY(cudaMemset(h->gate.p, 0, 4 * sizeof(unsigned)));
     CREATE_TRY(h->sc.ensure(1));
@@ -523,6 +527,7 @@ int ddc_destroy(ddc_handle_t h)
     h->mask_own.release();
     h->bits.release();
     h->colcount.release();
+    h->colsum.release();
     h->colpfx.release();
     h->rowcount.release();
     h->rowcount_all.release();
@@ -894,6 +899,8 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const int Rmax = (NY + G - 1) / G;
     CUDA_TRY(h, h->bits.ensure((size_t)std::max(rows, 1) * NB));
     CUDA_TRY(h, h->colcount.ensure(ncol));
+    if (G > 1)
+        CUDA_TRY(h, h->colsum.ensure(ncol));
     CUDA_TRY(h, h->strips.ensure((size_t)3 * (P + 1) + 3));
     CUDA_TRY(h, h->boxes.ensure((size_t)4 * P));
     CUDA_TRY(h, h->strip_of_col.ensure(NX));
@@ -966,7 +973,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     auto xrow = [&](int q, int slot) {
         return h->xpeer[q] + XFLAGS + 2 * (size_t)G * h->x_colcap + ((size_t)par * G + slot) * h->x_rowcap;
     };
-    unsigned* colcount = p2p ? xcol(h->rank, h->rank) : h->colcount.p;
+    // this rank's counts accumulate in plain device memory (the scan's atomics into the peer-mapped exchange buffer ran
+    // the scan ~5 % slower on 8 GPUs); only the peers' slots of the exchange buffer are used
+    unsigned* colcount = h->colcount.p;
     unsigned* rowcount = p2p ? xrow(h->rank, h->rank) : h->rowcount.p;
     PeerSync ps {};
     ps.rank = h->rank;
@@ -980,7 +989,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     if (p2p) {
         for (int q = 0; q < G; q++) {
             ps.flags[q] = h->xpeer[q];
-            pc.col[q] = xcol(h->rank, q); // what rank q pushed into my buffer
+            pc.col[q] = q == h->rank ? colcount : xcol(h->rank, q); // what rank q pushed into my buffer
             pr.row[q] = xrow(h->rank, q);
             push_col.dst[q] = xcol(q, h->rank); // my slot in rank q's buffer
             push_row.dst[q] = xrow(q, h->rank);
@@ -1051,11 +1060,11 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     if (pdl && (h->early & 8))
         w_strips = ChainWord { h->gate.p + 2, h->step };
     if (presum) {
-        CUDA_TRY(h, launch_k(k_sum_cols, dim3(gridx), dim3(256), 0, s, pdl, pc, ps, NX, yr_off, h->colcount.p, h->plan.p,
+        CUDA_TRY(h, launch_k(k_sum_cols, dim3(gridx), dim3(256), 0, s, pdl, pc, ps, NX, yr_off, h->colsum.p, h->plan.p,
             pdl && (h->early & 1) ? 1 : 0, h->done.p + d_sum, w_sum, dbg));
         launches++;
         pc = PeerCols {};
-        pc.col[0] = h->colcount.p;
+        pc.col[0] = h->colsum.p;
         pc.n = 1;
     }
     // who puts this rank's column-count slot back to zero once it is consumed: the labelling kernel when the slot is

@@ -7,7 +7,7 @@ export PYTHONUNBUFFERED=1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 port=29800
 timeout 900 $TR --master-port $port tests/mgpu_worker.py --big > gpurun_out/${T}_mgpu${N}_parity.log 2>&1; echo "parity rc=$?"; grep -E "MISMATCH|PARITY|Error|error" gpurun_out/${T}_mgpu${N}_parity.log | head -20
-for knobs in "DDC_ROW_FLAGS=1" "DDC_ROW_FLAGS=0" "DDC_STRIP_K=4" "DDC_STRIP_K=1" "DDC_EARLY=17" "DDC_ROW_FLAGS=1"; do
+for knobs in ${KNOBS:-"DDC_ROW_FLAGS=1" "DDC_ROW_FLAGS=0" "DDC_STRIP_K=4" "DDC_STRIP_K=1" "DDC_EARLY=17" "DDC_ROW_FLAGS=1"}; do
   port=$((port+1))
   env $knobs timeout 600 $TR --master-port $port bench.py --gpus $N --steps 30 --warmup 5 --no-e2e --no-cpu > gpurun_out/${T}_bench_c5_${N}gpu_$knobs.json 2> gpurun_out/${T}_bench_c5_${N}gpu_$knobs.err; echo "$knobs rc=$?"
   python - <<PY
