@@ -189,6 +189,7 @@ struct ddc_handle_s {
     int halo_parts = 0;
     DevBuf<unsigned> gate; // the word the gate kernel of the second stream waits for (see BoxGate)
     bool use_gate = true;
+    bool dev_join = true; // DDC_DEV_JOIN: the labelling kernel's last block waits for the neighbour kernels (no event join)
     bool row_flags = true; // DDC_ROW_FLAGS: exchange step 2 with one flag per block of the row-count kernel (default: 2 ranks
                            // only -- measured -2.4 us on 2 GPUs, +4 us on 8, where a block has 8 flags to send)
     int early = 17; // DDC_EARLY, bit mask (default 1 + 16): which kernels poll a flag / word instead of waiting for the previous kernel's
@@ -355,12 +356,12 @@ int run_neighbours(ddc_handle_t h, int P, int nx, int ny, int px, int py)
     const int warps_per_cta = 8;
     const int grid = (std::max(P, 8) + warps_per_cta - 1) / warps_per_cta; // >= 8 * pad32(P) threads
     CUDA_TRY(h, launch_k(k_neighbours<false>, dim3(grid), dim3(256), 0, s, false, t.bx, P, nx, ny, px, py, t.st,
-        h->nbr_counts.p, nullptr, nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, nullptr));
+        h->nbr_counts.p, nullptr, nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, nullptr, ChainWord { nullptr, 0u }, nullptr));
     CUDA_TRY(h, launch_k(k_scan_counts, dim3(8), dim3(1024), 0, s, false, h->nbr_counts.p, P, h->nbr_offsets.p,
         h->nbr_totals.p, nullptr));
     CUDA_TRY(h, launch_k(k_neighbours<true>, dim3(grid), dim3(256), 0, s, false, t.bx, P, nx, ny, px, py, t.st,
         h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
-        h->sc.p, nullptr));
+        h->sc.p, nullptr, ChainWord { nullptr, 0u }, nullptr));
     h->stats.gpu_launches += 3;
     CUDA_TRY(h, cudaGetLastError());
     h->totals_valid = false;
@@ -391,7 +392,7 @@ int fetch_totals(ddc_handle_t h)
         const int grid = (std::max(h->nparts, 8) + 7) / 8;
         CUDA_TRY(h, launch_k(k_neighbours<true>, dim3(grid), dim3(256), 0, h->stream, false, t.bx, h->nparts, h->nx, h->ny,
             h->px, h->py, t.st, h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p,
-            h->nbr_halos.p, h->nbr_starts.p, h->sc.p, nullptr));
+            h->nbr_halos.p, h->nbr_starts.p, h->sc.p, nullptr, ChainWord { nullptr, 0u }, nullptr));
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaMemcpyAsync(&hs, h->sc.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -485,6 +486,7 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     h->label_rpc = env_int("DDC_LABEL_RPC", 0);
     h->use_gate = env_int("DDC_GATE", 1) != 0;
     h->early = env_int("DDC_EARLY", 17);
+    h->dev_join = env_int("DDC_DEV_JOIN", 1) != 0;
     h->row_flags = env_int("DDC_ROW_FLAGS", nranks <= 2 ? 1 : 0) != 0;
     CREATE_TRY(h->gate.ensure(4)); // [0] K4 -> labelling kernel / second stream, [1] k_sum_cols -> K2, [2] K2 -> K3 (ChainWord)
     CREATE_TRY(cudaMemset(h->gate.p, 0, 4 * sizeof(unsigned)));
@@ -1010,7 +1012,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     const int gridx = (NG + 7) / 8;
     // counters of the "last block" patterns: [0, gridx] mask scan, [gridx + 1] strip row counts, then the
     // 64-bit counter of the labelling kernel; all zero between steps (their last blocks reset them)
-    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, d_sum = d_ycuts + 1, ndone = d_sum + 1;
+    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, d_sum = d_ycuts + 1, d_nbr = d_sum + 1, ndone = d_nbr + 1;
     CUDA_TRY(h, h->done.ensure((size_t)ndone));
     ddc_handle_s::CleanSig sig;
     sig.col = colcount;
@@ -1208,6 +1210,13 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     h->px = px;
     h->py = py;
     const int ngrid = (std::max(P, 8) + 7) / 8; // >= 8 * pad32(P) threads
+    // The labelling kernel's last block also ends the step (`changes`, exchange step 3, the plan into the host's
+    // pinned copy) unless there is no labelling kernel on this rank or the exchange goes through NCCL ...
+    const bool fuse = h->fuse_fin && label_runs && (G == 1 || p2p);
+    // ... and then it also waits for the neighbour kernels of the second stream (a word in device memory) instead of
+    // the host joining the streams with an event
+    const bool dev_join = h->dev_join && fuse && want_nbr;
+    const ChainWord w_nbr = dev_join ? ChainWord { h->gate.p + 3, h->step } : ChainWord { nullptr, 0u };
     if (want_nbr) {
         cudaStream_t q = h->side_stream;
         if (!gated) {
@@ -1215,19 +1224,18 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
             CUDA_TRY(h, cudaStreamWaitEvent(q, h->ev_fork, 0));
         }
         CUDA_TRY(h, launch_k(k_neighbours<false>, dim3(ngrid), dim3(256), 0, q, false, t.bx, P, NX, NY, px, py, t.st,
-            h->nbr_counts.p, nullptr, nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p));
+            h->nbr_counts.p, nullptr, nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p, ChainWord { nullptr, 0u }, nullptr));
         CUDA_TRY(h, launch_k(k_scan_counts, dim3(8), dim3(1024), 0, q, false, h->nbr_counts.p, P, h->nbr_offsets.p,
             h->nbr_totals.p, h->plan.p));
         CUDA_TRY(h, launch_k(k_neighbours<true>, dim3(ngrid), dim3(256), 0, q, false, t.bx, P, NX, NY, px, py, t.st,
             h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
-            h->sc.p, h->plan.p));
+            h->sc.p, h->plan.p, w_nbr, h->done.p + d_nbr));
         launches += 3;
         CUDA_TRY(h, cudaEventRecord(h->ev_join, q));
     }
     // ---- K6: labels + `changes` -----------------------------------------------------------------
     // The labelling kernel's last block also ends the step (`changes`, exchange step 3, the plan into the host's
     // pinned copy) unless there is no labelling kernel on this rank or the exchange goes through NCCL.
-    const bool fuse = h->fuse_fin && label_runs && (G == 1 || p2p);
     h->fin_ps = ps;
     if (label_runs) {
         const bool vecp = want_pid && (NX % 4 == 0) && (((uintptr_t)h->pid.p) % 16 == 0);
@@ -1248,6 +1256,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         fin.yr_off = yr_off;
         if (label_polls)
             fin.prev = ChainWord { h->gate.p, h->step };
+        fin.nbr = w_nbr;
         auto kernel = !want_pid ? k_label<false, false> : (vecp ? k_label<true, true> : k_label<false, true>);
         // (behind K4 without a stream operation in between when the second stream is gated: programmatic launch)
         CUDA_TRY(h, launch_k(kernel, grid, dim3(256), 0, s, pdl && (gated || !want_nbr), h->bits.p, NX, rows, h->y_begin, NB, rpc, h->strip_of_col.p,
@@ -1257,7 +1266,7 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     if (G > 1 && !p2p)
         NCCL_TRY(h, g_nccl.AllReduce(&h->sc.p->changes, &h->sc.p->changes, 1, nccl_Int32, nccl_Max, h->comm, s));
     mark(5);
-    if (want_nbr)
+    if (want_nbr && !dev_join)
         CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0)); // the step is over when the neighbour tables are, too
     // ---- K5 as a kernel of its own (see above; otherwise only from validate(), when nothing moved) ----
     if (!fuse) {

@@ -2127,6 +2127,7 @@ struct LabelEnd {
     unsigned* reset_col; // != nullptr: this rank's column-count slot, consumed by k_sum_cols: zeroed here for the next step
     int reset_n, yr_off;
     ChainWord prev; // the gate word the last block of K4 writes (boxes_ready), polled instead of the kernel boundary
+    ChainWord nbr; // published by the neighbour kernels on the second stream: the step ends when they have, too
 };
 
 template <bool VEC, bool WRITE>
@@ -2136,6 +2137,7 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
     NaiveParams nv, int32_t* __restrict__ pid, DevScalars* __restrict__ sc, Plan* __restrict__ plan, LabelEnd fin)
 {
     __shared__ int s_changed, s_last;
+    pdl_trigger(); // the next step's mask scan may become resident behind the last blocks of this grid
     if (threadIdx.x == 0)
         stamp_first(fin.dbg, TS_RES + 4);
     chain_wait(fin.prev);
@@ -2179,6 +2181,28 @@ __global__ void __launch_bounds__(256, 5) k_label(const uint8_t* __restrict__ bi
         sc->changes = changes;
         sc->changes_all = changes;
         plan->fixup = (changes || fin.P <= 1) ? 0 : (fin.ps.enabled ? 2 : 1);
+        // The neighbour tables are built beside this kernel on a second stream.  Instead of joining the streams with
+        // an event (a stream operation between this kernel and the next step's scan: no programmatic launch there,
+        // and ~2 us more per step), this block waits for the word their last block publishes: when this grid has
+        // completed, the whole step has.
+        if (fin.nbr.word) {
+#ifndef DDC_HOST_EMU
+            const unsigned long long t0 = global_ns();
+            for (;;) {
+                unsigned v;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(fin.nbr.word) : "memory");
+                if (v == fin.nbr.step)
+                    break;
+                if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+                    plan->mismatch = 3;
+                    break;
+                }
+            }
+#else
+            if (*fin.nbr.word != fin.nbr.step)
+                plan->mismatch = 3;
+#endif
+        }
         stamp_last(fin.dbg, TS_LABEL + 2);
     }
     __syncthreads();
@@ -2276,12 +2300,14 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, int NY, int px, int py,
     StripTable st, int* __restrict__ counts, const int* __restrict__ offsets,
     const int* __restrict__ totals, int cap, int* __restrict__ ids, int* __restrict__ halos,
-    int* __restrict__ starts, DevScalars* sc, const Plan* __restrict__ plan)
+    int* __restrict__ starts, DevScalars* sc, const Plan* __restrict__ plan,
+    ChainWord tables_done /* FILL: published by the last block on every path (the labelling kernel's last block waits
+                             for it: no join of the two streams between two steps) */,
+    unsigned* __restrict__ done_ctr)
 {
-    if (plan && plan->mismatch)
-        return;
+    bool run = !(plan && plan->mismatch);
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (FILL) {
+    if (run && FILL) {
         bool over = false;
 #pragma unroll
         for (int l = 0; l < 8; l++)
@@ -2289,20 +2315,32 @@ __global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, 
         if (over) {
             if (t == 0)
                 sc->overflow = 1;
-            return;
+            run = false;
         }
     }
-    if (*st.always) {
-        const int me = (int)(t >> 5);
-        if (me < P)
-            neighbours_all_pairs<FILL>(bx, P, NX, NY, px, py, me, counts, offsets, cap, ids, halos, starts, sc);
-    } else {
-        // thread = list * Ppad + part with Ppad a multiple of 32: a warp works on 32 consecutive
-        // parts of ONE list (uniform control flow, coalesced box loads)
-        const int Ppad = (P + 31) & ~31;
-        if (t < 8LL * Ppad)
-            neighbours_structured<FILL>(bx, P, NX, NY, px, py, st, (int)(t / Ppad), (int)(t % Ppad), counts,
-                offsets, cap, ids, halos, starts, sc);
+    if (run) {
+        if (*st.always) {
+            const int me = (int)(t >> 5);
+            if (me < P)
+                neighbours_all_pairs<FILL>(bx, P, NX, NY, px, py, me, counts, offsets, cap, ids, halos, starts, sc);
+        } else {
+            // thread = list * Ppad + part with Ppad a multiple of 32: a warp works on 32 consecutive
+            // parts of ONE list (uniform control flow, coalesced box loads)
+            const int Ppad = (P + 31) & ~31;
+            if (t < 8LL * Ppad)
+                neighbours_structured<FILL>(bx, P, NX, NY, px, py, st, (int)(t / Ppad), (int)(t % Ppad), counts,
+                    offsets, cap, ids, halos, starts, sc);
+        }
+    }
+    if (FILL && tables_done.word) {
+        __syncthreads(); // the block's entries are written ...
+        if (threadIdx.x == 0) {
+            __threadfence(); // ... and visible to the device before the block is counted
+            if (atomicAdd(done_ctr, 1u) == gridDim.x - 1u) {
+                *done_ctr = 0u;
+                chain_signal(tables_done);
+            }
+        }
     }
 }
 

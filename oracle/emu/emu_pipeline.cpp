@@ -74,6 +74,7 @@ struct Rank {
     std::vector<int> nbr_counts, nbr_offsets, nbr_totals, nbr_ids, nbr_halos, nbr_starts;
     DevScalars sc {};
     unsigned gate_word = 0;
+    unsigned nbr_word = 0; // published by the fill kernel's last block, awaited by the labelling kernel's
     unsigned chain_words[2] = { 0u, 0u }; // k_sum_cols -> K2, K2 -> K3 (ChainWord)
     Plan plan {}, host_plan {};
 };
@@ -113,7 +114,7 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
     const bool x_smem = xneed + 1024 <= (size_t)opt.smem_limit, y_smem = yneed + 1024 <= (size_t)opt.smem_limit;
     const int ygrid = std::max(1, std::min(Scap, 148 * 2));
     const int gridx = (NG + 7) / 8;
-    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, d_sum = d_ycuts + 1, ndone = d_sum + 1; // ddc_api.cu: the "last block" counters
+    const int d_rows = gridx + 1, d_label = (gridx + 3) & ~1, d_ycuts = d_label + 2, d_sum = d_ycuts + 1, d_nbr = d_sum + 1, ndone = d_nbr + 1; // ddc_api.cu: the "last block" counters
     const NaiveParams nv = naive_params(P, NX, NY);
     const int nchunk = (NY + 31) / 32;
     const int par = (int)(step & 1u);
@@ -379,12 +380,13 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             }
             LAUNCH(Dim3(ngrid), Dim3(256), 0,
                 k_neighbours<false>(bx, P, NX, NY, px, py, st, r.nbr_counts.data(), nullptr, nullptr, cap, nullptr, nullptr,
-                    nullptr, &r.sc, &r.plan));
+                    nullptr, &r.sc, &r.plan, ChainWord { nullptr, 0u }, nullptr));
             LAUNCH(Dim3(8), Dim3(1024), 0,
                 k_scan_counts(r.nbr_counts.data(), P, r.nbr_offsets.data(), r.nbr_totals.data(), &r.plan));
             LAUNCH(Dim3(ngrid), Dim3(256), 0,
                 k_neighbours<true>(bx, P, NX, NY, px, py, st, r.nbr_counts.data(), r.nbr_offsets.data(), r.nbr_totals.data(),
-                    cap, r.nbr_ids.data(), r.nbr_halos.data(), r.nbr_starts.data(), &r.sc, &r.plan));
+                    cap, r.nbr_ids.data(), r.nbr_halos.data(), r.nbr_starts.data(), &r.sc, &r.plan,
+                    ChainWord { &r.nbr_word, step }, r.done.data() + d_nbr));
         }
         if (r.rows > 0) {
             const bool vecp = (NX % 4 == 0) && (((uintptr_t)r.pid.data()) % 16 == 0);
@@ -404,6 +406,8 @@ bool run_step(std::vector<Rank>& R, int NX, int NY, int P, int px, int py, int a
             fin.yr_off = yr_off;
             if (chained && ycuts)
                 fin.prev = ChainWord { &r.gate_word, step };
+            if (fin.fuse && want_nbr)
+                fin.nbr = ChainWord { &r.nbr_word, step };
             if (vecp)
                 LAUNCH(grid, Dim3(256), 0,
                     (k_label<true, true>(r.bits.data(), NX, r.rows, r.y_begin, NB, rpc, r.strip_of_col.data(), st.p0, bx.y0,
