@@ -445,20 +445,18 @@ def main():
         plugin = None
         if world > 1:  # rank 0 needs the whole mask / pid on the host: gather the shards through shared memory
             shm = "/dev/shm/ddc_bench_%s" % os.environ.get("MASTER_PORT", "0")
+            gathered = {}
             for name, t in (("mask", h_mask), ("pid", h_pid)):
-                mm = np.lib.format.open_memmap if False else None
-                arr = np.memmap("%s_%s.i32" % (shm, name), dtype=np.int32, mode="r+" if rank else "w+", shape=(ny, nx)) \
-                    if rank == 0 else None
+                path = "%s_%s.i32" % (shm, name)
+                arr = np.memmap(path, dtype=np.int32, mode="w+", shape=(ny, nx)) if rank == 0 else None  # rank 0 creates
                 dist.barrier()
                 if rank != 0:
-                    arr = np.memmap("%s_%s.i32" % (shm, name), dtype=np.int32, mode="r+", shape=(ny, nx))
+                    arr = np.memmap(path, dtype=np.int32, mode="r+", shape=(ny, nx))
                 arr[y_begin:y_begin + y_count] = t.numpy()[:y_count]
                 arr.flush()
                 dist.barrier()
-                if name == "mask":
-                    g_mask = arr
-                else:
-                    g_pid = arr
+                gathered[name] = arr
+            g_mask, g_pid = gathered["mask"], gathered["pid"]
         else:
             g_mask, g_pid = h_mask.numpy(), h_pid.numpy()
         if rank == 0:
