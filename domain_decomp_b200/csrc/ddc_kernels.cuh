@@ -895,38 +895,6 @@ __device__ __forceinline__ int walk_lanes(int leaves, int threads)
 // ------------------------------------------------------------------------------------------------
 // K2: column prefix sums, preset directions, all x levels, strip table
 // ------------------------------------------------------------------------------------------------
-// The column counts of one thread's tile -- 4 consecutive counts in each of the 8 sub-tiles -- summed over the
-// ranks' slots (one buffer when the counts are already global).  Slot by slot: the 8 loads of a slot are
-// independent and requested together, so that summing G slots costs G L2 round trips, not 8 G (with the
-// per-slot loop inside each sub-tile load K2 spent 24 us here on 8 GPUs).  One 16-byte load per slot and
-// sub-tile when the chunk is whole and aligned (8 bytes for 16-bit slots).  ld.global.cg: the slots of the
-// other ranks are written by other GPUs.
-__device__ __forceinline__ uint4 load_slot4(const PeerCols& pc, int g, int i, int n)
-{
-    uint4 t = make_uint4(0u, 0u, 0u, 0u);
-    if (i >= n)
-        return t;
-    if (pc.packed && g != pc.own) {
-        const uint16_t* src = reinterpret_cast<const uint16_t*>(pc.col[g]) + i;
-        if (i + 4 <= n && ((uintptr_t)src & 7) == 0) {
-            const uint2 u = __ldcg(reinterpret_cast<const uint2*>(src));
-            return make_uint4(u.x & 0xffffu, u.x >> 16, u.y & 0xffffu, u.y >> 16);
-        }
-        t.x = (unsigned)__ldcg(src);
-        t.y = i + 1 < n ? (unsigned)__ldcg(src + 1) : 0u;
-        t.z = i + 2 < n ? (unsigned)__ldcg(src + 2) : 0u;
-        t.w = i + 3 < n ? (unsigned)__ldcg(src + 3) : 0u;
-        return t;
-    }
-    const unsigned* src = pc.col[g] + i;
-    if (i + 4 <= n && ((uintptr_t)src & 15) == 0)
-        return __ldcg(reinterpret_cast<const uint4*>(src));
-    t.x = __ldcg(src);
-    t.y = i + 1 < n ? __ldcg(src + 1) : 0u;
-    t.z = i + 2 < n ? __ldcg(src + 2) : 0u;
-    t.w = i + 3 < n ? __ldcg(src + 3) : 0u;
-    return t;
-}
 // the plan (levels, mismatch flag, iteration count, fix-up request) goes straight into the host's pinned copy,
 // so that a step ends without a separate device -> host copy; called by all threads of a block (>= 128)
 __device__ __forceinline__ void publish_plan(const Plan* plan, Plan* host_plan)
@@ -1099,24 +1067,6 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
         loadmm[1] = -1;
     }
 
-    // 0. exchange step 1: every rank's mask scan has pushed its column counts into my buffer
-    if (ps.enabled) {
-        bool ok = true;
-        unsigned seen;
-        if (tid < ps.G)
-            ok = peer_wait(ps, 0, &seen);
-        if (__syncthreads_or(!ok)) {
-            if (tid == 0)
-                plan->mismatch = 3;
-            __syncthreads();
-            publish_plan(plan, host_plan);
-            __syncthreads();
-            if (tid == 0)
-                chain_signal(next);
-            return;
-        }
-    }
-
     // 1. pfx[i] = ocean cells in columns [0, i)
     if (tid == 0)
         plan->ts[1] = global_ns();
@@ -1148,7 +1098,7 @@ __global__ void __launch_bounds__(1024) k_xcuts(PeerCols pc, PeerSync ps, int NX
             // counts (and, after an all-reduce, in slot g of the one global buffer)
             int a = (int)0x80000000, b = -1;
             for (int g = 0; g < G; g++) {
-                const unsigned* src = (pc.n == 1 ? pc.col[0] : pc.col[g]) + yr_off + 2 * g;
+                const unsigned* src = pc.col[0] + yr_off + 2 * g;
                 a = max(a, (int)__ldcg(src));
                 b = max(b, (int)__ldcg(src + 1));
             }

@@ -153,6 +153,22 @@ def test_column_counts_travel_as_data_and_flag_words(oracle):
         assert_same(d, oracle.partition(mask, P, True, False, use_hist=True), (nx, ny, P, ranks))
 
 
+def test_row_counts_with_one_flag_per_rank_or_per_block(oracle, monkeypatch):
+    """exchange step 2: the row-count kernel's last block raises one flag per rank (block counter), or every block
+    raises its own and the y-cut kernel polls ranks x blocks flags (DDC_ROW_FLAGS); both on 2 and 3 ranks, with more
+    row blocks than one y-cut block has threads to poll them in one go"""
+    from domain_decomp_b200 import capi
+    for nx, ny, P, ranks in ((70, 9000, 6, 2), (150, 301, 12, 3)):
+        mask = capi.generate_mask_host(nx, ny, 11, 0.4)
+        o = oracle.partition(mask, P, False, True, use_hist=True)
+        for mode in ("0", "1"):
+            monkeypatch.setenv("DDC_ROW_FLAGS", mode)
+            for strip_k in (0, 1):
+                d, _ = oracle.emu_partition(mask, P, False, True, ranks=ranks, strip_k=strip_k)
+                assert_same(d, o, (nx, ny, P, ranks, mode, strip_k))
+    monkeypatch.delenv("DDC_ROW_FLAGS")
+
+
 def test_results_do_not_depend_on_the_schedule(oracle, monkeypatch):
     """the emulation can run the blocks of a grid in a random order and the threads of a block in a new random order
     every scheduling round (DDC_EMU_SCHED_SEED): a missing barrier, an assumption about block order or about
