@@ -208,12 +208,12 @@ def reference_arm(args):
     whole = args.sample == "whole" or (args.sample == "auto" and avail > need)
     t0 = time.perf_counter()
     mask, sp, px, py, desc = cpu_sample(args.workload, threads, whole=whole)
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-    # keep the whole run within a few minutes whatever K is
-    sec = run_cpu(mask, sp, px, py, threads, 1, 0)
-    budget = 150.0
-    steps = max(1, min(steps, int(budget / max(sec, 1e-3))))
-    sec = run_cpu(mask, sp, px, py, threads, steps, warmup) if steps > 1 else sec
+    # keep the whole run within a few minutes whatever K is: the first decomposition is timed and sizes the rest
+    # (a CPU pass over a fresh mask has nothing to warm up: every step counts)
+    first = run_cpu(mask, sp, px, py, threads, 1, 0)
+    budget = 120.0
+    steps, warmup = max(1, min(args.steps, int(budget / max(first, 1e-3)))), 0
+    sec = first if steps == 1 else (first + run_cpu(mask, sp, px, py, threads, steps - 1, 0) * (steps - 1)) / steps
     value = mask.size / sec
     same_config = mask.shape == (ny, nx) and sp == P
     line = {
