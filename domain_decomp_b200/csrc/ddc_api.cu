@@ -332,7 +332,12 @@ int pick_rows_per_cta(K kernel, int rows, int gridx)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
         per_sm = 1;
-    const long long want = 2LL * per_sm * sms; // CTAs for two full waves
+    // CTAs for two full waves -- but on a narrow grid (few column blocks) all CTAs in flight add into the same few
+    // thousand column counters, and chunks small enough for two waves spend their time in those atomics: there,
+    // three quarters of ONE wave (everything resident at once) with 4-16 x fewer atomics is faster
+    // (measured, profiles/r2r_sweep.jsonl: 4096^2 113 -> 107 us with 32 rows instead of 8, 8192^2 174 -> 170 us
+    //  with 64-128 instead of 32; 32768 columns: unchanged)
+    const long long want = (gridx <= 8 ? 3LL : 8LL) * per_sm * sms / 4;
     int rpc = 128;
     while (rpc > 8 && (long long)gridx * ((rows + rpc - 1) / rpc) < want)
         rpc >>= 1;
