@@ -189,6 +189,8 @@ struct ddc_handle_s {
     int halo_parts = 0;
     DevBuf<unsigned> gate; // the word the gate kernel of the second stream waits for (see BoxGate)
     bool use_gate = true;
+    bool side_pdl = true; // DDC_SIDE_PDL: the scan of the neighbour counts launched programmatically behind the count kernel
+                          // (-4 us at C2, neutral elsewhere)
     bool dev_join = false; // DDC_DEV_JOIN: the labelling kernel's last block waits for the neighbour kernels instead of an event join
                            // (off: measured +13 us at C5, +2.5 us at C2 / C3, -1 us at C4 on one GPU)
     bool row_flags = true; // DDC_ROW_FLAGS: exchange step 2 with one flag per block of the row-count kernel (default: 2 ranks
@@ -493,6 +495,7 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     h->use_gate = env_int("DDC_GATE", 1) != 0;
     h->early = env_int("DDC_EARLY", 17);
     h->dev_join = env_int("DDC_DEV_JOIN", 0) != 0;
+    h->side_pdl = env_int("DDC_SIDE_PDL", 1) != 0;
     h->row_flags = env_int("DDC_ROW_FLAGS", nranks <= 2 ? 1 : 0) != 0;
     CREATE_TRY(h->gate.ensure(4)); // [0] K4 -> labelling kernel / second stream, [1] k_sum_cols -> K2, [2] K2 -> K3 (ChainWord)
     CREATE_TRY(cudaMemset(h->gate.p, 0, 4 * sizeof(unsigned)));
@@ -1231,8 +1234,10 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
         }
         CUDA_TRY(h, launch_k(k_neighbours<false>, dim3(ngrid), dim3(256), 0, q, false, t.bx, P, NX, NY, px, py, t.st,
             h->nbr_counts.p, nullptr, nullptr, h->nbr_cap, nullptr, nullptr, nullptr, h->sc.p, h->plan.p, ChainWord { nullptr, 0u }, nullptr));
-        CUDA_TRY(h, launch_k(k_scan_counts, dim3(8), dim3(1024), 0, q, false, h->nbr_counts.p, P, h->nbr_offsets.p,
+        CUDA_TRY(h, launch_k(k_scan_counts, dim3(8), dim3(1024), 0, q, pdl && h->side_pdl, h->nbr_counts.p, P, h->nbr_offsets.p,
             h->nbr_totals.p, h->plan.p));
+        // (the fill kernel with a plain launch: its P / 8 blocks, resident and waiting on the high-priority stream while the
+        //  8 blocks of the scan run, took the SMs from the labelling kernel -- +15 us at C5)
         CUDA_TRY(h, launch_k(k_neighbours<true>, dim3(ngrid), dim3(256), 0, q, false, t.bx, P, NX, NY, px, py, t.st,
             h->nbr_counts.p, h->nbr_offsets.p, h->nbr_totals.p, h->nbr_cap, h->nbr_ids.p, h->nbr_halos.p, h->nbr_starts.p,
             h->sc.p, h->plan.p, w_nbr, h->done.p + d_nbr));

@@ -2255,6 +2255,12 @@ __global__ void __launch_bounds__(256) k_neighbours(BoxTable bx, int P, int NX, 
                              for it: no join of the two streams between two steps) */,
     unsigned* __restrict__ done_ctr)
 {
+    // (the scan of the counts is launched programmatically behind the count kernel; the count and the fill kernel
+    //  themselves follow their predecessors with plain launches: P / 8 blocks waiting behind the gate kernel would hold
+    //  SMs that the y-cut kernel, which opens the gate, still needs, and waiting behind the scan they take them from
+    //  the labelling kernel)
+    pdl_trigger();
+    pdl_wait();
     bool run = !(plan && plan->mismatch);
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (run && FILL) {
@@ -2299,6 +2305,8 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
     int* __restrict__ offsets, int* __restrict__ totals, const Plan* __restrict__ plan)
 {
     __shared__ unsigned long long wsum64[33];
+    pdl_trigger();
+    pdl_wait();
     if (plan && plan->mismatch)
         return;
     const int l = blockIdx.x;
