@@ -188,7 +188,7 @@ struct ddc_handle_s {
     DevBuf<long long> halo_off; // tile offsets of the halo exchange (ddc_halo_tile_offsets)
     int halo_parts = 0;
     DevBuf<unsigned> gate; // the word the gate kernel of the second stream waits for (see BoxGate)
-    bool use_gate = true;
+    int use_gate = 1; // DDC_GATE: 0 never, 1 unless the shard is tiny, 2 always
     bool side_pdl = true; // DDC_SIDE_PDL: the scan of the neighbour counts launched programmatically behind the count kernel
                           // (-4 us at C2, neutral elsewhere)
     bool dev_join = false; // DDC_DEV_JOIN: the labelling kernel's last block waits for the neighbour kernels instead of an event join
@@ -492,7 +492,7 @@ int ddc_create(ddc_handle_t* out, int device, int rank, int nranks, const void* 
     h->scan_rpc = env_int("DDC_SCAN_RPC", 0);
     h->scan_tail = std::max(0, std::min(90, env_int("DDC_SCAN_TAIL", 25)));
     h->label_rpc = env_int("DDC_LABEL_RPC", 0);
-    h->use_gate = env_int("DDC_GATE", 1) != 0;
+    h->use_gate = env_int("DDC_GATE", 1);
     h->early = env_int("DDC_EARLY", 17);
     h->dev_join = env_int("DDC_DEV_JOIN", 0) != 0;
     h->side_pdl = env_int("DDC_SIDE_PDL", 1) != 0;
@@ -1106,7 +1106,10 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     mark(2);
     // the second stream (neighbour tables beside the labelling kernel) is forked by a device-side gate when K4 runs
     // and nothing else has to sit between K4 and the labelling kernel (no profiling events)
-    const bool gated = h->use_gate && want_nbr && ycuts && !profile;
+    // (not on tiny shards: there the neighbour kernels end the step, and starting them behind a polling kernel instead of
+    //  an event costs more than the programmatic launch of a 9 us labelling kernel saves -- 528 x 522: +3 us with the gate;
+    //  DDC_GATE=2 forces it)
+    const bool gated = h->use_gate && want_nbr && ycuts && !profile && (h->use_gate > 1 || (long long)rows * NX >= (1LL << 21));
     const bool label_polls = pdl && ycuts && (h->early & 4); // the labelling kernel polls the same word
     BoxGate gate {};
     if (gated || label_polls) {
