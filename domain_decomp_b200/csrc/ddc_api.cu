@@ -1221,7 +1221,9 @@ int enqueue_partition(ddc_handle_t h, int nparts, int px, int py, int flags)
     h->nparts = P;
     h->px = px;
     h->py = py;
-    const int ngrid = (std::max(P, 8) + 7) / 8; // >= 8 * pad32(P) threads
+    // the boxes of a step come in strips (K2 has just cleared `always`): thread = (list, part), 8 * pad32(P) threads --
+    // a quarter of the warp-per-part grid that caller-supplied boxes need (run_neighbours)
+    const int ngrid = std::max(1, (8 * ((P + 31) & ~31) + 255) / 256);
     // The labelling kernel's last block also ends the step (`changes`, exchange step 3, the plan into the host's
     // pinned copy) unless there is no labelling kernel on this rank or the exchange goes through NCCL ...
     const bool fuse = h->fuse_fin && label_runs && (G == 1 || p2p);
