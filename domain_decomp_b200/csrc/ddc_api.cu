@@ -745,11 +745,16 @@ int ddc_peer_connect(ddc_handle_t* handles, int n, int nx, int ny, int nparts)
         CUDA_TRY(h, cudaMalloc((void**)&h->xbuf, words * sizeof(unsigned)));
         CUDA_TRY(h, cudaMemset(h->xbuf, 0, words * sizeof(unsigned)));
     }
+    // the words and flags of the exchange carry the step number: the ranks count their steps together from here on
+    unsigned step = 0;
+    for (int q = 0; q < n; q++)
+        step = std::max(step, handles[q]->step);
     for (int q = 0; q < n; q++) {
         for (int r = 0; r < n; r++)
             handles[q]->xpeer[r] = handles[r]->xbuf;
         handles[q]->p2p = true;
         handles[q]->peer_local = true;
+        handles[q]->step = step;
     }
     return DDC_OK;
 }

@@ -104,7 +104,10 @@ DDC_API const char* ddc_last_error(ddc_handle_t h);
    to nx * ny into nparts parts (one slot per rank and histogram) and returns its CUDA IPC
    handle; the host gathers the handles of all ranks (MPI_Allgather / torch.distributed) and hands
    them, in rank order, to ddc_peer_import().  Without these two calls -- or for a decomposition
-   that does not fit the exported capacity -- the exchange steps are NCCL collectives. */
+   that does not fit the exported capacity -- the exchange steps are NCCL collectives.
+   The flags and data words of the exchange carry the number of the decomposition: every rank must have made the
+   same number of ddc_partition() calls when the buffers are imported (normally none), and make them together
+   afterwards.  (ddc_peer_connect, all handles in one process, aligns the counters itself.) */
 DDC_API int ddc_peer_export(ddc_handle_t h, int nx, int ny, int nparts, void* ipc_handle_out /* DDC_IPC_HANDLE_BYTES */);
 DDC_API int ddc_peer_import(ddc_handle_t h, const void* all_handles /* nranks * DDC_IPC_HANDLE_BYTES */);
 /* unmap the other ranks' buffers (back to NCCL).  Shutdown order: every rank calls ddc_peer_close(),
