@@ -169,6 +169,25 @@ def test_row_counts_with_one_flag_per_rank_or_per_block(oracle, monkeypatch):
     monkeypatch.delenv("DDC_ROW_FLAGS")
 
 
+def test_random_multi_rank_cases(oracle, monkeypatch):
+    """random shapes, part counts, periodic flags, 2-8 ranks (ragged and empty shards included), both ways of flagging
+    the row counts, random block / thread schedules: boxes, pid, neighbour tables and `changes` equal the oracle's"""
+    import random
+    from domain_decomp_b200 import capi
+    rng = random.Random(20261018)
+    for _ in range(40):
+        nx, ny = rng.choice([5, 33, 130, 1030, 2500]), rng.choice([7, 40, 203, 900])
+        P, ranks = rng.randint(2, 24), rng.choice([2, 3, 4, 5, 8])
+        px, py = rng.random() < .5, rng.random() < .5
+        monkeypatch.setenv("DDC_EMU_SCHED_SEED", str(rng.randint(1, 2 ** 40)))
+        monkeypatch.setenv("DDC_ROW_FLAGS", rng.choice(["0", "1"]))
+        mask = capi.generate_mask_host(nx, ny, rng.randint(1, 99), rng.choice([0.2, 0.5, 0.8]))
+        d, _ = oracle.emu_partition(mask, P, px, py, ranks=ranks, scan_rpc=rng.choice([8, 16, 64]))
+        assert_same(d, oracle.partition(mask, P, px, py, use_hist=True), (nx, ny, P, ranks, px, py))
+    monkeypatch.delenv("DDC_EMU_SCHED_SEED")
+    monkeypatch.delenv("DDC_ROW_FLAGS")
+
+
 def test_results_do_not_depend_on_the_schedule(oracle, monkeypatch):
     """the emulation can run the blocks of a grid in a random order and the threads of a block in a new random order
     every scheduling round (DDC_EMU_SCHED_SEED): a missing barrier, an assumption about block order or about
